@@ -1,0 +1,1184 @@
+// engine.cu — handle state, HBM layout management and the C ABI of include/fvdb.h.
+//
+// Device state behind one handle (= one HybridIndex, src/hybrid/core.rs:202-213):
+//   centroids  C[nlist x D] fp32                            (Vec<Centroid>, src/ivf/core.rs:156)
+//   IVF arena  X[ivf_n x D] fp32, rows of list l contiguous at [list_off[l], list_off[l+1]),
+//              ids[ivf_n] (caller row ids), list[ivf_n]      (inverted_lists, :157)
+//   pending    rows appended since the last seal (assigned, not yet grouped)
+//   flat tier  R[flat_n x D] fp32 + ids[flat_n]              (HNSW nodes, src/hnsw/core.rs:141)
+//   tombstones u64 bitmap over row ids                       (deleted: HashSet, src/ivf/core.rs:167)
+// There is no CPU fallback anywhere in this file: every numeric result comes from a kernel.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fvdb.h"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_scan.cuh"
+
+using namespace fvdb;
+
+namespace {
+
+std::mutex g_err_mu;
+std::string g_create_err;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // grow to >= n elements; preserve the first `keep` elements
+    cudaError_t ensure(size_t n, size_t keep, cudaStream_t s, size_t* total_bytes, bool exact = false) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = exact ? n : std::max(n, cap + cap / 2);
+        T* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p) {
+            e = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) { cudaFree(np); return e; }
+            e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { cudaFree(np); return e; }
+        }
+        if (p) cudaFree(p);
+        if (total_bytes) *total_bytes += (ncap - cap) * sizeof(T);
+        p = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void swap(DevBuf& o) { std::swap(p, o.p); std::swap(cap, o.cap); }
+};
+
+struct SplitMix {
+    uint64_t s;
+    explicit SplitMix(uint64_t seed) : s(seed) {}
+    uint64_t next() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    double u01() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+}  // namespace
+
+struct fvdb_index {
+    int device = 0;
+    uint32_t dim = 0, k_max = 0;
+    int metric = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
+    std::mutex mu;
+    std::string err;
+    uint32_t scan_mode = FVDB_SCAN_EXACT;
+    uint32_t shortlist = 0;
+    uint32_t kmeans_tc = 0;
+    size_t dev_bytes = 0;
+
+    uint32_t nlist = 0;
+    bool trained = false;
+    DevBuf<float> centroids;
+
+    DevBuf<float> ivf_rows;
+    DevBuf<uint32_t> ivf_ids, ivf_list;
+    uint64_t ivf_n = 0;
+    DevBuf<uint32_t> list_off;  // nlist + 2
+
+    DevBuf<float> pend_rows;
+    DevBuf<uint32_t> pend_ids, pend_list;
+    uint64_t pend_n = 0;
+
+    DevBuf<float> flat_rows;
+    DevBuf<uint32_t> flat_ids;
+    uint64_t flat_n = 0;
+
+    DevBuf<uint64_t> tomb;
+    uint64_t tomb_bits = 0;
+    uint64_t deleted_count = 0;
+
+    // host-side presence map over row ids: 0 absent, 1 flat, 2 ivf; bit 7 = tombstoned.
+    std::vector<uint8_t> id_state;
+    bool track_ids = true;
+
+    // scratch (grow-only)
+    DevBuf<float> s_q, s_x;              // staged queries / staged rows
+    DevBuf<uint32_t> s_u32a, s_u32b, s_u32c, s_perm, s_keys32;
+    DevBuf<uint64_t> s_filter;
+    DevBuf<uint64_t> s_partial, s_partial2, s_coarse, s_ivf_keys, s_flat_keys;
+    DevBuf<ScanItem> s_items, s_items2;
+    DevBuf<uint32_t> s_list_cnt, s_pair_off, s_cursor, s_pair_q, s_pair_slot, s_misc;
+    DevBuf<unsigned char> s_group;
+    DevBuf<uint32_t> s_out_ids, s_out_cnt;
+    DevBuf<float> s_out_dist, s_f32a;
+    DevBuf<double> s_f64;
+    DevBuf<uint64_t> s_tmpbits;
+    TcScratch tc;
+
+    // pinned staging
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
+
+    fvdb_stats stats{};
+
+    int fail(int code, const std::string& m) {
+        err = m;
+        return code;
+    }
+    int fail_cuda(cudaError_t e, const char* what) {
+        err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? FVDB_ERR_OOM : FVDB_ERR_CUDA;
+    }
+    cudaError_t ensure_pin(size_t bytes) {
+        if (bytes <= pin_bytes) return cudaSuccess;
+        if (pin) cudaFreeHost(pin);
+        pin = nullptr;
+        pin_bytes = 0;
+        size_t nb = std::max(bytes, (size_t)1 << 20);
+        cudaError_t e = cudaMallocHost(&pin, nb);
+        if (e == cudaSuccess) pin_bytes = nb;
+        return e;
+    }
+};
+
+#define CK(call)                                                      \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return h->fail_cuda(e__, #call);      \
+    } while (0)
+#define RET(call)                         \
+    do {                                  \
+        int r__ = (call);                 \
+        if (r__ != FVDB_OK) return r__;   \
+    } while (0)
+
+namespace {
+
+// ---- host <-> device staging through pinned memory ------------------------------------------
+int h2d(fvdb_index* h, void* dst, const void* src, size_t bytes) {
+    const size_t CH = (size_t)64 << 20;
+    CK(h->ensure_pin(std::min(bytes, CH)));
+    size_t off = 0;
+    while (off < bytes) {
+        const size_t n = std::min(CH, bytes - off);
+        std::memcpy(h->pin, (const char*)src + off, n);
+        CK(cudaMemcpyAsync((char*)dst + off, h->pin, n, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        off += n;
+    }
+    return FVDB_OK;
+}
+int d2h(fvdb_index* h, void* dst, const void* src, size_t bytes) {
+    const size_t CH = (size_t)64 << 20;
+    CK(h->ensure_pin(std::min(bytes, CH)));
+    size_t off = 0;
+    while (off < bytes) {
+        const size_t n = std::min(CH, bytes - off);
+        CK(cudaMemcpyAsync(h->pin, (const char*)src + off, n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        std::memcpy((char*)dst + off, h->pin, n);
+        off += n;
+    }
+    return FVDB_OK;
+}
+
+int check_nan_device(fvdb_index* h, const float* d_x, size_t n, cudaStream_t st) {
+    CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
+    int* flag = reinterpret_cast<int*>(h->s_misc.p);
+    CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    CK(launch_nan_check(d_x, n, flag, st));
+    int hf = 0;
+    CK(cudaMemcpyAsync(&hf, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hf) return h->fail(FVDB_ERR_NAN, "NaN in input (the reference panics on partial_cmp().unwrap())");
+    return FVDB_OK;
+}
+
+uint32_t pick_nsplit(fvdb_index* h, uint32_t nq, uint64_t rows) {
+    const uint32_t n_qt = (nq + exact_scan_tq() - 1) / exact_scan_tq();
+    const uint32_t tiles = (uint32_t)((rows + exact_scan_tr() - 1) / exact_scan_tr());
+    uint32_t target = (uint32_t)h->sm_count * 4;
+    uint32_t s = (target + n_qt - 1) / std::max(1u, n_qt);
+    s = std::max(1u, std::min(s, std::max(1u, tiles)));
+    s = std::min(s, 256u);
+    return s;
+}
+
+// Scan every query against rows [0,rows) of X; result keys[nq][k] sorted (exact arithmetic).
+int scan_all_exact(fvdb_index* h, const float* X, const uint32_t* ids, uint64_t rows, const float* Q,
+                   uint32_t nq, uint32_t k, const uint64_t* tomb, uint64_t tomb_bits,
+                   const uint64_t* filt, uint64_t filt_bits, uint64_t* out_keys, cudaStream_t st) {
+    if (rows >= 0xFFFFFFFFull) return h->fail(FVDB_ERR_INVALID_ARG, "row count exceeds u32");
+    const uint32_t nsplit = pick_nsplit(h, nq, rows);
+    uint32_t n_items = 0;
+    const uint32_t n_qt = (nq + exact_scan_tq() - 1) / exact_scan_tq();
+    CK(h->s_items2.ensure((size_t)n_qt * nsplit, 0, st, &h->dev_bytes));
+    CK(launch_build_identity_items(h->s_items2.p, nq, 0, (uint32_t)rows, nsplit, &n_items, st));
+    uint64_t* partial = out_keys;
+    if (nsplit > 1) {
+        CK(h->s_partial2.ensure((size_t)nq * nsplit * k, 0, st, &h->dev_bytes));
+        partial = h->s_partial2.p;
+        CK(cudaMemsetAsync(partial, 0xFF, (size_t)nq * nsplit * k * sizeof(uint64_t), st));
+    } else {
+        CK(cudaMemsetAsync(partial, 0xFF, (size_t)nq * k * sizeof(uint64_t), st));
+    }
+    ExactScanArgs a{};
+    a.X = X; a.ids = ids; a.Q = Q; a.D = h->dim;
+    a.items = h->s_items2.p; a.item_count = nullptr; a.n_items = n_items;
+    a.pair_q = nullptr; a.pair_slot = nullptr;
+    a.P = nsplit; a.k = k;
+    a.tomb = tomb; a.tomb_bits = tomb_bits; a.filt = filt; a.filt_bits = filt_bits;
+    a.partial = partial;
+    CK(launch_exact_scan(a, n_items, st));
+    h->stats.last_launches += 3;
+    if (nsplit > 1) {
+        CK(launch_merge_partials(partial, nq, nsplit, k, out_keys, st));
+        h->stats.last_launches += 1;
+    }
+    return FVDB_OK;
+}
+
+// Regroup sealed + pending IVF rows so every list is one contiguous row range.
+int seal(fvdb_index* h) {
+    if (h->pend_n == 0) return FVDB_OK;
+    cudaStream_t st = h->stream;
+    const uint64_t total = h->ivf_n + h->pend_n;
+    if (total >= 0xFFFFFFF0ull) return h->fail(FVDB_ERR_INVALID_ARG, "IVF tier exceeds u32 rows");
+    const uint32_t D = h->dim;
+    CK(h->s_keys32.ensure(total, 0, st, &h->dev_bytes));
+    if (h->ivf_n)
+        CK(cudaMemcpyAsync(h->s_keys32.p, h->ivf_list.p, h->ivf_n * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->s_keys32.p + h->ivf_n, h->pend_list.p, h->pend_n * 4,
+                       cudaMemcpyDeviceToDevice, st));
+    CK(h->s_perm.ensure(total, 0, st, &h->dev_bytes));
+    CK(h->s_group.ensure(stable_group_scratch_bytes(total, h->nlist), 0, st, &h->dev_bytes));
+    CK(h->list_off.ensure(h->nlist + 2, 0, st, &h->dev_bytes));
+    CK(launch_stable_group(h->s_keys32.p, total, h->nlist, h->list_off.p, h->s_perm.p, h->s_group.p, st));
+    uint32_t kept = 0;
+    CK(cudaMemcpyAsync(&kept, h->list_off.p + h->nlist, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    DevBuf<float> nrows;
+    DevBuf<uint32_t> nids, nlist_ids;
+    CK(nrows.ensure((size_t)std::max<uint64_t>(kept, 1) * D, 0, st, &h->dev_bytes, true));
+    CK(nids.ensure(std::max<uint64_t>(kept, 1), 0, st, &h->dev_bytes, true));
+    CK(nlist_ids.ensure(std::max<uint64_t>(kept, 1), 0, st, &h->dev_bytes, true));
+    CK(launch_gather_rows(h->ivf_rows.p, h->ivf_n, h->pend_rows.p, h->s_perm.p, kept, D, nrows.p, st));
+    CK(launch_gather_u32(h->ivf_ids.p, h->ivf_n, h->pend_ids.p, h->s_perm.p, kept, nids.p, st));
+    CK(launch_gather_u32(h->ivf_list.p, h->ivf_n, h->pend_list.p, h->s_perm.p, kept, nlist_ids.p, st));
+    CK(cudaStreamSynchronize(st));
+    h->dev_bytes -= h->ivf_rows.cap * sizeof(float) + (h->ivf_ids.cap + h->ivf_list.cap) * 4;
+    h->dev_bytes -= h->pend_rows.cap * sizeof(float) + (h->pend_ids.cap + h->pend_list.cap) * 4;
+    h->ivf_rows.swap(nrows);
+    h->ivf_ids.swap(nids);
+    h->ivf_list.swap(nlist_ids);
+    h->pend_rows.release();
+    h->pend_ids.release();
+    h->pend_list.release();
+    h->ivf_n = kept;
+    h->pend_n = 0;
+    h->tc.arena_dirty = true;
+    return FVDB_OK;
+}
+
+int ensure_tomb(fvdb_index* h, uint64_t nbits) {
+    if (nbits <= h->tomb_bits) return FVDB_OK;
+    const uint64_t words_old = (h->tomb_bits + 63) / 64;
+    uint64_t nb = std::max<uint64_t>(nbits, h->tomb_bits * 2);
+    nb = (nb + 4095) / 4096 * 4096;
+    const uint64_t words = nb / 64;
+    CK(h->tomb.ensure(words, words_old, h->stream, &h->dev_bytes));
+    CK(cudaMemsetAsync(h->tomb.p + words_old, 0, (words - words_old) * 8, h->stream));
+    h->tomb_bits = nb;
+    return FVDB_OK;
+}
+
+int append_pending(fvdb_index* h, const float* d_x, const uint32_t* d_ids, const uint32_t* d_list,
+                   uint64_t n) {
+    if (n == 0) return FVDB_OK;
+    cudaStream_t st = h->stream;
+    const uint32_t D = h->dim;
+    CK(h->pend_rows.ensure((h->pend_n + n) * D, h->pend_n * D, st, &h->dev_bytes));
+    CK(h->pend_ids.ensure(h->pend_n + n, h->pend_n, st, &h->dev_bytes));
+    CK(h->pend_list.ensure(h->pend_n + n, h->pend_n, st, &h->dev_bytes));
+    CK(cudaMemcpyAsync(h->pend_rows.p + h->pend_n * D, d_x, n * D * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->pend_ids.p + h->pend_n, d_ids, n * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->pend_list.p + h->pend_n, d_list, n * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    h->pend_n += n;
+    return FVDB_OK;
+}
+
+// assign rows to their nearest centroid: out d_assign[n] (and optionally distances)
+int assign_device(fvdb_index* h, const float* d_x, uint64_t n, uint32_t* d_assign, float* d_dist,
+                  const uint32_t* prev, uint32_t* d_changed, cudaStream_t st) {
+    if (n == 0) return FVDB_OK;
+    if (n >= 0xFFFFFFFFull) return h->fail(FVDB_ERR_INVALID_ARG, "batch exceeds u32 rows");
+    CK(h->s_ivf_keys.ensure(n, 0, st, &h->dev_bytes));
+    if (h->kmeans_tc && tc_supported(h->dim)) {
+        int r = tc_assign(h->tc, h->centroids.p, h->nlist, d_x, n, h->dim, h->s_ivf_keys.p, st,
+                          &h->dev_bytes, &h->err);
+        if (r != FVDB_OK) return r;
+    } else {
+        RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_x, (uint32_t)n, 1, nullptr, 0,
+                           nullptr, 0, h->s_ivf_keys.p, st));
+    }
+    CK(launch_extract_assign(h->s_ivf_keys.p, n, d_assign, d_dist, prev, d_changed, st));
+    return FVDB_OK;
+}
+
+int ivf_add_device_impl(fvdb_index* h, const float* d_x, const uint32_t* d_ids, uint64_t n,
+                        uint32_t mod, uint32_t rem, uint64_t* kept_out, uint32_t* h_out_list) {
+    if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");
+    if (kept_out) *kept_out = 0;
+    if (n == 0) return FVDB_OK;
+    cudaStream_t st = h->stream;
+    const uint32_t D = h->dim;
+    RET(check_nan_device(h, d_x, n * D, st));
+    CK(h->s_u32a.ensure(n, 0, st, &h->dev_bytes));
+    RET(assign_device(h, d_x, n, h->s_u32a.p, nullptr, nullptr, nullptr, st));
+    if (h_out_list) RET(d2h(h, h_out_list, h->s_u32a.p, n * 4));
+    if (mod <= 1) {
+        RET(append_pending(h, d_x, d_ids, h->s_u32a.p, n));
+        if (kept_out) *kept_out = n;
+        return FVDB_OK;
+    }
+    // list-sharded load: keep only rows whose list % mod == rem, compacted (grouped by list)
+    CK(h->s_u32b.ensure(n, 0, st, &h->dev_bytes));
+    CK(launch_filter_keys_mod(h->s_u32a.p, n, mod, rem, h->nlist, h->s_u32b.p, st));
+    CK(h->s_perm.ensure(n, 0, st, &h->dev_bytes));
+    CK(h->s_group.ensure(stable_group_scratch_bytes(n, h->nlist), 0, st, &h->dev_bytes));
+    CK(h->s_u32c.ensure(h->nlist + 2, 0, st, &h->dev_bytes));
+    CK(launch_stable_group(h->s_u32b.p, n, h->nlist, h->s_u32c.p, h->s_perm.p, h->s_group.p, st));
+    uint32_t kept = 0;
+    CK(cudaMemcpyAsync(&kept, h->s_u32c.p + h->nlist, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (kept) {
+        CK(h->pend_rows.ensure((h->pend_n + kept) * D, h->pend_n * D, st, &h->dev_bytes));
+        CK(h->pend_ids.ensure(h->pend_n + kept, h->pend_n, st, &h->dev_bytes));
+        CK(h->pend_list.ensure(h->pend_n + kept, h->pend_n, st, &h->dev_bytes));
+        CK(launch_gather_rows(d_x, n, nullptr, h->s_perm.p, kept, D, h->pend_rows.p + h->pend_n * D, st));
+        CK(launch_gather_u32(d_ids, n, nullptr, h->s_perm.p, kept, h->pend_ids.p + h->pend_n, st));
+        CK(launch_gather_u32(h->s_u32b.p, n, nullptr, h->s_perm.p, kept, h->pend_list.p + h->pend_n, st));
+        CK(cudaStreamSynchronize(st));
+        h->pend_n += kept;
+    }
+    if (kept_out) *kept_out = kept;
+    return FVDB_OK;
+}
+
+int flat_add_device_impl(fvdb_index* h, const float* d_x, const uint32_t* d_ids, uint64_t n) {
+    if (n == 0) return FVDB_OK;
+    cudaStream_t st = h->stream;
+    const uint32_t D = h->dim;
+    RET(check_nan_device(h, d_x, n * D, st));
+    if (h->flat_n + n >= 0xFFFFFFF0ull) return h->fail(FVDB_ERR_INVALID_ARG, "flat tier exceeds u32 rows");
+    CK(h->flat_rows.ensure((h->flat_n + n) * D, h->flat_n * D, st, &h->dev_bytes));
+    CK(h->flat_ids.ensure(h->flat_n + n, h->flat_n, st, &h->dev_bytes));
+    CK(cudaMemcpyAsync(h->flat_rows.p + h->flat_n * D, d_x, n * D * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->flat_ids.p + h->flat_n, d_ids, n * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    h->flat_n += n;
+    h->tc.flat_dirty = true;
+    return FVDB_OK;
+}
+
+// host-side duplicate screen + presence update (HybridIndex::insert dup check, src/hybrid/core.rs:368;
+// InvertedList::insert, src/ivf/core.rs:128-134)
+int track_insert(fvdb_index* h, const uint32_t* ids, uint64_t n, uint8_t tier) {
+    if (!h->track_ids) return FVDB_OK;
+    uint32_t mx = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (ids[i] == ID_NONE) return h->fail(FVDB_ERR_INVALID_ARG, "row id 0xFFFFFFFF is reserved");
+        mx = std::max(mx, ids[i]);
+    }
+    if (h->id_state.size() <= mx) h->id_state.resize((size_t)mx + 1, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (h->id_state[ids[i]] & 3) {
+            // roll back what this call marked
+            for (uint64_t j = 0; j < i; ++j) h->id_state[ids[j]] = 0;
+            return h->fail(FVDB_ERR_DUPLICATE, "Vector with row id " + std::to_string(ids[i]) + " already exists");
+        }
+        h->id_state[ids[i]] = tier;
+    }
+    return FVDB_OK;
+}
+
+void clear_lists(fvdb_index* h) {
+    if (h->track_ids)
+        for (auto& s : h->id_state) if ((s & 3) == 2) { if (s & 0x80) h->deleted_count--; s = 0; }
+    h->ivf_n = 0;
+    h->pend_n = 0;
+    h->tc.arena_dirty = true;
+}
+
+float host_mean_sq(const std::vector<float>& dist) {
+    // compute_error, src/ivf/core.rs:419-429: f32 left fold of dist*dist, then / n
+    volatile float total = 0.0f;
+    for (size_t i = 0; i < dist.size(); ++i) {
+        volatile float sq = dist[i] * dist[i];
+        total = total + sq;
+    }
+    return total / (float)dist.size();
+}
+
+int compute_error_device(fvdb_index* h, const float* d_data, uint64_t n, const uint32_t* d_assign,
+                         float* out) {
+    cudaStream_t st = h->stream;
+    CK(h->s_f32a.ensure(n, 0, st, &h->dev_bytes));
+    CK(launch_rowwise_dist(d_data, n, h->dim, h->centroids.p, d_assign, h->s_f32a.p, st));
+    std::vector<float> dist(n);
+    RET(d2h(h, dist.data(), h->s_f32a.p, n * 4));
+    *out = host_mean_sq(dist);
+    return FVDB_OK;
+}
+
+int train_device_impl(fvdb_index* h, const float* d_data, uint64_t n, uint32_t nlist,
+                      uint32_t max_iterations, const float* d_init, uint64_t seed,
+                      fvdb_train_result* out) {
+    cudaStream_t st = h->stream;
+    const uint32_t D = h->dim;
+    if (nlist == 0 || max_iterations == 0) return h->fail(FVDB_ERR_INVALID_CONFIG, "Invalid IVFConfig");
+    if (n == 0 || n < nlist)
+        return h->fail(FVDB_ERR_INSUFFICIENT_TRAINING, "Insufficient training data: got " +
+                       std::to_string(n) + ", need at least " + std::to_string(nlist));
+    if (n >= 0xFFFFFFF0ull) return h->fail(FVDB_ERR_INVALID_ARG, "training set exceeds u32 rows");
+    RET(check_nan_device(h, d_data, n * D, st));
+    CK(h->centroids.ensure((size_t)nlist * D, 0, st, &h->dev_bytes));
+    h->nlist = nlist;
+    h->trained = false;
+    h->tc.centroids_dirty = true;
+    if (d_init) {
+        RET(check_nan_device(h, d_init, (size_t)nlist * D, st));
+        CK(cudaMemcpyAsync(h->centroids.p, d_init, (size_t)nlist * D * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+        // k-means++ (src/ivf/core.rs:336-371), running-min form, device-side picks
+        SplitMix rng(seed);
+        CK(h->s_f32a.ensure(n, 0, st, &h->dev_bytes));
+        std::vector<float> inf(1, INFINITY);
+        // fill mind with +inf: 0x7f800000 pattern
+        CK(cudaMemsetAsync(h->s_f32a.p, 0, n * 4, st));
+        {
+            // memset cannot write 0x7f800000; use iota-free trick: copy from a host vector in chunks
+            std::vector<float> tmp(std::min<uint64_t>(n, 1 << 20), INFINITY);
+            for (uint64_t off = 0; off < n; off += tmp.size()) {
+                const uint64_t c = std::min<uint64_t>(tmp.size(), n - off);
+                CK(cudaMemcpyAsync(h->s_f32a.p + off, tmp.data(), c * 4, cudaMemcpyHostToDevice, st));
+                CK(cudaStreamSynchronize(st));
+            }
+        }
+        const uint32_t nb = (uint32_t)((n + 1023) / 1024);
+        CK(h->s_f64.ensure(nb + 1, 0, st, &h->dev_bytes));
+        CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
+        uint32_t* d_pick = h->s_misc.p + 8;
+        const uint32_t first = (uint32_t)(rng.next() % n);
+        CK(cudaMemcpyAsync(d_pick, &first, 4, cudaMemcpyHostToDevice, st));
+        CK(launch_copy_row(d_data, d_pick, D, h->centroids.p, st));
+        for (uint32_t i = 1; i < nlist; ++i) {
+            uint32_t nblocks = 0;
+            CK(launch_kmeanspp_update(d_data, n, D, h->centroids.p + (size_t)(i - 1) * D, h->s_f32a.p,
+                                      h->s_f64.p, &nblocks, st));
+            const double u = (double)(float)((rng.next() >> 40) * (1.0 / 16777216.0));
+            CK(launch_kmeanspp_pick(h->s_f32a.p, n, h->s_f64.p, nblocks, u, d_pick, st));
+            CK(launch_copy_row(d_data, d_pick, D, h->centroids.p + (size_t)i * D, st));
+        }
+        CK(cudaStreamSynchronize(st));
+    }
+
+    // Lloyd loop (src/ivf/core.rs:279-322)
+    DevBuf<uint32_t> assign;
+    CK(assign.ensure(n, 0, st, nullptr, true));
+    CK(cudaMemsetAsync(assign.p, 0, n * 4, st));  // vec![ClusterId(0); n]
+    CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
+    uint32_t* d_changed = h->s_misc.p + 4;
+    float prev_error = INFINITY;
+    float initial_error = 0.f;
+    RET(compute_error_device(h, d_data, n, assign.p, &initial_error));
+    bool converged = false;
+    uint32_t iterations = 0;
+    for (uint32_t iter = 0; iter < max_iterations; ++iter) {
+        iterations = iter + 1;
+        CK(cudaMemsetAsync(d_changed, 0, 4, st));
+        RET(assign_device(h, d_data, n, assign.p, nullptr, assign.p, d_changed, st));
+        uint32_t changed = 0;
+        CK(cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st));
+        // update step: order-faithful per-cluster sums
+        CK(h->s_perm.ensure(n, 0, st, &h->dev_bytes));
+        CK(h->s_group.ensure(stable_group_scratch_bytes(n, nlist), 0, st, &h->dev_bytes));
+        CK(h->s_u32c.ensure(nlist + 2, 0, st, &h->dev_bytes));
+        CK(launch_stable_group(assign.p, n, nlist, h->s_u32c.p, h->s_perm.p, h->s_group.p, st));
+        CK(launch_centroid_update(d_data, D, h->s_u32c.p, h->s_perm.p, nlist, h->centroids.p, st));
+        CK(cudaStreamSynchronize(st));
+        h->tc.centroids_dirty = true;
+        if (iterations >= max_iterations) break;
+        float current_error = 0.f;
+        RET(compute_error_device(h, d_data, n, assign.p, &current_error));
+        volatile float diff = std::fabs(prev_error - current_error);
+        const float error_change = diff / prev_error;
+        if (!changed || error_change < 1e-4f) {
+            converged = true;
+            if (max_iterations == 10 && n < 20) {  // src/ivf/core.rs:313-317
+                prev_error = current_error;
+                continue;
+            }
+            break;
+        }
+        prev_error = current_error;
+    }
+    float final_error = 0.f;
+    RET(compute_error_device(h, d_data, n, assign.p, &final_error));
+    h->trained = true;
+    clear_lists(h);
+    CK(h->list_off.ensure(nlist + 2, 0, st, &h->dev_bytes));
+    CK(cudaMemsetAsync(h->list_off.p, 0, (nlist + 2) * 4, st));
+    CK(cudaStreamSynchronize(st));
+    if (out) {
+        out->iterations = iterations;
+        out->converged = converged ? 1u : 0u;
+        out->initial_error = initial_error;
+        out->final_error = final_error;
+    }
+    return FVDB_OK;
+}
+
+int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,
+                       uint32_t tiers, const uint64_t* d_filter, uint64_t filter_bits,
+                       uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count,
+                       cudaStream_t st) {
+    if (k == 0) return h->fail(FVDB_ERR_INVALID_ARG, "k must be >= 1");
+    if (k > h->k_max) return h->fail(FVDB_ERR_K_TOO_LARGE, "k exceeds k_max given at fvdb_create");
+    h->stats.last_nq = nq;
+    h->stats.last_fallback_queries = 0;
+    h->stats.last_scanned_rows = 0;
+    h->stats.last_algorithmic_bytes = 0;
+    h->stats.last_launches = 0;
+    h->stats.last_device_ms = 0.f;
+    h->stats.last_scan_ms = 0.f;
+    if (nq == 0) return FVDB_OK;
+    RET(seal(h));
+    const uint32_t D = h->dim;
+    const bool use_ivf = (tiers & FVDB_TIER_HISTORICAL) && h->trained && h->ivf_n > 0 && nprobe > 0;
+    const bool use_flat = (tiers & FVDB_TIER_RECENT) && h->flat_n > 0;
+    const uint64_t* tomb = h->deleted_count ? h->tomb.p : nullptr;
+    const uint64_t* filt = d_filter;
+
+    CK(cudaEventRecord(h->ev_a, st));
+    CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
+    int* d_nan = reinterpret_cast<int*>(h->s_misc.p);
+    uint64_t* d_scanned = reinterpret_cast<uint64_t*>(h->s_misc.p + 2);
+    CK(cudaMemsetAsync(h->s_misc.p, 0, 64, st));
+    CK(launch_nan_check(d_q, (size_t)nq * D, d_nan, st));
+    h->stats.last_launches += 1;
+
+    uint64_t* ivf_keys = nullptr;
+    uint64_t* flat_keys = nullptr;
+    bool scan_timed = false;
+
+    if (use_ivf) {
+        const uint32_t np = std::min(nprobe, h->nlist);
+        if (np > 512) return h->fail(FVDB_ERR_INVALID_ARG, "nprobe > 512 is not supported");
+        CK(h->s_ivf_keys.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
+        ivf_keys = h->s_ivf_keys.p;
+        const bool tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D);
+        if (tc) {
+            TcSearchArgs ta{};
+            ta.centroids = h->centroids.p; ta.nlist = h->nlist;
+            ta.rows = h->ivf_rows.p; ta.ids = h->ivf_ids.p; ta.n_rows = h->ivf_n;
+            ta.list_off = h->list_off.p;
+            ta.Q = d_q; ta.nq = nq; ta.D = D; ta.k = k; ta.nprobe = np;
+            ta.tomb = tomb; ta.tomb_bits = h->tomb_bits; ta.filt = filt; ta.filt_bits = filter_bits;
+            ta.shortlist = h->shortlist;
+            ta.out_keys = ivf_keys;
+            ta.d_scanned_rows = d_scanned;
+            ta.ev_scan0 = h->ev_s0; ta.ev_scan1 = h->ev_s1;
+            ta.sm_count = h->sm_count;
+            uint32_t launches = 0, fallback = 0;
+            int r = tc_ivf_search(h->tc, ta, st, &h->dev_bytes, &launches, &fallback, &h->err);
+            if (r != FVDB_OK) return r;
+            h->stats.last_launches += launches;
+            h->stats.last_fallback_queries = fallback;
+            scan_timed = true;
+        } else {
+            // coarse step: all centroid distances, nearest np lists (src/ivf/core.rs:646-656)
+            CK(h->s_coarse.ensure((size_t)nq * np, 0, st, &h->dev_bytes));
+            RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_q, nq, np, nullptr, 0, nullptr, 0,
+                               h->s_coarse.p, st));
+            // bucket (query, probe) pairs by list
+            const uint32_t tq = exact_scan_tq();
+            const size_t n_pairs = (size_t)nq * np;
+            const size_t max_items = (size_t)h->nlist + (n_pairs + tq - 1) / tq + 1;
+            CK(h->s_list_cnt.ensure(h->nlist + 1, 0, st, &h->dev_bytes));
+            CK(h->s_pair_off.ensure(h->nlist + 2, 0, st, &h->dev_bytes));
+            CK(h->s_cursor.ensure(h->nlist + 1, 0, st, &h->dev_bytes));
+            CK(h->s_pair_q.ensure(n_pairs, 0, st, &h->dev_bytes));
+            CK(h->s_pair_slot.ensure(n_pairs, 0, st, &h->dev_bytes));
+            CK(h->s_items.ensure(max_items, 0, st, &h->dev_bytes));
+            uint32_t* d_n_items = h->s_misc.p + 6;
+            CK(launch_probe_bucketing(h->s_coarse.p, nq, np, h->list_off.p, h->nlist, tq, h->s_list_cnt.p,
+                                      h->s_pair_off.p, h->s_cursor.p, h->s_pair_q.p, h->s_pair_slot.p,
+                                      h->s_items.p, d_n_items, d_scanned, st));
+            h->stats.last_launches += 3;
+            // posting-list scan (src/ivf/core.rs:661-674), one sorted partial per (query, probe)
+            uint32_t Ppad = np;
+            if (np > 256) Ppad = (np + 255) / 256 * 256;
+            CK(h->s_partial.ensure((size_t)nq * Ppad * k, 0, st, &h->dev_bytes));
+            CK(cudaMemsetAsync(h->s_partial.p, 0xFF, (size_t)nq * Ppad * k * 8, st));
+            ExactScanArgs a{};
+            a.X = h->ivf_rows.p; a.ids = h->ivf_ids.p; a.Q = d_q; a.D = D;
+            a.items = h->s_items.p; a.item_count = d_n_items; a.n_items = 0;
+            a.pair_q = h->s_pair_q.p; a.pair_slot = h->s_pair_slot.p;
+            a.P = Ppad; a.k = k;
+            a.tomb = tomb; a.tomb_bits = h->tomb_bits; a.filt = filt; a.filt_bits = filter_bits;
+            a.partial = h->s_partial.p;
+            CK(cudaEventRecord(h->ev_s0, st));
+            CK(launch_exact_scan(a, (uint32_t)max_items, st));
+            CK(cudaEventRecord(h->ev_s1, st));
+            scan_timed = true;
+            h->stats.last_launches += 1;
+            // sort + truncate(k) (src/ivf/core.rs:677-678)
+            if (Ppad > 256) {
+                CK(h->s_partial2.ensure((size_t)nq * (Ppad / 256) * k, 0, st, &h->dev_bytes));
+                CK(launch_merge_partials(h->s_partial.p, nq * (Ppad / 256), 256, k, h->s_partial2.p, st));
+                CK(launch_merge_partials(h->s_partial2.p, nq, Ppad / 256, k, ivf_keys, st));
+                h->stats.last_launches += 2;
+            } else {
+                CK(launch_merge_partials(h->s_partial.p, nq, Ppad, k, ivf_keys, st));
+                h->stats.last_launches += 1;
+            }
+        }
+    }
+    if (use_flat) {
+        CK(h->s_flat_keys.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
+        flat_keys = h->s_flat_keys.p;
+        const bool tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D);
+        if (tc) {
+            TcFlatArgs fa{};
+            fa.rows = h->flat_rows.p; fa.ids = h->flat_ids.p; fa.n_rows = h->flat_n;
+            fa.Q = d_q; fa.nq = nq; fa.D = D; fa.k = k;
+            fa.tomb = tomb; fa.tomb_bits = h->tomb_bits; fa.filt = filt; fa.filt_bits = filter_bits;
+            fa.shortlist = h->shortlist; fa.out_keys = flat_keys; fa.sm_count = h->sm_count;
+            uint32_t launches = 0, fallback = 0;
+            int r = tc_flat_search(h->tc, fa, st, &h->dev_bytes, &launches, &fallback, &h->err);
+            if (r != FVDB_OK) return r;
+            h->stats.last_launches += launches;
+            h->stats.last_fallback_queries += fallback;
+        } else {
+            RET(scan_all_exact(h, h->flat_rows.p, h->flat_ids.p, h->flat_n, d_q, nq, k, tomb, h->tomb_bits,
+                               filt, filter_bits, flat_keys, st));
+        }
+    }
+    CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
+    h->stats.last_launches += 1;
+    CK(cudaEventRecord(h->ev_b, st));
+
+    // one synchronisation point per batch: NaN flag + counters
+    struct { int nan; int pad; uint64_t scanned; } host_misc{};
+    CK(cudaMemcpyAsync(&host_misc, h->s_misc.p, sizeof(host_misc), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (host_misc.nan)
+        return h->fail(FVDB_ERR_NAN, "NaN in query (the reference panics on partial_cmp().unwrap())");
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
+    h->stats.last_device_ms = ms;
+    if (scan_timed) {
+        float sms = 0.f;
+        if (cudaEventElapsedTime(&sms, h->ev_s0, h->ev_s1) == cudaSuccess) h->stats.last_scan_ms = sms;
+        else cudaGetLastError();
+    }
+    uint64_t rows = host_misc.scanned + (use_flat ? h->flat_n : 0);
+    h->stats.last_scanned_rows = rows;
+    uint64_t bytes = rows * D * 4ull + (uint64_t)nq * D * 4ull + (uint64_t)nq * k * 8ull;
+    if (use_ivf) bytes += (uint64_t)h->nlist * D * 4ull;
+    if (tomb) bytes += rows / 8;
+    if (filt) bytes += rows / 8;
+    h->stats.last_algorithmic_bytes = bytes;
+    return FVDB_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int fvdb_abi_version(void) { return FVDB_ABI_VERSION; }
+
+const char* fvdb_last_error(const fvdb_index* h) {
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> g(g_err_mu);
+    return g_create_err.c_str();
+}
+
+int fvdb_create(int device, uint32_t dim, int metric, uint32_t k_max, fvdb_index** out) {
+    auto fail = [&](int code, const std::string& m) {
+        std::lock_guard<std::mutex> g(g_err_mu);
+        g_create_err = m;
+        return code;
+    };
+    if (!out) return fail(FVDB_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (dim == 0) return fail(FVDB_ERR_INVALID_CONFIG, "dim must be > 0");
+    if (metric != FVDB_METRIC_L2) return fail(FVDB_ERR_INVALID_CONFIG, "only FVDB_METRIC_L2 is implemented");
+    if (k_max == 0 || k_max > 512) return fail(FVDB_ERR_INVALID_CONFIG, "k_max must be in 1..512");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(FVDB_ERR_NO_DEVICE, std::string("no CUDA device: ") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                    " (libfvdb_b200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= count) return fail(FVDB_ERR_NO_DEVICE, "device ordinal out of range");
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail(FVDB_ERR_NO_DEVICE, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(FVDB_ERR_NO_DEVICE, std::string("device ") + prop.name +
+                    " is not sm_100; libfvdb_b200 ships sm_100a code only");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(FVDB_ERR_NO_DEVICE, "cudaSetDevice failed");
+    fvdb_index* h = new fvdb_index();
+    h->device = device;
+    h->dim = dim;
+    h->metric = metric;
+    h->k_max = k_max;
+    h->sm_count = prop.multiProcessorCount;
+    h->scan_mode = tc_supported(dim) ? FVDB_SCAN_TC : FVDB_SCAN_EXACT;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev_a) != cudaSuccess || cudaEventCreate(&h->ev_b) != cudaSuccess ||
+        cudaEventCreate(&h->ev_s0) != cudaSuccess || cudaEventCreate(&h->ev_s1) != cudaSuccess) {
+        delete h;
+        return fail(FVDB_ERR_CUDA, "stream/event creation failed");
+    }
+    *out = h;
+    return FVDB_OK;
+}
+
+void fvdb_destroy(fvdb_index* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    tc_release(h->tc);
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->ev_a) cudaEventDestroy(h->ev_a);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    if (h->ev_s0) cudaEventDestroy(h->ev_s0);
+    if (h->ev_s1) cudaEventDestroy(h->ev_s1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+#define ENTER(h)                                            \
+    if (!(h)) return FVDB_ERR_INVALID_ARG;                  \
+    std::lock_guard<std::mutex> guard__((h)->mu);           \
+    (h)->err.clear();                                       \
+    if (cudaSetDevice((h)->device) != cudaSuccess) return (h)->fail(FVDB_ERR_CUDA, "cudaSetDevice failed")
+
+int fvdb_set_option(fvdb_index* h, int option, uint64_t value) {
+    ENTER(h);
+    switch (option) {
+        case FVDB_OPT_SCAN_MODE:
+            if (value == FVDB_SCAN_TC && !tc_supported(h->dim))
+                return h->fail(FVDB_ERR_INVALID_CONFIG, "tensor-core scan needs dim % 32 == 0 and dim <= 1024");
+            if (value > FVDB_SCAN_TC) return h->fail(FVDB_ERR_INVALID_ARG, "unknown scan mode");
+            h->scan_mode = (uint32_t)value;
+            return FVDB_OK;
+        case FVDB_OPT_SHORTLIST:
+            h->shortlist = (uint32_t)value;
+            return FVDB_OK;
+        case FVDB_OPT_KMEANS_TC:
+            h->kmeans_tc = value ? 1u : 0u;
+            return FVDB_OK;
+        default:
+            return h->fail(FVDB_ERR_INVALID_ARG, "unknown option");
+    }
+}
+
+int fvdb_get_stats(fvdb_index* h, fvdb_stats* out) {
+    ENTER(h);
+    if (!out) return h->fail(FVDB_ERR_INVALID_ARG, "out is NULL");
+    h->stats.dim = h->dim;
+    h->stats.nlist = h->nlist;
+    h->stats.trained = h->trained ? 1u : 0u;
+    h->stats.ivf_rows = h->ivf_n + h->pend_n;
+    h->stats.flat_rows = h->flat_n;
+    h->stats.deleted_rows = h->deleted_count;
+    h->stats.device_bytes = h->dev_bytes;
+    *out = h->stats;
+    return FVDB_OK;
+}
+
+int fvdb_ivf_set_centroids(fvdb_index* h, const float* centroids, uint32_t nlist) {
+    ENTER(h);
+    if (!centroids || nlist == 0) return h->fail(FVDB_ERR_INVALID_CONFIG, "centroids empty");
+    for (size_t i = 0; i < (size_t)nlist * h->dim; ++i)
+        if (std::isnan(centroids[i])) return h->fail(FVDB_ERR_NAN, "NaN in centroids");
+    CK(h->centroids.ensure((size_t)nlist * h->dim, 0, h->stream, &h->dev_bytes));
+    RET(h2d(h, h->centroids.p, centroids, (size_t)nlist * h->dim * 4));
+    h->nlist = nlist;
+    h->trained = true;
+    h->tc.centroids_dirty = true;
+    clear_lists(h);
+    CK(h->list_off.ensure(nlist + 2, 0, h->stream, &h->dev_bytes));
+    CK(cudaMemsetAsync(h->list_off.p, 0, (nlist + 2) * 4, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FVDB_OK;
+}
+
+int fvdb_ivf_get_centroids(fvdb_index* h, float* out, uint32_t* nlist) {
+    ENTER(h);
+    if (nlist) *nlist = h->trained ? h->nlist : 0;
+    if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained.");
+    if (out) RET(d2h(h, out, h->centroids.p, (size_t)h->nlist * h->dim * 4));
+    return FVDB_OK;
+}
+
+int fvdb_ivf_train_device(fvdb_index* h, const float* d_data, uint64_t n, uint32_t nlist,
+                          uint32_t max_iterations, const float* d_init_centroids, uint64_t seed,
+                          fvdb_train_result* out) {
+    ENTER(h);
+    return train_device_impl(h, d_data, n, nlist, max_iterations, d_init_centroids, seed, out);
+}
+
+int fvdb_ivf_train(fvdb_index* h, const float* data, uint64_t n, uint32_t nlist,
+                   uint32_t max_iterations, const float* init_centroids, uint64_t seed,
+                   fvdb_train_result* out) {
+    ENTER(h);
+    if (nlist == 0 || max_iterations == 0) return h->fail(FVDB_ERR_INVALID_CONFIG, "Invalid IVFConfig");
+    if (n == 0 || n < nlist)
+        return h->fail(FVDB_ERR_INSUFFICIENT_TRAINING, "Insufficient training data: got " +
+                       std::to_string(n) + ", need at least " + std::to_string(nlist));
+    if (!data) return h->fail(FVDB_ERR_INVALID_ARG, "data is NULL");
+    DevBuf<float> d_data, d_init;
+    CK(d_data.ensure(n * h->dim, 0, h->stream, nullptr, true));
+    RET(h2d(h, d_data.p, data, n * h->dim * 4));
+    if (init_centroids) {
+        CK(d_init.ensure((size_t)nlist * h->dim, 0, h->stream, nullptr, true));
+        RET(h2d(h, d_init.p, init_centroids, (size_t)nlist * h->dim * 4));
+    }
+    return train_device_impl(h, d_data.p, n, nlist, max_iterations, init_centroids ? d_init.p : nullptr,
+                             seed, out);
+}
+
+int fvdb_assign(fvdb_index* h, const float* x, uint64_t n, uint32_t* out_list) {
+    ENTER(h);
+    if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");
+    if (n == 0) return FVDB_OK;
+    if (!x || !out_list) return h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+    const uint64_t CH = 1u << 20;
+    for (uint64_t off = 0; off < n; off += CH) {
+        const uint64_t c = std::min(CH, n - off);
+        CK(h->s_x.ensure(c * h->dim, 0, h->stream, &h->dev_bytes));
+        CK(h->s_u32a.ensure(c, 0, h->stream, &h->dev_bytes));
+        RET(h2d(h, h->s_x.p, x + off * h->dim, c * h->dim * 4));
+        RET(check_nan_device(h, h->s_x.p, c * h->dim, h->stream));
+        RET(assign_device(h, h->s_x.p, c, h->s_u32a.p, nullptr, nullptr, nullptr, h->stream));
+        RET(d2h(h, out_list + off, h->s_u32a.p, c * 4));
+    }
+    return FVDB_OK;
+}
+
+int fvdb_ivf_add(fvdb_index* h, const float* x, const uint32_t* row_ids, uint64_t n, uint32_t* out_list) {
+    ENTER(h);
+    if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");
+    if (n == 0) return FVDB_OK;
+    if (!x || !row_ids) return h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+    RET(track_insert(h, row_ids, n, 2));
+    const uint64_t CH = 1u << 20;
+    for (uint64_t off = 0; off < n; off += CH) {
+        const uint64_t c = std::min(CH, n - off);
+        CK(h->s_x.ensure(c * h->dim, 0, h->stream, &h->dev_bytes));
+        CK(h->s_out_ids.ensure(c, 0, h->stream, &h->dev_bytes));
+        RET(h2d(h, h->s_x.p, x + off * h->dim, c * h->dim * 4));
+        RET(h2d(h, h->s_out_ids.p, row_ids + off, c * 4));
+        int r = ivf_add_device_impl(h, h->s_x.p, h->s_out_ids.p, c, 1, 0, nullptr,
+                                    out_list ? out_list + off : nullptr);
+        if (r != FVDB_OK) {
+            if (h->track_ids) for (uint64_t i = off; i < n; ++i) h->id_state[row_ids[i]] = 0;
+            return r;
+        }
+    }
+    return FVDB_OK;
+}
+
+int fvdb_ivf_add_device(fvdb_index* h, const float* d_x, const uint32_t* d_row_ids, uint64_t n,
+                        uint32_t list_filter_mod, uint32_t list_filter_rem, uint64_t* kept) {
+    ENTER(h);
+    h->track_ids = false;  // ids never visit the host on this path
+    return ivf_add_device_impl(h, d_x, d_row_ids, n, list_filter_mod, list_filter_rem, kept, nullptr);
+}
+
+int fvdb_flat_add(fvdb_index* h, const float* x, const uint32_t* row_ids, uint64_t n) {
+    ENTER(h);
+    if (n == 0) return FVDB_OK;
+    if (!x || !row_ids) return h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+    RET(track_insert(h, row_ids, n, 1));
+    const uint64_t CH = 1u << 20;
+    for (uint64_t off = 0; off < n; off += CH) {
+        const uint64_t c = std::min(CH, n - off);
+        CK(h->s_x.ensure(c * h->dim, 0, h->stream, &h->dev_bytes));
+        CK(h->s_out_ids.ensure(c, 0, h->stream, &h->dev_bytes));
+        RET(h2d(h, h->s_x.p, x + off * h->dim, c * h->dim * 4));
+        RET(h2d(h, h->s_out_ids.p, row_ids + off, c * 4));
+        int r = flat_add_device_impl(h, h->s_x.p, h->s_out_ids.p, c);
+        if (r != FVDB_OK) {
+            if (h->track_ids) for (uint64_t i = off; i < n; ++i) h->id_state[row_ids[i]] = 0;
+            return r;
+        }
+    }
+    return FVDB_OK;
+}
+
+int fvdb_flat_add_device(fvdb_index* h, const float* d_x, const uint32_t* d_row_ids, uint64_t n) {
+    ENTER(h);
+    h->track_ids = false;
+    return flat_add_device_impl(h, d_x, d_row_ids, n);
+}
+
+int fvdb_set_deleted(fvdb_index* h, const uint32_t* row_ids, uint64_t n, int deleted) {
+    ENTER(h);
+    if (n == 0) return FVDB_OK;
+    if (!row_ids) return h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+    uint32_t mx = 0;
+    for (uint64_t i = 0; i < n; ++i) mx = std::max(mx, row_ids[i]);
+    if (h->track_ids) {
+        for (uint64_t i = 0; i < n; ++i)
+            if (row_ids[i] >= h->id_state.size() || (h->id_state[row_ids[i]] & 3) == 0)
+                return h->fail(FVDB_ERR_NOT_FOUND, "Vector not found: row id " + std::to_string(row_ids[i]));
+        for (uint64_t i = 0; i < n; ++i) {
+            uint8_t& s = h->id_state[row_ids[i]];
+            if (deleted && !(s & 0x80)) { s |= 0x80; h->deleted_count++; }
+            else if (!deleted && (s & 0x80)) { s &= 0x7f; h->deleted_count--; }
+        }
+    } else {
+        if (deleted) h->deleted_count += n;  // upper bound; only used as "any tombstones" flag
+    }
+    RET(ensure_tomb(h, (uint64_t)mx + 1));
+    CK(h->s_out_ids.ensure(n, 0, h->stream, &h->dev_bytes));
+    RET(h2d(h, h->s_out_ids.p, row_ids, n * 4));
+    CK(launch_set_bits(h->tomb.p, h->tomb_bits, h->s_out_ids.p, n, deleted ? 1 : 0, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FVDB_OK;
+}
+
+int fvdb_vacuum(fvdb_index* h, uint64_t* removed) {
+    ENTER(h);
+    if (removed) *removed = 0;
+    RET(seal(h));
+    if (h->deleted_count == 0 || h->tomb_bits == 0) return FVDB_OK;
+    cudaStream_t st = h->stream;
+    const uint32_t D = h->dim;
+    uint64_t gone = 0;
+    if (h->ivf_n) {
+        const uint64_t n = h->ivf_n;
+        CK(h->s_keys32.ensure(n, 0, st, &h->dev_bytes));
+        CK(launch_keys_from_bitmap(h->ivf_ids.p, n, h->tomb.p, h->tomb_bits, h->nlist, h->ivf_list.p, 0,
+                                   h->s_keys32.p, st));
+        CK(h->s_perm.ensure(n, 0, st, &h->dev_bytes));
+        CK(h->s_group.ensure(stable_group_scratch_bytes(n, h->nlist), 0, st, &h->dev_bytes));
+        CK(launch_stable_group(h->s_keys32.p, n, h->nlist, h->list_off.p, h->s_perm.p, h->s_group.p, st));
+        uint32_t kept = 0;
+        CK(cudaMemcpyAsync(&kept, h->list_off.p + h->nlist, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        DevBuf<float> nrows;
+        DevBuf<uint32_t> nids, nl;
+        CK(nrows.ensure((size_t)std::max<uint64_t>(kept, 1) * D, 0, st, &h->dev_bytes, true));
+        CK(nids.ensure(std::max<uint64_t>(kept, 1), 0, st, &h->dev_bytes, true));
+        CK(nl.ensure(std::max<uint64_t>(kept, 1), 0, st, &h->dev_bytes, true));
+        CK(launch_gather_rows(h->ivf_rows.p, n, nullptr, h->s_perm.p, kept, D, nrows.p, st));
+        CK(launch_gather_u32(h->ivf_ids.p, n, nullptr, h->s_perm.p, kept, nids.p, st));
+        CK(launch_gather_u32(h->ivf_list.p, n, nullptr, h->s_perm.p, kept, nl.p, st));
+        CK(cudaStreamSynchronize(st));
+        h->dev_bytes -= h->ivf_rows.cap * 4 + (h->ivf_ids.cap + h->ivf_list.cap) * 4;
+        h->ivf_rows.swap(nrows);
+        h->ivf_ids.swap(nids);
+        h->ivf_list.swap(nl);
+        gone += n - kept;
+        h->ivf_n = kept;
+        h->tc.arena_dirty = true;
+    }
+    if (h->flat_n) {
+        const uint64_t n = h->flat_n;
+        CK(h->s_keys32.ensure(n, 0, st, &h->dev_bytes));
+        CK(launch_keys_from_bitmap(h->flat_ids.p, n, h->tomb.p, h->tomb_bits, 1, nullptr, 0, h->s_keys32.p, st));
+        CK(h->s_perm.ensure(n, 0, st, &h->dev_bytes));
+        CK(h->s_group.ensure(stable_group_scratch_bytes(n, 1), 0, st, &h->dev_bytes));
+        CK(h->s_u32c.ensure(8, 0, st, &h->dev_bytes));
+        CK(launch_stable_group(h->s_keys32.p, n, 1, h->s_u32c.p, h->s_perm.p, h->s_group.p, st));
+        uint32_t kept = 0;
+        CK(cudaMemcpyAsync(&kept, h->s_u32c.p + 1, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        DevBuf<float> nrows;
+        DevBuf<uint32_t> nids;
+        CK(nrows.ensure((size_t)std::max<uint64_t>(kept, 1) * D, 0, st, &h->dev_bytes, true));
+        CK(nids.ensure(std::max<uint64_t>(kept, 1), 0, st, &h->dev_bytes, true));
+        CK(launch_gather_rows(h->flat_rows.p, n, nullptr, h->s_perm.p, kept, D, nrows.p, st));
+        CK(launch_gather_u32(h->flat_ids.p, n, nullptr, h->s_perm.p, kept, nids.p, st));
+        CK(cudaStreamSynchronize(st));
+        h->dev_bytes -= h->flat_rows.cap * 4 + h->flat_ids.cap * 4;
+        h->flat_rows.swap(nrows);
+        h->flat_ids.swap(nids);
+        gone += n - kept;
+        h->flat_n = kept;
+        h->tc.flat_dirty = true;
+    }
+    CK(cudaMemsetAsync(h->tomb.p, 0, (h->tomb_bits + 63) / 64 * 8, st));
+    CK(cudaStreamSynchronize(st));
+    if (h->track_ids)
+        for (auto& s : h->id_state) if (s & 0x80) s = 0;
+    h->deleted_count = 0;
+    if (removed) *removed = gone;
+    return FVDB_OK;
+}
+
+int fvdb_move_flat_to_ivf(fvdb_index* h, const uint32_t* row_ids, uint64_t n, uint64_t* moved) {
+    ENTER(h);
+    if (moved) *moved = 0;
+    if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");
+    if (n == 0 || h->flat_n == 0) return FVDB_OK;
+    if (!row_ids) return h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+    cudaStream_t st = h->stream;
+    const uint32_t D = h->dim;
+    uint32_t mx = 0;
+    for (uint64_t i = 0; i < n; ++i) mx = std::max(mx, row_ids[i]);
+    const uint64_t nbits = ((uint64_t)mx + 64) / 64 * 64;
+    CK(h->s_tmpbits.ensure(nbits / 64, 0, st, &h->dev_bytes));
+    CK(cudaMemsetAsync(h->s_tmpbits.p, 0, nbits / 8, st));
+    CK(h->s_out_ids.ensure(n, 0, st, &h->dev_bytes));
+    RET(h2d(h, h->s_out_ids.p, row_ids, n * 4));
+    CK(launch_set_bits(h->s_tmpbits.p, nbits, h->s_out_ids.p, n, 1, st));
+    const uint64_t fn = h->flat_n;
+    CK(h->s_keys32.ensure(fn, 0, st, &h->dev_bytes));
+    CK(launch_keys_from_bitmap(h->flat_ids.p, fn, h->s_tmpbits.p, nbits, 1, nullptr, 0, h->s_keys32.p, st));
+    CK(h->s_perm.ensure(fn, 0, st, &h->dev_bytes));
+    CK(h->s_group.ensure(stable_group_scratch_bytes(fn, 2), 0, st, &h->dev_bytes));
+    CK(h->s_u32c.ensure(8, 0, st, &h->dev_bytes));
+    CK(launch_stable_group(h->s_keys32.p, fn, 2, h->s_u32c.p, h->s_perm.p, h->s_group.p, st));
+    uint32_t offs[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(offs, h->s_u32c.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t stay = offs[1], mv = offs[2] - offs[1];
+    if (mv == 0) return FVDB_OK;
+    DevBuf<float> nrows;
+    DevBuf<uint32_t> nids;
+    CK(nrows.ensure((size_t)fn * D, 0, st, &h->dev_bytes, true));
+    CK(nids.ensure(fn, 0, st, &h->dev_bytes, true));
+    CK(launch_gather_rows(h->flat_rows.p, fn, nullptr, h->s_perm.p, fn, D, nrows.p, st));
+    CK(launch_gather_u32(h->flat_ids.p, fn, nullptr, h->s_perm.p, fn, nids.p, st));
+    CK(cudaStreamSynchronize(st));
+    h->dev_bytes -= h->flat_rows.cap * 4 + h->flat_ids.cap * 4;
+    h->flat_rows.swap(nrows);
+    h->flat_ids.swap(nids);
+    h->flat_n = stay;
+    h->tc.flat_dirty = true;
+    RET(ivf_add_device_impl(h, h->flat_rows.p + stay * D, h->flat_ids.p + stay, mv, 1, 0, nullptr, nullptr));
+    if (h->track_ids)
+        for (uint64_t i = 0; i < n; ++i)
+            if (row_ids[i] < h->id_state.size() && (h->id_state[row_ids[i]] & 3) == 1)
+                h->id_state[row_ids[i]] = (h->id_state[row_ids[i]] & 0x80) | 2;
+    if (moved) *moved = mv;
+    return FVDB_OK;
+}
+
+int fvdb_search_device(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,
+                       uint32_t tiers, const uint64_t* d_filter_bits, uint64_t filter_nbits,
+                       uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count, void* stream) {
+    ENTER(h);
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return search_device_impl(h, d_q, nq, k, nprobe, tiers, d_filter_bits, filter_nbits, d_out_ids,
+                              d_out_dist, d_out_count, st);
+}
+
+int fvdb_search(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t nprobe, uint32_t tiers,
+                const uint64_t* filter_bits, uint64_t filter_nbits, uint32_t* out_ids, float* out_dist,
+                uint32_t* out_count) {
+    ENTER(h);
+    if (k == 0) return h->fail(FVDB_ERR_INVALID_ARG, "k must be >= 1");
+    if (k > h->k_max) return h->fail(FVDB_ERR_K_TOO_LARGE, "k exceeds k_max given at fvdb_create");
+    if (nq == 0) return FVDB_OK;
+    if (!q || !out_ids || !out_dist || !out_count) return h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+    cudaStream_t st = h->stream;
+    const uint32_t D = h->dim;
+    const size_t qb = (size_t)nq * D * 4, ob = (size_t)nq * k * 4, cb = (size_t)nq * 4;
+    CK(h->s_q.ensure((size_t)nq * D, 0, st, &h->dev_bytes));
+    CK(h->s_out_ids.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
+    CK(h->s_out_dist.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
+    CK(h->s_out_cnt.ensure(nq, 0, st, &h->dev_bytes));
+    // pinned staging: queries in, results out, one async copy each way
+    CK(h->ensure_pin(std::max(qb, 2 * ob + cb)));
+    std::memcpy(h->pin, q, qb);
+    CK(cudaMemcpyAsync(h->s_q.p, h->pin, qb, cudaMemcpyHostToDevice, st));
+    const uint64_t* d_filter = nullptr;
+    if (filter_bits && filter_nbits) {
+        const size_t words = (filter_nbits + 63) / 64;
+        CK(h->s_filter.ensure(words, 0, st, &h->dev_bytes));
+        CK(cudaStreamSynchronize(st));  // pin buffer is about to be reused
+        RET(h2d(h, h->s_filter.p, filter_bits, words * 8));
+        d_filter = h->s_filter.p;
+    } else if (filter_bits) {
+        // an empty bitmap filters everything out
+        CK(h->s_filter.ensure(1, 0, st, &h->dev_bytes));
+        CK(cudaMemsetAsync(h->s_filter.p, 0, 8, st));
+        d_filter = h->s_filter.p;
+        filter_nbits = 0;
+    }
+    RET(search_device_impl(h, h->s_q.p, nq, k, nprobe, tiers, d_filter, filter_nbits, h->s_out_ids.p,
+                           h->s_out_dist.p, h->s_out_cnt.p, st));
+    char* pin = (char*)h->pin;
+    CK(cudaMemcpyAsync(pin, h->s_out_ids.p, ob, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pin + ob, h->s_out_dist.p, ob, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pin + 2 * ob, h->s_out_cnt.p, cb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::memcpy(out_ids, pin, ob);
+    std::memcpy(out_dist, pin + ob, ob);
+    std::memcpy(out_count, pin + 2 * ob, cb);
+    return FVDB_OK;
+}
+
+int fvdb_merge_topk_device(fvdb_index* h, const uint32_t* d_ids, const float* d_dist, const uint32_t* d_count,
+                           uint32_t parts, uint32_t nq, uint32_t k, uint32_t* d_out_ids, float* d_out_dist,
+                           uint32_t* d_out_count, void* stream) {
+    ENTER(h);
+    if (parts == 0 || parts > 64) return h->fail(FVDB_ERR_INVALID_ARG, "parts must be in 1..64");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    CK(launch_merge_parts(d_ids, d_dist, d_count, parts, nq, k, d_out_ids, d_out_dist, d_out_count, st));
+    return FVDB_OK;
+}
+
+int fvdb_kmeans_accumulate_device(fvdb_index* h, const float* d_data, uint64_t n, float* d_sums,
+                                  uint32_t* d_counts, double* d_sqerr, uint32_t* d_assign,
+                                  uint32_t* d_changed, void* stream) {
+    ENTER(h);
+    if (!h->nlist || !h->centroids.p) return h->fail(FVDB_ERR_NOT_TRAINED, "centroids not set");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (n == 0) return FVDB_OK;
+    CK(h->s_f32a.ensure(n, 0, st, &h->dev_bytes));
+    RET(assign_device(h, d_data, n, d_assign, h->s_f32a.p, d_assign, d_changed, st));
+    CK(launch_accumulate_sums(d_data, n, h->dim, d_assign, h->s_f32a.p, d_sums, d_counts, d_sqerr, st));
+    return FVDB_OK;
+}
+
+int fvdb_kmeans_apply_device(fvdb_index* h, const float* d_sums, const uint32_t* d_counts, void* stream) {
+    ENTER(h);
+    if (!h->nlist || !h->centroids.p) return h->fail(FVDB_ERR_NOT_TRAINED, "centroids not set");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    CK(launch_apply_means(d_sums, d_counts, h->nlist, h->dim, h->centroids.p, st));
+    h->tc.centroids_dirty = true;
+    return FVDB_OK;
+}
+
+}  // extern "C"

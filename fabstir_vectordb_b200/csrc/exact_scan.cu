@@ -1,0 +1,571 @@
+// exact_scan.cu — the fp32 CUDA-core scan: every (query,row) distance is accumulated in the
+// reference's own operation order (euclidean_distance_scalar, src/core/vector_ops.rs:51-57:
+// t = a-b; acc = acc + t*t, index order, no FMA; then sqrt), so distances are bit-identical to
+// the Rust reference.  One kernel serves four callers, all as "rows of a matrix against a
+// group of queries -> per-query sorted partial top-k of u64 keys":
+//   * IVF coarse step        (rows = centroids, k = nprobe)     src/ivf/core.rs:646-656
+//   * IVF posting-list scan  (rows = one list, queries = probers) src/ivf/core.rs:661-678
+//   * recent-tier flat scan  (rows = flat tier)                 replaces src/hnsw/core.rs:398-467
+//   * k-means assignment     (rows = centroids, queries = points, k = 1) src/ivf/core.rs:291-297
+// It is also the fallback / re-rank arithmetic of the tensor-core mode (tc_scan.cu).
+//
+// Tiling: CTA = 256 threads = 32 queries x 128 rows per tile, each thread a 4x4 register
+// tile; D is walked in 32-wide chunks staged transposed in shared memory so the inner loop is
+// 2 x LDS.128 + 48 ALU ops per d.  Bounded by the fp32 pipe (3 instructions per element, no
+// FMA allowed), not by HBM: this path is the parity anchor, the tensor-core path is the fast one.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace fvdb {
+
+namespace {
+
+constexpr int TQ = 32;    // queries per tile
+constexpr int TR = 128;   // rows per tile
+constexpr int DK = 32;    // d-chunk
+constexpr int NT = 256;   // threads
+constexpr int QS_LD = TQ + 4;
+constexpr int XS_LD = TR + 4;
+
+// Insert `cand` into the ascending list[0..k) held in shared memory, dropping the largest.
+// Whole warp cooperates.  Precondition: cand < list[k-1].
+__device__ __forceinline__ void warp_insert(uint64_t* list, int k, uint64_t cand, int lane) {
+    // position = number of entries < cand (keys are unique per (dist,id); equal keys keep
+    // the incumbent first)
+    int cnt = 0;
+    for (int i = lane; i < k; i += 32) cnt += (list[i] <= cand) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const int pos = cnt;
+    // shift [pos, k-1) up by one, chunk by chunk from the top
+    for (int base = ((k - 1) / 32) * 32; base >= 0 && base + 31 > pos; base -= 32) {
+        int i = base + lane;
+        uint64_t tmp = 0;
+        bool mv = (i > pos) && (i < k);
+        if (mv) tmp = list[i - 1];
+        __syncwarp();
+        if (mv) list[i] = tmp;
+        __syncwarp();
+    }
+    if (lane == 0) list[pos] = cand;
+    __syncwarp();
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(NT) exact_scan_kernel(ExactScanArgs a) {
+    const uint32_t n_items = a.item_count ? *a.item_count : a.n_items;
+    if (blockIdx.x >= n_items) return;
+    const ScanItem it = a.items[blockIdx.x];
+    if (it.pair_count == 0) return;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Qs = reinterpret_cast<float*>(smem_raw);                 // [DK][QS_LD]
+    float* Xs = Qs + DK * QS_LD;                                    // [DK][XS_LD]; later dist tile [TQ][XS_LD]
+    uint32_t* rowid_s = reinterpret_cast<uint32_t*>(Xs + DK * XS_LD);  // [TR]
+    uint32_t* qidx_s = rowid_s + TR;                                // [TQ]
+    uint32_t* qslot_s = qidx_s + TQ;                                // [TQ]
+    uint64_t* topk_s = reinterpret_cast<uint64_t*>(qslot_s + TQ);   // [TQ][k]
+
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+    const int tq = t & 7;    // query sub-tile: queries tq*4..+3
+    const int tr = t >> 3;   // row sub-tile: rows tr*4..+3
+    const uint32_t D = a.D;
+    const int k = a.k;
+
+    if (t < TQ) {
+        uint32_t qi = ID_NONE, sl = 0;
+        if ((uint32_t)t < it.pair_count) {
+            if (it.identity) { qi = it.pair_begin + t; sl = it.slot; }
+            else { qi = a.pair_q[it.pair_begin + t]; sl = a.pair_slot[it.pair_begin + t]; }
+        }
+        qidx_s[t] = qi;
+        qslot_s[t] = sl;
+    }
+    for (int i = t; i < TQ * k; i += NT) topk_s[i] = KEY_NONE;
+    __syncthreads();
+
+    // global-load coordinates of this thread for a chunk
+    const int ld_c4 = t & 7;          // float4 column within the 32-wide chunk
+    const int ld_row = t >> 3;        // 0..31 ; X rows ld_row + 32*i, Q row ld_row
+    const uint32_t my_q = qidx_s[ld_row];
+    const float* qptr = (my_q != ID_NONE) ? a.Q + (size_t)my_q * D : nullptr;
+
+    for (uint32_t rt = it.row_begin; rt < it.row_end; rt += TR) {
+        if (t < TR) {
+            uint32_t r = rt + t;
+            uint32_t id = ID_NONE;
+            if (r < it.row_end) {
+                id = a.ids ? a.ids[r] : r;
+                if (a.tomb && bit_test(a.tomb, a.tomb_bits, id)) id = ID_NONE;
+                else if (a.filt && !bit_test(a.filt, a.filt_bits, id)) id = ID_NONE;
+            }
+            rowid_s[t] = id;
+        }
+
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+        float4 xv[4], qv;
+        auto gload = [&](uint32_t kc) {
+            const uint32_t c = kc + ld_c4 * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t r = rt + ld_row + 32 * i;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < it.row_end) {
+                    const float* p = a.X + (size_t)r * D + c;
+                    if (VEC) {
+                        if (c < D) v = __ldg(reinterpret_cast<const float4*>(p));
+                    } else {
+                        if (c + 0 < D) v.x = __ldg(p + 0);
+                        if (c + 1 < D) v.y = __ldg(p + 1);
+                        if (c + 2 < D) v.z = __ldg(p + 2);
+                        if (c + 3 < D) v.w = __ldg(p + 3);
+                    }
+                }
+                xv[i] = v;
+            }
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (qptr) {
+                const float* p = qptr + c;
+                if (VEC) {
+                    if (c < D) v = __ldg(reinterpret_cast<const float4*>(p));
+                } else {
+                    if (c + 0 < D) v.x = __ldg(p + 0);
+                    if (c + 1 < D) v.y = __ldg(p + 1);
+                    if (c + 2 < D) v.z = __ldg(p + 2);
+                    if (c + 3 < D) v.w = __ldg(p + 3);
+                }
+            }
+            qv = v;
+        };
+
+        gload(0);
+        for (uint32_t kc = 0; kc < D; kc += DK) {
+            // registers -> transposed shared tiles
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = ld_row + 32 * i;
+                Xs[(ld_c4 * 4 + 0) * XS_LD + r] = xv[i].x;
+                Xs[(ld_c4 * 4 + 1) * XS_LD + r] = xv[i].y;
+                Xs[(ld_c4 * 4 + 2) * XS_LD + r] = xv[i].z;
+                Xs[(ld_c4 * 4 + 3) * XS_LD + r] = xv[i].w;
+            }
+            Qs[(ld_c4 * 4 + 0) * QS_LD + ld_row] = qv.x;
+            Qs[(ld_c4 * 4 + 1) * QS_LD + ld_row] = qv.y;
+            Qs[(ld_c4 * 4 + 2) * QS_LD + ld_row] = qv.z;
+            Qs[(ld_c4 * 4 + 3) * QS_LD + ld_row] = qv.w;
+            __syncthreads();
+            if (kc + DK < D) gload(kc + DK);  // prefetch the next chunk behind the math
+#pragma unroll 8
+            for (int d = 0; d < DK; ++d) {
+                const float4 q4 = *reinterpret_cast<const float4*>(&Qs[d * QS_LD + tq * 4]);
+                const float4 x4 = *reinterpret_cast<const float4*>(&Xs[d * XS_LD + tr * 4]);
+                const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
+                const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // reference order: (a - b), squared, added — never fused
+                        const float df = __fsub_rn(qq[i], xx[j]);
+                        acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(df, df));
+                    }
+            }
+            __syncthreads();
+        }
+
+        // distances -> shared tile (aliases Xs; all reads of Xs are behind the barrier above)
+        float* dist_s = Xs;  // [TQ][XS_LD]
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 o;
+            o.x = __fsqrt_rn(acc[i][0]);
+            o.y = __fsqrt_rn(acc[i][1]);
+            o.z = __fsqrt_rn(acc[i][2]);
+            o.w = __fsqrt_rn(acc[i][3]);
+            *reinterpret_cast<float4*>(&dist_s[(tq * 4 + i) * XS_LD + tr * 4]) = o;
+        }
+        __syncthreads();
+
+        // selection: warp w owns queries 4w..4w+3; running sorted top-k per query in smem
+#pragma unroll 1
+        for (int qi = 0; qi < 4; ++qi) {
+            const int q = warp * 4 + qi;
+            if ((uint32_t)q >= it.pair_count) break;
+            uint64_t* list = topk_s + (size_t)q * k;
+            uint64_t thr = list[k - 1];
+#pragma unroll 1
+            for (int c = 0; c < TR / 32; ++c) {
+                const int r = lane + 32 * c;
+                const uint32_t id = rowid_s[r];
+                uint64_t key = (id == ID_NONE) ? KEY_NONE : make_key(dist_s[q * XS_LD + r], id);
+                unsigned m = __ballot_sync(0xffffffffu, key < thr);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    const uint64_t cand = __shfl_sync(0xffffffffu, key, src);
+                    warp_insert(list, k, cand, lane);
+                    thr = list[k - 1];
+                    if (lane == src) key = KEY_NONE;
+                    m = __ballot_sync(0xffffffffu, key < thr);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // write the partial lists
+    for (int q = warp; q < (int)it.pair_count; q += NT / 32) {
+        const uint32_t qi = qidx_s[q];
+        uint64_t* dst = a.partial + ((size_t)qi * a.P + qslot_s[q]) * k;
+        const uint64_t* src = topk_s + (size_t)q * k;
+        for (int i = lane; i < k; i += 32) dst[i] = src[i];
+    }
+}
+
+}  // namespace
+
+size_t exact_scan_smem_bytes(uint32_t k) {
+    return (size_t)(DK * QS_LD + DK * XS_LD) * sizeof(float) + (TR + 2 * TQ) * sizeof(uint32_t) +
+           (size_t)TQ * k * sizeof(uint64_t);
+}
+
+cudaError_t launch_exact_scan(const ExactScanArgs& a, uint32_t grid, cudaStream_t stream) {
+    if (grid == 0) return cudaSuccess;
+    const size_t smem = exact_scan_smem_bytes(a.k);
+    const bool vec = (a.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.X) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a.Q) & 15) == 0);
+    cudaError_t e;
+    if (vec) {
+        e = cudaFuncSetAttribute(exact_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+        if (e != cudaSuccess) return e;
+        exact_scan_kernel<true><<<grid, NT, smem, stream>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(exact_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+        if (e != cudaSuccess) return e;
+        exact_scan_kernel<false><<<grid, NT, smem, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Item builders
+// ---------------------------------------------------------------------------------------------
+
+// identity items: every query against rows [row_begin,row_end) split into `nsplit` chunks.
+__global__ void build_identity_items_kernel(ScanItem* items, uint32_t nq, uint32_t row_begin,
+                                            uint32_t row_end, uint32_t nsplit) {
+    const uint32_t n_qt = (nq + TQ - 1) / TQ;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_qt * nsplit) return;
+    const uint32_t qt = i / nsplit, sp = i % nsplit;
+    const uint32_t rows = row_end - row_begin;
+    // chunk boundaries on multiples of TR so tiles stay aligned
+    const uint32_t tiles = (rows + TR - 1) / TR;
+    const uint32_t t0 = (uint32_t)(((uint64_t)tiles * sp) / nsplit);
+    const uint32_t t1 = (uint32_t)(((uint64_t)tiles * (sp + 1)) / nsplit);
+    ScanItem it;
+    it.row_begin = row_begin + t0 * TR;
+    it.row_end = min(row_end, row_begin + t1 * TR);
+    it.pair_begin = qt * TQ;
+    it.pair_count = min((uint32_t)TQ, nq - qt * TQ);
+    it.slot = sp;
+    it.identity = 1;
+    if (it.row_begin >= it.row_end) it.pair_count = 0;
+    items[i] = it;
+}
+
+cudaError_t launch_build_identity_items(ScanItem* items, uint32_t nq, uint32_t row_begin,
+                                        uint32_t row_end, uint32_t nsplit, uint32_t* n_items_out,
+                                        cudaStream_t stream) {
+    const uint32_t n_qt = (nq + TQ - 1) / TQ;
+    const uint32_t n = n_qt * nsplit;
+    *n_items_out = n;
+    if (n == 0) return cudaSuccess;
+    build_identity_items_kernel<<<(n + 255) / 256, 256, 0, stream>>>(items, nq, row_begin, row_end,
+                                                                    nsplit);
+    return cudaGetLastError();
+}
+
+uint32_t exact_scan_tq() { return TQ; }
+uint32_t exact_scan_tr() { return TR; }
+
+// ---------------------------------------------------------------------------------------------
+// Probe bucketing: (query, rank) pairs grouped by list  (builds the list -> queries CSR that
+// lets each posting list be streamed once per batch instead of once per query)
+// ---------------------------------------------------------------------------------------------
+
+// coarse_keys [nq][nprobe]: low 32 bits = list id.  KEY_NONE entries (nprobe > nlist) skipped.
+__global__ void probe_hist_kernel(const uint64_t* __restrict__ coarse_keys, uint32_t n_pairs,
+                                  uint32_t* __restrict__ list_cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const uint64_t key = coarse_keys[i];
+    if (key == KEY_NONE) return;
+    atomicAdd(&list_cnt[key_id(key)], 1u);
+}
+
+// single-CTA exclusive scan over lists: pair offsets and work-item offsets; also emits the
+// items.  tile_q = queries per item (TQ for the exact kernel, the query-tile of the TC kernel).
+// Items of one list are adjacent so a list re-read by a second query tile hits L2.
+__global__ void probe_scan_kernel(const uint32_t* __restrict__ list_cnt,
+                                  const uint32_t* __restrict__ list_off, uint32_t nlist,
+                                  uint32_t tile_q, uint32_t* __restrict__ pair_off,
+                                  uint32_t* __restrict__ cursor, ScanItem* __restrict__ items,
+                                  uint32_t* __restrict__ n_items, uint64_t* __restrict__ scanned_rows) {
+    __shared__ uint32_t s_pairs[1024];
+    __shared__ uint32_t s_items[1024];
+    __shared__ uint32_t carry_pairs, carry_items;
+    __shared__ unsigned long long s_rows;
+    const int t = threadIdx.x;
+    if (t == 0) { carry_pairs = 0; carry_items = 0; s_rows = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < nlist; base += 1024) {
+        const uint32_t l = base + t;
+        uint32_t c = 0, len = 0;
+        if (l < nlist) { c = list_cnt[l]; len = list_off[l + 1] - list_off[l]; }
+        if (len == 0) c = 0;  // nothing to scan in an empty list
+        const uint32_t ni = (c + tile_q - 1) / tile_q;
+        s_pairs[t] = c;
+        s_items[t] = ni;
+        __syncthreads();
+        // Hillis-Steele inclusive scan over 1024 entries
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint32_t a = 0, b = 0;
+            if (t >= o) { a = s_pairs[t - o]; b = s_items[t - o]; }
+            __syncthreads();
+            s_pairs[t] += a;
+            s_items[t] += b;
+            __syncthreads();
+        }
+        const uint32_t p_excl = carry_pairs + s_pairs[t] - c;
+        const uint32_t i_excl = carry_items + s_items[t] - ni;
+        if (l < nlist) {
+            pair_off[l] = p_excl;
+            cursor[l] = p_excl;
+            for (uint32_t j = 0; j < ni; ++j) {
+                ScanItem it;
+                it.row_begin = list_off[l];
+                it.row_end = list_off[l + 1];
+                it.pair_begin = p_excl + j * tile_q;
+                it.pair_count = min(tile_q, c - j * tile_q);
+                it.slot = 0;
+                it.identity = 0;
+                items[i_excl + j] = it;
+            }
+            if (c > 0) atomicAdd(&s_rows, (unsigned long long)len);
+        }
+        __syncthreads();
+        if (t == 1023) { carry_pairs += s_pairs[1023]; carry_items += s_items[1023]; }
+        __syncthreads();
+    }
+    if (t == 0) {
+        pair_off[nlist] = carry_pairs;
+        *n_items = carry_items;
+        if (scanned_rows) *scanned_rows = s_rows;
+    }
+}
+
+__global__ void probe_scatter_kernel(const uint64_t* __restrict__ coarse_keys, uint32_t n_pairs,
+                                     uint32_t nprobe, const uint32_t* __restrict__ list_off,
+                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ pair_q,
+                                     uint32_t* __restrict__ pair_slot) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const uint64_t key = coarse_keys[i];
+    if (key == KEY_NONE) return;
+    const uint32_t l = key_id(key);
+    if (list_off[l + 1] == list_off[l]) return;
+    const uint32_t p = atomicAdd(&cursor[l], 1u);
+    pair_q[p] = i / nprobe;
+    pair_slot[p] = i % nprobe;
+}
+
+cudaError_t launch_probe_bucketing(const uint64_t* coarse_keys, uint32_t nq, uint32_t nprobe,
+                                   const uint32_t* list_off, uint32_t nlist, uint32_t tile_q,
+                                   uint32_t* list_cnt, uint32_t* pair_off, uint32_t* cursor,
+                                   uint32_t* pair_q, uint32_t* pair_slot, ScanItem* items,
+                                   uint32_t* n_items, uint64_t* scanned_rows, cudaStream_t stream) {
+    const uint32_t n_pairs = nq * nprobe;
+    cudaError_t e = cudaMemsetAsync(list_cnt, 0, sizeof(uint32_t) * nlist, stream);
+    if (e != cudaSuccess) return e;
+    if (n_pairs == 0) {
+        return cudaMemsetAsync(n_items, 0, sizeof(uint32_t), stream);
+    }
+    probe_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, list_cnt);
+    probe_scan_kernel<<<1, 1024, 0, stream>>>(list_cnt, list_off, nlist, tile_q, pair_off, cursor,
+                                              items, n_items, scanned_rows);
+    probe_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, nprobe,
+                                                                   list_off, cursor, pair_q,
+                                                                   pair_slot);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merging sorted partial lists
+// ---------------------------------------------------------------------------------------------
+
+// One warp per query: P ascending lists of k keys -> the k smallest, ascending.
+// in [nq][P][k], out [nq][k_out stride]; KEY_NONE pads.
+__global__ void merge_partials_kernel(const uint64_t* __restrict__ in, uint32_t nq, uint32_t P,
+                                      uint32_t k, uint64_t* __restrict__ out) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const uint64_t* base = in + (size_t)q * P * k;
+    // each lane walks lists lane, lane+32, ... keeping the smallest current head among them
+    // (per-lane: index of the list with the smallest head, found by a linear pass — P/32 small)
+    constexpr int MAXL = 8;  // lists per lane handled in registers => P <= 256 per pass
+    uint32_t pos[MAXL];
+#pragma unroll
+    for (int j = 0; j < MAXL; ++j) pos[j] = 0;
+    for (uint32_t o = 0; o < k; ++o) {
+        uint64_t best = KEY_NONE;
+        int bj = -1;
+#pragma unroll
+        for (int j = 0; j < MAXL; ++j) {
+            const uint32_t p = lane + 32 * j;
+            if (p < P && pos[j] < k) {
+                const uint64_t v = base[(size_t)p * k + pos[j]];
+                if (v < best) { best = v; bj = j; }
+            }
+        }
+        // warp argmin on (key, lane) — keys with equal value can only be KEY_NONE or true
+        // duplicates (same id twice); either choice gives the same output value
+        uint64_t wbest = best;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, wbest, s);
+            wbest = other < wbest ? other : wbest;
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, best == wbest && bj >= 0);
+        if (wbest == KEY_NONE || who == 0) {
+            for (uint32_t r = o + lane; r < k; r += 32) out[(size_t)q * k + r] = KEY_NONE;
+            return;
+        }
+        const int winner = __ffs(who) - 1;
+        if (lane == winner) {
+#pragma unroll
+            for (int j = 0; j < MAXL; ++j) if (j == bj) pos[j]++;
+        }
+        if (lane == 0) out[(size_t)q * k + o] = wbest;
+    }
+}
+
+cudaError_t launch_merge_partials(const uint64_t* in, uint32_t nq, uint32_t P, uint32_t k,
+                                  uint64_t* out, cudaStream_t stream) {
+    if (nq == 0) return cudaSuccess;
+    if (P > 256) return cudaErrorInvalidValue;
+    const uint32_t threads = 128;
+    const uint32_t blocks = (nq * 32 + threads - 1) / threads;
+    merge_partials_kernel<<<blocks, threads, 0, stream>>>(in, nq, P, k, out);
+    return cudaGetLastError();
+}
+
+// Final hybrid merge (src/hybrid/core.rs:482-483): recent-tier keys and IVF keys, each sorted,
+// two-pointer merged by distance with the recent tier first on ties, truncated to k, split
+// into ids / distances / count.  Either input may be null.
+__global__ void finalize_kernel(const uint64_t* __restrict__ recent, const uint64_t* __restrict__ ivf,
+                                uint32_t nq, uint32_t k, uint32_t* __restrict__ out_ids,
+                                float* __restrict__ out_dist, uint32_t* __restrict__ out_count) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint64_t* a = recent ? recent + (size_t)q * k : nullptr;
+    const uint64_t* b = ivf ? ivf + (size_t)q * k : nullptr;
+    uint32_t ia = 0, ib = 0, o = 0;
+    while (o < k) {
+        const uint64_t ka = (a && ia < k) ? a[ia] : KEY_NONE;
+        const uint64_t kb = (b && ib < k) ? b[ib] : KEY_NONE;
+        if (ka == KEY_NONE && kb == KEY_NONE) break;
+        uint64_t pick;
+        // compare distances only; recent wins ties (stable sort, recent results pushed first)
+        if (kb == KEY_NONE || (ka != KEY_NONE && (uint32_t)(ka >> 32) <= (uint32_t)(kb >> 32))) { pick = ka; ++ia; }
+        else { pick = kb; ++ib; }
+        out_ids[(size_t)q * k + o] = key_id(pick);
+        out_dist[(size_t)q * k + o] = key_dist(pick);
+        ++o;
+    }
+    out_count[q] = o;
+    for (; o < k; ++o) {
+        out_ids[(size_t)q * k + o] = ID_NONE;
+        out_dist[(size_t)q * k + o] = __uint_as_float(0x7f800000u);
+    }
+}
+
+cudaError_t launch_finalize(const uint64_t* recent, const uint64_t* ivf, uint32_t nq, uint32_t k,
+                            uint32_t* out_ids, float* out_dist, uint32_t* out_count,
+                            cudaStream_t stream) {
+    if (nq == 0) return cudaSuccess;
+    finalize_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(recent, ivf, nq, k, out_ids, out_dist,
+                                                         out_count);
+    return cudaGetLastError();
+}
+
+// Cross-GPU merge after the all-gather (fvdb_merge_topk_device): parts x [nq][k] (ids, dist,
+// count) -> [nq][k].  Order: (distance, part, position) — each part is already sorted, lower
+// part first on ties.  One thread per query (k and parts are small).
+__global__ void merge_parts_kernel(const uint32_t* __restrict__ ids, const float* __restrict__ dist,
+                                   const uint32_t* __restrict__ cnt, uint32_t parts, uint32_t nq,
+                                   uint32_t k, uint32_t* __restrict__ out_ids,
+                                   float* __restrict__ out_dist, uint32_t* __restrict__ out_count) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    constexpr int MAXP = 64;
+    uint16_t pos[MAXP];
+    for (uint32_t p = 0; p < parts; ++p) pos[p] = 0;
+    uint32_t o = 0;
+    for (; o < k; ++o) {
+        float best = 0.f;
+        int bp = -1;
+        for (uint32_t p = 0; p < parts; ++p) {
+            const uint32_t c = min(cnt[(size_t)p * nq + q], k);
+            if (pos[p] < c) {
+                const float d = dist[((size_t)p * nq + q) * k + pos[p]];
+                if (bp < 0 || d < best) { best = d; bp = (int)p; }
+            }
+        }
+        if (bp < 0) break;
+        out_ids[(size_t)q * k + o] = ids[((size_t)bp * nq + q) * k + pos[bp]];
+        out_dist[(size_t)q * k + o] = best;
+        pos[bp]++;
+    }
+    out_count[q] = o;
+    for (; o < k; ++o) {
+        out_ids[(size_t)q * k + o] = ID_NONE;
+        out_dist[(size_t)q * k + o] = __uint_as_float(0x7f800000u);
+    }
+}
+
+cudaError_t launch_merge_parts(const uint32_t* ids, const float* dist, const uint32_t* cnt,
+                               uint32_t parts, uint32_t nq, uint32_t k, uint32_t* out_ids,
+                               float* out_dist, uint32_t* out_count, cudaStream_t stream) {
+    if (nq == 0) return cudaSuccess;
+    if (parts > 64) return cudaErrorInvalidValue;
+    merge_parts_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(ids, dist, cnt, parts, nq, k, out_ids,
+                                                            out_dist, out_count);
+    return cudaGetLastError();
+}
+
+// NaN screen over a float matrix (the reference panics on NaN: src/ivf/core.rs:655,677).
+__global__ void nan_check_kernel(const float* __restrict__ x, size_t n, int* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) bad |= isnan(x[i]);
+    if (bad) *flag = 1;
+}
+
+cudaError_t launch_nan_check(const float* x, size_t n, int* flag, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t blocks = (uint32_t)min((size_t)148 * 8, (n + 255) / 256);
+    nan_check_kernel<<<blocks, 256, 0, stream>>>(x, n, flag);
+    return cudaGetLastError();
+}
+
+}  // namespace fvdb

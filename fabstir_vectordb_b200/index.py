@@ -1,0 +1,691 @@
+"""Host-side mirror of the reference's index API for the hot path — same names, argument
+meaning and error behaviour as IVFIndex (src/ivf/core.rs), HNSWIndex (src/hnsw/core.rs) and
+HybridIndex (src/hybrid/core.rs) — over the C ABI of libfvdb_b200.so.
+
+The reference is Rust; neither rustc nor cargo exists in this image, so the Rust shim is shipped
+as source in INTEGRATION.md and this module is the executable mirror the parity tests drive.
+Everything numeric (distances, argmin, top-k, k-means) happens on the GPU behind the ABI; this
+file only keeps what the reference keeps host-side: the VectorId <-> row-id map, timestamps,
+metadata filter evaluation and the error enums.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Any, Dict, Hashable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .engine import (DimensionMismatch, DuplicateVector, Engine, FvdbError,
+                     InconsistentDimensions, InsufficientTrainingData, InvalidConfig, NotTrained,
+                     VectorNotFound)
+
+
+class NotInitialized(FvdbError):
+    """HybridError::NotInitialized, src/hybrid/core.rs:16-35."""
+
+
+@dataclass
+class SearchResult:
+    """SearchResult{vector_id, distance, metadata}, src/core/types.rs:191-195."""
+    vector_id: Hashable
+    distance: float
+    metadata: Any = None
+
+
+@dataclass
+class TrainResult:
+    """src/ivf/core.rs:103-109."""
+    iterations: int
+    converged: bool
+    initial_error: float
+    final_error: float
+
+
+@dataclass
+class IVFConfig:
+    """src/ivf/core.rs:42-70 (defaults :50-60)."""
+    n_clusters: int = 256
+    n_probe: int = 16
+    train_size: int = 10000
+    max_iterations: int = 25
+    seed: Optional[int] = None
+
+    def is_valid(self) -> bool:
+        return (self.n_clusters > 0 and self.n_probe > 0 and self.n_probe <= self.n_clusters
+                and self.train_size > 0 and self.max_iterations > 0)
+
+
+@dataclass
+class HNSWConfig:
+    """src/hnsw/core.rs:30-46.  Graph parameters are accepted and ignored: the recent tier is
+    served by an exact scan, whose results dominate any graph walk."""
+    max_connections: int = 16
+    max_connections_layer_0: int = 32
+    ef_construction: int = 200
+    seed: Optional[int] = None
+
+
+class _IdMap:
+    """VectorId <-> dense u32 row id (stays host-side)."""
+
+    def __init__(self):
+        self.to_row: Dict[Hashable, int] = {}
+        self.to_id: List[Hashable] = []
+
+    def add(self, vid: Hashable) -> int:
+        if vid in self.to_row:
+            raise DuplicateVector(f"Vector with ID {vid!r} already exists")
+        r = len(self.to_id)
+        self.to_row[vid] = r
+        self.to_id.append(vid)
+        return r
+
+    def rollback(self, n: int):
+        for _ in range(n):
+            vid = self.to_id.pop()
+            del self.to_row[vid]
+
+
+def _as_matrix(vectors: Sequence[Sequence[float]], dim: Optional[int]) -> np.ndarray:
+    rows = [np.asarray(v, dtype=np.float32).reshape(-1) for v in vectors]
+    if not rows:
+        return np.zeros((0, dim or 0), dtype=np.float32)
+    d0 = rows[0].shape[0]
+    for r in rows:
+        if r.shape[0] != d0:
+            raise InconsistentDimensions(
+                f"Inconsistent dimensions in training data: expected {d0}, found {r.shape[0]}")
+    return np.stack(rows)
+
+
+def _results(idmap: _IdMap, ids, dist, cnt) -> List[List[SearchResult]]:
+    out = []
+    for q in range(ids.shape[0]):
+        c = int(cnt[q])
+        out.append([SearchResult(idmap.to_id[int(ids[q, j])], float(dist[q, j])) for j in range(c)])
+    return out
+
+
+class IVFIndex:
+    """IVFIndex, src/ivf/core.rs:154-682 + the operations of src/ivf/operations.rs that touch
+    the search path (batch_insert :107, batch_search :132, mark_deleted :569, vacuum :625)."""
+
+    def __init__(self, config: IVFConfig = None, *, k_max: int = 128, device: int = 0):
+        config = config or IVFConfig()
+        if not config.is_valid():
+            raise InvalidConfig("Invalid IVFConfig")  # the reference panics, src/ivf/core.rs:171-174
+        self.config = config
+        self._k_max = k_max
+        self._device = device
+        self._eng: Optional[Engine] = None
+        self._ids = _IdMap()
+        self._deleted = set()
+        self._dimension: Optional[int] = None
+        self._trained = False
+        self._lists: Dict[Hashable, int] = {}
+
+    # -- accessors ------------------------------------------------------------------------
+    def is_trained(self) -> bool:
+        return self._trained
+
+    def dimension(self) -> Optional[int]:
+        return self._dimension
+
+    def total_vectors(self) -> int:
+        return len(self._lists)
+
+    def active_count(self) -> int:  # src/ivf/operations.rs:615
+        return len(self._lists) - len(self._deleted)
+
+    def engine(self) -> Engine:
+        return self._eng
+
+    def get_centroids(self) -> np.ndarray:
+        return self._eng.get_centroids() if self._trained else np.zeros((0, 0), np.float32)
+
+    def get_cluster_sizes(self) -> Dict[int, int]:
+        sizes = {i: 0 for i in range(self.config.n_clusters)}
+        for l in self._lists.values():
+            sizes[l] += 1
+        return sizes
+
+    def _ensure_engine(self, dim: int):
+        if self._eng is None or self._eng.dim != dim:
+            self._eng = Engine(dim, k_max=self._k_max, device=self._device)
+
+    # -- training -------------------------------------------------------------------------
+    def train(self, training_data, init_centroids=None) -> TrainResult:
+        """IVFIndex::train, src/ivf/core.rs:240-334.  `init_centroids` (extension) replaces the
+        seeded k-means++ draw so Lloyd parity can be checked from a shared start."""
+        if isinstance(training_data, np.ndarray):
+            data = np.ascontiguousarray(training_data, dtype=np.float32)
+            n = data.shape[0]
+        else:
+            n = len(training_data)
+            data = None
+        if n == 0:
+            raise InsufficientTrainingData(
+                f"Insufficient training data: got 0, need at least {self.config.n_clusters}")
+        if n < self.config.n_clusters:
+            raise InsufficientTrainingData(
+                f"Insufficient training data: got {n}, need at least {self.config.n_clusters}")
+        if data is None:
+            data = _as_matrix(training_data, None)
+        dim = data.shape[1]
+        self._ensure_engine(dim)
+        self._dimension = dim
+        seed = self.config.seed if self.config.seed is not None else time.time_ns()
+        r = self._eng.train(data, self.config.n_clusters, self.config.max_iterations,
+                            init_centroids=init_centroids, seed=seed)
+        self._trained = True
+        self._ids = _IdMap()
+        self._lists = {}
+        self._deleted = set()
+        return TrainResult(**r)
+
+    def set_trained(self, centroids, dimension: int):
+        """src/ivf/core.rs:509-520."""
+        c = np.ascontiguousarray(centroids, dtype=np.float32).reshape(-1, dimension)
+        self._ensure_engine(dimension)
+        self._eng.set_centroids(c)
+        self._dimension = dimension
+        self._trained = True
+        self._ids = _IdMap()
+        self._lists = {}
+        self._deleted = set()
+
+    # -- insertion ------------------------------------------------------------------------
+    def insert(self, vid: Hashable, vector) -> None:
+        """src/ivf/core.rs:431-455."""
+        self.batch_insert([vid], [vector])
+
+    def batch_insert(self, ids: Sequence[Hashable], vectors) -> None:
+        """src/ivf/operations.rs:107 — one coarse-assignment launch for the whole batch."""
+        if not self._trained:
+            raise NotTrained("Index not trained. Call train() before inserting or searching.")
+        x = vectors if isinstance(vectors, np.ndarray) else _as_matrix(vectors, self._dimension)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self._dimension:
+            raise DimensionMismatch(self._dimension, x.shape[-1] if x.ndim else 0)
+        rows = []
+        try:
+            for v in ids:
+                rows.append(self._ids.add(v))
+        except DuplicateVector:
+            self._ids.rollback(len(rows))
+            raise
+        try:
+            lists = self._eng.ivf_add(x, np.asarray(rows, dtype=np.uint32), want_lists=True)
+        except FvdbError:
+            self._ids.rollback(len(rows))
+            raise
+        for v, l in zip(ids, lists):
+            self._lists[v] = int(l)
+
+    def find_cluster(self, vector) -> int:
+        """src/ivf/core.rs:493-499."""
+        if not self._trained:
+            raise NotTrained("Index not trained. Call train() before inserting or searching.")
+        x = np.asarray(vector, dtype=np.float32).reshape(1, -1)
+        if x.shape[1] != self._dimension:
+            raise DimensionMismatch(self._dimension, x.shape[1])
+        return int(self._eng.assign(x)[0])
+
+    # -- soft delete (src/ivf/operations.rs:569-640) ----------------------------------------
+    def mark_deleted(self, vid: Hashable) -> None:
+        if vid not in self._lists:
+            raise VectorNotFound(f"Vector not found: {vid!r}")
+        self._eng.set_deleted([self._ids.to_row[vid]], True)
+        self._deleted.add(vid)
+
+    def is_deleted(self, vid: Hashable) -> bool:
+        return vid in self._deleted
+
+    def vacuum(self) -> int:
+        removed = self._eng.vacuum() if self._eng else 0
+        for v in self._deleted:
+            self._lists.pop(v, None)
+        self._deleted = set()
+        return removed
+
+    # -- search ---------------------------------------------------------------------------
+    def search(self, query, k: int) -> List[SearchResult]:
+        """src/ivf/core.rs:622-624."""
+        return self.search_with_config(query, k, self.config.n_probe)
+
+    def search_with_config(self, query, k: int, n_probe: int) -> List[SearchResult]:
+        """src/ivf/core.rs:626-681."""
+        return self.batch_search_with_config([query], k, n_probe)[0]
+
+    def batch_search(self, queries, k: int) -> List[List[SearchResult]]:
+        """src/ivf/operations.rs:132-145, as ONE device batch."""
+        return self.batch_search_with_config(queries, k, self.config.n_probe)
+
+    def batch_search_with_config(self, queries, k: int, n_probe: int):
+        if not self._trained:
+            raise NotTrained("Index not trained. Call train() before inserting or searching.")
+        q = queries if isinstance(queries, np.ndarray) else _as_matrix(queries, self._dimension)
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        if q.shape[1] != self._dimension:
+            raise DimensionMismatch(self._dimension, q.shape[1])
+        if k == 0:
+            return [[] for _ in range(q.shape[0])]
+        ids, dist, cnt = self._eng.search(q, k, n_probe, tiers=L.TIER_HISTORICAL)
+        return _results(self._ids, ids, dist, cnt)
+
+
+class HNSWIndex:
+    """HNSWIndex, src/hnsw/core.rs — the recent tier.  search() is an exact scan; the `ef`
+    argument is accepted and ignored (results are a superset-in-quality of the graph walk)."""
+
+    def __init__(self, config: HNSWConfig = None, *, k_max: int = 128, device: int = 0):
+        self.config = config or HNSWConfig()
+        self._k_max = k_max
+        self._device = device
+        self._eng: Optional[Engine] = None
+        self._ids = _IdMap()
+        self._deleted = set()
+        self._dimension: Optional[int] = None
+
+    def node_count(self) -> int:
+        return len(self._ids.to_id)
+
+    def dimension(self) -> Optional[int]:
+        return self._dimension
+
+    def insert(self, vid: Hashable, vector) -> None:
+        """src/hnsw/core.rs:226."""
+        self.batch_insert([vid], [vector])
+
+    def batch_insert(self, ids, vectors) -> None:
+        x = vectors if isinstance(vectors, np.ndarray) else _as_matrix(vectors, self._dimension)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if self._dimension is None:
+            self._dimension = x.shape[1]
+            self._eng = Engine(self._dimension, k_max=self._k_max, device=self._device)
+        if x.shape[1] != self._dimension:
+            raise DimensionMismatch(self._dimension, x.shape[1])
+        rows = []
+        try:
+            for v in ids:
+                rows.append(self._ids.add(v))
+        except DuplicateVector:
+            self._ids.rollback(len(rows))
+            raise
+        self._eng.flat_add(x, np.asarray(rows, dtype=np.uint32))
+
+    def search(self, query, k: int, ef: int = 50) -> List[SearchResult]:
+        """src/hnsw/core.rs:398-467.  Empty index -> [] (:404-407)."""
+        if self._eng is None:
+            return []
+        q = np.asarray(query, dtype=np.float32).reshape(1, -1)
+        if q.shape[1] != self._dimension:
+            raise DimensionMismatch(self._dimension, q.shape[1])
+        if k == 0:
+            return []
+        ids, dist, cnt = self._eng.search(q, k, 0, tiers=L.TIER_RECENT)
+        return _results(self._ids, ids, dist, cnt)[0]
+
+    def mark_deleted(self, vid: Hashable) -> None:
+        if vid not in self._ids.to_row:
+            raise VectorNotFound(f"Vector not found: {vid!r}")
+        self._eng.set_deleted([self._ids.to_row[vid]], True)
+        self._deleted.add(vid)
+
+    def is_deleted(self, vid: Hashable) -> bool:
+        return vid in self._deleted
+
+    def vacuum(self) -> int:
+        removed = self._eng.vacuum() if self._eng else 0
+        self._deleted = set()
+        return removed
+
+
+# ---- metadata filter (host side: producer of the bitmap) -------------------------------------
+
+class FilterError(ValueError):
+    pass
+
+
+class MetadataFilter:
+    """MetadataFilter, src/core/metadata_filter.rs:32-357: Mongo-style Equals / In / Range /
+    And / Or with dotted paths (get_field :359-373) and array-contains equality (:272-281)."""
+
+    def __init__(self, kind, **kw):
+        self.kind = kind
+        self.__dict__.update(kw)
+
+    @staticmethod
+    def from_json(value) -> "MetadataFilter":
+        if not isinstance(value, dict):
+            raise FilterError("Filter must be a JSON object")
+        if "$and" in value:
+            v = value["$and"]
+            if not isinstance(v, list):
+                raise FilterError("$and must be an array")
+            return MetadataFilter("and", filters=[MetadataFilter.from_json(f) for f in v])
+        if "$or" in value:
+            v = value["$or"]
+            if not isinstance(v, list):
+                raise FilterError("$or must be an array")
+            return MetadataFilter("or", filters=[MetadataFilter.from_json(f) for f in v])
+        for key in value:
+            if key.startswith("$"):
+                raise FilterError(f"Unsupported operator: {key}")
+        if len(value) == 1:
+            (f, fv), = value.items()
+            return MetadataFilter._field(f, fv)
+        return MetadataFilter("and", filters=[MetadataFilter._field(f, fv) for f, fv in value.items()])
+
+    @staticmethod
+    def _num(v):
+        return float(v) if isinstance(v, (int, float)) and not isinstance(v, bool) else None
+
+    @staticmethod
+    def _field(fld, value) -> "MetadataFilter":
+        if isinstance(value, dict):
+            if "$in" in value:
+                if not isinstance(value["$in"], list):
+                    raise FilterError("$in value must be an array")
+                return MetadataFilter("in", field=fld, values=value["$in"])
+            gte, gt = MetadataFilter._num(value.get("$gte")), MetadataFilter._num(value.get("$gt"))
+            lte, lt = MetadataFilter._num(value.get("$lte")), MetadataFilter._num(value.get("$lt"))
+            if gte is not None and gt is not None:
+                raise FilterError("Cannot use both $gte and $gt in the same range filter")
+            if lte is not None and lt is not None:
+                raise FilterError("Cannot use both $lte and $lt in the same range filter")
+            mn, mn_inc = (gte, True) if gte is not None else ((gt, False) if gt is not None else (None, True))
+            mx, mx_inc = (lte, True) if lte is not None else ((lt, False) if lt is not None else (None, True))
+            if mn is not None or mx is not None:
+                return MetadataFilter("range", field=fld, min=mn, max=mx, min_inclusive=mn_inc,
+                                      max_inclusive=mx_inc)
+            for key in value:
+                if key.startswith("$") and key not in ("$in", "$gte", "$gt", "$lte", "$lt"):
+                    raise FilterError(f"Unsupported operator: {key}")
+            if not value:
+                raise FilterError(f"Empty object for field '{fld}' - must specify a value or operator")
+        return MetadataFilter("equals", field=fld, value=value)
+
+    @staticmethod
+    def _get(metadata, path):
+        cur = metadata
+        for part in path.split("."):
+            if not isinstance(cur, dict) or part not in cur:
+                return None, False
+            cur = cur[part]
+        return cur, True
+
+    @staticmethod
+    def _json_eq(a, b) -> bool:
+        # serde_json Value equality: bool is not a number; 1 == 1.0 is false in serde_json for
+        # differing representations only when one is a float with a fractional part
+        if isinstance(a, bool) or isinstance(b, bool):
+            return isinstance(a, bool) and isinstance(b, bool) and a == b
+        return a == b
+
+    def matches(self, metadata) -> bool:
+        k = self.kind
+        if k == "equals":
+            fv, ok = self._get(metadata, self.field)
+            if not ok:
+                return False
+            if isinstance(fv, list):
+                return any(self._json_eq(x, self.value) for x in fv)
+            return self._json_eq(fv, self.value)
+        if k == "in":
+            fv, ok = self._get(metadata, self.field)
+            return ok and any(self._json_eq(fv, v) for v in self.values)
+        if k == "range":
+            fv, ok = self._get(metadata, self.field)
+            num = self._num(fv) if ok else None
+            if num is None:
+                return False
+            mn_ok = True if self.min is None else (num >= self.min if self.min_inclusive else num > self.min)
+            mx_ok = True if self.max is None else (num <= self.max if self.max_inclusive else num < self.max)
+            return mn_ok and mx_ok
+        if k == "and":
+            return all(f.matches(metadata) for f in self.filters)
+        if k == "or":
+            return any(f.matches(metadata) for f in self.filters)
+        raise FilterError(f"unknown filter kind {k}")
+
+
+@dataclass
+class HybridConfig:
+    """src/hybrid/core.rs:38-85 (defaults :69-85: n_clusters 3, n_probe 2, train_size 9)."""
+    recent_threshold: float = 7 * 24 * 3600.0  # seconds
+    hnsw_config: HNSWConfig = field(default_factory=HNSWConfig)
+    ivf_config: IVFConfig = field(default_factory=lambda: IVFConfig(n_clusters=3, n_probe=2, train_size=9))
+    migration_batch_size: int = 100
+    auto_migrate: bool = True
+    min_ivf_training_size: int = 10
+
+    def is_valid(self) -> bool:
+        return self.recent_threshold > 0 and self.migration_batch_size > 0
+
+
+@dataclass
+class HybridSearchConfig:
+    """src/hybrid/core.rs:173-196."""
+    search_recent: bool = True
+    search_historical: bool = True
+    recent_k: int = 0
+    historical_k: int = 0
+    recent_threshold_override: Optional[float] = None
+    k: int = 10
+    hnsw_ef: int = 50
+    ivf_n_probe: int = 10
+
+
+SearchConfig = HybridSearchConfig
+
+
+class HybridIndex:
+    """HybridIndex, src/hybrid/core.rs:202-700: recent tier (exact scan in place of HNSW) +
+    historical IVF tier behind one device handle; search = union, stable sort by distance with
+    the recent tier first on ties, truncate(k), no de-duplication (:425-486)."""
+
+    def __init__(self, config: HybridConfig = None, *, k_max: int = 128, device: int = 0):
+        config = config or HybridConfig()
+        if not config.is_valid():
+            raise InvalidConfig("Invalid HybridConfig")
+        self.config = config
+        self._k_max = k_max
+        self._device = device
+        self._eng: Optional[Engine] = None
+        self._ids = _IdMap()
+        self.timestamps: Dict[Hashable, float] = {}
+        self._tier: Dict[Hashable, int] = {}
+        self._deleted = set()
+        self.initialized = False
+        self.ivf_trained = False
+        self._dimension: Optional[int] = None
+
+    def is_initialized(self) -> bool:
+        return self.initialized
+
+    def engine(self) -> Engine:
+        return self._eng
+
+    def recent_count(self) -> int:
+        return sum(1 for t in self._tier.values() if t == 1)
+
+    def historical_count(self) -> int:
+        return sum(1 for t in self._tier.values() if t == 2)
+
+    def _ensure_engine(self, dim: int):
+        if self._eng is None:
+            self._eng = Engine(dim, k_max=self._k_max, device=self._device)
+            self._dimension = dim
+
+    def initialize(self, training_data, init_centroids=None) -> None:
+        """src/hybrid/core.rs:262-289: fewer than min_ivf_training_size rows => HNSW-only mode;
+        else train IVF and leave its lists empty."""
+        n = len(training_data)
+        if n < self.config.min_ivf_training_size:
+            self.ivf_trained = False
+            self.initialized = True
+            return
+        data = training_data if isinstance(training_data, np.ndarray) else _as_matrix(training_data, None)
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        c = self.config.ivf_config
+        if n < c.n_clusters:
+            raise InsufficientTrainingData(
+                f"Insufficient training data: got {n}, need at least {c.n_clusters}")
+        self._ensure_engine(data.shape[1])
+        seed = c.seed if c.seed is not None else time.time_ns()
+        self._eng.train(data, c.n_clusters, c.max_iterations, init_centroids=init_centroids, seed=seed)
+        self.ivf_trained = True
+        self.initialized = True
+
+    def insert(self, vid, vector) -> None:
+        self.insert_with_timestamp(vid, vector, time.time())
+
+    def insert_with_timestamp(self, vid, vector, timestamp: float) -> None:
+        """src/hybrid/core.rs:357-413."""
+        self.batch_insert_with_timestamps([vid], [vector], [timestamp])
+
+    def batch_insert_with_timestamps(self, ids, vectors, timestamps) -> None:
+        if not self.initialized:
+            raise NotInitialized("Index not initialized")
+        x = vectors if isinstance(vectors, np.ndarray) else _as_matrix(vectors, self._dimension)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        self._ensure_engine(x.shape[1])
+        if x.shape[1] != self._dimension:
+            raise DimensionMismatch(self._dimension, x.shape[1])
+        for v in ids:
+            if v in self.timestamps:
+                raise DuplicateVector(f"Vector with ID {v!r} already exists")
+        now = time.time()
+        rows = [self._ids.add(v) for v in ids]
+        rows = np.asarray(rows, dtype=np.uint32)
+        ts = np.asarray(timestamps, dtype=np.float64)
+        age = np.maximum(now - ts, 0.0)
+        recent = np.ones(len(rows), dtype=bool) if not self.ivf_trained else (age < self.config.recent_threshold)
+        if recent.any():
+            self._eng.flat_add(x[recent], rows[recent])
+        if (~recent).any():
+            self._eng.ivf_add(x[~recent], rows[~recent])
+        for v, t, r in zip(ids, ts, recent):
+            self.timestamps[v] = float(t)
+            self._tier[v] = 1 if r else 2
+
+    def migrate_with_threshold(self, threshold: float) -> int:
+        """src/hybrid/core.rs:600-649: move recent-tier vectors older than `threshold` seconds
+        into the IVF tier.  Unlike the reference (which leaves a stale copy in HNSW, :626-635)
+        the row is dropped from the recent tier, so no duplicate ids appear."""
+        if not self.ivf_trained or self._eng is None:
+            return 0
+        now = time.time()
+        move = [v for v, t in self.timestamps.items()
+                if self._tier.get(v) == 1 and max(now - t, 0.0) >= threshold]
+        if not move:
+            return 0
+        rows = np.asarray([self._ids.to_row[v] for v in move], dtype=np.uint32)
+        moved = self._eng.move_flat_to_ivf(rows)
+        for v in move:
+            self._tier[v] = 2
+        return moved
+
+    def migrate_old_vectors(self) -> int:
+        return self.migrate_with_threshold(self.config.recent_threshold)
+
+    def delete(self, vid) -> None:
+        if vid not in self._tier:
+            raise VectorNotFound(f"Vector not found: {vid!r}")
+        self._eng.set_deleted([self._ids.to_row[vid]], True)
+        self._deleted.add(vid)
+
+    def is_deleted(self, vid) -> bool:
+        return vid in self._deleted
+
+    def vacuum(self) -> int:
+        removed = self._eng.vacuum() if self._eng else 0
+        for v in self._deleted:
+            self._tier.pop(v, None)
+        self._deleted = set()
+        return removed
+
+    # -- search ---------------------------------------------------------------------------
+    def search(self, query, k: int) -> List[SearchResult]:
+        """src/hybrid/core.rs:419-423: SearchConfig::default() with k => ivf_n_probe = 10."""
+        return self.search_with_config(query, HybridSearchConfig(k=k))
+
+    def search_with_config(self, query, config: HybridSearchConfig) -> List[SearchResult]:
+        return self.batch_search_with_config([query], config)[0]
+
+    def batch_search(self, queries, k: int) -> List[List[SearchResult]]:
+        return self.batch_search_with_config(queries, HybridSearchConfig(k=k))
+
+    def batch_search_with_config(self, queries, config: HybridSearchConfig, filter_bits=None,
+                                 raw: bool = False):
+        nq = len(queries)
+        if not self.initialized or self._eng is None:
+            return [[] for _ in range(nq)]  # :431-434
+        if self.config.auto_migrate:
+            self.migrate_old_vectors()  # :437-439
+        q = queries if isinstance(queries, np.ndarray) else _as_matrix(queries, self._dimension)
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.shape[1] != self._dimension:
+            # the reference swallows per-tier errors (`if let Ok`, :459,469,475) => empty result
+            return [[] for _ in range(nq)]
+        k = config.k
+        if k == 0:
+            return [[] for _ in range(nq)]
+        tiers = (L.TIER_RECENT if config.search_recent else 0) | \
+                (L.TIER_HISTORICAL if (config.search_historical and self.ivf_trained) else 0)
+        if config.recent_k or config.historical_k:
+            # per-tier k differs from k: run the tiers separately and merge on the host exactly
+            # as :482-483 does (stable sort, recent first)
+            rk = config.recent_k or k
+            hk = config.historical_k or k
+            parts = []
+            if tiers & L.TIER_RECENT:
+                parts.append(self._eng.search(q, rk, 0, L.TIER_RECENT, filter_bits))
+            if tiers & L.TIER_HISTORICAL:
+                parts.append(self._eng.search(q, hk, config.ivf_n_probe, L.TIER_HISTORICAL, filter_bits))
+            out = []
+            for i in range(nq):
+                cand = []
+                for ids, dist, cnt in parts:
+                    cand += [(float(dist[i, j]), int(ids[i, j])) for j in range(int(cnt[i]))]
+                cand.sort(key=lambda t: t[0])  # stable
+                out.append([SearchResult(self._ids.to_id[r], d) for d, r in cand[:k]])
+            return out
+        ids, dist, cnt = self._eng.search(q, k, config.ivf_n_probe, tiers, filter_bits)
+        if raw:
+            return ids, dist, cnt
+        return _results(self._ids, ids, dist, cnt)
+
+    def filter_bitmap(self, flt: MetadataFilter, metadata_map: Dict[str, Any]) -> np.ndarray:
+        """Evaluate the filter once per row on the host -> 1 bit per row id."""
+        n = len(self._ids.to_id)
+        words = np.zeros((n + 63) // 64 or 1, dtype=np.uint64)
+        for vid, row in self._ids.to_row.items():
+            md = metadata_map.get(str(vid))
+            if md is not None and flt.matches(md):
+                words[row >> 6] |= np.uint64(1) << np.uint64(row & 63)
+        return words
+
+    def search_with_filter(self, query, k: int, flt: Optional[MetadataFilter],
+                           metadata_map: Dict[str, Any]) -> List[SearchResult]:
+        """src/hybrid/core.rs:513-549 — the reference's 3x oversample POST-filter."""
+        if flt is None:
+            return self.search(query, k)
+        cands = self.search(query, k * 3)
+        out = []
+        for r in cands:
+            md = metadata_map.get(str(r.vector_id))
+            if md is not None and flt.matches(md):
+                out.append(r)
+        return out[:k]
+
+    def search_with_prefilter(self, query, k: int, flt: MetadataFilter, metadata_map) -> List[SearchResult]:
+        """In-kernel bitmap PRE-filter (semantics of bindings/wasm/src/index.rs:164-186): never
+        returns fewer than k when >= k matching rows are reachable."""
+        bits = self.filter_bitmap(flt, metadata_map)
+        return self.batch_search_with_config([query], HybridSearchConfig(k=k), filter_bits=bits)[0]

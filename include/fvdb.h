@@ -1,0 +1,245 @@
+/*
+ * fvdb.h — C ABI of libfvdb_b200.so, the B200 (sm_100a) engine for the one data-parallel
+ * hot path of Fabstir/fabstir-vectordb: batched query x database L2 distance + top-k behind
+ * HybridIndex::search (IVF coarse assignment, IVF posting-list scan, exact scan of the
+ * recent tier, k-means centroid training).
+ *
+ * The reference has no FFI seam for this path today: the seam is the Rust
+ * method set of IVFIndex / HNSWIndex / HybridIndex.  Every entry point below names the
+ * reference function body it replaces (paths relative to the reference repository).
+ * The Rust-side `extern "C"` block that binds these symbols is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns int: FVDB_OK (0) or a negative fvdb_status; no exceptions and
+ *     no panics cross the ABI; fvdb_last_error() returns a human-readable message.
+ *   - the caller owns every host buffer; the library copies (pinned staging inside).
+ *   - ids crossing the boundary are dense caller-chosen u32 row ids.  The 32-byte VectorId
+ *     <-> row-id map, timestamps, JSON metadata and duplicate detection stay in the host
+ *     language (reference: src/core/types.rs:10-35, src/hybrid/core.rs:206,368).
+ *   - distances returned are TRUE L2 (sqrt applied), ascending, exactly as
+ *     euclidean_distance_scalar (src/core/vector_ops.rs:51-57) computes them:
+ *     sequential f32 accumulation in index order, no FMA contraction.
+ *   - ties: (distance, row id) ascending.  The reference's own order of equal distances is
+ *     HashMap iteration order (undefined); coarse ties resolve to the lower cluster id, as the
+ *     reference's stable sort does (src/ivf/core.rs:655), argmin to the lowest id (:379).
+ *   - NaN in any input returns FVDB_ERR_NAN (the reference panics: src/ivf/core.rs:655,677).
+ *   - there is NO CPU fallback: without a CUDA device fvdb_create returns FVDB_ERR_NO_DEVICE.
+ *   - a handle may be searched from several OS threads at once (searches serialise on an
+ *     internal mutex per handle for now); mutation is exclusive, like the reference's
+ *     tokio RwLock (src/hybrid/core.rs:202-213).
+ */
+#ifndef FVDB_H_
+#define FVDB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define FVDB_ABI_VERSION 1
+
+typedef struct fvdb_index fvdb_index; /* opaque engine handle: one per HybridIndex */
+
+/* Status codes.  -1..-8 map 1:1 onto IVFError (src/ivf/core.rs:14-39) / HNSWError /
+ * HybridError (src/hybrid/core.rs:16-35); the rest are ABI-level. */
+typedef enum fvdb_status {
+    FVDB_OK = 0,
+    FVDB_ERR_NOT_TRAINED = -1,           /* IVFError::NotTrained */
+    FVDB_ERR_DUPLICATE = -2,             /* IVFError::DuplicateVector (row id already present) */
+    FVDB_ERR_DIM_MISMATCH = -3,          /* IVFError::DimensionMismatch */
+    FVDB_ERR_INSUFFICIENT_TRAINING = -4, /* IVFError::InsufficientTrainingData */
+    FVDB_ERR_INCONSISTENT_DIM = -5,      /* IVFError::InconsistentDimensions (host side) */
+    FVDB_ERR_INVALID_CONFIG = -6,        /* IVFError::InvalidConfig */
+    FVDB_ERR_CHUNK_LOAD = -7,            /* IVFError::ChunkLoadError (host side; reserved) */
+    FVDB_ERR_NOT_FOUND = -8,             /* IVFError::VectorNotFound */
+    FVDB_ERR_NAN = -9,                   /* NaN in an input (reference panics) */
+    FVDB_ERR_CUDA = -10,                 /* CUDA runtime / driver failure, see last_error */
+    FVDB_ERR_NO_DEVICE = -11,            /* no usable sm_100 device: there is no CPU path */
+    FVDB_ERR_INVALID_ARG = -12,
+    FVDB_ERR_K_TOO_LARGE = -13,          /* k > k_max given at create */
+    FVDB_ERR_OOM = -14
+} fvdb_status;
+
+typedef enum fvdb_metric {
+    FVDB_METRIC_L2 = 0 /* euclidean_distance_scalar, src/core/vector_ops.rs:51-57 */
+} fvdb_metric;
+
+/* Tier selection bits for fvdb_search: HybridSearchConfig.search_recent /
+ * search_historical, src/hybrid/core.rs:173-196. */
+#define FVDB_TIER_RECENT 1u     /* the "HNSW" tier, served by an exact flat scan */
+#define FVDB_TIER_HISTORICAL 2u /* the IVF tier */
+#define FVDB_TIER_BOTH 3u
+
+/* Search precision modes (fvdb_set_option FVDB_OPT_SCAN_MODE). */
+#define FVDB_SCAN_EXACT 0u /* fp32 CUDA-core scan in the reference's own operation order */
+#define FVDB_SCAN_TC 1u    /* tcgen05 TF32 shortlist + exact fp32 re-rank + proof check,   \
+                              falling back to EXACT for any query whose proof fails */
+
+typedef enum fvdb_option {
+    FVDB_OPT_SCAN_MODE = 1,   /* FVDB_SCAN_EXACT | FVDB_SCAN_TC (default TC when dim%32==0) */
+    FVDB_OPT_SHORTLIST = 2,   /* shortlist length k' of the TC mode (default max(32, ..)) */
+    FVDB_OPT_KMEANS_TC = 3    /* 1: k-means assignment on tensor cores with exact verify */
+} fvdb_option;
+
+/* TrainResult, src/ivf/core.rs:103-109. */
+typedef struct fvdb_train_result {
+    uint32_t iterations;
+    uint32_t converged; /* bool */
+    float initial_error;
+    float final_error;
+} fvdb_train_result;
+
+typedef struct fvdb_stats {
+    uint32_t dim;
+    uint32_t nlist;        /* 0 until centroids are set / trained */
+    uint32_t trained;      /* IVFIndex::is_trained */
+    uint64_t ivf_rows;     /* IVFIndex::total_vectors (including tombstoned) */
+    uint64_t flat_rows;    /* recent-tier rows (including tombstoned) */
+    uint64_t deleted_rows; /* rows tombstoned and not yet vacuumed */
+    uint64_t device_bytes; /* HBM held by the handle */
+    /* counters of the most recent fvdb_search call */
+    uint32_t last_nq;
+    uint32_t last_fallback_queries; /* TC mode: queries re-run on the exact path */
+    uint64_t last_scanned_rows;     /* distinct posting-list + flat rows streamed */
+    uint64_t last_algorithmic_bytes;/* SURVEY §8(d) bytes: each probed list once + flat tier +
+                                       queries + centroids + bitmaps + outputs */
+    float last_device_ms;           /* device time of the last search (CUDA events) */
+    float last_scan_ms;             /* device time of the posting-list scan kernel alone */
+    uint32_t last_launches;         /* kernels launched by the last search */
+    uint32_t reserved;
+} fvdb_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+/* IVFIndex::new / HNSWIndex::new / HybridIndex::new (src/ivf/core.rs:171, src/hnsw/core.rs,
+ * src/hybrid/core.rs).  device: CUDA ordinal.  k_max: largest k any search will ask for
+ * (<= 1024).  Fails with FVDB_ERR_NO_DEVICE when no CUDA device is usable. */
+int fvdb_create(int device, uint32_t dim, int metric, uint32_t k_max, fvdb_index **out);
+void fvdb_destroy(fvdb_index *h);
+const char *fvdb_last_error(const fvdb_index *h); /* h may be NULL: last create error */
+int fvdb_abi_version(void);
+int fvdb_set_option(fvdb_index *h, int option, uint64_t value);
+int fvdb_get_stats(fvdb_index *h, fvdb_stats *out);
+
+/* ---- IVF centroids / training ---------------------------------------------------------- */
+
+/* IVFIndex::set_trained (src/ivf/core.rs:509-520): install centroids [nlist x dim], mark the
+ * index trained and clear every posting list. */
+int fvdb_ivf_set_centroids(fvdb_index *h, const float *centroids, uint32_t nlist);
+/* IVFIndex::get_centroids (:236).  out may be NULL to query nlist only. */
+int fvdb_ivf_get_centroids(fvdb_index *h, float *out, uint32_t *nlist);
+
+/* IVFIndex::train (src/ivf/core.rs:240-334): Lloyd k-means with the reference's stop rule
+ * (:303-321), empty-cluster rule (:410-415) and error definition (:419-429).
+ *   init_centroids != NULL : Lloyd starts from these [nlist x dim] (shared-init parity mode).
+ *   init_centroids == NULL : k-means++ (:336-371) driven by `seed`; same distribution as the
+ *                            reference, not the same rand-0.8 bit stream (parity unpinned).
+ * Errors: n == 0 or n < nlist -> FVDB_ERR_INSUFFICIENT_TRAINING (:242-254).
+ * Like the reference, training leaves every posting list empty (:273-277). */
+int fvdb_ivf_train(fvdb_index *h, const float *data, uint64_t n, uint32_t nlist,
+                   uint32_t max_iterations, const float *init_centroids, uint64_t seed,
+                   fvdb_train_result *out);
+
+/* IVFIndex::find_cluster / find_nearest_centroid (src/ivf/core.rs:373-386,493-499) for a batch:
+ * out_list[i] = argmin_c L2(x_i, c), strict '<' so the lowest cluster id wins ties.  Also the
+ * bulk re-assignment of load_index_chunked (src/hybrid/persistence.rs:626-653). */
+int fvdb_assign(fvdb_index *h, const float *x, uint64_t n, uint32_t *out_list);
+
+/* ---- insertion -------------------------------------------------------------------------- */
+
+/* IVFIndex::insert / batch_insert (src/ivf/core.rs:431-455, src/ivf/operations.rs:107): assign
+ * each row to its nearest centroid and append it to that posting list.  out_list (nullable)
+ * receives the chosen list per row.  FVDB_ERR_NOT_TRAINED before centroids exist. */
+int fvdb_ivf_add(fvdb_index *h, const float *x, const uint32_t *row_ids, uint64_t n,
+                 uint32_t *out_list);
+/* HNSWIndex::insert (src/hnsw/core.rs:226) for the recent tier: append rows to the flat tier. */
+int fvdb_flat_add(fvdb_index *h, const float *x, const uint32_t *row_ids, uint64_t n);
+/* HybridIndex::migrate_with_threshold (src/hybrid/core.rs:600-649): move the given recent-tier
+ * rows into the IVF tier (assign + append) and drop them from the flat tier. */
+int fvdb_move_flat_to_ivf(fvdb_index *h, const uint32_t *row_ids, uint64_t n, uint64_t *moved);
+
+/* ---- soft delete ------------------------------------------------------------------------ */
+
+/* IVFIndex::mark_deleted / HNSWIndex::mark_deleted (src/ivf/operations.rs:569-600): tombstone
+ * (deleted=1) or revive (0) rows by id; tombstoned rows are skipped by every search
+ * (src/ivf/core.rs:667, src/hnsw/core.rs:452-459). */
+int fvdb_set_deleted(fvdb_index *h, const uint32_t *row_ids, uint64_t n, int deleted);
+/* IVFIndex::vacuum / HNSWIndex::vacuum (src/ivf/operations.rs:625): physically drop
+ * tombstoned rows from both tiers. */
+int fvdb_vacuum(fvdb_index *h, uint64_t *removed);
+
+/* ---- search ----------------------------------------------------------------------------- */
+
+/* Batched HybridIndex::search_with_config (src/hybrid/core.rs:425-486) =
+ *   HNSWIndex::search of the recent tier (replaced by an exact scan, src/hnsw/core.rs:398-467)
+ *   ∪ IVFIndex::search_with_config (src/ivf/core.rs:626-681), stable-sorted by distance with
+ *   recent-tier rows first on ties, truncated to k, no de-duplication across tiers.
+ * One call = IVFIndex::batch_search (src/ivf/operations.rs:132-145) done as one batch.
+ *   q            [nq x dim] host, row-major
+ *   nprobe       lists probed per query (clamped to nlist, like truncate(n_probe) :656)
+ *   tiers        FVDB_TIER_* bits; FVDB_TIER_HISTORICAL is ignored until trained
+ *                (src/hybrid/core.rs:465)
+ *   filter_bits  NULL, or a bitmap over row ids (bit id set = row passes): the in-kernel
+ *                pre-filter (semantics of bindings/wasm/src/index.rs:164-186); rows with
+ *                id >= filter_nbits fail.  The reference's 3x post-filter
+ *                (src/hybrid/core.rs:513-549) is reproduced by the host mirror on top of this.
+ *   out_ids      [nq x k], out_dist [nq x k], out_count [nq] (<= k valid entries per query;
+ *                fewer than k is legal, src/ivf/core.rs:386-398 of the tests).
+ * Empty index or untrained+no recent rows: counts are 0 (Ok(vec![]) :431-434). */
+int fvdb_search(fvdb_index *h, const float *q, uint32_t nq, uint32_t k, uint32_t nprobe,
+                uint32_t tiers, const uint64_t *filter_bits, uint64_t filter_nbits,
+                uint32_t *out_ids, float *out_dist, uint32_t *out_count);
+
+/* Same, with every buffer already resident in device memory of the handle's GPU and the
+ * work enqueued on `stream` (a cudaStream_t; NULL = the handle's own stream).  Used for
+ * HBM-resident throughput measurement and by the multi-GPU shard driver, which all-gathers
+ * the per-GPU [nq x k] partial results over NCCL and merges them with fvdb_merge_topk_device.
+ * Returns after enqueueing unless a fallback pass is needed (which synchronises). */
+int fvdb_search_device(fvdb_index *h, const float *d_q, uint32_t nq, uint32_t k,
+                       uint32_t nprobe, uint32_t tiers, const uint64_t *d_filter_bits,
+                       uint64_t filter_nbits, uint32_t *d_out_ids, float *d_out_dist,
+                       uint32_t *d_out_count, void *stream);
+
+/* K-way merge of `parts` per-query partial results laid out [parts][nq][k] (ids, dist) with
+ * counts [parts][nq] into [nq][k]: the `sort_by(distance); truncate(k)` of
+ * src/hybrid/core.rs:482-483 applied across GPUs after the all-gather.  Ties: lower part first,
+ * then lower id.  Device pointers. */
+int fvdb_merge_topk_device(fvdb_index *h, const uint32_t *d_ids, const float *d_dist,
+                           const uint32_t *d_count, uint32_t parts, uint32_t nq, uint32_t k,
+                           uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count,
+                           void *stream);
+
+/* Device-resident variants of the bulk loaders (row data already in HBM, e.g. generated on
+ * the device for the 100M-row sharded configuration).  `list_filter_mod`/`list_filter_rem`:
+ * when mod > 1 only rows whose assigned list satisfies list % mod == rem are kept — the
+ * list-sharding rule of the multi-GPU driver. */
+int fvdb_ivf_add_device(fvdb_index *h, const float *d_x, const uint32_t *d_row_ids, uint64_t n,
+                        uint32_t list_filter_mod, uint32_t list_filter_rem, uint64_t *kept);
+int fvdb_flat_add_device(fvdb_index *h, const float *d_x, const uint32_t *d_row_ids, uint64_t n);
+int fvdb_ivf_train_device(fvdb_index *h, const float *d_data, uint64_t n, uint32_t nlist,
+                          uint32_t max_iterations, const float *d_init_centroids, uint64_t seed,
+                          fvdb_train_result *out);
+
+/* One Lloyd iteration on device data with externally reduced sums — the multi-GPU k-means
+ * building blocks: step 1 assigns this rank's points and accumulates
+ * per-cluster f32 sums [nlist x dim] and counts [nlist] (u32) plus the squared-error sum
+ * (f64 scalar, device) into caller buffers; the caller all-reduces them; step 2 installs
+ * means (empty cluster keeps its centroid, src/ivf/core.rs:410-415). */
+int fvdb_kmeans_accumulate_device(fvdb_index *h, const float *d_data, uint64_t n,
+                                  float *d_sums, uint32_t *d_counts, double *d_sqerr,
+                                  uint32_t *d_assign, uint32_t *d_changed, void *stream);
+int fvdb_kmeans_apply_device(fvdb_index *h, const float *d_sums, const uint32_t *d_counts,
+                             void *stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVDB_H_ */
