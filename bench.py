@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""bench.py — QPS of batched IVF search (BASELINE.json configs[1]: 1M x 384, nlist=1024,
+nprobe=32, 1024-query batches, k=10) on N B200s, with recall@10, the HBM roofline of the
+posting-list scan kernel, an end-to-end number through the host-buffer C-ABI call and the CPU
+baseline (the oracle port of the Rust reference) timed on this box's host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (torchrun, one rank per GPU): weak scaling — every GPU holds 1M rows / 1024 lists of an
+N-times larger index (list l on rank l % N), the batch is 1024*N queries, each rank scans the
+probed lists it owns, one NCCL all-gather of the per-rank top-k feeds the final merge.
+A "step" = one query batch.  The index (1.5 GB per GPU) is 12x larger than L2, so successive
+steps cannot be served from cache; query batches rotate through distinct pre-generated sets.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM = 384
+ROWS_PER_GPU = int(os.environ.get("FVDB_BENCH_ROWS", 1_000_000))
+NLIST_PER_GPU = int(os.environ.get("FVDB_BENCH_NLIST", 1024))
+NQ_PER_GPU = int(os.environ.get("FVDB_BENCH_NQ", 1024))
+NPROBE = int(os.environ.get("FVDB_BENCH_NPROBE", 32))
+K = 10
+SIGMA = float(os.environ.get("FVDB_BENCH_SIGMA", 1.0))
+SEED = 1234
+SEED_Q = 5678
+TRAIN_ITERS = int(os.environ.get("FVDB_BENCH_TRAIN_ITERS", 8))
+TRAIN_ROWS_PER_LIST = 64
+N_QUERY_SETS = 4
+RECALL_QUERIES = 256
+CPU_SAMPLE_QUERIES = int(os.environ.get("FVDB_BENCH_CPU_QUERIES", 128))
+
+
+def n_comp_for(nlist):  # 4 mixture components per list
+    return 4 * nlist
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_name(world):
+    return (f"IVF search {ROWS_PER_GPU * world}x{DIM} nlist={NLIST_PER_GPU * world} nprobe={NPROBE} "
+            f"nq={NQ_PER_GPU * world}/batch k={K}")
+
+
+# ---------------------------------------------------------------------------------------------
+# index construction (shared by both arms so they search the identical index)
+# ---------------------------------------------------------------------------------------------
+def build_index(torch, eng, rank, world, log):
+    """Generate the synthetic database on the device, train centroids, load this rank's lists.
+    Returns (centroids tensor [nlist x D], n_total, nlist, n_comp)."""
+    from fabstir_vectordb_b200 import _lib as L
+    lib = L.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_total = ROWS_PER_GPU * world
+    nlist = NLIST_PER_GPU * world
+    n_comp = n_comp_for(nlist)
+    stream = torch.cuda.current_stream().cuda_stream
+    t0 = time.time()
+    # training sample: TRAIN_ROWS_PER_LIST rows per list, strided through the database
+    n_train = min(n_total, TRAIN_ROWS_PER_LIST * nlist)
+    train = torch.empty((n_train, DIM), dtype=torch.float32, device=dev)
+    CH = 1 << 18
+    stride = max(1, n_total // n_train)
+    if stride == 1:
+        rc = lib.fvdb_synth_rows_device(train.data_ptr(), 0, n_train, DIM, n_comp, SIGMA, SEED, stream)
+        assert rc == 0
+    else:
+        # blocks of 64 consecutive rows every 64*stride rows
+        blk = 64
+        nb = n_train // blk
+        for b in range(nb):
+            rc = lib.fvdb_synth_rows_device(train[b * blk:].data_ptr(), b * blk * stride, blk, DIM, n_comp,
+                                            SIGMA, SEED, stream)
+            assert rc == 0
+    torch.cuda.synchronize()
+    init = train[torch.arange(nlist, device=dev) * (n_train // nlist)].contiguous()
+    res = eng.train_device(train.data_ptr(), n_train, nlist, TRAIN_ITERS, init.data_ptr(), SEED)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    log(f"trained nlist={nlist} on {n_train} rows: {res} in {t1 - t0:.1f}s")
+    del train
+    buf = torch.empty((CH, DIM), dtype=torch.float32, device=dev)
+    ids = torch.empty((CH,), dtype=torch.int32, device=dev)
+    kept = 0
+    for r0 in range(0, n_total, CH):
+        n = min(CH, n_total - r0)
+        rc = lib.fvdb_synth_rows_device(buf.data_ptr(), r0, n, DIM, n_comp, SIGMA, SEED, stream)
+        assert rc == 0
+        ids[:n] = torch.arange(r0, r0 + n, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        kept += eng.ivf_add_device(buf.data_ptr(), ids.data_ptr(), n, world, rank)
+    log(f"rank {rank}: loaded {kept} of {n_total} rows in {time.time() - t1:.1f}s")
+    return n_total, nlist, n_comp
+
+
+def make_queries(torch, lib, nq, n_total, n_comp, set_idx):
+    from fabstir_vectordb_b200 import synth
+    dev = torch.device("cuda", torch.cuda.current_device())
+    q = torch.empty((nq, DIM), dtype=torch.float32, device=dev)
+    rc = lib.fvdb_synth_queries_device(q.data_ptr(), set_idx * nq, nq, DIM, n_total, n_comp, SIGMA, SEED,
+                                       synth.default_qnoise(DIM, SIGMA), SEED_Q,
+                                       torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return q
+
+
+def ground_truth(torch, lib, q, n_total, n_comp, rank, world, k):
+    """Exact top-k over ALL rows: each rank flat-scans the rows r % world == rank of the
+    database (exact fp32 scan), partial results are all-gathered and merged."""
+    from fabstir_vectordb_b200 import Engine, _lib as L
+    from fabstir_vectordb_b200.shard import ShardedIndex
+    dev = q.device
+    eng = Engine(DIM, k_max=max(16, k))
+    eng.set_option(L.OPT_SCAN_MODE, L.SCAN_EXACT)
+    CH = 1 << 18
+    buf = torch.empty((CH, DIM), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    # contiguous slab per rank
+    per = (n_total + world - 1) // world
+    lo, hi = rank * per, min(n_total, (rank + 1) * per)
+    for r0 in range(lo, hi, CH):
+        n = min(CH, hi - r0)
+        rc = lib.fvdb_synth_rows_device(buf.data_ptr(), r0, n, DIM, n_comp, SIGMA, SEED, stream)
+        assert rc == 0
+        ids = torch.arange(r0, r0 + n, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        eng.flat_add_device(buf.data_ptr(), ids.data_ptr(), n)
+    sh = ShardedIndex(eng, rank, world)
+    ids, dist, cnt = sh.search(q, k, 0, tiers=L.TIER_RECENT)
+    torch.cuda.synchronize()
+    out = ids.cpu().numpy().view(np.uint32).copy(), dist.cpu().numpy().copy(), cnt.cpu().numpy().view(np.uint32).copy()
+    eng.close()
+    return out
+
+
+def recall_of(found_ids, found_cnt, truth_ids, truth_cnt, k):
+    acc = 0.0
+    for i in range(found_ids.shape[0]):
+        t = set(truth_ids[i, :truth_cnt[i]].tolist())
+        f = set(found_ids[i, :found_cnt[i]].tolist())
+        acc += len(t & f) / max(1, len(t))
+    return acc / found_ids.shape[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference (the Rust reference cannot be built in this image)
+# ---------------------------------------------------------------------------------------------
+def host_index_from_device(torch, lib, eng, n_total, n_comp):
+    """Copy the database to the host and build the oracle's IVF over the same centroids and the
+    same (parity-tested) list assignment."""
+    import oracle as O
+    dev = torch.device("cuda", torch.cuda.current_device())
+    CH = 1 << 18
+    buf = torch.empty((CH, DIM), dtype=torch.float32, device=dev)
+    x = np.empty((n_total, DIM), dtype=np.float32)
+    stream = torch.cuda.current_stream().cuda_stream
+    for r0 in range(0, n_total, CH):
+        n = min(CH, n_total - r0)
+        rc = lib.fvdb_synth_rows_device(buf.data_ptr(), r0, n, DIM, n_comp, SIGMA, SEED, stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        x[r0:r0 + n] = buf[:n].cpu().numpy()
+    cents = eng.get_centroids()
+    assign = eng.assign(x)
+    return O.IVF(cents, x, np.arange(n_total, dtype=np.uint32), assign_=assign), x
+
+
+def cpu_search_qps(ivf, q_host, k, nprobe, threads=0):
+    import oracle as O
+    t0 = time.perf_counter()
+    ids, dist, cnt = O.hybrid_batch_search(ivf, None, None, q_host, k, nprobe, tiers=2, threads=threads)
+    dt = time.perf_counter() - t0
+    return q_host.shape[0] / dt, dt, (ids, dist, cnt)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU search path (oracle port, all host threads) on the
+    same index / metric / config.  Rank 0 only; a step = a bounded sample of one batch."""
+    if rank != 0:
+        return
+    import torch
+    import oracle as O
+    from fabstir_vectordb_b200 import Engine, _lib as L
+    lib = L.load()
+    torch.cuda.set_device(0)
+    log = lambda m: print(f"[reference] {m}", file=sys.stderr, flush=True)
+    # the index is built exactly as in the product arm (same generator, same centroids, same
+    # assignment) so both arms search identical data; only index construction touches the GPU,
+    # the timed path below is pure host code.
+    eng = Engine(DIM, k_max=16)
+    eng.set_option(L.OPT_SCAN_MODE, L.SCAN_EXACT)
+    n_total, nlist, n_comp = build_index(torch, eng, 0, 1, log)
+    ivf, _ = host_index_from_device(torch, lib, eng, n_total, n_comp)
+    sample = CPU_SAMPLE_QUERIES
+    qsets = [make_queries(torch, lib, NQ_PER_GPU, n_total, n_comp, s).cpu().numpy()[:sample]
+             for s in range(N_QUERY_SETS)]
+    eng.close()
+    threads = O.num_threads()
+    for w in range(args.warmup):
+        cpu_search_qps(ivf, qsets[w % N_QUERY_SETS][:16], K, NPROBE)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_search_qps(ivf, qsets[s % N_QUERY_SETS], K, NPROBE)
+    dt = time.perf_counter() - t0
+    qps = args.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": "QPS @ recall@10>=0.95, 1M x 384 IVF", "value": qps,
+        "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(1), "note": "oracle C port of the Rust reference "
+                   "(rustc/cargo absent), tight mode, OpenMP over queries"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} of {NQ_PER_GPU} queries per step, full 1M-row index"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("FVDB_BENCH_MODE", "auto"), choices=["auto", "exact", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fabstir_vectordb_b200 import Engine, _lib as L
+    from fabstir_vectordb_b200.shard import ShardedIndex
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.load()
+    log = (lambda m: print(f"[bench r{rank}] {m}", file=sys.stderr, flush=True))
+
+    eng = Engine(DIM, k_max=16, device=local_rank)
+    if args.mode == "exact":
+        eng.set_option(L.OPT_SCAN_MODE, L.SCAN_EXACT)
+    elif args.mode == "tc":
+        eng.set_option(L.OPT_SCAN_MODE, L.SCAN_TC)
+        eng.set_option(L.OPT_KMEANS_TC, 1)
+    n_total, nlist, n_comp = build_index(torch, eng, rank, world, log)
+    sh = ShardedIndex(eng, rank, world)
+    nq = NQ_PER_GPU * world
+    qsets = [make_queries(torch, lib, nq, n_total, n_comp, s) for s in range(N_QUERY_SETS)]
+
+    def step(i):
+        return sh.search(qsets[i % N_QUERY_SETS], K, NPROBE, tiers=L.TIER_HISTORICAL)
+
+    # first call seals the index (regroup by list) — outside the timed region
+    step(0)
+    torch.cuda.synchronize()
+
+    # ---- recall@10 against exact ground truth --------------------------------------------
+    rq = qsets[0][:RECALL_QUERIES].contiguous()
+    f_ids, f_dist, f_cnt = sh.search(rq, K, NPROBE, tiers=L.TIER_HISTORICAL)
+    torch.cuda.synchronize()
+    found = (f_ids.cpu().numpy().view(np.uint32).copy(), f_dist.cpu().numpy().copy(),
+             f_cnt.cpu().numpy().view(np.uint32).copy())
+    fallback_q = eng.stats().last_fallback_queries
+    truth = ground_truth(torch, lib, rq, n_total, n_comp, rank, world, K)
+    recall = recall_of(found[0], found[2], truth[0], truth[2], K)
+    log(f"recall@{K} = {recall:.4f} over {RECALL_QUERIES} queries (fallback queries {fallback_q})")
+
+    # ---- timed region: HBM-resident inputs ---------------------------------------------------
+    for w in range(args.warmup):
+        step(w)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_ms, launches, alg_bytes, scan_rows = [], 0, 0, 0
+    torch.cuda.synchronize()
+    ev0.record()
+    for s in range(args.steps):
+        step(s)
+        st = eng.stats()
+        scan_ms.append(st.last_scan_ms)
+        launches += st.last_launches + (1 if world > 1 else 0)
+        alg_bytes = st.last_algorithmic_bytes
+        scan_rows = st.last_scanned_rows
+    ev1.record()
+    torch.cuda.synchronize()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    qps = nq * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end: host buffers through the C-ABI call (H2D + search + D2H per step) -------
+    h_q = [q.cpu().numpy() for q in qsets]
+    if world == 1:
+        for w in range(2):
+            eng.search(h_q[w % N_QUERY_SETS], K, NPROBE, tiers=L.TIER_HISTORICAL)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            eng.search(h_q[s % N_QUERY_SETS], K, NPROBE, tiers=L.TIER_HISTORICAL)
+        e2e_dt = time.perf_counter() - t0
+    else:
+        pinned = [torch.from_numpy(a).pin_memory() for a in h_q]
+        dq = torch.empty_like(qsets[0])
+        out_h = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            dq.copy_(pinned[s % N_QUERY_SETS], non_blocking=True)
+            ids_, dist_, cnt_ = sh.search(dq, K, NPROBE, tiers=L.TIER_HISTORICAL)
+            out_h = (ids_.cpu(), dist_.cpu(), cnt_.cpu())
+        torch.cuda.synchronize()
+        e2e_dt = time.perf_counter() - t0
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_qps = nq * args.steps / e2e_dt
+    h2d = nq * DIM * 4
+    d2h = nq * K * 8 + nq * 4
+
+    # ---- roofline of the dominant kernel (posting-list scan) -----------------------------------
+    peak, peak_src = measured_peak_hbm()
+    scan_bytes = scan_rows * DIM * 4 + scan_rows * 4  # rows + row norms/ids touched once
+    mean_scan_ms = float(np.mean(scan_ms)) if scan_ms else 0.0
+    achieved = scan_bytes / (mean_scan_ms * 1e-3) / 1e9 if mean_scan_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": None,
+                "kernel": "ivf posting-list scan", "kernel_ms": mean_scan_ms,
+                "algorithmic_bytes_per_launch": scan_bytes, "peak_source": peak_src,
+                "share_of_step": mean_scan_ms / (elapsed_ms / args.steps) if elapsed_ms else None}
+
+    # ---- CPU baseline beside it (rank 0, N == 1) -------------------------------------------------
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle as O
+        ivf, _ = host_index_from_device(torch, lib, eng, n_total, n_comp)
+        sample = CPU_SAMPLE_QUERIES
+        cq = h_q[0][:sample]
+        cpu_qps, cpu_dt, cres = cpu_search_qps(ivf, cq, K, NPROBE)
+        f1 = 16
+        _, dt1, _ = cpu_search_qps(ivf, cq[:f1], K, NPROBE, threads=1)
+        # parity of the GPU results with the oracle on the same queries
+        g_ids, g_dist, g_cnt = eng.search(cq, K, NPROBE, tiers=L.TIER_HISTORICAL)
+        same_ids = int((g_ids == cres[0]).all(axis=1).sum())
+        same_bits = int((g_dist.view(np.uint32) == cres[1].view(np.uint32)).all(axis=1).sum())
+        parity = {"queries": sample, "identical_id_lists": same_ids, "identical_distance_bits": same_bits}
+        cpu = {"value": cpu_qps, "unit": "queries/s", "cores": O.num_threads(), "kind": "port",
+               "sample": f"{sample} of {nq} queries of one batch, full index; 1-thread: "
+                         f"{f1 / dt1:.1f} q/s on {f1} queries",
+               "host_cpus": os.cpu_count()}
+        log(f"cpu baseline {cpu_qps:.1f} q/s on {O.num_threads()} threads; parity {parity}")
+
+    line = {
+        "metric": "QPS @ recall@10>=0.95, 1M x 384 IVF", "value": qps, "unit": "queries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(world), "rows_per_gpu": ROWS_PER_GPU, "dim": DIM,
+                   "nlist": nlist, "nprobe": NPROBE, "nq_per_batch": nq, "k": K, "sigma": SIGMA,
+                   "mixture_components": n_comp, "scan_mode": args.mode,
+                   "cache": "index (1.5 GB/GPU) >> 126 MB L2; 4 rotating query sets",
+                   "sharding": f"list l on rank l % {world}; all-gather top-k + merge" if world > 1 else "single GPU"},
+        "recall_at_10": recall, "recall_queries": RECALL_QUERIES, "fallback_queries": int(fallback_q),
+        "clocks": clocks,
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "parity_vs_oracle": parity,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,102 @@
+"""Multi-GPU list-sharded search: one process per GPU, torch.distributed for the
+plumbing.  IVF list l lives on rank (l % world); centroids are replicated, so every rank runs
+the same coarse step, scans only the probed lists it owns (the others are empty in its arena)
+and emits a local top-k.  One exchange step: all-gather of the per-rank [nq x k] results, then
+the k-way merge of src/hybrid/core.rs:482-483 (`fvdb_merge_topk_device`).
+
+The collective is torch.distributed (NCCL on GPUs; gloo in the CPU tests of the layout logic).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .engine import Engine
+
+
+def owner_of_list(list_id: int, world: int) -> int:
+    """List -> rank placement rule; must match fvdb_ivf_add_device(list_filter_mod=world)."""
+    return list_id % world
+
+
+def gather_layout(nq: int, k: int, world: int) -> Tuple[Tuple[int, ...], Tuple[int, ...]]:
+    """Shapes of the all-gathered buffers consumed by fvdb_merge_topk_device:
+    ids/dist [world][nq][k], count [world][nq]."""
+    return (world, nq, k), (world, nq)
+
+
+def merge_parts_reference(ids: np.ndarray, dist: np.ndarray, cnt: np.ndarray, k: int):
+    """Host statement of the merge rule (distance, then part, then position) used by the CPU
+    gloo tests to validate the gather layout; the product path merges on the GPU."""
+    parts, nq, _ = ids.shape
+    out_ids = np.full((nq, k), 0xFFFFFFFF, dtype=np.uint32)
+    out_dist = np.full((nq, k), np.inf, dtype=np.float32)
+    out_cnt = np.zeros(nq, dtype=np.uint32)
+    for q in range(nq):
+        cand = []
+        for p in range(parts):
+            for j in range(min(int(cnt[p, q]), k)):
+                cand.append((float(dist[p, q, j]), p, j, int(ids[p, q, j])))
+        cand.sort(key=lambda t: (t[0], t[1], t[2]))
+        cand = cand[:k]
+        out_cnt[q] = len(cand)
+        for o, c in enumerate(cand):
+            out_ids[q, o] = c[3]
+            out_dist[q, o] = c[0]
+    return out_ids, out_dist, out_cnt
+
+
+class ShardedIndex:
+    """One rank's shard + the exchange step.  All tensors are torch CUDA tensors."""
+
+    def __init__(self, engine: Engine, rank: int, world: int, group=None):
+        self.eng = engine
+        self.rank = rank
+        self.world = world
+        self.group = group
+        self._bufs = {}
+
+    def add_rows_device(self, x, row_ids) -> int:
+        """Assign rows to lists and keep those this rank owns."""
+        return self.eng.ivf_add_device(x.data_ptr(), row_ids.data_ptr(), x.shape[0], self.world, self.rank)
+
+    def _buffers(self, nq: int, k: int, device):
+        import torch
+        key = (nq, k)
+        if key not in self._bufs:
+            self._bufs[key] = dict(
+                ids=torch.empty((nq, k), dtype=torch.int32, device=device),
+                dist=torch.empty((nq, k), dtype=torch.float32, device=device),
+                cnt=torch.empty((nq,), dtype=torch.int32, device=device),
+                g_ids=torch.empty((self.world, nq, k), dtype=torch.int32, device=device),
+                g_dist=torch.empty((self.world, nq, k), dtype=torch.float32, device=device),
+                g_cnt=torch.empty((self.world, nq), dtype=torch.int32, device=device),
+                o_ids=torch.empty((nq, k), dtype=torch.int32, device=device),
+                o_dist=torch.empty((nq, k), dtype=torch.float32, device=device),
+                o_cnt=torch.empty((nq,), dtype=torch.int32, device=device),
+            )
+        return self._bufs[key]
+
+    def search(self, q, k: int, nprobe: int, tiers: int = L.TIER_HISTORICAL, filter_bits=None,
+               filter_nbits: int = 0):
+        """q: [nq x dim] CUDA tensor, identical on every rank.  Returns (ids, dist, cnt) CUDA
+        tensors holding the GLOBAL top-k on every rank."""
+        import torch
+        import torch.distributed as dist
+        nq = q.shape[0]
+        b = self._buffers(nq, k, q.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        self.eng.search_device(q.data_ptr(), nq, k, nprobe, tiers,
+                               filter_bits.data_ptr() if filter_bits is not None else 0, filter_nbits,
+                               b["ids"].data_ptr(), b["dist"].data_ptr(), b["cnt"].data_ptr(), stream)
+        if self.world == 1:
+            return b["ids"], b["dist"], b["cnt"]
+        dist.all_gather_into_tensor(b["g_ids"], b["ids"], group=self.group)
+        dist.all_gather_into_tensor(b["g_dist"], b["dist"], group=self.group)
+        dist.all_gather_into_tensor(b["g_cnt"], b["cnt"], group=self.group)
+        self.eng.merge_topk_device(b["g_ids"].data_ptr(), b["g_dist"].data_ptr(), b["g_cnt"].data_ptr(),
+                                   self.world, nq, k, b["o_ids"].data_ptr(), b["o_dist"].data_ptr(),
+                                   b["o_cnt"].data_ptr(), stream)
+        return b["o_ids"], b["o_dist"], b["o_cnt"]
