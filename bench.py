@@ -350,13 +350,13 @@ def main():
     log(f"recall@{K} = {recall:.4f} over {RECALL_QUERIES} queries (fallback queries {fallback_q})")
 
     # ---- timed region: HBM-resident inputs ---------------------------------------------------
+    sampler = ClockSampler(local_rank)  # samples clocks through warm-up + timed region
+    sampler.start()
     for w in range(args.warmup):
         step(w)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, launches, alg_bytes, scan_rows = [], 0, 0, 0
     torch.cuda.synchronize()

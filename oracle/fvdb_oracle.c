@@ -521,7 +521,7 @@ FO_EXPORT void fo_hybrid_batch_search(const fo_ivf *ivf, const float *flat_rows,
                                       int faithful, uint32_t *out_ids, float *out_dist,
                                       uint32_t *out_count) {
 #if defined(_OPENMP)
-    if (threads > 0) omp_set_num_threads(threads);
+    omp_set_num_threads(threads > 0 ? threads : omp_get_num_procs());
 #else
     (void)threads;
 #endif
@@ -541,7 +541,7 @@ FO_EXPORT void fo_hybrid_batch_search(const fo_ivf *ivf, const float *flat_rows,
 
 FO_EXPORT int fo_num_threads(void) {
 #if defined(_OPENMP)
-    return omp_get_max_threads();
+    return omp_get_num_procs();
 #else
     return 1;
 #endif

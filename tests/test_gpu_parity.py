@@ -280,13 +280,19 @@ def test_kmeans_lloyd_parity_shared_init(n, d, nlist, iters):
 
 
 def test_kmeanspp_seeded_training_quality():
-    # seeded k-means++ is parity-unpinned (rand 0.8 stream); check it is a sane k-means++:
-    # final error no worse than 1.5x the oracle's own seeded run on well-separated clusters
+    # seeded k-means++ is parity-unpinned (rand 0.8 stream is an un-vendored dependency): check
+    # that the device k-means++ behaves like the oracle's — its final error falls inside the
+    # spread the oracle's own seeded runs produce on the same data
     n, d, nlist = 6000, 32, 12
     x = _data(n, d, 71, n_comp=nlist, sigma=0.2)
-    eng = Engine(d)
-    res = eng.train(x, nlist, 10, seed=42)
-    init, _ = O.kmeanspp_init(x, nlist, 42)
-    _, _, want = O.train_lloyd(x, init, 10)
-    assert res["final_error"] <= 1.5 * want["final_error"] + 1e-6
-    assert res["final_error"] < res["initial_error"]
+    errs = []
+    for seed in range(8):
+        init, _ = O.kmeanspp_init(x, nlist, seed)
+        errs.append(O.train_lloyd(x, init, 10)[2]["final_error"])
+    for seed in (42, 43):
+        eng = Engine(d)
+        res = eng.train(x, nlist, 10, seed=seed)
+        assert res["final_error"] <= 1.25 * max(errs)
+        assert res["final_error"] >= 0.99 * min(errs)
+        assert res["final_error"] < res["initial_error"]
+        assert eng.get_centroids().shape == (nlist, d)
