@@ -127,6 +127,9 @@ struct fvdb_index {
     DevBuf<float> s_out_dist, s_f32a;
     DevBuf<double> s_f64;
     DevBuf<uint64_t> s_tmpbits;
+    DevBuf<uint32_t> s_fb_idx;
+    DevBuf<float> s_fb_q;
+    DevBuf<uint64_t> s_fb_keys, s_fb_coarse;
     TcScratch tc;
 
     // pinned staging
@@ -329,14 +332,8 @@ int assign_device(fvdb_index* h, const float* d_x, uint64_t n, uint32_t* d_assig
     if (n == 0) return FVDB_OK;
     if (n >= 0xFFFFFFFFull) return h->fail(FVDB_ERR_INVALID_ARG, "batch exceeds u32 rows");
     CK(h->s_ivf_keys.ensure(n, 0, st, &h->dev_bytes));
-    if (h->kmeans_tc && tc_supported(h->dim)) {
-        int r = tc_assign(h->tc, h->centroids.p, h->nlist, d_x, n, h->dim, h->s_ivf_keys.p, st,
-                          &h->dev_bytes, &h->err);
-        if (r != FVDB_OK) return r;
-    } else {
-        RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_x, (uint32_t)n, 1, nullptr, 0,
-                           nullptr, 0, h->s_ivf_keys.p, st));
-    }
+    RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_x, (uint32_t)n, 1, nullptr, 0,
+                       nullptr, 0, h->s_ivf_keys.p, st));
     CK(launch_extract_assign(h->s_ivf_keys.p, n, d_assign, d_dist, prev, d_changed, st));
     return FVDB_OK;
 }
@@ -555,6 +552,55 @@ int train_device_impl(fvdb_index* h, const float* d_data, uint64_t n, uint32_t n
     return FVDB_OK;
 }
 
+// Exact IVF search of `nq` queries given their exact coarse ranking (src/ivf/core.rs:661-678):
+// bucket (query, probe) pairs by list, scan every probed list once, merge per query.
+int ivf_scan_exact(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t np,
+                   const uint64_t* coarse, const uint64_t* tomb, const uint64_t* filt,
+                   uint64_t filter_bits, uint64_t* out_keys, uint64_t* d_scanned, bool timed,
+                   cudaStream_t st) {
+    const uint32_t D = h->dim;
+    const uint32_t tq = exact_scan_tq();
+    const size_t n_pairs = (size_t)nq * np;
+    const size_t max_items = (size_t)h->nlist + (n_pairs + tq - 1) / tq + 1;
+    CK(h->s_list_cnt.ensure(h->nlist + 1, 0, st, &h->dev_bytes));
+    CK(h->s_pair_off.ensure(h->nlist + 2, 0, st, &h->dev_bytes));
+    CK(h->s_cursor.ensure(h->nlist + 1, 0, st, &h->dev_bytes));
+    CK(h->s_pair_q.ensure(n_pairs, 0, st, &h->dev_bytes));
+    CK(h->s_pair_slot.ensure(n_pairs, 0, st, &h->dev_bytes));
+    CK(h->s_items.ensure(max_items, 0, st, &h->dev_bytes));
+    uint32_t* d_n_items = h->s_misc.p + 6;
+    CK(launch_probe_bucketing(coarse, nq, np, h->list_off.p, h->nlist, tq, h->s_list_cnt.p,
+                              h->s_pair_off.p, h->s_cursor.p, h->s_pair_q.p, h->s_pair_slot.p,
+                              h->s_items.p, d_n_items, d_scanned, st));
+    h->stats.last_launches += 3;
+    uint32_t Ppad = np;
+    if (np > 256) Ppad = (np + 255) / 256 * 256;
+    CK(h->s_partial.ensure((size_t)nq * Ppad * k, 0, st, &h->dev_bytes));
+    CK(cudaMemsetAsync(h->s_partial.p, 0xFF, (size_t)nq * Ppad * k * 8, st));
+    ExactScanArgs a{};
+    a.X = h->ivf_rows.p; a.ids = h->ivf_ids.p; a.Q = d_q; a.D = D;
+    a.items = h->s_items.p; a.item_count = d_n_items; a.n_items = 0;
+    a.pair_q = h->s_pair_q.p; a.pair_slot = h->s_pair_slot.p;
+    a.P = Ppad; a.k = k;
+    a.tomb = tomb; a.tomb_bits = h->tomb_bits; a.filt = filt; a.filt_bits = filter_bits;
+    a.partial = h->s_partial.p;
+    if (timed) CK(cudaEventRecord(h->ev_s0, st));
+    CK(launch_exact_scan(a, (uint32_t)max_items, st));
+    if (timed) CK(cudaEventRecord(h->ev_s1, st));
+    h->stats.last_launches += 1;
+    // sort + truncate(k) (src/ivf/core.rs:677-678)
+    if (Ppad > 256) {
+        CK(h->s_partial2.ensure((size_t)nq * (Ppad / 256) * k, 0, st, &h->dev_bytes));
+        CK(launch_merge_partials(h->s_partial.p, nq * (Ppad / 256), 256, k, h->s_partial2.p, st));
+        CK(launch_merge_partials(h->s_partial2.p, nq, Ppad / 256, k, out_keys, st));
+        h->stats.last_launches += 2;
+    } else {
+        CK(launch_merge_partials(h->s_partial.p, nq, Ppad, k, out_keys, st));
+        h->stats.last_launches += 1;
+    }
+    return FVDB_OK;
+}
+
 int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,
                        uint32_t tiers, const uint64_t* d_filter, uint64_t filter_bits,
                        uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count,
@@ -578,119 +624,72 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
 
     CK(cudaEventRecord(h->ev_a, st));
     CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
+    // s_misc words: [0] nan flag, [2..3] scanned rows (u64), [4] kmeans changed, [6] item count,
+    // [8] kmeans++ pick, [10] TC fallback count
     int* d_nan = reinterpret_cast<int*>(h->s_misc.p);
     uint64_t* d_scanned = reinterpret_cast<uint64_t*>(h->s_misc.p + 2);
+    uint32_t* d_fb_count = h->s_misc.p + 10;
     CK(cudaMemsetAsync(h->s_misc.p, 0, 64, st));
     CK(launch_nan_check(d_q, (size_t)nq * D, d_nan, st));
     h->stats.last_launches += 1;
 
     uint64_t* ivf_keys = nullptr;
     uint64_t* flat_keys = nullptr;
-    bool scan_timed = false;
+    bool scan_timed = false, used_tc = false;
+    uint32_t np = 0;
 
     if (use_ivf) {
-        const uint32_t np = std::min(nprobe, h->nlist);
+        np = std::min(nprobe, h->nlist);
         if (np > 512) return h->fail(FVDB_ERR_INVALID_ARG, "nprobe > 512 is not supported");
         CK(h->s_ivf_keys.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
         ivf_keys = h->s_ivf_keys.p;
-        const bool tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D);
-        if (tc) {
+        // coarse step: all centroid distances, nearest np lists (src/ivf/core.rs:646-656), exact
+        CK(h->s_coarse.ensure((size_t)nq * np, 0, st, &h->dev_bytes));
+        RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_q, nq, np, nullptr, 0, nullptr, 0,
+                           h->s_coarse.p, st));
+        used_tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D) && k <= TC_MAX_K && np <= TC_MAX_NPROBE;
+        if (used_tc) {
+            CK(h->s_fb_idx.ensure(nq, 0, st, &h->dev_bytes));
             TcSearchArgs ta{};
-            ta.centroids = h->centroids.p; ta.nlist = h->nlist;
             ta.rows = h->ivf_rows.p; ta.ids = h->ivf_ids.p; ta.n_rows = h->ivf_n;
-            ta.list_off = h->list_off.p;
+            ta.list_off = h->list_off.p; ta.nlist = h->nlist;
             ta.Q = d_q; ta.nq = nq; ta.D = D; ta.k = k; ta.nprobe = np;
+            ta.coarse_keys = h->s_coarse.p;
             ta.tomb = tomb; ta.tomb_bits = h->tomb_bits; ta.filt = filt; ta.filt_bits = filter_bits;
-            ta.shortlist = h->shortlist;
             ta.out_keys = ivf_keys;
             ta.d_scanned_rows = d_scanned;
+            ta.d_fallback_count = d_fb_count; ta.d_fallback_idx = h->s_fb_idx.p;
             ta.ev_scan0 = h->ev_s0; ta.ev_scan1 = h->ev_s1;
             ta.sm_count = h->sm_count;
-            uint32_t launches = 0, fallback = 0;
-            int r = tc_ivf_search(h->tc, ta, st, &h->dev_bytes, &launches, &fallback, &h->err);
+            uint32_t launches = 0;
+            int r = tc_ivf_search(h->tc, ta, st, &h->dev_bytes, &launches, &h->err);
             if (r != FVDB_OK) return r;
             h->stats.last_launches += launches;
-            h->stats.last_fallback_queries = fallback;
             scan_timed = true;
         } else {
-            // coarse step: all centroid distances, nearest np lists (src/ivf/core.rs:646-656)
-            CK(h->s_coarse.ensure((size_t)nq * np, 0, st, &h->dev_bytes));
-            RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_q, nq, np, nullptr, 0, nullptr, 0,
-                               h->s_coarse.p, st));
-            // bucket (query, probe) pairs by list
-            const uint32_t tq = exact_scan_tq();
-            const size_t n_pairs = (size_t)nq * np;
-            const size_t max_items = (size_t)h->nlist + (n_pairs + tq - 1) / tq + 1;
-            CK(h->s_list_cnt.ensure(h->nlist + 1, 0, st, &h->dev_bytes));
-            CK(h->s_pair_off.ensure(h->nlist + 2, 0, st, &h->dev_bytes));
-            CK(h->s_cursor.ensure(h->nlist + 1, 0, st, &h->dev_bytes));
-            CK(h->s_pair_q.ensure(n_pairs, 0, st, &h->dev_bytes));
-            CK(h->s_pair_slot.ensure(n_pairs, 0, st, &h->dev_bytes));
-            CK(h->s_items.ensure(max_items, 0, st, &h->dev_bytes));
-            uint32_t* d_n_items = h->s_misc.p + 6;
-            CK(launch_probe_bucketing(h->s_coarse.p, nq, np, h->list_off.p, h->nlist, tq, h->s_list_cnt.p,
-                                      h->s_pair_off.p, h->s_cursor.p, h->s_pair_q.p, h->s_pair_slot.p,
-                                      h->s_items.p, d_n_items, d_scanned, st));
-            h->stats.last_launches += 3;
-            // posting-list scan (src/ivf/core.rs:661-674), one sorted partial per (query, probe)
-            uint32_t Ppad = np;
-            if (np > 256) Ppad = (np + 255) / 256 * 256;
-            CK(h->s_partial.ensure((size_t)nq * Ppad * k, 0, st, &h->dev_bytes));
-            CK(cudaMemsetAsync(h->s_partial.p, 0xFF, (size_t)nq * Ppad * k * 8, st));
-            ExactScanArgs a{};
-            a.X = h->ivf_rows.p; a.ids = h->ivf_ids.p; a.Q = d_q; a.D = D;
-            a.items = h->s_items.p; a.item_count = d_n_items; a.n_items = 0;
-            a.pair_q = h->s_pair_q.p; a.pair_slot = h->s_pair_slot.p;
-            a.P = Ppad; a.k = k;
-            a.tomb = tomb; a.tomb_bits = h->tomb_bits; a.filt = filt; a.filt_bits = filter_bits;
-            a.partial = h->s_partial.p;
-            CK(cudaEventRecord(h->ev_s0, st));
-            CK(launch_exact_scan(a, (uint32_t)max_items, st));
-            CK(cudaEventRecord(h->ev_s1, st));
+            RET(ivf_scan_exact(h, d_q, nq, k, np, h->s_coarse.p, tomb, filt, filter_bits, ivf_keys,
+                               d_scanned, true, st));
             scan_timed = true;
-            h->stats.last_launches += 1;
-            // sort + truncate(k) (src/ivf/core.rs:677-678)
-            if (Ppad > 256) {
-                CK(h->s_partial2.ensure((size_t)nq * (Ppad / 256) * k, 0, st, &h->dev_bytes));
-                CK(launch_merge_partials(h->s_partial.p, nq * (Ppad / 256), 256, k, h->s_partial2.p, st));
-                CK(launch_merge_partials(h->s_partial2.p, nq, Ppad / 256, k, ivf_keys, st));
-                h->stats.last_launches += 2;
-            } else {
-                CK(launch_merge_partials(h->s_partial.p, nq, Ppad, k, ivf_keys, st));
-                h->stats.last_launches += 1;
-            }
         }
     }
     if (use_flat) {
         CK(h->s_flat_keys.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
         flat_keys = h->s_flat_keys.p;
-        const bool tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D);
-        if (tc) {
-            TcFlatArgs fa{};
-            fa.rows = h->flat_rows.p; fa.ids = h->flat_ids.p; fa.n_rows = h->flat_n;
-            fa.Q = d_q; fa.nq = nq; fa.D = D; fa.k = k;
-            fa.tomb = tomb; fa.tomb_bits = h->tomb_bits; fa.filt = filt; fa.filt_bits = filter_bits;
-            fa.shortlist = h->shortlist; fa.out_keys = flat_keys; fa.sm_count = h->sm_count;
-            uint32_t launches = 0, fallback = 0;
-            int r = tc_flat_search(h->tc, fa, st, &h->dev_bytes, &launches, &fallback, &h->err);
-            if (r != FVDB_OK) return r;
-            h->stats.last_launches += launches;
-            h->stats.last_fallback_queries += fallback;
-        } else {
-            RET(scan_all_exact(h, h->flat_rows.p, h->flat_ids.p, h->flat_n, d_q, nq, k, tomb, h->tomb_bits,
-                               filt, filter_bits, flat_keys, st));
-        }
+        RET(scan_all_exact(h, h->flat_rows.p, h->flat_ids.p, h->flat_n, d_q, nq, k, tomb, h->tomb_bits,
+                           filt, filter_bits, flat_keys, st));
     }
     CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
     h->stats.last_launches += 1;
     CK(cudaEventRecord(h->ev_b, st));
 
     // one synchronisation point per batch: NaN flag + counters
-    struct { int nan; int pad; uint64_t scanned; } host_misc{};
-    CK(cudaMemcpyAsync(&host_misc, h->s_misc.p, sizeof(host_misc), cudaMemcpyDeviceToHost, st));
+    uint32_t host_misc[16] = {0};
+    CK(cudaMemcpyAsync(host_misc, h->s_misc.p, sizeof(host_misc), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (host_misc.nan)
+    if (host_misc[0])
         return h->fail(FVDB_ERR_NAN, "NaN in query (the reference panics on partial_cmp().unwrap())");
+    uint64_t scanned = 0;
+    std::memcpy(&scanned, &host_misc[2], 8);
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
     h->stats.last_device_ms = ms;
@@ -699,7 +698,25 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         if (cudaEventElapsedTime(&sms, h->ev_s0, h->ev_s1) == cudaSuccess) h->stats.last_scan_ms = sms;
         else cudaGetLastError();
     }
-    uint64_t rows = host_misc.scanned + (use_flat ? h->flat_n : 0);
+    const uint32_t n_fb = used_tc ? std::min(host_misc[10], nq) : 0;
+    if (n_fb) {
+        // the tensor-core proof failed for n_fb queries: re-run exactly those on the exact path
+        // and patch their rows of the result (rare: only near-duplicate-heavy neighbourhoods)
+        CK(h->s_fb_q.ensure((size_t)n_fb * D, 0, st, &h->dev_bytes));
+        CK(h->s_fb_keys.ensure((size_t)n_fb * k, 0, st, &h->dev_bytes));
+        CK(h->s_fb_coarse.ensure((size_t)n_fb * np, 0, st, &h->dev_bytes));
+        CK(launch_gather_rows(d_q, nq, nullptr, h->s_fb_idx.p, n_fb, D, h->s_fb_q.p, st));
+        RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, h->s_fb_q.p, n_fb, np, nullptr, 0, nullptr,
+                           0, h->s_fb_coarse.p, st));
+        RET(ivf_scan_exact(h, h->s_fb_q.p, n_fb, k, np, h->s_fb_coarse.p, tomb, filt, filter_bits,
+                           h->s_fb_keys.p, nullptr, false, st));
+        CK(launch_scatter_keys(h->s_fb_keys.p, h->s_fb_idx.p, n_fb, k, ivf_keys, st));
+        CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
+        CK(cudaStreamSynchronize(st));
+        h->stats.last_launches += 3;
+        h->stats.last_fallback_queries = n_fb;
+    }
+    uint64_t rows = scanned + (use_flat ? h->flat_n : 0);
     h->stats.last_scanned_rows = rows;
     uint64_t bytes = rows * D * 4ull + (uint64_t)nq * D * 4ull + (uint64_t)nq * k * 8ull;
     if (use_ivf) bytes += (uint64_t)h->nlist * D * 4ull;
@@ -793,7 +810,7 @@ int fvdb_set_option(fvdb_index* h, int option, uint64_t value) {
     switch (option) {
         case FVDB_OPT_SCAN_MODE:
             if (value == FVDB_SCAN_TC && !tc_supported(h->dim))
-                return h->fail(FVDB_ERR_INVALID_CONFIG, "tensor-core scan needs dim % 32 == 0 and dim <= 1024");
+                return h->fail(FVDB_ERR_INVALID_CONFIG, "tensor-core scan needs dim % 32 == 0 and dim <= 512");
             if (value > FVDB_SCAN_TC) return h->fail(FVDB_ERR_INVALID_ARG, "unknown scan mode");
             h->scan_mode = (uint32_t)value;
             return FVDB_OK;

@@ -552,6 +552,20 @@ cudaError_t launch_merge_parts(const uint32_t* ids, const float* dist, const uin
     return cudaGetLastError();
 }
 
+__global__ void scatter_keys_kernel(const uint64_t* __restrict__ src, const uint32_t* __restrict__ idx,
+                                    uint32_t n, uint32_t k, uint64_t* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * k) return;
+    dst[(size_t)idx[i / k] * k + (i % k)] = src[i];
+}
+
+cudaError_t launch_scatter_keys(const uint64_t* src, const uint32_t* idx, uint32_t n, uint32_t k,
+                                uint64_t* dst, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    scatter_keys_kernel<<<(n * k + 255) / 256, 256, 0, stream>>>(src, idx, n, k, dst);
+    return cudaGetLastError();
+}
+
 // NaN screen over a float matrix (the reference panics on NaN: src/ivf/core.rs:655,677).
 __global__ void nan_check_kernel(const float* __restrict__ x, size_t n, int* __restrict__ flag) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,26 +1,670 @@
-// tc_scan.cu — tensor-core scan path (placeholder until the tcgen05 kernels land).
-#include "tc_scan.cuh"
+// tc_scan.cu — the Blackwell-native posting-list scan:
+//   TMA (cp.async.bulk.tensor, 128B swizzle)  ->  shared-memory ring
+//   tcgen05.mma kind::tf32 (fp32 accumulate)  ->  TMEM accumulators, double buffered
+//   tcgen05.ld epilogue: d2 = |x|^2 + |q|^2 - 2 x.q, threshold filter, per-query shortlist
+// followed by an exact fp32 re-rank of the shortlist in the reference's operation order
+// (euclidean_distance_scalar, src/core/vector_ops.rs:51-57) and a proof that no row outside the
+// shortlist can belong to the exact top-k; queries whose proof fails are handed back to the
+// exact path.  Replaces the loop of IVFIndex::search_with_config (src/ivf/core.rs:661-678).
+//
+// Tile orientation: the 128 database rows of a tile sit on the MMA M dimension (= the 128 TMEM
+// lanes = one epilogue thread per row), the <= 64 queries that probe the list on N.  Every list
+// is streamed from HBM once per batch; the query tile stays resident in shared memory.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2-5 = epilogue.  Persistent CTAs, one per SM, static round-robin over work items.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
 #include "../../include/fvdb.h"
+#include "kernels.cuh"
+#include "tc_scan.cuh"
 
 namespace fvdb {
 
-bool tc_supported(uint32_t) { return false; }
+namespace {
 
-int tc_ivf_search(TcScratch&, const TcSearchArgs&, cudaStream_t, size_t*, uint32_t*, uint32_t*,
+constexpr int TC_ROWS = 128;                     // rows per tile (MMA M)
+constexpr int TC_NQ = (int)TC_TILE_Q;            // queries per item (MMA N max)
+constexpr int TC_KB_FLOATS = 32;                 // one 128-byte swizzle atom
+constexpr int TC_STAGE_BYTES = TC_ROWS * 128;    // 16 KB
+constexpr int TC_QBLK_BYTES = TC_NQ * 128;       // 8 KB per k-block of the query tile
+constexpr int TC_KP = 32;                        // shortlist entries per (query, item)
+constexpr int TC_CAP = 128;                      // candidate slots per query per tile
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 128;                // 2 accumulator buffers x 64 columns
+constexpr uint32_t F32_INF_BITS = 0x7f800000u;
+
+struct TcScanParams {
+    const ScanItem* items;
+    const uint32_t* item_count;
+    const uint32_t* pair_q;
+    const uint32_t* pair_slot;
+    const float* Q;
+    const float* qnorm;
+    uint32_t D;
+    uint32_t KB;
+    const float* xnorm;
+    const uint32_t* ids;
+    const uint64_t* tomb;
+    uint64_t tomb_bits;
+    const uint64_t* filt;
+    uint64_t filt_bits;
+    uint32_t P;
+    uint64_t* partial;  // [nq][P][TC_KP] approx keys: (approx d2 bits << 32) | arena row
+    uint32_t* thr_g;    // [nq] running upper bound of the query's TC_KP-th approx d2 (f32 bits)
+    uint32_t stages;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0,
+                                            int c1, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// UMMA shared-memory descriptor, K-major, 128-byte swizzle: start>>4 | LBO=1 | SBO=1024>>4 |
+// version=1 (bit 46) | layout SWIZZLE_128B (2 << 61).  (cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor kind::tf32: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both,
+// N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ---- warp-level sorted-list primitives over u64 keys (one key per lane) -----------------------
+__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+
+__device__ __forceinline__ uint64_t warp_sort32(uint64_t v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t o = shfl_xor64(v, j);
+            const bool up = (lane & k) == 0;
+            const bool lower = (lane & j) == 0;
+            const uint64_t mn = v < o ? v : o, mx = v < o ? o : v;
+            v = (lower == up) ? mn : mx;
+        }
+    }
+    return v;
+}
+// list, cand both ascending across lanes -> the 32 smallest of the union, ascending
+__device__ __forceinline__ uint64_t warp_merge32(uint64_t list, uint64_t cand_sorted, int lane) {
+    const uint64_t rev = shfl64(cand_sorted, 31 - lane);
+    uint64_t v = list < rev ? list : rev;
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const uint64_t o = shfl_xor64(v, j);
+        const bool lower = (lane & j) == 0;
+        const uint64_t mn = v < o ? v : o, mx = v < o ? o : v;
+        v = lower ? mn : mx;
+    }
+    return v;
+}
+// insert one key (warp-uniform) into the ascending list
+__device__ __forceinline__ uint64_t warp_insert1(uint64_t list, uint64_t c, int lane) {
+    const unsigned le = __ballot_sync(0xffffffffu, list <= c);
+    const int pos = __popc(le);
+    const uint64_t up = shfl_up64(list, 1);
+    if (lane > pos) list = up;
+    if (lane == pos) list = c;
+    return list;
+}
+
+// ---- the scan kernel ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t KB = p.KB;
+    const uint32_t STAGES = p.stages;
+    unsigned char* q_tile = smem;                                       // KB x 8 KB
+    unsigned char* ring = q_tile + (size_t)KB * TC_QBLK_BYTES;          // STAGES x 16 KB
+    uint32_t* cand_s = reinterpret_cast<uint32_t*>(ring + (size_t)STAGES * TC_STAGE_BYTES);  // [NQ][CAP]
+    uint64_t* list_s = reinterpret_cast<uint64_t*>(cand_s + TC_NQ * TC_CAP);                 // [NQ][KP]
+    float* thrp_s = reinterpret_cast<float*>(list_s + TC_NQ * TC_KP);   // [NQ] threshold - |q|^2
+    float* qn_s = thrp_s + TC_NQ;                                       // [NQ]
+    uint32_t* cnt_s = reinterpret_cast<uint32_t*>(qn_s + TC_NQ);        // [NQ]
+    uint32_t* qidx_s = cnt_s + TC_NQ;                                   // [NQ]
+    uint32_t* qslot_s = qidx_s + TC_NQ;                                 // [NQ]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qslot_s + TC_NQ);      // full[S] empty[S] tfull[2] tempty[2] qready
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * STAGES;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    const uint32_t bar_qready = bar_tempty + 16;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tfull + 8, 1);
+        mbar_init(bar_tempty, 4);
+        mbar_init(bar_tempty + 8, 4);
+        mbar_init(bar_qready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                     "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+    const uint32_t n_items = *p.item_count;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint64_t hint = 0x12F0000000000000ull;  // L2 evict-first: rows are read once
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const ScanItem it = p.items[item];
+                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+                for (uint32_t rt = it.row_begin; rt < it.row_end; rt += TC_ROWS) {
+                    for (uint32_t kb = 0; kb < KB; ++kb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
+                        tma_load_2d(smem_u32(ring + (size_t)stage * TC_STAGE_BYTES), &tmap, bar_full + 8 * stage,
+                                    (int)(kb * TC_KB_FLOATS), (int)rt, hint);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, buf = 0, qphase = 0;
+            uint32_t tphase[2] = {0, 0};
+            const uint32_t q_base = smem_u32(q_tile);
+            const uint32_t ring_base = smem_u32(ring);
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const ScanItem it = p.items[item];
+                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+                const uint32_t ncols = (it.pair_count + 15u) & ~15u;
+                const uint32_t idesc = umma_idesc_tf32(TC_ROWS, ncols);
+                mbar_wait(bar_qready, qphase);
+                qphase ^= 1;
+                tc_fence_after();
+                for (uint32_t rt = it.row_begin; rt < it.row_end; rt += TC_ROWS) {
+                    mbar_wait(bar_tempty + 8 * buf, tphase[buf] ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * TC_NQ;
+                    for (uint32_t kb = 0; kb < KB; ++kb) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint64_t a0 = umma_desc_sw128(ring_base + stage * TC_STAGE_BYTES);
+                        const uint64_t b0 = umma_desc_sw128(q_base + kb * TC_QBLK_BYTES);
+#pragma unroll
+                        for (uint32_t k4 = 0; k4 < 4; ++k4)  // UMMA_K = 8 tf32 = 32 bytes = +2 in the descriptor
+                            umma_tf32(d_tmem, a0 + 2 * k4, b0 + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        umma_commit(bar_empty + 8 * stage);  // frees the ring slot once these MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bar_tfull + 8 * buf);  // accumulator ready for the epilogue
+                    tphase[buf] ^= 1;
+                    buf ^= 1;
+                }
+            }
+        }
+    } else {
+        // ================= epilogue (128 threads) =================
+        const int ew = warp - 2;                 // 0..3: query stripe of this warp in the merge phase
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+        const int trow = quarter * 32 + lane;    // row within the tile == TMEM lane
+        const int et = ew * 32 + lane;           // 0..127
+        const uint32_t D = p.D;
+        uint32_t buf = 0;
+        uint32_t fphase[2] = {0, 0};
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const ScanItem it = p.items[item];
+            if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+            const uint32_t cnt = it.pair_count;
+            const uint32_t ncols = (cnt + 15u) & ~15u;
+            // ---- item prologue: query bookkeeping + query tile into swizzled shared memory ----
+            if (et < TC_NQ) {
+                uint32_t qi = ID_NONE, sl = 0;
+                float qn = 0.f, thr = __uint_as_float(F32_INF_BITS);
+                if ((uint32_t)et < cnt) {
+                    if (it.identity) { qi = it.pair_begin + et; sl = it.slot; }
+                    else { qi = p.pair_q[it.pair_begin + et]; sl = p.pair_slot[it.pair_begin + et]; }
+                    qn = p.qnorm[qi];
+                    thr = __uint_as_float(*(volatile uint32_t*)(p.thr_g + qi));
+                }
+                qidx_s[et] = qi;
+                qslot_s[et] = sl;
+                qn_s[et] = qn;
+                // padded query columns (et >= cnt) must never pass the filter: threshold -inf
+                thrp_s[et] = ((uint32_t)et < cnt) ? thr - qn : -__uint_as_float(F32_INF_BITS);
+                cnt_s[et] = 0;
+            }
+            for (int i = et; i < TC_NQ * TC_KP; i += 128) list_s[i] = KEY_NONE;
+            epi_bar(1);
+            {
+                const uint32_t f4_per_row = KB * 8;
+                const uint32_t total = ncols * f4_per_row;
+                for (uint32_t idx = et; idx < total; idx += 128) {
+                    const uint32_t q = idx / f4_per_row, c = idx - q * f4_per_row;
+                    const uint32_t kb = c >> 3, ch = c & 7;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const uint32_t qi = qidx_s[q];
+                    if (qi != ID_NONE) v = __ldg(reinterpret_cast<const float4*>(p.Q + (size_t)qi * D) + c);
+                    *reinterpret_cast<float4*>(q_tile + (size_t)kb * TC_QBLK_BYTES + q * 128 + ((ch ^ (q & 7)) << 4)) = v;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+            epi_bar(2);
+            if (et == 0) mbar_arrive(bar_qready);
+
+            // ---- row tiles ----
+            for (uint32_t rt = it.row_begin; rt < it.row_end; rt += TC_ROWS) {
+                const uint32_t pos = rt + trow;
+                float xn = __uint_as_float(F32_INF_BITS);  // +inf => masked / out of range
+                if (pos < it.row_end) {
+                    bool live = true;
+                    if (p.tomb || p.filt) {
+                        const uint32_t id = p.ids[pos];
+                        if (p.tomb && bit_test(p.tomb, p.tomb_bits, id)) live = false;
+                        else if (p.filt && !bit_test(p.filt, p.filt_bits, id)) live = false;
+                    }
+                    if (live) xn = __ldg(p.xnorm + pos);
+                }
+                mbar_wait(bar_tfull + 8 * buf, fphase[buf]);
+                fphase[buf] ^= 1;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + buf * TC_NQ + ((uint32_t)(quarter * 32) << 16);
+                for (uint32_t c0 = 0; c0 < ncols; c0 += 16) {
+                    uint32_t acc[16];
+                    tmem_ld16(taddr + c0, acc);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t q = c0 + j;
+                        const float v = fmaf(-2.0f, __uint_as_float(acc[j]), xn);  // |x|^2 - 2 x.q
+                        if (v < thrp_s[q]) {
+                            const float d2 = fmaxf(v + qn_s[q], 0.0f);
+                            const uint32_t slot = atomicAdd(&cnt_s[q], 1u);
+                            cand_s[q * TC_CAP + slot] = (__float_as_uint(d2) & ~127u) | (uint32_t)trow;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);  // accumulator may be overwritten
+                epi_bar(1);
+                // ---- merge this tile's candidates into the per-query shortlists ----
+                for (uint32_t q = ew; q < cnt; q += 4) {
+                    const uint32_t n = cnt_s[q];
+                    if (n == 0) continue;
+                    uint64_t mine = list_s[q * TC_KP + lane];
+                    for (uint32_t b = 0; b < n; b += 32) {
+                        uint64_t key = KEY_NONE;
+                        if (b + lane < n) {
+                            const uint32_t c = cand_s[q * TC_CAP + b + lane];
+                            key = ((uint64_t)(c & ~127u) << 32) | (uint64_t)(rt + (c & 127u));
+                        }
+                        const uint32_t m = min(32u, n - b);
+                        if (m <= 3) {
+                            for (uint32_t i = 0; i < m; ++i) {
+                                const uint64_t c = shfl64(key, (int)i);
+                                if (c < shfl64(mine, 31)) mine = warp_insert1(mine, c, lane);
+                            }
+                        } else {
+                            mine = warp_merge32(mine, warp_sort32(key, lane), lane);
+                        }
+                    }
+                    list_s[q * TC_KP + lane] = mine;
+                    if (lane == 31) {
+                        thrp_s[q] = (mine == KEY_NONE) ? __uint_as_float(F32_INF_BITS)
+                                                       : __uint_as_float((uint32_t)(mine >> 32)) - qn_s[q];
+                    }
+                    if (lane == 0) cnt_s[q] = 0;
+                }
+                epi_bar(2);
+                buf ^= 1;
+            }
+            // ---- item epilogue: publish shortlists and tighten the shared thresholds ----
+            for (uint32_t q = ew; q < cnt; q += 4) {
+                const uint64_t mine = list_s[q * TC_KP + lane];
+                const uint32_t qi = qidx_s[q];
+                p.partial[((size_t)qi * p.P + qslot_s[q]) * TC_KP + lane] = mine;
+                if (lane == 31 && mine != KEY_NONE) atomicMin(p.thr_g + qi, (uint32_t)(mine >> 32));
+            }
+            epi_bar(1);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+size_t tc_scan_smem_bytes(uint32_t KB, uint32_t stages) {
+    return (size_t)KB * TC_QBLK_BYTES + (size_t)stages * TC_STAGE_BYTES + (size_t)TC_NQ * TC_CAP * 4 +
+           (size_t)TC_NQ * TC_KP * 8 + (size_t)TC_NQ * 5 * 4 + (size_t)(2 * stages + 5) * 8 + 16;
+}
+
+// ---- small support kernels ----------------------------------------------------------------------
+__global__ void row_norms_kernel(const float* __restrict__ x, uint64_t n, uint32_t D, float* __restrict__ out,
+                                 uint32_t* __restrict__ max_bits) {
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    float mx = 0.f;
+    for (uint64_t r = w; r < n; r += nw) {
+        const float4* row = reinterpret_cast<const float4*>(x + (size_t)r * D);
+        float s = 0.f;
+        for (uint32_t c = lane; c < D / 4; c += 32) {
+            const float4 v = __ldg(row + c);
+            s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[r] = s;
+        mx = fmaxf(mx, s);
+    }
+    if (max_bits && lane == 0 && mx > 0.f) atomicMax(max_bits, __float_as_uint(mx));
+}
+
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+// Exact re-rank + proof.  One warp per query, lane = shortlist entry.  Distances are recomputed
+// as euclidean_distance_scalar does (sequential f32, (q - x)^2, no FMA, sqrt), so the returned
+// keys are bit-identical to the exact path.  Proof: every row outside the shortlist has
+// approx d2 >= a_last (the largest approx d2 kept), hence exact d2 >= a_last - eps, where eps
+// bounds |approx - exact| for TF32 operands (2^-10 relative each) — if that is above the exact
+// k-th d2 the shortlist provably contains the exact top-k.
+__global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict__ shortlist,  // [nq][KP]
+                                                     const float* __restrict__ rows, const uint32_t* __restrict__ ids,
+                                                     const float* __restrict__ Q, const float* __restrict__ qnorm,
+                                                     const uint32_t* __restrict__ xmax_bits, uint32_t nq, uint32_t D,
+                                                     uint32_t k, uint64_t* __restrict__ out_keys,
+                                                     uint32_t* __restrict__ fb_count, uint32_t* __restrict__ fb_idx) {
+    __shared__ float xs[4][32][33];
+    __shared__ float qs[4][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * 4 + w;
+    if (q >= nq) return;
+    const uint64_t akey = shortlist[(size_t)q * TC_KP + lane];
+    const bool have = akey != KEY_NONE;
+    const uint32_t pos = have ? (uint32_t)akey : 0u;
+    float acc = 0.0f;
+    for (uint32_t kc = 0; kc < D; kc += 32) {
+        for (int r = 0; r < 32; ++r) {
+            const uint32_t pr = __shfl_sync(0xffffffffu, pos, r);
+            xs[w][r][lane] = __ldg(rows + (size_t)pr * D + kc + lane);
+        }
+        qs[w][lane] = __ldg(Q + (size_t)q * D + kc + lane);
+        __syncwarp();
+#pragma unroll 8
+        for (int d = 0; d < 32; ++d) {
+            const float t = __fsub_rn(qs[w][d], xs[w][lane][d]);
+            acc = __fadd_rn(acc, __fmul_rn(t, t));
+        }
+        __syncwarp();
+    }
+    uint64_t ekey = KEY_NONE;
+    if (have) ekey = make_key(__fsqrt_rn(acc), ids[pos]);
+    ekey = warp_sort32(ekey, lane);
+    if ((uint32_t)lane < k) out_keys[(size_t)q * k + lane] = ekey;
+    // proof
+    const uint64_t a_last_key = shfl64(akey, 31);
+    const uint64_t kth = shfl64(ekey, (int)k - 1);
+    if (lane == 0 && a_last_key != KEY_NONE) {
+        const float a_last = __uint_as_float((uint32_t)(a_last_key >> 32));
+        const float xmax = sqrtf(__uint_as_float(*xmax_bits));
+        const float eps = 1.05f * 0.00390625f * sqrtf(qnorm[q]) * xmax + 3.1e-5f * a_last + 1e-30f;
+        bool ok = false;
+        if (kth != KEY_NONE) {
+            const float dk = key_dist(kth);
+            ok = (a_last - eps) > dk * dk * 1.000001f;
+        }
+        if (!ok) fb_idx[atomicAdd(fb_count, 1u)] = q;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+template <typename T>
+struct Buf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n, size_t* bytes) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        const size_t ncap = std::max(n, cap + cap / 2);
+        cudaError_t e = cudaMalloc(&p, ncap * sizeof(T));
+        if (e != cudaSuccess) { cap = 0; return e; }
+        if (bytes) *bytes += (ncap - cap) * sizeof(T);
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct TcScratchImpl {
+    Buf<float> xnorm, qnorm;
+    Buf<uint32_t> misc;  // [0] = max |x|^2 bits
+    Buf<uint32_t> thr_g, list_cnt, pair_off, cursor, pair_q, pair_slot, n_items;
+    Buf<ScanItem> items;
+    Buf<uint64_t> partial, shortlist;
+    CUtensorMap tmap_arena;
+    const float* tmap_rows = nullptr;
+    uint64_t tmap_n = 0;
+    bool smem_attr_set = false;
+};
+
+bool tc_supported(uint32_t D) { return D % 32 == 0 && D >= 32 && D <= 512; }
+
+void tc_release(TcScratch& s) {
+    if (!s.impl) return;
+    TcScratchImpl* m = s.impl;
+    m->xnorm.release(); m->qnorm.release(); m->misc.release(); m->thr_g.release(); m->list_cnt.release();
+    m->pair_off.release(); m->cursor.release(); m->pair_q.release(); m->pair_slot.release(); m->n_items.release();
+    m->items.release(); m->partial.release(); m->shortlist.release();
+    delete m;
+    s.impl = nullptr;
+}
+
+#define TCK(call)                                                                      \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            if (err) *err = std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #call; \
+            cudaGetLastError();                                                        \
+            return e__ == cudaErrorMemoryAllocation ? FVDB_ERR_OOM : FVDB_ERR_CUDA;    \
+        }                                                                              \
+    } while (0)
+
+int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* dev_bytes, uint32_t* launches,
                   std::string* err) {
-    if (err) *err = "tensor-core scan not built";
-    return FVDB_ERR_INVALID_CONFIG;
+    if (!s.impl) s.impl = new TcScratchImpl();
+    TcScratchImpl* m = s.impl;
+    const uint32_t D = a.D, KB = D / 32, nq = a.nq, np = a.nprobe;
+    if (a.n_rows >= 0x7FFFFFFFull) { if (err) *err = "arena too large for the TC path"; return FVDB_ERR_INVALID_ARG; }
+
+    // ---- per-arena state: row norms, max norm, TMA descriptor ----
+    TCK(m->misc.ensure(16, dev_bytes));
+    if (s.arena_dirty || m->tmap_rows != a.rows || m->tmap_n != a.n_rows) {
+        TCK(m->xnorm.ensure(a.n_rows, dev_bytes));
+        TCK(cudaMemsetAsync(m->misc.p, 0, 16 * 4, st));
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((a.n_rows * 32 + 255) / 256, (uint64_t)a.sm_count * 16);
+        row_norms_kernel<<<blocks, 256, 0, st>>>(a.rows, a.n_rows, D, m->xnorm.p, m->misc.p);
+        TCK(cudaGetLastError());
+        (*launches)++;
+        EncodeTiledFn enc = get_encode_fn();
+        if (!enc) { if (err) *err = "cuTensorMapEncodeTiled unavailable"; return FVDB_ERR_CUDA; }
+        const cuuint64_t gdim[2] = {D, a.n_rows};
+        const cuuint64_t gstride[1] = {(cuuint64_t)D * 4};
+        const cuuint32_t box[2] = {TC_KB_FLOATS, TC_ROWS};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&m->tmap_arena, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.rows), gdim, gstride,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            if (err) *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+            return FVDB_ERR_CUDA;
+        }
+        m->tmap_rows = a.rows;
+        m->tmap_n = a.n_rows;
+        s.arena_dirty = false;
+    }
+
+    // ---- per-batch state ----
+    const size_t n_pairs = (size_t)nq * np;
+    const size_t max_items = (size_t)a.nlist + (n_pairs + TC_TILE_Q - 1) / TC_TILE_Q + 1;
+    TCK(m->qnorm.ensure(nq, dev_bytes));
+    TCK(m->thr_g.ensure(nq, dev_bytes));
+    TCK(m->list_cnt.ensure(a.nlist + 1, dev_bytes));
+    TCK(m->pair_off.ensure(a.nlist + 2, dev_bytes));
+    TCK(m->cursor.ensure(a.nlist + 1, dev_bytes));
+    TCK(m->pair_q.ensure(n_pairs, dev_bytes));
+    TCK(m->pair_slot.ensure(n_pairs, dev_bytes));
+    TCK(m->n_items.ensure(4, dev_bytes));
+    TCK(m->items.ensure(max_items, dev_bytes));
+    TCK(m->partial.ensure(n_pairs * TC_KP, dev_bytes));
+    TCK(m->shortlist.ensure((size_t)nq * TC_KP, dev_bytes));
+
+    {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)nq * 32 + 255) / 256, (uint64_t)a.sm_count * 8);
+        row_norms_kernel<<<blocks, 256, 0, st>>>(a.Q, nq, D, m->qnorm.p, nullptr);
+        fill_u32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m->thr_g.p, nq, F32_INF_BITS);
+        TCK(cudaGetLastError());
+        (*launches) += 2;
+    }
+    TCK(launch_probe_bucketing(a.coarse_keys, nq, np, a.list_off, a.nlist, TC_TILE_Q, m->list_cnt.p, m->pair_off.p,
+                               m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st));
+    (*launches) += 3;
+    TCK(cudaMemsetAsync(m->partial.p, 0xFF, n_pairs * TC_KP * sizeof(uint64_t), st));
+
+    // ---- the scan ----
+    TcScanParams p{};
+    p.items = m->items.p; p.item_count = m->n_items.p; p.pair_q = m->pair_q.p; p.pair_slot = m->pair_slot.p;
+    p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = m->xnorm.p; p.ids = a.ids;
+    p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
+    p.P = np; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
+    uint32_t stages = 8;
+    while (stages > 2 && tc_scan_smem_bytes(KB, stages) > 227 * 1024) --stages;
+    p.stages = stages;
+    const size_t smem = tc_scan_smem_bytes(KB, stages) + 1024;  // slack for the 1024-byte alignment
+    if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
+    if (!m->smem_attr_set) {
+        TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        m->smem_attr_set = true;
+    }
+    const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
+    if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
+    tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(m->tmap_arena, p);
+    TCK(cudaGetLastError());
+    if (a.ev_scan1) TCK(cudaEventRecord(a.ev_scan1, st));
+    (*launches)++;
+
+    // ---- merge the per-(query, probe) shortlists, exact re-rank, proof ----
+    TCK(launch_merge_partials(m->partial.p, nq, np, TC_KP, m->shortlist.p, st));
+    rerank_kernel<<<(nq + 3) / 4, 128, 0, st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k,
+                                               a.out_keys, a.d_fallback_count, a.d_fallback_idx);
+    TCK(cudaGetLastError());
+    (*launches) += 2;
+    return FVDB_OK;
 }
-int tc_flat_search(TcScratch&, const TcFlatArgs&, cudaStream_t, size_t*, uint32_t*, uint32_t*,
-                   std::string* err) {
-    if (err) *err = "tensor-core scan not built";
-    return FVDB_ERR_INVALID_CONFIG;
-}
-int tc_assign(TcScratch&, const float*, uint32_t, const float*, uint64_t, uint32_t, uint64_t*,
-              cudaStream_t, size_t*, std::string* err) {
-    if (err) *err = "tensor-core scan not built";
-    return FVDB_ERR_INVALID_CONFIG;
-}
-void tc_release(TcScratch&) {}
 
 }  // namespace fvdb

@@ -21,51 +21,39 @@ struct TcScratch {
     TcScratchImpl* impl = nullptr;
 };
 
+constexpr uint32_t TC_MAX_K = 16;        // largest k served by the 32-entry shortlist
+constexpr uint32_t TC_MAX_NPROBE = 256;  // partial lists merged in one pass
+constexpr uint32_t TC_TILE_Q = 64;       // queries per work item of the TC scan
+
 struct TcSearchArgs {
-    const float* centroids;
-    uint32_t nlist;
-    const float* rows;        // IVF arena
-    const uint32_t* ids;
+    const float* rows;        // IVF arena [n_rows x D]
+    const uint32_t* ids;      // [n_rows]
     uint64_t n_rows;
     const uint32_t* list_off; // [nlist + 1] device
-    const float* Q;
+    uint32_t nlist;
+    const float* Q;           // [nq x D]
     uint32_t nq, D, k, nprobe;
+    const uint64_t* coarse_keys;  // [nq][nprobe] exact coarse ranking (low 32 bits = list id)
     const uint64_t* tomb;
     uint64_t tomb_bits;
     const uint64_t* filt;
     uint64_t filt_bits;
-    uint32_t shortlist;       // 0 = default
-    uint64_t* out_keys;       // [nq][k] exact keys, sorted
+    uint64_t* out_keys;       // [nq][k] exact keys (distance bits << 32 | row id), sorted
     uint64_t* d_scanned_rows; // device counter (distinct posting-list rows streamed)
+    uint32_t* d_fallback_count;   // device: number of queries whose proof failed
+    uint32_t* d_fallback_idx;     // device [nq]: their indices
     cudaEvent_t ev_scan0, ev_scan1;
     int sm_count;
 };
 
-struct TcFlatArgs {
-    const float* rows;
-    const uint32_t* ids;
-    uint64_t n_rows;
-    const float* Q;
-    uint32_t nq, D, k;
-    const uint64_t* tomb;
-    uint64_t tomb_bits;
-    const uint64_t* filt;
-    uint64_t filt_bits;
-    uint32_t shortlist;
-    uint64_t* out_keys;
-    int sm_count;
-};
-
-// dim % 32 == 0 (one 128-byte swizzle atom per k-block) and dim <= 1024
+// dim % 32 == 0 (one 128-byte swizzle atom per k-block), dim <= 512 (query tile in smem)
 bool tc_supported(uint32_t D);
 
+// Tensor-core shortlist scan of the probed posting lists + exact fp32 re-rank + proof check.
+// Enqueues everything on `st`; queries whose proof fails are listed in d_fallback_idx and must
+// be re-run on the exact path by the caller.
 int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* dev_bytes,
-                  uint32_t* launches, uint32_t* fallback_queries, std::string* err);
-int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* dev_bytes,
-                   uint32_t* launches, uint32_t* fallback_queries, std::string* err);
-// keys[i] = (exact distance bits << 32) | nearest centroid, exact strict-'<' argmin semantics
-int tc_assign(TcScratch& s, const float* centroids, uint32_t nlist, const float* x, uint64_t n,
-              uint32_t D, uint64_t* keys, cudaStream_t st, size_t* dev_bytes, std::string* err);
+                  uint32_t* launches, std::string* err);
 void tc_release(TcScratch& s);
 
 }  // namespace fvdb
