@@ -90,6 +90,8 @@ SIGNATURES = {
     "fvdb_kmeans_apply_device": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fvdb_synth_rows_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
                                          C.c_float, C.c_uint64, _vp]),
+    "fvdb_synth_rows_strided_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                 C.c_float, C.c_uint64, C.c_uint32, C.c_uint64, _vp]),
     "fvdb_synth_queries_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64,
                                             C.c_uint32, C.c_float, C.c_uint64, C.c_float, C.c_uint64,
                                             _vp]),

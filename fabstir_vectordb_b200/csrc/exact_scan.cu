@@ -355,7 +355,7 @@ __global__ void probe_scan_kernel(const uint32_t* __restrict__ list_cnt,
                 it.row_end = list_off[l + 1];
                 it.pair_begin = p_excl + j * tile_q;
                 it.pair_count = min(tile_q, c - j * tile_q);
-                it.slot = 0;
+                it.slot = ni;  // items sharing this list (the TC scan keeps such lists in L2)
                 it.identity = 0;
                 items[i_excl + j] = it;
             }

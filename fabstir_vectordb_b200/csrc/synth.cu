@@ -44,15 +44,16 @@ __device__ __forceinline__ float inv_norm_seq(const float* v, uint32_t D, int la
     return __shfl_sync(0xffffffffu, inv, 0);
 }
 
+// row index of output i: row0 + (i / blk) * blk * stride + (i % blk)   (blk = stride = 1: dense)
 __global__ void synth_rows_kernel(float* __restrict__ out, uint64_t row0, uint64_t n, uint32_t D,
-                                  uint32_t n_comp, float sigma, uint64_t seed) {
+                                  uint32_t n_comp, float sigma, uint64_t seed, uint32_t blk, uint64_t stride) {
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* v = sm + (size_t)w * D;
     const uint64_t kc = stream_key(seed, 1), kx = stream_key(seed, 2);
     const uint64_t nw = (uint64_t)gridDim.x * (blockDim.x >> 5);
     for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + w; i < n; i += nw) {
-        const uint64_t row = row0 + i;
+        const uint64_t row = row0 + (i / blk) * blk * stride + (i % blk);
         const uint32_t comp = (uint32_t)(row % n_comp);
         for (uint32_t d = lane; d < D; d += 32) v[d] = row_elem(kc, kx, row, comp, d, sigma);
         __syncwarp();
@@ -106,16 +107,24 @@ __global__ void synth_filter_kernel(uint64_t* __restrict__ bits, uint64_t nwords
 
 extern "C" {
 
+int fvdb_synth_rows_strided_device(float* d_out, uint64_t row0, uint64_t n, uint32_t dim, uint32_t n_comp,
+                                   float sigma, uint64_t seed, uint32_t blk, uint64_t stride, void* stream);
+
 int fvdb_synth_rows_device(float* d_out, uint64_t row0, uint64_t n, uint32_t dim, uint32_t n_comp,
                            float sigma, uint64_t seed, void* stream) {
+    return fvdb_synth_rows_strided_device(d_out, row0, n, dim, n_comp, sigma, seed, 1, 1, stream);
+}
+
+int fvdb_synth_rows_strided_device(float* d_out, uint64_t row0, uint64_t n, uint32_t dim, uint32_t n_comp,
+                                   float sigma, uint64_t seed, uint32_t blk, uint64_t stride, void* stream) {
     if (n == 0) return 0;
-    if (dim == 0 || dim > 8192 || n_comp == 0) return -12;
+    if (dim == 0 || dim > 8192 || n_comp == 0 || blk == 0 || stride == 0) return -12;
     const size_t smem = (size_t)4 * dim * sizeof(float);
     cudaFuncSetAttribute(synth_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     uint64_t blocks = (n + 3) / 4;
     if (blocks > 148ull * 8) blocks = 148ull * 8;
     synth_rows_kernel<<<(uint32_t)blocks, 128, smem, (cudaStream_t)stream>>>(d_out, row0, n, dim, n_comp,
-                                                                            sigma, seed);
+                                                                            sigma, seed, blk, stride);
     return cudaGetLastError() == cudaSuccess ? 0 : -10;
 }
 

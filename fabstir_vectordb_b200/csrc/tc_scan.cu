@@ -56,8 +56,11 @@ struct TcScanParams {
     uint32_t P;
     uint64_t* partial;  // [nq][P][TC_KP] approx keys: (approx d2 bits << 32) | arena row
     uint32_t* thr_g;    // [nq] running upper bound of the query's TC_KP-th approx d2 (f32 bits)
+    uint32_t* work_counter;  // dynamic tile scheduler: next unclaimed work item
     uint32_t stages;
 };
+constexpr int TC_SCHED = 4;          // depth of the in-CTA work-item ring
+constexpr uint32_t ITEM_END = 0xFFFFFFFFu;
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -165,6 +168,44 @@ __device__ __forceinline__ uint64_t warp_merge32(uint64_t list, uint64_t cand_so
     }
     return v;
 }
+// Four independent 32-lane networks advanced in lockstep: the shuffle chains of one network are
+// latency bound (~25 cycles per dependent SHFL), interleaving four hides most of it.
+__device__ __forceinline__ void warp_sort32x4_u32(uint32_t (&v)[4], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+            uint32_t o[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) o[g] = __shfl_xor_sync(0xffffffffu, v[g], j);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) v[g] = keep_min ? min(v[g], o[g]) : max(v[g], o[g]);
+        }
+    }
+}
+__device__ __forceinline__ void warp_merge32x4(uint64_t (&list)[4], const uint64_t (&cand_sorted)[4], int lane) {
+    uint64_t v[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint64_t rev = shfl64(cand_sorted[g], 31 - lane);
+        v[g] = list[g] < rev ? list[g] : rev;
+    }
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const bool lower = (lane & j) == 0;
+        uint64_t o[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) o[g] = shfl_xor64(v[g], j);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint64_t mn = v[g] < o[g] ? v[g] : o[g], mx = v[g] < o[g] ? o[g] : v[g];
+            v[g] = lower ? mn : mx;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) list[g] = v[g];
+}
 // insert one key (warp-uniform) into the ascending list
 __device__ __forceinline__ uint64_t warp_insert1(uint64_t list, uint64_t c, int lane) {
     const unsigned le = __ballot_sync(0xffffffffu, list <= c);
@@ -192,8 +233,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     uint32_t* cnt_s = reinterpret_cast<uint32_t*>(qn_s + TC_NQ);        // [NQ]
     uint32_t* qidx_s = cnt_s + TC_NQ;                                   // [NQ]
     uint32_t* qslot_s = qidx_s + TC_NQ;                                 // [NQ]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(qslot_s + TC_NQ);      // full[S] empty[S] tfull[2] tempty[2] qready
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qslot_s + TC_NQ);      // full[S] empty[S] tfull[2] tempty[2] qready sfull[4] sempty[4]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5 + 2 * TC_SCHED);
+    uint32_t* sched_s = tmem_ptr_s + 1;                                 // [TC_SCHED] claimed work items
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = smem_u32(bars);
@@ -201,6 +243,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     const uint32_t bar_tfull = bar_empty + 8 * STAGES;
     const uint32_t bar_tempty = bar_tfull + 16;
     const uint32_t bar_qready = bar_tempty + 16;
+    const uint32_t bar_sfull = bar_qready + 8;
+    const uint32_t bar_sempty = bar_sfull + 8 * TC_SCHED;
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < STAGES; ++s) {
@@ -212,6 +256,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
         mbar_init(bar_tempty, 4);
         mbar_init(bar_tempty + 8, 4);
         mbar_init(bar_qready, 1);
+        for (int i = 0; i < TC_SCHED; ++i) {
+            mbar_init(bar_sfull + 8 * i, 1);
+            mbar_init(bar_sempty + 8 * i, 5);  // MMA lane + one lane of each epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -225,15 +273,26 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
     const uint32_t n_items = *p.item_count;
+    // Work items are claimed dynamically (atomic counter) by the producer lane and broadcast to
+    // the other roles through a small shared-memory ring, so all roles walk the same sequence.
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            const uint64_t hint = 0x12F0000000000000ull;  // L2 evict-first: rows are read once
-            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            uint32_t stage = 0, phase = 0, ss = 0, sphase = 0;
+            const uint64_t hint_first = 0x12F0000000000000ull;   // L2 evict-first: rows read once
+            const uint64_t hint_normal = 0x1000000000000000ull;  // list shared by several items
+            while (true) {
+                mbar_wait(bar_sempty + 8 * ss, sphase ^ 1);
+                uint32_t item = atomicAdd(p.work_counter, 1u);
+                if (item >= n_items) item = ITEM_END;
+                sched_s[ss] = item;
+                mbar_arrive(bar_sfull + 8 * ss);
+                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+                if (item == ITEM_END) break;
                 const ScanItem it = p.items[item];
                 if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+                const uint64_t hint = (!it.identity && it.slot > 1) ? hint_normal : hint_first;
                 for (uint32_t rt = it.row_begin; rt < it.row_end; rt += TC_ROWS) {
                     for (uint32_t kb = 0; kb < KB; ++kb) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -248,11 +307,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, buf = 0, qphase = 0;
+            uint32_t stage = 0, phase = 0, buf = 0, qphase = 0, ss = 0, sphase = 0;
             uint32_t tphase[2] = {0, 0};
             const uint32_t q_base = smem_u32(q_tile);
             const uint32_t ring_base = smem_u32(ring);
-            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            while (true) {
+                mbar_wait(bar_sfull + 8 * ss, sphase);
+                const uint32_t item = sched_s[ss];
+                mbar_arrive(bar_sempty + 8 * ss);
+                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+                if (item == ITEM_END) break;
                 const ScanItem it = p.items[item];
                 if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
                 const uint32_t ncols = (it.pair_count + 15u) & ~15u;
@@ -288,9 +352,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
         const int trow = quarter * 32 + lane;    // row within the tile == TMEM lane
         const int et = ew * 32 + lane;           // 0..127
         const uint32_t D = p.D;
-        uint32_t buf = 0;
+        uint32_t buf = 0, ss = 0, sphase = 0;
         uint32_t fphase[2] = {0, 0};
-        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const unsigned lt_mask = (1u << lane) - 1u;
+        while (true) {
+            mbar_wait(bar_sfull + 8 * ss, sphase);
+            const uint32_t item = sched_s[ss];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
+            if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            if (item == ITEM_END) break;
             const ScanItem it = p.items[item];
             if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
             const uint32_t cnt = it.pair_count;
@@ -350,15 +421,28 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                 for (uint32_t c0 = 0; c0 < ncols; c0 += 16) {
                     uint32_t acc[16];
                     tmem_ld16(taddr + c0, acc);
+                    float thr[16];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(thrp_s + c0 + 4 * j4);
+                        thr[4 * j4 + 0] = t4.x; thr[4 * j4 + 1] = t4.y; thr[4 * j4 + 2] = t4.z; thr[4 * j4 + 3] = t4.w;
+                    }
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const uint32_t q = c0 + j;
                         const float v = fmaf(-2.0f, __uint_as_float(acc[j]), xn);  // |x|^2 - 2 x.q
-                        if (v < thrp_s[q]) {
-                            const float d2 = fmaxf(v + qn_s[q], 0.0f);
-                            const uint32_t slot = atomicAdd(&cnt_s[q], 1u);
-                            cand_s[q * TC_CAP + slot] = (__float_as_uint(d2) & ~127u) | (uint32_t)trow;
+                        const bool pass = v < thr[j];
+                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                        if (bal) {  // warp-uniform: one shared-memory atomic per warp per query
+                            const uint32_t q = c0 + j;
+                            uint32_t base = 0;
+                            if (lane == 0) base = atomicAdd(&cnt_s[q], (uint32_t)__popc(bal));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (pass) {
+                                const float d2 = fmaxf(v + qn_s[q], 0.0f);
+                                cand_s[q * TC_CAP + base + __popc(bal & lt_mask)] =
+                                    (__float_as_uint(d2) & ~127u) | (uint32_t)trow;
+                            }
                         }
                     }
                 }
@@ -367,32 +451,42 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);  // accumulator may be overwritten
                 epi_bar(1);
                 // ---- merge this tile's candidates into the per-query shortlists ----
-                for (uint32_t q = ew; q < cnt; q += 4) {
-                    const uint32_t n = cnt_s[q];
-                    if (n == 0) continue;
-                    uint64_t mine = list_s[q * TC_KP + lane];
-                    for (uint32_t b = 0; b < n; b += 32) {
-                        uint64_t key = KEY_NONE;
-                        if (b + lane < n) {
-                            const uint32_t c = cand_s[q * TC_CAP + b + lane];
-                            key = ((uint64_t)(c & ~127u) << 32) | (uint64_t)(rt + (c & 127u));
-                        }
-                        const uint32_t m = min(32u, n - b);
-                        if (m <= 3) {
-                            for (uint32_t i = 0; i < m; ++i) {
-                                const uint64_t c = shfl64(key, (int)i);
-                                if (c < shfl64(mine, 31)) mine = warp_insert1(mine, c, lane);
-                            }
-                        } else {
-                            mine = warp_merge32(mine, warp_sort32(key, lane), lane);
-                        }
+                for (uint32_t g0 = 0; g0 < (uint32_t)TC_NQ / 4; g0 += 4) {
+                    // this warp's queries: ew + 4*i; four at a time
+                    uint32_t qs[4], n[4];
+                    uint32_t nmax = 0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        qs[g] = ew + 4 * (g0 + g);
+                        n[g] = (qs[g] < cnt) ? cnt_s[qs[g]] : 0u;
+                        nmax = max(nmax, n[g]);
                     }
-                    list_s[q * TC_KP + lane] = mine;
-                    if (lane == 31) {
-                        thrp_s[q] = (mine == KEY_NONE) ? __uint_as_float(F32_INF_BITS)
-                                                       : __uint_as_float((uint32_t)(mine >> 32)) - qn_s[q];
+                    if (nmax == 0) continue;
+                    uint64_t lst[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) lst[g] = list_s[qs[g] * TC_KP + lane];
+                    for (uint32_t b = 0; b < nmax; b += 32) {
+                        uint32_t c[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            c[g] = (b + lane < n[g]) ? cand_s[qs[g] * TC_CAP + b + lane] : 0xFFFFFFFFu;
+                        warp_sort32x4_u32(c, lane);
+                        uint64_t key[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            key[g] = (c[g] == 0xFFFFFFFFu) ? KEY_NONE
+                                                           : (((uint64_t)(c[g] & ~127u) << 32) | (uint64_t)(rt + (c[g] & 127u)));
+                        warp_merge32x4(lst, key, lane);
                     }
-                    if (lane == 0) cnt_s[q] = 0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (n[g] == 0) continue;
+                        list_s[qs[g] * TC_KP + lane] = lst[g];
+                        if (lane == 31)
+                            thrp_s[qs[g]] = (lst[g] == KEY_NONE) ? __uint_as_float(F32_INF_BITS)
+                                                                 : __uint_as_float((uint32_t)(lst[g] >> 32)) - qn_s[qs[g]];
+                        if (lane == 0) cnt_s[qs[g]] = 0;
+                    }
                 }
                 epi_bar(2);
                 buf ^= 1;
@@ -419,7 +513,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
 
 size_t tc_scan_smem_bytes(uint32_t KB, uint32_t stages) {
     return (size_t)KB * TC_QBLK_BYTES + (size_t)stages * TC_STAGE_BYTES + (size_t)TC_NQ * TC_CAP * 4 +
-           (size_t)TC_NQ * TC_KP * 8 + (size_t)TC_NQ * 5 * 4 + (size_t)(2 * stages + 5) * 8 + 16;
+           (size_t)TC_NQ * TC_KP * 8 + (size_t)TC_NQ * 5 * 4 + (size_t)(2 * stages + 5 + 2 * TC_SCHED) * 8 + 16 +
+           (size_t)TC_SCHED * 4;
 }
 
 // ---- small support kernels ----------------------------------------------------------------------
@@ -642,6 +737,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = m->xnorm.p; p.ids = a.ids;
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
     p.P = np; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
+    p.work_counter = m->n_items.p + 1;
+    TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
     uint32_t stages = 8;
     while (stages > 2 && tc_scan_smem_bytes(KB, stages) > 227 * 1024) --stages;
     p.stages = stages;

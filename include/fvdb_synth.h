@@ -21,6 +21,10 @@ extern "C" {
  *   row r belongs to component r % n_comp; value = centre[comp] + sigma * noise, normalised. */
 int fvdb_synth_rows_device(float *d_out, uint64_t row0, uint64_t n, uint32_t dim, uint32_t n_comp,
                            float sigma, uint64_t seed, void *stream);
+/* strided variant: output row i is database row row0 + (i / blk) * blk * stride + (i % blk) */
+int fvdb_synth_rows_strided_device(float *d_out, uint64_t row0, uint64_t n, uint32_t dim,
+                                   uint32_t n_comp, float sigma, uint64_t seed, uint32_t blk,
+                                   uint64_t stride, void *stream);
 /* queries [q0, q0+n): database row (hash(seed_q, i) % n_total) + qnoise * noise, re-normalised */
 int fvdb_synth_queries_device(float *d_out, uint64_t q0, uint64_t n, uint32_t dim, uint64_t n_total,
                               uint32_t n_comp, float sigma, uint64_t seed, float qnoise,
