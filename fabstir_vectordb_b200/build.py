@@ -18,7 +18,7 @@ SO = os.path.join(HERE, "libfvdb_b200.so")
 STAMP = os.path.join(HERE, ".libfvdb_b200.stamp")
 
 SOURCES = ["engine.cu", "exact_scan.cu", "layout.cu", "kmeans.cu", "tc_scan.cu", "synth.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "tc_scan.cuh"]
+HEADERS = ["common.cuh", "kernels.cuh", "tc_scan.cuh", "tc_ptx.cuh"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -1,0 +1,196 @@
+// tc_ptx.cuh — inline-PTX wrappers for sm_100a (mbarrier, TMA, tcgen05 MMA / TMEM) and the
+// warp-level sorted-list primitives shared by the tensor-core scan kernels.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace fvdb {
+namespace tcx {
+
+constexpr uint32_t F32_INF_BITS = 0x7f800000u;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0,
+                                            int c1, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// UMMA shared-memory descriptor, K-major, 128-byte swizzle: start>>4 | LBO=1 | SBO=1024>>4 |
+// version=1 (bit 46) | layout SWIZZLE_128B (2 << 61).  (cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor kind::tf32: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both,
+// N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ---- warp-level sorted-list primitives over u64 keys (one key per lane) -----------------------
+__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+
+__device__ __forceinline__ uint64_t warp_sort32(uint64_t v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t o = shfl_xor64(v, j);
+            const bool up = (lane & k) == 0;
+            const bool lower = (lane & j) == 0;
+            const uint64_t mn = v < o ? v : o, mx = v < o ? o : v;
+            v = (lower == up) ? mn : mx;
+        }
+    }
+    return v;
+}
+// list, cand both ascending across lanes -> the 32 smallest of the union, ascending
+__device__ __forceinline__ uint64_t warp_merge32(uint64_t list, uint64_t cand_sorted, int lane) {
+    const uint64_t rev = shfl64(cand_sorted, 31 - lane);
+    uint64_t v = list < rev ? list : rev;
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const uint64_t o = shfl_xor64(v, j);
+        const bool lower = (lane & j) == 0;
+        const uint64_t mn = v < o ? v : o, mx = v < o ? o : v;
+        v = lower ? mn : mx;
+    }
+    return v;
+}
+// Four independent 32-lane networks advanced in lockstep: the shuffle chains of one network are
+// latency bound (~25 cycles per dependent SHFL), interleaving four hides most of it.
+__device__ __forceinline__ void warp_sort32x4_u32(uint32_t (&v)[4], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+            uint32_t o[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) o[g] = __shfl_xor_sync(0xffffffffu, v[g], j);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) v[g] = keep_min ? min(v[g], o[g]) : max(v[g], o[g]);
+        }
+    }
+}
+__device__ __forceinline__ void warp_merge32x4(uint64_t (&list)[4], const uint64_t (&cand_sorted)[4], int lane) {
+    uint64_t v[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint64_t rev = shfl64(cand_sorted[g], 31 - lane);
+        v[g] = list[g] < rev ? list[g] : rev;
+    }
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const bool lower = (lane & j) == 0;
+        uint64_t o[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) o[g] = shfl_xor64(v[g], j);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint64_t mn = v[g] < o[g] ? v[g] : o[g], mx = v[g] < o[g] ? o[g] : v[g];
+            v[g] = lower ? mn : mx;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) list[g] = v[g];
+}
+// insert one key (warp-uniform) into the ascending list
+__device__ __forceinline__ uint64_t warp_insert1(uint64_t list, uint64_t c, int lane) {
+    const unsigned le = __ballot_sync(0xffffffffu, list <= c);
+    const int pos = __popc(le);
+    const uint64_t up = shfl_up64(list, 1);
+    if (lane > pos) list = up;
+    if (lane == pos) list = c;
+    return list;
+}
+
+
+// tcgen05.mma with the A operand in tensor memory (TS form): D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> tensor memory: 32 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+}  // namespace tcx
+}  // namespace fvdb

@@ -18,9 +18,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/fvdb.h"
 #include "kernels.cuh"
+#include "tc_ptx.cuh"
 #include "tc_scan.cuh"
 
 namespace fvdb {
@@ -36,7 +38,6 @@ constexpr int TC_KP = 32;                        // shortlist entries per (query
 constexpr int TC_CAP = 128;                      // candidate slots per query per tile
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 128;                // 2 accumulator buffers x 64 columns
-constexpr uint32_t F32_INF_BITS = 0x7f800000u;
 
 struct TcScanParams {
     const ScanItem* items;
@@ -58,163 +59,12 @@ struct TcScanParams {
     uint32_t* thr_g;    // [nq] running upper bound of the query's TC_KP-th approx d2 (f32 bits)
     uint32_t* work_counter;  // dynamic tile scheduler: next unclaimed work item
     uint32_t stages;
+    uint32_t debug;          // bit 0: skip the epilogue math (pipeline ceiling experiment)
 };
 constexpr int TC_SCHED = 4;          // depth of the in-CTA work-item ring
 constexpr uint32_t ITEM_END = 0xFFFFFFFFu;
 
-// ---- PTX wrappers -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    const long long t0 = clock64();
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) break;
-        if (clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0,
-                                            int c1, uint64_t hint) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-
-// UMMA shared-memory descriptor, K-major, 128-byte swizzle: start>>4 | LBO=1 | SBO=1024>>4 |
-// version=1 (bit 46) | layout SWIZZLE_128B (2 << 61).  (cute/arch/mma_sm100_desc.hpp)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor kind::tf32: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both,
-// N>>3 at bit 17, M>>4 at bit 24.
-__device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-
-// ---- warp-level sorted-list primitives over u64 keys (one key per lane) -----------------------
-__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
-
-__device__ __forceinline__ uint64_t warp_sort32(uint64_t v, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const uint64_t o = shfl_xor64(v, j);
-            const bool up = (lane & k) == 0;
-            const bool lower = (lane & j) == 0;
-            const uint64_t mn = v < o ? v : o, mx = v < o ? o : v;
-            v = (lower == up) ? mn : mx;
-        }
-    }
-    return v;
-}
-// list, cand both ascending across lanes -> the 32 smallest of the union, ascending
-__device__ __forceinline__ uint64_t warp_merge32(uint64_t list, uint64_t cand_sorted, int lane) {
-    const uint64_t rev = shfl64(cand_sorted, 31 - lane);
-    uint64_t v = list < rev ? list : rev;
-#pragma unroll
-    for (int j = 16; j > 0; j >>= 1) {
-        const uint64_t o = shfl_xor64(v, j);
-        const bool lower = (lane & j) == 0;
-        const uint64_t mn = v < o ? v : o, mx = v < o ? o : v;
-        v = lower ? mn : mx;
-    }
-    return v;
-}
-// Four independent 32-lane networks advanced in lockstep: the shuffle chains of one network are
-// latency bound (~25 cycles per dependent SHFL), interleaving four hides most of it.
-__device__ __forceinline__ void warp_sort32x4_u32(uint32_t (&v)[4], int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
-            uint32_t o[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) o[g] = __shfl_xor_sync(0xffffffffu, v[g], j);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) v[g] = keep_min ? min(v[g], o[g]) : max(v[g], o[g]);
-        }
-    }
-}
-__device__ __forceinline__ void warp_merge32x4(uint64_t (&list)[4], const uint64_t (&cand_sorted)[4], int lane) {
-    uint64_t v[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const uint64_t rev = shfl64(cand_sorted[g], 31 - lane);
-        v[g] = list[g] < rev ? list[g] : rev;
-    }
-#pragma unroll
-    for (int j = 16; j > 0; j >>= 1) {
-        const bool lower = (lane & j) == 0;
-        uint64_t o[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) o[g] = shfl_xor64(v[g], j);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const uint64_t mn = v[g] < o[g] ? v[g] : o[g], mx = v[g] < o[g] ? o[g] : v[g];
-            v[g] = lower ? mn : mx;
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) list[g] = v[g];
-}
-// insert one key (warp-uniform) into the ascending list
-__device__ __forceinline__ uint64_t warp_insert1(uint64_t list, uint64_t c, int lane) {
-    const unsigned le = __ballot_sync(0xffffffffu, list <= c);
-    const int pos = __popc(le);
-    const uint64_t up = shfl_up64(list, 1);
-    if (lane > pos) list = up;
-    if (lane == pos) list = c;
-    return list;
-}
+using namespace tcx;
 
 // ---- the scan kernel ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -386,15 +236,31 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
             for (int i = et; i < TC_NQ * TC_KP; i += 128) list_s[i] = KEY_NONE;
             epi_bar(1);
             {
+                // warp ew stages queries ew, ew+4, ...; a lane moves float4 columns lane, lane+32, ...
+                // Loads of four query rows are issued before any store so ~12 LDG.128 per lane
+                // are in flight (the loop was latency bound with one).
                 const uint32_t f4_per_row = KB * 8;
-                const uint32_t total = ncols * f4_per_row;
-                for (uint32_t idx = et; idx < total; idx += 128) {
-                    const uint32_t q = idx / f4_per_row, c = idx - q * f4_per_row;
-                    const uint32_t kb = c >> 3, ch = c & 7;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const uint32_t qi = qidx_s[q];
-                    if (qi != ID_NONE) v = __ldg(reinterpret_cast<const float4*>(p.Q + (size_t)qi * D) + c);
-                    *reinterpret_cast<float4*>(q_tile + (size_t)kb * TC_QBLK_BYTES + q * 128 + ((ch ^ (q & 7)) << 4)) = v;
+                for (uint32_t q0 = ew; q0 < ncols; q0 += 16) {
+                    for (uint32_t c = lane; c < f4_per_row; c += 32) {
+                        float4 v[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint32_t q = q0 + 4 * g;
+                            v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (q < ncols) {
+                                const uint32_t qi = qidx_s[q];
+                                if (qi != ID_NONE) v[g] = __ldg(reinterpret_cast<const float4*>(p.Q + (size_t)qi * D) + c);
+                            }
+                        }
+                        const uint32_t kb = c >> 3, ch = c & 7;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint32_t q = q0 + 4 * g;
+                            if (q < ncols)
+                                *reinterpret_cast<float4*>(q_tile + (size_t)kb * TC_QBLK_BYTES + q * 128 +
+                                                           ((ch ^ (q & 7)) << 4)) = v[g];
+                        }
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
@@ -418,7 +284,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                 fphase[buf] ^= 1;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + buf * TC_NQ + ((uint32_t)(quarter * 32) << 16);
-                for (uint32_t c0 = 0; c0 < ncols; c0 += 16) {
+                for (uint32_t c0 = 0; c0 < ((p.debug & 1u) ? 0u : ncols); c0 += 16) {
                     uint32_t acc[16];
                     tmem_ld16(taddr + c0, acc);
                     float thr[16];
@@ -509,6 +375,355 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                      "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
     }
+}
+
+
+// ================================================================================================
+// Kernel Q ("queries on lanes"): the query tile is the MMA A operand and lives in TENSOR MEMORY
+// (128 TMEM lanes = 128 queries, D <= 384 columns), database rows stream through shared memory
+// as the B operand (64 rows x 128 B per stage), accumulators double-buffered in the remaining
+// 128 TMEM columns.  One epilogue thread owns one query: the threshold test and the candidate
+// append are thread-private (no atomics, no votes, no CTA barriers); a query's 32-entry
+// shortlist is re-sorted by its warp only when 16+ new candidates are pending.  Shared memory
+// holds nothing but the row ring (up to 18 x 8 KB in flight) and the candidate pools.
+// ================================================================================================
+constexpr int Q1_M = 128;                       // queries per work item
+constexpr int Q1_N = 64;                        // rows per tile
+constexpr int Q1_STAGE_BYTES = Q1_N * 128;      // 8 KB
+constexpr int Q1_POOL_LD = 65;                  // words per query: [0,32) sorted, [32,64) pending, +1 pad
+constexpr int Q1_TMEM_COLS = 512;
+constexpr int Q1_ACC_COL = 384;                 // accumulators at columns 384..511
+
+struct QPool {
+    uint32_t* d;  // [Q1_M][Q1_POOL_LD] approx d2 bits
+    uint32_t* p;  // [Q1_M][Q1_POOL_LD] arena row
+};
+
+// Merge the pending entries of up to four queries (lanes `src[g]` of this warp, query rows
+// m[g]) into their sorted shortlists.  Returns the merged lists in `lst` (lane i = entry i).
+__device__ __forceinline__ void q1_merge4(const QPool& pool, const uint32_t (&m)[4], const uint32_t (&n_new)[4],
+                                          const bool (&act)[4], uint64_t (&lst)[4], int lane) {
+    uint64_t nw[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        lst[g] = KEY_NONE;
+        nw[g] = KEY_NONE;
+        if (act[g]) {
+            const uint32_t base = m[g] * Q1_POOL_LD;
+            const uint32_t dd = pool.d[base + lane];
+            if (dd != 0xFFFFFFFFu) lst[g] = ((uint64_t)dd << 32) | pool.p[base + lane];
+            if ((uint32_t)lane < n_new[g]) nw[g] = ((uint64_t)pool.d[base + 32 + lane] << 32) | pool.p[base + 32 + lane];
+        }
+    }
+    // sort the pending entries (4 networks in lockstep), then bitonic-merge with the lists
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+            uint64_t o[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) o[g] = shfl_xor64(nw[g], j);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint64_t mn = nw[g] < o[g] ? nw[g] : o[g], mx = nw[g] < o[g] ? o[g] : nw[g];
+                nw[g] = keep_min ? mn : mx;
+            }
+        }
+    }
+    warp_merge32x4(lst, nw, lane);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t KB = p.KB;
+    const uint32_t STAGES = p.stages;
+    unsigned char* ring = smem;                                                     // STAGES x 8 KB
+    QPool pool;
+    pool.d = reinterpret_cast<uint32_t*>(ring + (size_t)STAGES * Q1_STAGE_BYTES);
+    pool.p = pool.d + Q1_M * Q1_POOL_LD;
+    float* xn_w = reinterpret_cast<float*>(pool.p + Q1_M * Q1_POOL_LD);             // [4][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xn_w + 4 * Q1_N);
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5 + 2 * TC_SCHED);
+    uint32_t* sched_s = tmem_ptr_s + 1;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * STAGES;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    const uint32_t bar_qready = bar_tempty + 16;
+    const uint32_t bar_sfull = bar_qready + 8;
+    const uint32_t bar_sempty = bar_sfull + 8 * TC_SCHED;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tfull + 8, 1);
+        mbar_init(bar_tempty, 4);
+        mbar_init(bar_tempty + 8, 4);
+        mbar_init(bar_qready, 4);  // one arrival per epilogue warp once its queries sit in TMEM
+        for (int i = 0; i < TC_SCHED; ++i) {
+            mbar_init(bar_sfull + 8 * i, 1);
+            mbar_init(bar_sempty + 8 * i, 5);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                     "r"((uint32_t)Q1_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+    const uint32_t n_items = *p.item_count;
+
+    if (warp == 0) {
+        // ================= TMA producer + tile scheduler =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, ss = 0, sphase = 0;
+            const uint64_t hint_first = 0x12F0000000000000ull;
+            const uint64_t hint_normal = 0x1000000000000000ull;
+            while (true) {
+                mbar_wait(bar_sempty + 8 * ss, sphase ^ 1);
+                uint32_t item = atomicAdd(p.work_counter, 1u);
+                if (item >= n_items) item = ITEM_END;
+                sched_s[ss] = item;
+                mbar_arrive(bar_sfull + 8 * ss);
+                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+                if (item == ITEM_END) break;
+                const ScanItem it = p.items[item];
+                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+                const uint64_t hint = (!it.identity && it.slot > 1) ? hint_normal : hint_first;
+                for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
+                    for (uint32_t kb = 0; kb < KB; ++kb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        mbar_expect_tx(bar_full + 8 * stage, Q1_STAGE_BYTES);
+                        tma_load_2d(smem_u32(ring + (size_t)stage * Q1_STAGE_BYTES), &tmap, bar_full + 8 * stage,
+                                    (int)(kb * TC_KB_FLOATS), (int)rt, hint);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, buf = 0, qphase = 0, ss = 0, sphase = 0;
+            uint32_t tphase[2] = {0, 0};
+            const uint32_t ring_base = smem_u32(ring);
+            const uint32_t idesc = umma_idesc_tf32(Q1_M, Q1_N);
+            while (true) {
+                mbar_wait(bar_sfull + 8 * ss, sphase);
+                const uint32_t item = sched_s[ss];
+                mbar_arrive(bar_sempty + 8 * ss);
+                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+                if (item == ITEM_END) break;
+                const ScanItem it = p.items[item];
+                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+                mbar_wait(bar_qready, qphase);
+                qphase ^= 1;
+                tc_fence_after();
+                for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
+                    mbar_wait(bar_tempty + 8 * buf, tphase[buf] ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + Q1_ACC_COL + buf * Q1_N;
+                    for (uint32_t kb = 0; kb < KB; ++kb) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint64_t b0 = umma_desc_sw128(ring_base + stage * Q1_STAGE_BYTES);
+#pragma unroll
+                        for (uint32_t k4 = 0; k4 < 4; ++k4)  // A: 8 tf32 = 8 TMEM columns per step
+                            umma_tf32_ts(d_tmem, tmem_base + kb * 32 + k4 * 8, b0 + 2 * k4, idesc,
+                                         (kb | k4) != 0 ? 1u : 0u);
+                        umma_commit(bar_empty + 8 * stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bar_tfull + 8 * buf);
+                    tphase[buf] ^= 1;
+                    buf ^= 1;
+                }
+            }
+        }
+    } else {
+        // ================= epilogue: one thread = one query =================
+        const int quarter = warp & 3;                 // TMEM lane quarter of this warp
+        const uint32_t m = quarter * 32 + lane;       // TMEM lane == query row of the tile
+        const uint32_t qslot_in_item = (uint32_t)lane * 4 + quarter;  // item query index held by this thread
+        const uint32_t lane_taddr = (uint32_t)(quarter * 32) << 16;
+        float* xn_mine = xn_w + quarter * Q1_N;
+        const uint32_t D = p.D;
+        uint32_t buf = 0, ss = 0, sphase = 0;
+        uint32_t fphase[2] = {0, 0};
+        while (true) {
+            mbar_wait(bar_sfull + 8 * ss, sphase);
+            const uint32_t item = sched_s[ss];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
+            if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            if (item == ITEM_END) break;
+            const ScanItem it = p.items[item];
+            if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+            // ---- item prologue: my query -> registers -> tensor memory ----
+            const bool have = qslot_in_item < it.pair_count;
+            uint32_t qi = ID_NONE, sl = 0;
+            float qn = 0.f, thrp = -__uint_as_float(F32_INF_BITS);
+            if (have) {
+                if (it.identity) { qi = it.pair_begin + qslot_in_item; sl = it.slot; }
+                else { qi = p.pair_q[it.pair_begin + qslot_in_item]; sl = p.pair_slot[it.pair_begin + qslot_in_item]; }
+                qn = p.qnorm[qi];
+                thrp = __uint_as_float(*(volatile uint32_t*)(p.thr_g + qi)) - qn;
+            }
+            for (int i = 0; i < 32; ++i) pool.d[m * Q1_POOL_LD + i] = 0xFFFFFFFFu;  // empty shortlist
+            uint32_t cnt_new = 0;
+            {
+                const float4* qrow = reinterpret_cast<const float4*>(p.Q + (size_t)(have ? qi : 0) * D);
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (have) v = __ldg(qrow + kb * 8 + i);
+                        r[4 * i + 0] = __float_as_uint(v.x); r[4 * i + 1] = __float_as_uint(v.y);
+                        r[4 * i + 2] = __float_as_uint(v.z); r[4 * i + 3] = __float_as_uint(v.w);
+                    }
+                    tmem_st32(tmem_base + lane_taddr + kb * 32, r);
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_qready);
+
+            // ---- row tiles ----
+            for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
+                // |x|^2 (+inf = masked) of the tile's 64 rows into this warp's private strip
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t pos = rt + h * 32 + lane;
+                    float xn = __uint_as_float(F32_INF_BITS);
+                    if (pos < it.row_end) {
+                        bool live = true;
+                        if (p.tomb || p.filt) {
+                            const uint32_t id = p.ids[pos];
+                            if (p.tomb && bit_test(p.tomb, p.tomb_bits, id)) live = false;
+                            else if (p.filt && !bit_test(p.filt, p.filt_bits, id)) live = false;
+                        }
+                        if (live) xn = __ldg(p.xnorm + pos);
+                    }
+                    xn_mine[h * 32 + lane] = xn;
+                }
+                __syncwarp();
+                mbar_wait(bar_tfull + 8 * buf, fphase[buf]);
+                fphase[buf] ^= 1;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + Q1_ACC_COL + buf * Q1_N + lane_taddr;
+                for (uint32_t c0 = 0; c0 < ((p.debug & 1u) ? 0u : (uint32_t)Q1_N); c0 += 16) {
+                    uint32_t acc[16];
+                    tmem_ld16(taddr + c0, acc);
+                    float xn[16];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(xn_mine + c0 + 4 * j4);
+                        xn[4 * j4 + 0] = t4.x; xn[4 * j4 + 1] = t4.y; xn[4 * j4 + 2] = t4.z; xn[4 * j4 + 3] = t4.w;
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float v = fmaf(-2.0f, __uint_as_float(acc[j]), xn[j]);  // |x|^2 - 2 q.x
+                        if (v < thrp) {
+                            const uint32_t o = m * Q1_POOL_LD + 32 + cnt_new;
+                            pool.d[o] = __float_as_uint(fmaxf(v + qn, 0.0f));
+                            pool.p[o] = rt + c0 + j;
+                            ++cnt_new;
+                        }
+                    }
+                    // another 16 columns could overflow the 32 pending slots: refresh those queries
+                    unsigned need = __ballot_sync(0xffffffffu, cnt_new > 16);
+                    while (need) {
+                        uint32_t mm[4], nn[4];
+                        bool act[4];
+                        int src[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            act[g] = need != 0;
+                            src[g] = act[g] ? (__ffs(need) - 1) : 0;
+                            if (act[g]) need &= need - 1;
+                            mm[g] = quarter * 32 + src[g];
+                            nn[g] = __shfl_sync(0xffffffffu, cnt_new, src[g]);
+                        }
+                        __syncwarp();
+                        uint64_t lst[4];
+                        q1_merge4(pool, mm, nn, act, lst, lane);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (!act[g]) continue;
+                            pool.d[mm[g] * Q1_POOL_LD + lane] = (uint32_t)(lst[g] >> 32);
+                            pool.p[mm[g] * Q1_POOL_LD + lane] = (uint32_t)lst[g];
+                            const uint64_t last = shfl64(lst[g], 31);
+                            if (lane == src[g]) {
+                                cnt_new = 0;
+                                if (last != KEY_NONE) thrp = __uint_as_float((uint32_t)(last >> 32)) - qn;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+                buf ^= 1;
+            }
+            // ---- item epilogue: final merge, publish the shortlists, tighten shared thresholds ----
+            unsigned todo = __ballot_sync(0xffffffffu, have);
+            while (todo) {
+                uint32_t mm[4], nn[4], qis[4], sls[4];
+                bool act[4];
+                int src[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    act[g] = todo != 0;
+                    src[g] = act[g] ? (__ffs(todo) - 1) : 0;
+                    if (act[g]) todo &= todo - 1;
+                    mm[g] = quarter * 32 + src[g];
+                    nn[g] = __shfl_sync(0xffffffffu, cnt_new, src[g]);
+                    qis[g] = __shfl_sync(0xffffffffu, qi, src[g]);
+                    sls[g] = __shfl_sync(0xffffffffu, sl, src[g]);
+                }
+                __syncwarp();
+                uint64_t lst[4];
+                q1_merge4(pool, mm, nn, act, lst, lane);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (!act[g]) continue;
+                    p.partial[((size_t)qis[g] * p.P + sls[g]) * TC_KP + lane] = lst[g];
+                    if (lane == 31 && lst[g] != KEY_NONE) atomicMin(p.thr_g + qis[g], (uint32_t)(lst[g] >> 32));
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)Q1_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+size_t tc_scan_q_smem_bytes(uint32_t stages) {
+    return (size_t)stages * Q1_STAGE_BYTES + (size_t)2 * Q1_M * Q1_POOL_LD * 4 + (size_t)4 * Q1_N * 4 +
+           (size_t)(2 * stages + 5 + 2 * TC_SCHED) * 8 + 16 + (size_t)TC_SCHED * 4;
 }
 
 size_t tc_scan_smem_bytes(uint32_t KB, uint32_t stages) {
@@ -642,7 +857,9 @@ struct TcScratchImpl {
     Buf<uint32_t> thr_g, list_cnt, pair_off, cursor, pair_q, pair_slot, n_items;
     Buf<ScanItem> items;
     Buf<uint64_t> partial, shortlist;
-    CUtensorMap tmap_arena;
+    CUtensorMap tmap_arena;  // box 32 floats x 128 rows (kernel R)
+    CUtensorMap tmap_q;      // box 32 floats x 64 rows  (kernel Q)
+    bool smem_attr_set_q = false;
     const float* tmap_rows = nullptr;
     uint64_t tmap_n = 0;
     bool smem_attr_set = false;
@@ -699,6 +916,14 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             if (err) *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
             return FVDB_ERR_CUDA;
         }
+        const cuuint32_t box_q[2] = {TC_KB_FLOATS, Q1_N};
+        r = enc(&m->tmap_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.rows), gdim, gstride, box_q, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            if (err) *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+            return FVDB_ERR_CUDA;
+        }
         m->tmap_rows = a.rows;
         m->tmap_n = a.n_rows;
         s.arena_dirty = false;
@@ -706,7 +931,12 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
 
     // ---- per-batch state ----
     const size_t n_pairs = (size_t)nq * np;
-    const size_t max_items = (size_t)a.nlist + (n_pairs + TC_TILE_Q - 1) / TC_TILE_Q + 1;
+    // kernel Q (queries in tensor memory) needs D <= 384 TMEM columns for the query tile;
+    // kernel R (rows on lanes, query tile in shared memory) covers 384 < D <= 512
+    const char* kenv = getenv("FVDB_TC_KERNEL");
+    const bool use_q = (D <= 384) && !(kenv && kenv[0] == 'R');
+    const uint32_t tile_q = use_q ? (uint32_t)Q1_M : TC_TILE_Q;
+    const size_t max_items = (size_t)a.nlist + (n_pairs + tile_q - 1) / tile_q + 1;
     TCK(m->qnorm.ensure(nq, dev_bytes));
     TCK(m->thr_g.ensure(nq, dev_bytes));
     TCK(m->list_cnt.ensure(a.nlist + 1, dev_bytes));
@@ -726,7 +956,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         TCK(cudaGetLastError());
         (*launches) += 2;
     }
-    TCK(launch_probe_bucketing(a.coarse_keys, nq, np, a.list_off, a.nlist, TC_TILE_Q, m->list_cnt.p, m->pair_off.p,
+    TCK(launch_probe_bucketing(a.coarse_keys, nq, np, a.list_off, a.nlist, tile_q, m->list_cnt.p, m->pair_off.p,
                                m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st));
     (*launches) += 3;
     TCK(cudaMemsetAsync(m->partial.p, 0xFF, n_pairs * TC_KP * sizeof(uint64_t), st));
@@ -738,20 +968,39 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
     p.P = np; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
     p.work_counter = m->n_items.p + 1;
-    TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
-    uint32_t stages = 8;
-    while (stages > 2 && tc_scan_smem_bytes(KB, stages) > 227 * 1024) --stages;
-    p.stages = stages;
-    const size_t smem = tc_scan_smem_bytes(KB, stages) + 1024;  // slack for the 1024-byte alignment
-    if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
-    if (!m->smem_attr_set) {
-        TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        m->smem_attr_set = true;
+    {
+        const char* dbg = getenv("FVDB_TC_DEBUG");
+        p.debug = dbg ? (uint32_t)atoi(dbg) : 0u;
     }
-    const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
-    if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
-    tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(m->tmap_arena, p);
-    TCK(cudaGetLastError());
+    TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
+    if (use_q) {
+        uint32_t stages = 18;
+        while (stages > 2 && tc_scan_q_smem_bytes(stages) + 1024 > 232448) --stages;
+        p.stages = stages;
+        const size_t smem = tc_scan_q_smem_bytes(stages) + 1024;
+        if (!m->smem_attr_set_q) {
+            TCK(cudaFuncSetAttribute(tc_scan_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+            m->smem_attr_set_q = true;
+        }
+        const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
+        if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
+        tc_scan_q_kernel<<<grid, TC_THREADS, smem, st>>>(m->tmap_q, p);
+        TCK(cudaGetLastError());
+    } else {
+        uint32_t stages = 8;
+        while (stages > 2 && tc_scan_smem_bytes(KB, stages) > 227 * 1024) --stages;
+        p.stages = stages;
+        const size_t smem = tc_scan_smem_bytes(KB, stages) + 1024;  // slack for the 1024-byte alignment
+        if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
+        if (!m->smem_attr_set) {
+            TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+            m->smem_attr_set = true;
+        }
+        const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
+        if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
+        tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(m->tmap_arena, p);
+        TCK(cudaGetLastError());
+    }
     if (a.ev_scan1) TCK(cudaEventRecord(a.ev_scan1, st));
     (*launches)++;
 
