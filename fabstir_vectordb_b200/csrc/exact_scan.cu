@@ -302,13 +302,17 @@ uint32_t exact_scan_tr() { return TR; }
 // ---------------------------------------------------------------------------------------------
 
 // coarse_keys [nq][nprobe]: low 32 bits = list id.  KEY_NONE entries (nprobe > nlist) skipped.
+// list_cnt[l] += 1 per probing query; bit 31 of list_cnt[l] is set when l is some query's
+// NEAREST list (rank 0) — those lists are scheduled first so per-query thresholds tighten early.
+constexpr uint32_t NEAREST_BIT = 0x80000000u;
 __global__ void probe_hist_kernel(const uint64_t* __restrict__ coarse_keys, uint32_t n_pairs,
-                                  uint32_t* __restrict__ list_cnt) {
+                                  uint32_t nprobe, uint32_t* __restrict__ list_cnt) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const uint64_t key = coarse_keys[i];
     if (key == KEY_NONE) return;
     atomicAdd(&list_cnt[key_id(key)], 1u);
+    if (i % nprobe == 0) atomicOr(&list_cnt[key_id(key)], NEAREST_BIT);
 }
 
 // single-CTA exclusive scan over lists: pair offsets and work-item offsets; also emits the
@@ -326,44 +330,52 @@ __global__ void probe_scan_kernel(const uint32_t* __restrict__ list_cnt,
     const int t = threadIdx.x;
     if (t == 0) { carry_pairs = 0; carry_items = 0; s_rows = 0; }
     __syncthreads();
-    for (uint32_t base = 0; base < nlist; base += 1024) {
-        const uint32_t l = base + t;
-        uint32_t c = 0, len = 0;
-        if (l < nlist) { c = list_cnt[l]; len = list_off[l + 1] - list_off[l]; }
-        if (len == 0) c = 0;  // nothing to scan in an empty list
-        const uint32_t ni = (c + tile_q - 1) / tile_q;
-        s_pairs[t] = c;
-        s_items[t] = ni;
-        __syncthreads();
-        // Hillis-Steele inclusive scan over 1024 entries
-        for (int o = 1; o < 1024; o <<= 1) {
-            uint32_t a = 0, b = 0;
-            if (t >= o) { a = s_pairs[t - o]; b = s_items[t - o]; }
-            __syncthreads();
-            s_pairs[t] += a;
-            s_items[t] += b;
-            __syncthreads();
-        }
-        const uint32_t p_excl = carry_pairs + s_pairs[t] - c;
-        const uint32_t i_excl = carry_items + s_items[t] - ni;
-        if (l < nlist) {
-            pair_off[l] = p_excl;
-            cursor[l] = p_excl;
-            for (uint32_t j = 0; j < ni; ++j) {
-                ScanItem it;
-                it.row_begin = list_off[l];
-                it.row_end = list_off[l + 1];
-                it.pair_begin = p_excl + j * tile_q;
-                it.pair_count = min(tile_q, c - j * tile_q);
-                it.slot = ni;  // items sharing this list (the TC scan keeps such lists in L2)
-                it.identity = 0;
-                items[i_excl + j] = it;
+    // pass 0: lists that are the nearest list of at least one query; pass 1: the others
+    for (int pass = 0; pass < 2; ++pass) {
+        for (uint32_t base = 0; base < nlist; base += 1024) {
+            const uint32_t l = base + t;
+            uint32_t c = 0, len = 0;
+            if (l < nlist) {
+                const uint32_t raw = list_cnt[l];
+                const bool nearest = (raw & NEAREST_BIT) != 0;
+                if ((pass == 0) == nearest) c = raw & ~NEAREST_BIT;
+                len = list_off[l + 1] - list_off[l];
             }
-            if (c > 0) atomicAdd(&s_rows, (unsigned long long)len);
+            if (len == 0) c = 0;  // nothing to scan in an empty list
+            const uint32_t ni = (c + tile_q - 1) / tile_q;
+            s_pairs[t] = c;
+            s_items[t] = ni;
+            __syncthreads();
+            // Hillis-Steele inclusive scan over 1024 entries
+            for (int o = 1; o < 1024; o <<= 1) {
+                uint32_t a = 0, b = 0;
+                if (t >= o) { a = s_pairs[t - o]; b = s_items[t - o]; }
+                __syncthreads();
+                s_pairs[t] += a;
+                s_items[t] += b;
+                __syncthreads();
+            }
+            const uint32_t p_excl = carry_pairs + s_pairs[t] - c;
+            const uint32_t i_excl = carry_items + s_items[t] - ni;
+            if (l < nlist && c > 0) {
+                pair_off[l] = p_excl;
+                cursor[l] = p_excl;
+                for (uint32_t j = 0; j < ni; ++j) {
+                    ScanItem it;
+                    it.row_begin = list_off[l];
+                    it.row_end = list_off[l + 1];
+                    it.pair_begin = p_excl + j * tile_q;
+                    it.pair_count = min(tile_q, c - j * tile_q);
+                    it.slot = ni;  // items sharing this list (the TC scan keeps such lists in L2)
+                    it.identity = 0;
+                    items[i_excl + j] = it;
+                }
+                atomicAdd(&s_rows, (unsigned long long)len);
+            }
+            __syncthreads();
+            if (t == 1023) { carry_pairs += s_pairs[1023]; carry_items += s_items[1023]; }
+            __syncthreads();
         }
-        __syncthreads();
-        if (t == 1023) { carry_pairs += s_pairs[1023]; carry_items += s_items[1023]; }
-        __syncthreads();
     }
     if (t == 0) {
         pair_off[nlist] = carry_pairs;
@@ -398,7 +410,7 @@ cudaError_t launch_probe_bucketing(const uint64_t* coarse_keys, uint32_t nq, uin
     if (n_pairs == 0) {
         return cudaMemsetAsync(n_items, 0, sizeof(uint32_t), stream);
     }
-    probe_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, list_cnt);
+    probe_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, nprobe, list_cnt);
     probe_scan_kernel<<<1, 1024, 0, stream>>>(list_cnt, list_off, nlist, tile_q, pair_off, cursor,
                                               items, n_items, scanned_rows);
     probe_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, nprobe,

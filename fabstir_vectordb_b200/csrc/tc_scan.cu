@@ -59,6 +59,7 @@ struct TcScanParams {
     uint32_t* thr_g;    // [nq] running upper bound of the query's TC_KP-th approx d2 (f32 bits)
     uint32_t* work_counter;  // dynamic tile scheduler: next unclaimed work item
     uint32_t stages;
+    uint32_t kbs;            // kernel Q: k-blocks (128 B each) per pipeline stage
     uint32_t debug;          // bit 0: skip the epilogue math (pipeline ceiling experiment)
 };
 constexpr int TC_SCHED = 4;          // depth of the in-CTA work-item ring
@@ -439,13 +440,16 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t KB = p.KB;
+    const uint32_t KBS = p.kbs;                     // k-blocks per stage
+    const uint32_t NST = KB / KBS;                  // stages per row tile
     const uint32_t STAGES = p.stages;
-    unsigned char* ring = smem;                                                     // STAGES x 8 KB
+    const uint32_t STAGE_BYTES = KBS * Q1_STAGE_BYTES;
+    unsigned char* ring = smem;                                                     // STAGES x KBS x 8 KB
     QPool pool;
-    pool.d = reinterpret_cast<uint32_t*>(ring + (size_t)STAGES * Q1_STAGE_BYTES);
+    pool.d = reinterpret_cast<uint32_t*>(ring + (size_t)STAGES * STAGE_BYTES);
     pool.p = pool.d + Q1_M * Q1_POOL_LD;
-    float* xn_w = reinterpret_cast<float*>(pool.p + Q1_M * Q1_POOL_LD);             // [4][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xn_w + 4 * Q1_N);
+    float* xn_w = reinterpret_cast<float*>(pool.p + Q1_M * Q1_POOL_LD);             // [4][2][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xn_w + 8 * Q1_N);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5 + 2 * TC_SCHED);
     uint32_t* sched_s = tmem_ptr_s + 1;
 
@@ -487,70 +491,90 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
     const uint32_t n_items = *p.item_count;
 
     if (warp == 0) {
-        // ================= TMA producer + tile scheduler =================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, ss = 0, sphase = 0;
-            const uint64_t hint_first = 0x12F0000000000000ull;
-            const uint64_t hint_normal = 0x1000000000000000ull;
-            while (true) {
-                mbar_wait(bar_sempty + 8 * ss, sphase ^ 1);
-                uint32_t item = atomicAdd(p.work_counter, 1u);
+        // ============ TMA producer + tile scheduler (whole warp converged, one lane issues) ============
+        uint32_t stage = 0, phase = 0, ss = 0, sphase = 0;
+        const uint64_t hint_first = 0x12F0000000000000ull;
+        const uint64_t hint_normal = 0x1000000000000000ull;
+        const uint32_t ring_base = smem_u32(ring);
+        while (true) {
+            mbar_wait(bar_sempty + 8 * ss, sphase ^ 1);
+            uint32_t item = 0;
+            if (lane == 0) {
+                item = atomicAdd(p.work_counter, 1u);
                 if (item >= n_items) item = ITEM_END;
                 sched_s[ss] = item;
                 mbar_arrive(bar_sfull + 8 * ss);
-                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
-                if (item == ITEM_END) break;
-                const ScanItem it = p.items[item];
-                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
-                const uint64_t hint = (!it.identity && it.slot > 1) ? hint_normal : hint_first;
-                for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
-                    for (uint32_t kb = 0; kb < KB; ++kb) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        mbar_expect_tx(bar_full + 8 * stage, Q1_STAGE_BYTES);
-                        tma_load_2d(smem_u32(ring + (size_t)stage * Q1_STAGE_BYTES), &tmap, bar_full + 8 * stage,
-                                    (int)(kb * TC_KB_FLOATS), (int)rt, hint);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            if (item == ITEM_END) break;
+            const ScanItem it = p.items[item];
+            if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+            const uint64_t hint = (!it.identity && it.slot > 1) ? hint_normal : hint_first;
+            for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
+                for (uint32_t st = 0; st < NST; ++st) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t fb = bar_full + 8 * stage;
+                        const uint32_t dst = ring_base + stage * STAGE_BYTES;
+                        if (p.debug & 4u) {
+                            mbar_arrive(fb);
+                        } else {
+                            mbar_expect_tx(fb, STAGE_BYTES);
+                            for (uint32_t j = 0; j < KBS; ++j)
+                                tma_load_2d(dst + j * Q1_STAGE_BYTES, &tmap, fb, (int)((st * KBS + j) * TC_KB_FLOATS),
+                                            (int)rt, hint);
+                        }
                     }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, buf = 0, qphase = 0, ss = 0, sphase = 0;
-            uint32_t tphase[2] = {0, 0};
-            const uint32_t ring_base = smem_u32(ring);
-            const uint32_t idesc = umma_idesc_tf32(Q1_M, Q1_N);
-            while (true) {
-                mbar_wait(bar_sfull + 8 * ss, sphase);
-                const uint32_t item = sched_s[ss];
-                mbar_arrive(bar_sempty + 8 * ss);
-                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
-                if (item == ITEM_END) break;
-                const ScanItem it = p.items[item];
-                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
-                mbar_wait(bar_qready, qphase);
-                qphase ^= 1;
+        // ============ MMA issuer (whole warp converged, one elected lane issues) ============
+        uint32_t stage = 0, phase = 0, buf = 0, qphase = 0, ss = 0, sphase = 0, tph0 = 0, tph1 = 0;
+        const uint32_t ring_base = smem_u32(ring);
+        const uint32_t idesc = umma_idesc_tf32(Q1_M, Q1_N);
+        while (true) {
+            mbar_wait(bar_sfull + 8 * ss, sphase);
+            const uint32_t item = sched_s[ss];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
+            if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            if (item == ITEM_END) break;
+            const ScanItem it = p.items[item];
+            if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+            mbar_wait(bar_qready, qphase);
+            qphase ^= 1;
+            tc_fence_after();
+            for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
+                const uint32_t tph = buf ? tph1 : tph0;
+                mbar_wait(bar_tempty + 8 * buf, tph ^ 1);
                 tc_fence_after();
-                for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
-                    mbar_wait(bar_tempty + 8 * buf, tphase[buf] ^ 1);
+                const uint32_t d_tmem = tmem_base + Q1_ACC_COL + buf * Q1_N;
+                for (uint32_t st = 0; st < NST; ++st) {
+                    mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + Q1_ACC_COL + buf * Q1_N;
-                    for (uint32_t kb = 0; kb < KB; ++kb) {
-                        mbar_wait(bar_full + 8 * stage, phase);
-                        tc_fence_after();
-                        const uint64_t b0 = umma_desc_sw128(ring_base + stage * Q1_STAGE_BYTES);
+                    if (elect_one()) {
+                        const uint32_t sbase = ring_base + stage * STAGE_BYTES;
+                        if (!(p.debug & 8u)) {
+                            for (uint32_t j = 0; j < KBS; ++j) {
+                                const uint64_t b0 = umma_desc_sw128(sbase + j * Q1_STAGE_BYTES);
+                                const uint32_t a0 = tmem_base + (st * KBS + j) * 32;
 #pragma unroll
-                        for (uint32_t k4 = 0; k4 < 4; ++k4)  // A: 8 tf32 = 8 TMEM columns per step
-                            umma_tf32_ts(d_tmem, tmem_base + kb * 32 + k4 * 8, b0 + 2 * k4, idesc,
-                                         (kb | k4) != 0 ? 1u : 0u);
+                                for (uint32_t k4 = 0; k4 < 4; ++k4)  // A: 8 tf32 = 8 TMEM columns per step
+                                    umma_tf32_ts(d_tmem, a0 + k4 * 8, b0 + 2 * k4, idesc, (st | j | k4) != 0 ? 1u : 0u);
+                            }
+                        }
                         umma_commit(bar_empty + 8 * stage);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (st + 1 == NST) umma_commit(bar_tfull + 8 * buf);
                     }
-                    umma_commit(bar_tfull + 8 * buf);
-                    tphase[buf] ^= 1;
-                    buf ^= 1;
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (buf) tph1 ^= 1; else tph0 ^= 1;
+                buf ^= 1;
             }
         }
     } else {
@@ -559,10 +583,29 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
         const uint32_t m = quarter * 32 + lane;       // TMEM lane == query row of the tile
         const uint32_t qslot_in_item = (uint32_t)lane * 4 + quarter;  // item query index held by this thread
         const uint32_t lane_taddr = (uint32_t)(quarter * 32) << 16;
-        float* xn_mine = xn_w + quarter * Q1_N;
+        float* xn_mine = xn_w + quarter * 2 * Q1_N;   // two strips: current tile / next tile
         const uint32_t D = p.D;
-        uint32_t buf = 0, ss = 0, sphase = 0;
-        uint32_t fphase[2] = {0, 0};
+        uint32_t buf = 0, ss = 0, sphase = 0, fph0 = 0, fph1 = 0;
+
+        // |x|^2 (+inf = masked / out of range) of rows pos and pos+32
+        auto load_xn = [&](uint32_t rt, uint32_t row_end, float (&out)[2]) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t pos = rt + h * 32 + lane;
+                float xn = __uint_as_float(F32_INF_BITS);
+                if (pos < row_end) {
+                    bool live = true;
+                    if (p.tomb || p.filt) {
+                        const uint32_t id = p.ids[pos];
+                        if (p.tomb && bit_test(p.tomb, p.tomb_bits, id)) live = false;
+                        else if (p.filt && !bit_test(p.filt, p.filt_bits, id)) live = false;
+                    }
+                    if (live) xn = __ldg(p.xnorm + pos);
+                }
+                out[h] = xn;
+            }
+        };
+
         while (true) {
             mbar_wait(bar_sfull + 8 * ss, sphase);
             const uint32_t item = sched_s[ss];
@@ -582,20 +625,31 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 qn = p.qnorm[qi];
                 thrp = __uint_as_float(*(volatile uint32_t*)(p.thr_g + qi)) - qn;
             }
+            float xnext[2];
+            load_xn(it.row_begin, it.row_end, xnext);   // first tile's norms, behind the query load
             for (int i = 0; i < 32; ++i) pool.d[m * Q1_POOL_LD + i] = 0xFFFFFFFFu;  // empty shortlist
             uint32_t cnt_new = 0;
             {
+                // two k-blocks of loads in flight per thread (software pipelined)
                 const float4* qrow = reinterpret_cast<const float4*>(p.Q + (size_t)(have ? qi : 0) * D);
+                float4 cur[8], nxt[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cur[i] = have ? __ldg(qrow + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                 for (uint32_t kb = 0; kb < KB; ++kb) {
+                    if (kb + 1 < KB) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            nxt[i] = have ? __ldg(qrow + (kb + 1) * 8 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                     uint32_t r[32];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (have) v = __ldg(qrow + kb * 8 + i);
-                        r[4 * i + 0] = __float_as_uint(v.x); r[4 * i + 1] = __float_as_uint(v.y);
-                        r[4 * i + 2] = __float_as_uint(v.z); r[4 * i + 3] = __float_as_uint(v.w);
+                        r[4 * i + 0] = __float_as_uint(cur[i].x); r[4 * i + 1] = __float_as_uint(cur[i].y);
+                        r[4 * i + 2] = __float_as_uint(cur[i].z); r[4 * i + 3] = __float_as_uint(cur[i].w);
                     }
                     tmem_st32(tmem_base + lane_taddr + kb * 32, r);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
                 }
                 tmem_st_wait();
             }
@@ -604,27 +658,21 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
             if (lane == 0) mbar_arrive(bar_qready);
 
             // ---- row tiles ----
+            uint32_t strip = 0;
             for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
-                // |x|^2 (+inf = masked) of the tile's 64 rows into this warp's private strip
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t pos = rt + h * 32 + lane;
-                    float xn = __uint_as_float(F32_INF_BITS);
-                    if (pos < it.row_end) {
-                        bool live = true;
-                        if (p.tomb || p.filt) {
-                            const uint32_t id = p.ids[pos];
-                            if (p.tomb && bit_test(p.tomb, p.tomb_bits, id)) live = false;
-                            else if (p.filt && !bit_test(p.filt, p.filt_bits, id)) live = false;
-                        }
-                        if (live) xn = __ldg(p.xnorm + pos);
-                    }
-                    xn_mine[h * 32 + lane] = xn;
-                }
+                float* xs = xn_mine + strip * Q1_N;
+                xs[lane] = xnext[0];
+                xs[32 + lane] = xnext[1];
                 __syncwarp();
-                mbar_wait(bar_tfull + 8 * buf, fphase[buf]);
-                fphase[buf] ^= 1;
+                if (rt + Q1_N < it.row_end) load_xn(rt + Q1_N, it.row_end, xnext);  // prefetch the next tile's norms
+                // thresholds tightened meanwhile by CTAs scanning other lists of the same query
+                uint32_t shared_thr = F32_INF_BITS;
+                if (have) shared_thr = *(volatile uint32_t*)(p.thr_g + qi);
+                const uint32_t fph = buf ? fph1 : fph0;
+                mbar_wait(bar_tfull + 8 * buf, fph);
+                if (buf) fph1 ^= 1; else fph0 ^= 1;
                 tc_fence_after();
+                if (have) thrp = fminf(thrp, __uint_as_float(shared_thr) - qn);
                 const uint32_t taddr = tmem_base + Q1_ACC_COL + buf * Q1_N + lane_taddr;
                 for (uint32_t c0 = 0; c0 < ((p.debug & 1u) ? 0u : (uint32_t)Q1_N); c0 += 16) {
                     uint32_t acc[16];
@@ -632,7 +680,7 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                     float xn[16];
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(xn_mine + c0 + 4 * j4);
+                        const float4 t4 = *reinterpret_cast<const float4*>(xs + c0 + 4 * j4);
                         xn[4 * j4 + 0] = t4.x; xn[4 * j4 + 1] = t4.y; xn[4 * j4 + 2] = t4.z; xn[4 * j4 + 3] = t4.w;
                     }
                     tmem_ld_wait();
@@ -671,7 +719,11 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                             const uint64_t last = shfl64(lst[g], 31);
                             if (lane == src[g]) {
                                 cnt_new = 0;
-                                if (last != KEY_NONE) thrp = __uint_as_float((uint32_t)(last >> 32)) - qn;
+                                if (last != KEY_NONE) {
+                                    thrp = __uint_as_float((uint32_t)(last >> 32)) - qn;
+                                    // any 32 rows below a value bound the global 32nd: share it at once
+                                    atomicMin(p.thr_g + qi, (uint32_t)(last >> 32));
+                                }
                             }
                         }
                         __syncwarp();
@@ -681,6 +733,7 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
                 buf ^= 1;
+                strip ^= 1;
             }
             // ---- item epilogue: final merge, publish the shortlists, tighten shared thresholds ----
             unsigned todo = __ballot_sync(0xffffffffu, have);
@@ -721,8 +774,8 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
     }
 }
 
-size_t tc_scan_q_smem_bytes(uint32_t stages) {
-    return (size_t)stages * Q1_STAGE_BYTES + (size_t)2 * Q1_M * Q1_POOL_LD * 4 + (size_t)4 * Q1_N * 4 +
+size_t tc_scan_q_smem_bytes(uint32_t stages, uint32_t kbs) {
+    return (size_t)stages * kbs * Q1_STAGE_BYTES + (size_t)2 * Q1_M * Q1_POOL_LD * 4 + (size_t)8 * Q1_N * 4 +
            (size_t)(2 * stages + 5 + 2 * TC_SCHED) * 8 + 16 + (size_t)TC_SCHED * 4;
 }
 
@@ -917,7 +970,13 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             return FVDB_ERR_CUDA;
         }
         const cuuint32_t box_q[2] = {TC_KB_FLOATS, Q1_N};
-        r = enc(&m->tmap_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.rows), gdim, gstride, box_q, estr,
+        const char* dbg_env = getenv("FVDB_TC_DEBUG");
+        cuuint64_t gdim_q[2] = {gdim[0], gdim[1]};
+        cuuint64_t gstride_q[1] = {gstride[0]};
+        if (dbg_env && (atoi(dbg_env) & 2)) {  // layout experiment: view the arena as [n_rows*KB][32]
+            gdim_q[0] = 32; gdim_q[1] = a.n_rows * KB; gstride_q[0] = 128;
+        }
+        r = enc(&m->tmap_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.rows), gdim_q, gstride_q, box_q, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -974,10 +1033,14 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     }
     TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
     if (use_q) {
+        uint32_t kbs = 1;
+        for (uint32_t c : {4u, 3u, 2u}) if (KB % c == 0) { kbs = c; break; }
+        if (const char* e = getenv("FVDB_TC_KBS")) { const uint32_t v = (uint32_t)atoi(e); if (v && KB % v == 0) kbs = v; }
         uint32_t stages = 18;
-        while (stages > 2 && tc_scan_q_smem_bytes(stages) + 1024 > 232448) --stages;
+        while (stages > 2 && tc_scan_q_smem_bytes(stages, kbs) + 1024 > 232448) --stages;
         p.stages = stages;
-        const size_t smem = tc_scan_q_smem_bytes(stages) + 1024;
+        p.kbs = kbs;
+        const size_t smem = tc_scan_q_smem_bytes(stages, kbs) + 1024;
         if (!m->smem_attr_set_q) {
             TCK(cudaFuncSetAttribute(tc_scan_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
             m->smem_attr_set_q = true;

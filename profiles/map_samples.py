@@ -31,4 +31,4 @@ tot = sum(agg.values())
 print('total samples', tot)
 for ln, c in sorted(agg.items(), key=lambda x: -x[1])[:topn]:
     top = sorted(st[ln].items(), key=lambda x: -x[1])[:2]
-    print(f"{ln} {c} {100*c/tot:.1f}% {src[ln-1].strip()[:90] if ln else None}  {top}")
+    print(f"{ln} {c} {100*c/tot:.1f}% {src[ln-1].strip()[:90] if (ln and ln <= len(src)) else None}  {top}")
