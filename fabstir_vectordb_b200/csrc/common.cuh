@@ -49,6 +49,86 @@ struct DeviceError {
     int overflow_flag;  // internal capacity exceeded (bug guard)
 };
 
+#ifdef __CUDACC__
+// Exact L2 in the reference's operation order for one row per lane: this lane walks its own row
+// (16-byte loads, eight in flight) against the query staged in shared memory; the accumulation is
+// the strictly sequential f32 chain of euclidean_distance_scalar (src/core/vector_ops.rs:51-57).
+__device__ __forceinline__ float exact_l2_lane(const float* __restrict__ q_s, const float* __restrict__ row, uint32_t D) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const float4* q4 = reinterpret_cast<const float4*>(q_s);
+    float acc = 0.0f;
+    const uint32_t n4 = D >> 2;
+    uint32_t i = 0;
+    for (; i + 8 <= n4; i += 8) {
+        float4 x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __ldg(r4 + i + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 qq = q4[i + j];
+            float t;
+            t = __fsub_rn(qq.x, x[j].x); acc = __fadd_rn(acc, __fmul_rn(t, t));
+            t = __fsub_rn(qq.y, x[j].y); acc = __fadd_rn(acc, __fmul_rn(t, t));
+            t = __fsub_rn(qq.z, x[j].z); acc = __fadd_rn(acc, __fmul_rn(t, t));
+            t = __fsub_rn(qq.w, x[j].w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+        }
+    }
+    for (; i < n4; ++i) {
+        const float4 xx = __ldg(r4 + i), qq = q4[i];
+        float t;
+        t = __fsub_rn(qq.x, xx.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
+        t = __fsub_rn(qq.y, xx.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
+        t = __fsub_rn(qq.z, xx.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
+        t = __fsub_rn(qq.w, xx.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+    }
+    return __fsqrt_rn(acc);
+}
+
+
+// two rows per lane in lockstep (two independent accumulation chains: same bits, twice the ILP)
+__device__ __forceinline__ void exact_l2_lane2(const float* __restrict__ q_s, const float* __restrict__ row0,
+                                               const float* __restrict__ row1, uint32_t D, float& d0, float& d1) {
+    const float4* a4 = reinterpret_cast<const float4*>(row0);
+    const float4* b4 = reinterpret_cast<const float4*>(row1);
+    const float4* q4 = reinterpret_cast<const float4*>(q_s);
+    float acc0 = 0.0f, acc1 = 0.0f;
+    const uint32_t n4 = D >> 2;
+    uint32_t i = 0;
+    for (; i + 8 <= n4; i += 8) {
+        float4 x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { x[j] = __ldg(a4 + i + j); y[j] = __ldg(b4 + i + j); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 qq = q4[i + j];
+            float t, u;
+            t = __fsub_rn(qq.x, x[j].x); u = __fsub_rn(qq.x, y[j].x);
+            acc0 = __fadd_rn(acc0, __fmul_rn(t, t)); acc1 = __fadd_rn(acc1, __fmul_rn(u, u));
+            t = __fsub_rn(qq.y, x[j].y); u = __fsub_rn(qq.y, y[j].y);
+            acc0 = __fadd_rn(acc0, __fmul_rn(t, t)); acc1 = __fadd_rn(acc1, __fmul_rn(u, u));
+            t = __fsub_rn(qq.z, x[j].z); u = __fsub_rn(qq.z, y[j].z);
+            acc0 = __fadd_rn(acc0, __fmul_rn(t, t)); acc1 = __fadd_rn(acc1, __fmul_rn(u, u));
+            t = __fsub_rn(qq.w, x[j].w); u = __fsub_rn(qq.w, y[j].w);
+            acc0 = __fadd_rn(acc0, __fmul_rn(t, t)); acc1 = __fadd_rn(acc1, __fmul_rn(u, u));
+        }
+    }
+    for (; i < n4; ++i) {
+        const float4 xx = __ldg(a4 + i), yy = __ldg(b4 + i), qq = q4[i];
+        float t, u;
+        t = __fsub_rn(qq.x, xx.x); u = __fsub_rn(qq.x, yy.x);
+        acc0 = __fadd_rn(acc0, __fmul_rn(t, t)); acc1 = __fadd_rn(acc1, __fmul_rn(u, u));
+        t = __fsub_rn(qq.y, xx.y); u = __fsub_rn(qq.y, yy.y);
+        acc0 = __fadd_rn(acc0, __fmul_rn(t, t)); acc1 = __fadd_rn(acc1, __fmul_rn(u, u));
+        t = __fsub_rn(qq.z, xx.z); u = __fsub_rn(qq.z, yy.z);
+        acc0 = __fadd_rn(acc0, __fmul_rn(t, t)); acc1 = __fadd_rn(acc1, __fmul_rn(u, u));
+        t = __fsub_rn(qq.w, xx.w); u = __fsub_rn(qq.w, yy.w);
+        acc0 = __fadd_rn(acc0, __fmul_rn(t, t)); acc1 = __fadd_rn(acc1, __fmul_rn(u, u));
+    }
+    d0 = __fsqrt_rn(acc0);
+    d1 = __fsqrt_rn(acc1);
+}
+#endif  // __CUDACC__
+
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline uint64_t div_up64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -561,6 +562,21 @@ int ivf_scan_exact(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uin
     const uint32_t D = h->dim;
     const uint32_t tq = exact_scan_tq();
     const size_t n_pairs = (size_t)nq * np;
+    uint32_t Ppad = np;
+    if (np > 256) Ppad = (np + 255) / 256 * 256;
+    CK(h->s_partial.ensure((size_t)nq * Ppad * k, 0, st, &h->dev_bytes));
+    CK(cudaMemsetAsync(h->s_partial.p, 0xFF, (size_t)nq * Ppad * k * 8, st));
+    // sparse batch (few queries per probed list): one warp per (query, list) pair instead of
+    // 32-query tiles that would be mostly padding
+    const bool sparse = n_pairs <= (size_t)4 * h->nlist && (size_t)4 * (D * 4 + k * 8) <= 200 * 1024;
+    if (sparse) {
+        if (timed) CK(cudaEventRecord(h->ev_s0, st));
+        CK(launch_exact_pair_scan(coarse, nq, np, h->list_off.p, h->ivf_rows.p, h->ivf_ids.p, d_q, D, Ppad, k, tomb,
+                                  h->tomb_bits, filt, filter_bits, h->s_partial.p, st));
+        if (timed) CK(cudaEventRecord(h->ev_s1, st));
+        h->stats.last_launches += 1;
+        if (d_scanned) CK(cudaMemsetAsync(d_scanned, 0, 8, st));
+    } else {
     const size_t max_items = (size_t)h->nlist + (n_pairs + tq - 1) / tq + 1;
     CK(h->s_list_cnt.ensure(h->nlist + 1, 0, st, &h->dev_bytes));
     CK(h->s_pair_off.ensure(h->nlist + 2, 0, st, &h->dev_bytes));
@@ -573,10 +589,6 @@ int ivf_scan_exact(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uin
                               h->s_pair_off.p, h->s_cursor.p, h->s_pair_q.p, h->s_pair_slot.p,
                               h->s_items.p, d_n_items, d_scanned, st));
     h->stats.last_launches += 3;
-    uint32_t Ppad = np;
-    if (np > 256) Ppad = (np + 255) / 256 * 256;
-    CK(h->s_partial.ensure((size_t)nq * Ppad * k, 0, st, &h->dev_bytes));
-    CK(cudaMemsetAsync(h->s_partial.p, 0xFF, (size_t)nq * Ppad * k * 8, st));
     ExactScanArgs a{};
     a.X = h->ivf_rows.p; a.ids = h->ivf_ids.p; a.Q = d_q; a.D = D;
     a.items = h->s_items.p; a.item_count = d_n_items; a.n_items = 0;
@@ -588,6 +600,7 @@ int ivf_scan_exact(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uin
     CK(launch_exact_scan(a, (uint32_t)max_items, st));
     if (timed) CK(cudaEventRecord(h->ev_s1, st));
     h->stats.last_launches += 1;
+    }
     // sort + truncate(k) (src/ivf/core.rs:677-678)
     if (Ppad > 256) {
         CK(h->s_partial2.ensure((size_t)nq * (Ppad / 256) * k, 0, st, &h->dev_bytes));
@@ -643,18 +656,23 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         if (np > 512) return h->fail(FVDB_ERR_INVALID_ARG, "nprobe > 512 is not supported");
         CK(h->s_ivf_keys.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
         ivf_keys = h->s_ivf_keys.p;
-        // coarse step: all centroid distances, nearest np lists (src/ivf/core.rs:646-656), exact
-        CK(h->s_coarse.ensure((size_t)nq * np, 0, st, &h->dev_bytes));
-        RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_q, nq, np, nullptr, 0, nullptr, 0,
-                           h->s_coarse.p, st));
         used_tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D) && k <= TC_MAX_K && np <= TC_MAX_NPROBE;
+        // coarse step: all centroid distances, nearest np lists (src/ivf/core.rs:646-656); exact
+        // CUDA-core scan, or (TC mode, D <= 384, np <= 128) tensor-core distances + exact verify
+        const bool tc_coarse = used_tc && D <= 384 && np <= TC_MAX_NPROBE_COARSE && !getenv("FVDB_EXACT_COARSE");
+        CK(h->s_coarse.ensure((size_t)nq * np, 0, st, &h->dev_bytes));
+        if (!tc_coarse)
+            RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_q, nq, np, nullptr, 0, nullptr, 0,
+                               h->s_coarse.p, st));
         if (used_tc) {
-            CK(h->s_fb_idx.ensure(nq, 0, st, &h->dev_bytes));
+            CK(h->s_fb_idx.ensure((size_t)2 * nq, 0, st, &h->dev_bytes));
             TcSearchArgs ta{};
             ta.rows = h->ivf_rows.p; ta.ids = h->ivf_ids.p; ta.n_rows = h->ivf_n;
             ta.list_off = h->list_off.p; ta.nlist = h->nlist;
             ta.Q = d_q; ta.nq = nq; ta.D = D; ta.k = k; ta.nprobe = np;
-            ta.coarse_keys = h->s_coarse.p;
+            ta.centroids = h->centroids.p;
+            ta.coarse_keys = tc_coarse ? nullptr : h->s_coarse.p;
+            ta.coarse_out = nullptr;
             ta.tomb = tomb; ta.tomb_bits = h->tomb_bits; ta.filt = filt; ta.filt_bits = filter_bits;
             ta.out_keys = ivf_keys;
             ta.d_scanned_rows = d_scanned;
@@ -698,7 +716,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         if (cudaEventElapsedTime(&sms, h->ev_s0, h->ev_s1) == cudaSuccess) h->stats.last_scan_ms = sms;
         else cudaGetLastError();
     }
-    const uint32_t n_fb = used_tc ? std::min(host_misc[10], nq) : 0;
+    const uint32_t n_fb = used_tc ? std::min(host_misc[10], 2 * nq) : 0;
     if (n_fb) {
         // the tensor-core proof failed for n_fb queries: re-run exactly those on the exact path
         // and patch their rows of the result (rare: only near-duplicate-heavy neighbourhoods)

@@ -318,69 +318,104 @@ __global__ void probe_hist_kernel(const uint64_t* __restrict__ coarse_keys, uint
 // single-CTA exclusive scan over lists: pair offsets and work-item offsets; also emits the
 // items.  tile_q = queries per item (TQ for the exact kernel, the query-tile of the TC kernel).
 // Items of one list are adjacent so a list re-read by a second query tile hits L2.
-__global__ void probe_scan_kernel(const uint32_t* __restrict__ list_cnt,
+// block-wide exclusive scan of a packed u64 (items << 32 | pairs) over 1024 threads;
+// returns the exclusive prefix, *total receives the block total (all threads)
+__device__ __forceinline__ uint64_t block_excl_scan_u64(uint64_t v, uint64_t* warp_tot, uint64_t* total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint64_t t = warp_tot[lane];
+        uint64_t ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t n = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += n;
+        }
+        warp_tot[lane] = ti - t;       // exclusive warp offsets
+        if (lane == 31) warp_tot[32] = ti;
+    }
+    __syncthreads();
+    const uint64_t r = warp_tot[w] + inc - v;
+    *total = warp_tot[32];
+    __syncthreads();
+    return r;
+}
+
+// One CTA: per-list pair offsets and the work-item table.  Lists that are the NEAREST list of
+// at least one query come first in the item order (their scan tightens that query's threshold
+// for every other list); items of one list stay adjacent so a re-read hits L2.
+__global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __restrict__ list_cnt,
                                   const uint32_t* __restrict__ list_off, uint32_t nlist,
                                   uint32_t tile_q, uint32_t* __restrict__ pair_off,
                                   uint32_t* __restrict__ cursor, ScanItem* __restrict__ items,
                                   uint32_t* __restrict__ n_items, uint64_t* __restrict__ scanned_rows) {
-    __shared__ uint32_t s_pairs[1024];
-    __shared__ uint32_t s_items[1024];
-    __shared__ uint32_t carry_pairs, carry_items;
-    __shared__ unsigned long long s_rows;
+    __shared__ uint64_t warp_tot[33];
     const int t = threadIdx.x;
-    if (t == 0) { carry_pairs = 0; carry_items = 0; s_rows = 0; }
-    __syncthreads();
-    // pass 0: lists that are the nearest list of at least one query; pass 1: the others
-    for (int pass = 0; pass < 2; ++pass) {
-        for (uint32_t base = 0; base < nlist; base += 1024) {
-            const uint32_t l = base + t;
-            uint32_t c = 0, len = 0;
-            if (l < nlist) {
-                const uint32_t raw = list_cnt[l];
-                const bool nearest = (raw & NEAREST_BIT) != 0;
-                if ((pass == 0) == nearest) c = raw & ~NEAREST_BIT;
-                len = list_off[l + 1] - list_off[l];
-            }
-            if (len == 0) c = 0;  // nothing to scan in an empty list
-            const uint32_t ni = (c + tile_q - 1) / tile_q;
-            s_pairs[t] = c;
-            s_items[t] = ni;
-            __syncthreads();
-            // Hillis-Steele inclusive scan over 1024 entries
-            for (int o = 1; o < 1024; o <<= 1) {
-                uint32_t a = 0, b = 0;
-                if (t >= o) { a = s_pairs[t - o]; b = s_items[t - o]; }
-                __syncthreads();
-                s_pairs[t] += a;
-                s_items[t] += b;
-                __syncthreads();
-            }
-            const uint32_t p_excl = carry_pairs + s_pairs[t] - c;
-            const uint32_t i_excl = carry_items + s_items[t] - ni;
-            if (l < nlist && c > 0) {
-                pair_off[l] = p_excl;
-                cursor[l] = p_excl;
-                for (uint32_t j = 0; j < ni; ++j) {
-                    ScanItem it;
-                    it.row_begin = list_off[l];
-                    it.row_end = list_off[l + 1];
-                    it.pair_begin = p_excl + j * tile_q;
-                    it.pair_count = min(tile_q, c - j * tile_q);
-                    it.slot = ni;  // items sharing this list (the TC scan keeps such lists in L2)
-                    it.identity = 0;
-                    items[i_excl + j] = it;
-                }
-                atomicAdd(&s_rows, (unsigned long long)len);
-            }
-            __syncthreads();
-            if (t == 1023) { carry_pairs += s_pairs[1023]; carry_items += s_items[1023]; }
-            __syncthreads();
+    uint64_t my_rows = 0;
+    // pass A: totals of the nearest-first group
+    uint64_t near_total = 0;
+    for (uint32_t base = 0; base < nlist; base += 1024) {
+        const uint32_t l = base + t;
+        uint64_t v = 0;
+        if (l < nlist) {
+            const uint32_t raw = list_cnt[l];
+            const uint32_t c = (list_off[l + 1] != list_off[l]) ? (raw & ~NEAREST_BIT) : 0u;
+            if ((raw & NEAREST_BIT) && c) v = ((uint64_t)((c + tile_q - 1) / tile_q) << 32) | c;
         }
+        uint64_t tot;
+        block_excl_scan_u64(v, warp_tot, &tot);
+        near_total += tot;
     }
+    // pass B: offsets
+    uint64_t carry_near = 0, carry_far = near_total;
+    for (uint32_t base = 0; base < nlist; base += 1024) {
+        const uint32_t l = base + t;
+        uint32_t c = 0, len = 0;
+        bool nearest = false;
+        if (l < nlist) {
+            const uint32_t raw = list_cnt[l];
+            len = list_off[l + 1] - list_off[l];
+            c = len ? (raw & ~NEAREST_BIT) : 0u;
+            nearest = (raw & NEAREST_BIT) != 0;
+        }
+        const uint32_t ni = (c + tile_q - 1) / tile_q;
+        const uint64_t v = ((uint64_t)ni << 32) | c;
+        uint64_t tn, tf;
+        const uint64_t en = block_excl_scan_u64(nearest ? v : 0ull, warp_tot, &tn);
+        const uint64_t ef = block_excl_scan_u64(nearest ? 0ull : v, warp_tot, &tf);
+        if (c > 0) {
+            const uint64_t off = nearest ? carry_near + en : carry_far + ef;
+            const uint32_t p_excl = (uint32_t)off, i_excl = (uint32_t)(off >> 32);
+            pair_off[l] = p_excl;
+            cursor[l] = p_excl;
+            for (uint32_t j = 0; j < ni; ++j) {
+                ScanItem it;
+                it.row_begin = list_off[l];
+                it.row_end = list_off[l + 1];
+                it.pair_begin = p_excl + j * tile_q;
+                it.pair_count = min(tile_q, c - j * tile_q);
+                it.slot = ni;  // items sharing this list (the TC scan keeps such lists in L2)
+                it.identity = 0;
+                items[i_excl + j] = it;
+            }
+            my_rows += len;
+        }
+        carry_near += tn;
+        carry_far += tf;
+    }
+    uint64_t rows_total;
+    block_excl_scan_u64(my_rows, warp_tot, &rows_total);
     if (t == 0) {
-        pair_off[nlist] = carry_pairs;
-        *n_items = carry_items;
-        if (scanned_rows) *scanned_rows = s_rows;
+        pair_off[nlist] = (uint32_t)carry_far;
+        *n_items = (uint32_t)(carry_far >> 32);
+        if (scanned_rows) *scanned_rows = rows_total;
     }
 }
 
@@ -416,6 +451,96 @@ cudaError_t launch_probe_bucketing(const uint64_t* coarse_keys, uint32_t nq, uin
     probe_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, nprobe,
                                                                    list_off, cursor, pair_q,
                                                                    pair_slot);
+    return cudaGetLastError();
+}
+
+// Sparse exact scan: one CTA (4 warps) per (query, probed list) pair — for small batches
+// (single-query search, the fallback queries of the tensor-core mode) where a 32-query tile would
+// be mostly padding.  Lane = row; every lane walks its own row in the reference's operation
+// order with eight 16-byte loads in flight; each warp keeps a sorted top-k, warp 0 merges them.
+__global__ void __launch_bounds__(128) exact_pair_scan_kernel(const uint64_t* __restrict__ coarse_keys, uint32_t n_pairs,
+                                                              const uint32_t* __restrict__ list_off,
+                                                              const float* __restrict__ X, const uint32_t* __restrict__ ids,
+                                                              const float* __restrict__ Q, uint32_t D, uint32_t nprobe,
+                                                              uint32_t P, uint32_t k, const uint64_t* __restrict__ tomb,
+                                                              uint64_t tomb_bits, const uint64_t* __restrict__ filt,
+                                                              uint64_t filt_bits, uint64_t* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char pair_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t pair = blockIdx.x;
+    float* q_s = reinterpret_cast<float*>(pair_smem);
+    uint64_t* list = reinterpret_cast<uint64_t*>(pair_smem + (((size_t)D * sizeof(float) + 15) & ~(size_t)15)) + (size_t)w * k;
+    const uint32_t q = pair / nprobe, slot = pair % nprobe;
+    const uint64_t ck = coarse_keys[pair];
+    if (ck == KEY_NONE) return;  // partial pre-filled with KEY_NONE
+    const uint32_t l = key_id(ck);
+    const uint32_t b = list_off[l], e = list_off[l + 1];
+    for (uint32_t d = threadIdx.x; d < D; d += 128) q_s[d] = __ldg(Q + (size_t)q * D + d);
+    for (uint32_t i = lane; i < k; i += 32) list[i] = KEY_NONE;
+    __syncthreads();
+    uint64_t thr = KEY_NONE;
+    for (uint32_t r0 = b + w * 32; r0 < e; r0 += 128) {
+        const uint32_t r = r0 + lane;
+        uint64_t key = KEY_NONE;
+        if (r < e) {
+            const uint32_t id = ids ? ids[r] : r;
+            bool live = true;
+            if (tomb && bit_test(tomb, tomb_bits, id)) live = false;
+            else if (filt && !bit_test(filt, filt_bits, id)) live = false;
+            if (live) {
+                float dist;
+                if ((D & 3) == 0) {
+                    dist = exact_l2_lane(q_s, X + (size_t)r * D, D);
+                } else {
+                    const float* xr = X + (size_t)r * D;
+                    float acc = 0.0f;
+                    for (uint32_t i = 0; i < D; ++i) {
+                        const float t = __fsub_rn(q_s[i], __ldg(xr + i));
+                        acc = __fadd_rn(acc, __fmul_rn(t, t));
+                    }
+                    dist = __fsqrt_rn(acc);
+                }
+                key = make_key(dist, id);
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, key < thr);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            const uint64_t cand = __shfl_sync(0xffffffffu, key, src);
+            warp_insert(list, (int)k, cand, lane);
+            thr = list[k - 1];
+            if (lane == src) key = KEY_NONE;
+            m = __ballot_sync(0xffffffffu, key < thr);
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        // fold the other warps' lists into mine (ascending lists: stop at the first non-improving key)
+        uint64_t* base = reinterpret_cast<uint64_t*>(pair_smem + (((size_t)D * sizeof(float) + 15) & ~(size_t)15));
+        for (int ow = 1; ow < 4; ++ow) {
+            const uint64_t* other = base + (size_t)ow * k;
+            for (uint32_t i = 0; i < k; ++i) {
+                const uint64_t cand = other[i];
+                if (cand >= list[k - 1]) break;
+                warp_insert(list, (int)k, cand, lane);
+            }
+        }
+        uint64_t* dst = partial + ((size_t)q * P + slot) * k;
+        for (uint32_t i = lane; i < k; i += 32) dst[i] = list[i];
+    }
+}
+
+cudaError_t launch_exact_pair_scan(const uint64_t* coarse_keys, uint32_t nq, uint32_t nprobe, const uint32_t* list_off,
+                                   const float* X, const uint32_t* ids, const float* Q, uint32_t D, uint32_t P,
+                                   uint32_t k, const uint64_t* tomb, uint64_t tomb_bits, const uint64_t* filt,
+                                   uint64_t filt_bits, uint64_t* partial, cudaStream_t stream) {
+    const uint32_t n_pairs = nq * nprobe;
+    if (n_pairs == 0) return cudaSuccess;
+    const size_t smem = (((size_t)D * sizeof(float) + 15) & ~(size_t)15) + (size_t)4 * k * sizeof(uint64_t);
+    cudaError_t e = cudaFuncSetAttribute(exact_pair_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    exact_pair_scan_kernel<<<n_pairs, 128, smem, stream>>>(coarse_keys, n_pairs, list_off, X, ids, Q, D, nprobe,
+                                                                     P, k, tomb, tomb_bits, filt, filt_bits, partial);
     return cudaGetLastError();
 }
 

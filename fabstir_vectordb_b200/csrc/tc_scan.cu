@@ -60,6 +60,8 @@ struct TcScanParams {
     uint32_t* work_counter;  // dynamic tile scheduler: next unclaimed work item
     uint32_t stages;
     uint32_t kbs;            // kernel Q: k-blocks (128 B each) per pipeline stage
+    float* dense_out;        // kernel Q dense mode (coarse step): out[q * dense_ld + row] = approx d2
+    uint32_t dense_ld;
     uint32_t debug;          // bit 0: skip the epilogue math (pipeline ceiling experiment)
 };
 constexpr int TC_SCHED = 4;          // depth of the in-CTA work-item ring
@@ -623,7 +625,7 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 if (it.identity) { qi = it.pair_begin + qslot_in_item; sl = it.slot; }
                 else { qi = p.pair_q[it.pair_begin + qslot_in_item]; sl = p.pair_slot[it.pair_begin + qslot_in_item]; }
                 qn = p.qnorm[qi];
-                thrp = __uint_as_float(*(volatile uint32_t*)(p.thr_g + qi)) - qn;
+                if (p.thr_g) thrp = __uint_as_float(*(volatile uint32_t*)(p.thr_g + qi)) - qn;
             }
             float xnext[2];
             load_xn(it.row_begin, it.row_end, xnext);   // first tile's norms, behind the query load
@@ -667,7 +669,7 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 if (rt + Q1_N < it.row_end) load_xn(rt + Q1_N, it.row_end, xnext);  // prefetch the next tile's norms
                 // thresholds tightened meanwhile by CTAs scanning other lists of the same query
                 uint32_t shared_thr = F32_INF_BITS;
-                if (have) shared_thr = *(volatile uint32_t*)(p.thr_g + qi);
+                if (have && p.thr_g) shared_thr = *(volatile uint32_t*)(p.thr_g + qi);
                 const uint32_t fph = buf ? fph1 : fph0;
                 mbar_wait(bar_tfull + 8 * buf, fph);
                 if (buf) fph1 ^= 1; else fph0 ^= 1;
@@ -684,6 +686,22 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                         xn[4 * j4 + 0] = t4.x; xn[4 * j4 + 1] = t4.y; xn[4 * j4 + 2] = t4.z; xn[4 * j4 + 3] = t4.w;
                     }
                     tmem_ld_wait();
+                    if (p.dense_out) {
+                        // coarse step: keep every approximate distance (rows = centroids)
+                        if (have) {
+                            float* dst = p.dense_out + (size_t)qi * p.dense_ld + (rt - it.row_begin + it.slot) + c0;
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                float4 o;
+                                o.x = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 0]), xn[4 * j4 + 0]) + qn;
+                                o.y = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 1]), xn[4 * j4 + 1]) + qn;
+                                o.z = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 2]), xn[4 * j4 + 2]) + qn;
+                                o.w = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 3]), xn[4 * j4 + 3]) + qn;
+                                *reinterpret_cast<float4*>(dst + 4 * j4) = o;
+                            }
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float v = fmaf(-2.0f, __uint_as_float(acc[j]), xn[j]);  // |x|^2 - 2 q.x
@@ -736,7 +754,7 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 strip ^= 1;
             }
             // ---- item epilogue: final merge, publish the shortlists, tighten shared thresholds ----
-            unsigned todo = __ballot_sync(0xffffffffu, have);
+            unsigned todo = __ballot_sync(0xffffffffu, have && p.dense_out == nullptr);
             while (todo) {
                 uint32_t mm[4], nn[4], qis[4], sls[4];
                 bool act[4];
@@ -785,6 +803,7 @@ size_t tc_scan_smem_bytes(uint32_t KB, uint32_t stages) {
            (size_t)TC_SCHED * 4;
 }
 
+
 // ---- small support kernels ----------------------------------------------------------------------
 __global__ void row_norms_kernel(const float* __restrict__ x, uint64_t n, uint32_t D, float* __restrict__ out,
                                  uint32_t* __restrict__ max_bits) {
@@ -825,31 +844,19 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
                                                      const uint32_t* __restrict__ xmax_bits, uint32_t nq, uint32_t D,
                                                      uint32_t k, uint64_t* __restrict__ out_keys,
                                                      uint32_t* __restrict__ fb_count, uint32_t* __restrict__ fb_idx) {
-    __shared__ float xs[4][32][33];
-    __shared__ float qs[4][32];
+    extern __shared__ __align__(16) float q_sm[];  // [4][D]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * 4 + w;
     if (q >= nq) return;
+    float* q_s = q_sm + (size_t)w * D;
+    for (uint32_t d = lane; d < D; d += 32) q_s[d] = __ldg(Q + (size_t)q * D + d);
+    __syncwarp();
     const uint64_t akey = shortlist[(size_t)q * TC_KP + lane];
     const bool have = akey != KEY_NONE;
     const uint32_t pos = have ? (uint32_t)akey : 0u;
-    float acc = 0.0f;
-    for (uint32_t kc = 0; kc < D; kc += 32) {
-        for (int r = 0; r < 32; ++r) {
-            const uint32_t pr = __shfl_sync(0xffffffffu, pos, r);
-            xs[w][r][lane] = __ldg(rows + (size_t)pr * D + kc + lane);
-        }
-        qs[w][lane] = __ldg(Q + (size_t)q * D + kc + lane);
-        __syncwarp();
-#pragma unroll 8
-        for (int d = 0; d < 32; ++d) {
-            const float t = __fsub_rn(qs[w][d], xs[w][lane][d]);
-            acc = __fadd_rn(acc, __fmul_rn(t, t));
-        }
-        __syncwarp();
-    }
+    const float dist = exact_l2_lane(q_s, rows + (size_t)pos * D, D);
     uint64_t ekey = KEY_NONE;
-    if (have) ekey = make_key(__fsqrt_rn(acc), ids[pos]);
+    if (have) ekey = make_key(dist, ids[pos]);
     ekey = warp_sort32(ekey, lane);
     if ((uint32_t)lane < k) out_keys[(size_t)q * k + lane] = ekey;
     // proof
@@ -863,6 +870,155 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
         if (kth != KEY_NONE) {
             const float dk = key_dist(kth);
             ok = (a_last - eps) > dk * dk * 1.000001f;
+        }
+        if (!ok) fb_idx[atomicAdd(fb_count, 1u)] = q;
+    }
+}
+
+
+// ---- tensor-core coarse step (src/ivf/core.rs:646-656) ---------------------------------------
+// 1. kernel Q in dense mode writes approx d2(query, centroid) for every pair   [nq][ld]
+// 2. coarse_select_kernel: per query, the KC = nprobe + 8 approximately nearest centroids are
+//    extracted, their distances recomputed exactly (reference operation order), sorted by
+//    (distance, list id) and the first nprobe kept.  Proof: the next approximate value minus the
+//    TF32 error bound must exceed the exact nprobe-th distance^2, else the query is handed to the
+//    exact path (fallback list).
+
+// identity work items for the dense pass: (query group of 128) x (row chunk); `slot` carries the
+// row offset of the chunk so the kernel addresses the dense matrix with absolute centroid ids
+__global__ void coarse_items_kernel(ScanItem* items, uint32_t nq, uint32_t nlist, uint32_t chunk_rows,
+                                    uint32_t n_chunks, uint32_t* n_items) {
+    const uint32_t n_qg = (nq + Q1_M - 1) / Q1_M;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_items = n_qg * n_chunks;
+    if (i >= n_qg * n_chunks) return;
+    const uint32_t g = i / n_chunks, c = i % n_chunks;
+    ScanItem it;
+    it.row_begin = c * chunk_rows;
+    it.row_end = min(nlist, (c + 1) * chunk_rows);
+    it.pair_begin = g * Q1_M;
+    it.pair_count = min((uint32_t)Q1_M, nq - g * Q1_M);
+    it.slot = it.row_begin;
+    it.identity = 1;
+    if (it.row_begin >= it.row_end) it.pair_count = 0;
+    items[i] = it;
+}
+
+template <int T>
+__global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restrict__ dense, uint32_t ld,
+                                                            const float* __restrict__ centroids,
+                                                            const float* __restrict__ Q, const float* __restrict__ qnorm,
+                                                            const uint32_t* __restrict__ cmax_bits, uint32_t nq,
+                                                            uint32_t nlist, uint32_t D, uint32_t np, uint32_t KC,
+                                                            uint64_t* __restrict__ out_keys,
+                                                            uint32_t* __restrict__ fb_count, uint32_t* __restrict__ fb_idx) {
+    extern __shared__ __align__(16) float q_sm[];  // [4][D]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * 4 + w;
+    if (q >= nq) return;
+    float* q_s = q_sm + (size_t)w * D;
+    for (uint32_t d = lane; d < D; d += 32) q_s[d] = __ldg(Q + (size_t)q * D + d);
+    // lane-local sorted top-T of this lane's strided share: (approx d2 bits, list id) pairs
+    uint32_t ld2[T], lid[T];
+#pragma unroll
+    for (int i = 0; i < T; ++i) { ld2[i] = 0xFFFFFFFFu; lid[i] = 0xFFFFFFFFu; }
+    const float* row = dense + (size_t)q * ld;
+    for (uint32_t c = lane; c < nlist; c += 32) {
+        uint32_t kd = __float_as_uint(fmaxf(row[c], 0.0f)), ki = c;
+        if (kd < ld2[T - 1]) {  // ids ascend within a lane, so equal d2 keeps the earlier (lower) id first
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                const bool sw = kd < ld2[i];
+                const uint32_t td = sw ? ld2[i] : kd, ti = sw ? lid[i] : ki;
+                ld2[i] = sw ? kd : ld2[i];
+                lid[i] = sw ? ki : lid[i];
+                kd = td; ki = ti;
+            }
+        }
+    }
+    __syncwarp();
+    // extract the KC smallest (d2, id) across lanes with two REDUX per round; round r's winner is
+    // kept by lane r % 32 in slot r / 32
+    uint32_t cand[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    uint32_t taken = 0, next_d2 = 0xFFFFFFFFu;
+    for (uint32_t r = 0; r <= KC; ++r) {
+        const uint32_t md = __reduce_min_sync(0xffffffffu, ld2[0]);
+        if (r == KC) { next_d2 = md; break; }
+        if (md == 0xFFFFFFFFu) break;
+        const uint32_t mi = __reduce_min_sync(0xffffffffu, ld2[0] == md ? lid[0] : 0xFFFFFFFFu);
+        if (ld2[0] == md && lid[0] == mi) {
+#pragma unroll
+            for (int i = 0; i + 1 < T; ++i) { ld2[i] = ld2[i + 1]; lid[i] = lid[i + 1]; }
+            ld2[T - 1] = 0xFFFFFFFFu; lid[T - 1] = 0xFFFFFFFFu;
+            ++taken;
+        }
+        if ((r & 31) == (uint32_t)lane) {
+            if ((r >> 5) == 0) cand[0] = mi;
+            else if ((r >> 5) == 1) cand[1] = mi;
+            else if ((r >> 5) == 2) cand[2] = mi;
+            else cand[3] = mi;
+        }
+    }
+    // a lane whose T local entries were all consumed may have dropped keys below next_d2
+    const bool uncertain = __any_sync(0xffffffffu, taken == (uint32_t)T && nlist > (uint32_t)T * 32u);
+    // exact distances of the candidates (reference operation order), then sort by (distance, id)
+    uint64_t ex[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ch += 2) {
+        ex[ch] = KEY_NONE;
+        ex[ch + 1] = KEY_NONE;
+        if ((uint32_t)ch * 32 < KC) {  // warp-uniform; two candidate rows per lane in one pass (ILP)
+            const bool h0 = cand[ch] != 0xFFFFFFFFu, h1 = cand[ch + 1] != 0xFFFFFFFFu;
+            const uint32_t c0 = h0 ? cand[ch] : 0u, c1 = h1 ? cand[ch + 1] : 0u;
+            float d0, d1;
+            exact_l2_lane2(q_s, centroids + (size_t)c0 * D, centroids + (size_t)c1 * D, D, d0, d1);
+            if (h0) ex[ch] = make_key(d0, c0);
+            if (h1) ex[ch + 1] = make_key(d1, c1);
+            ex[ch] = warp_sort32(ex[ch], lane);
+            ex[ch + 1] = warp_sort32(ex[ch + 1], lane);
+        }
+    }
+    // merge-split passes over the sorted 32-chunks: afterwards ex[0] <= ex[1] <= ... globally
+#pragma unroll
+    for (int a2 = 0; a2 < 3; ++a2) {
+#pragma unroll
+        for (int b2 = 3; b2 > a2; --b2) {
+            if ((uint32_t)b2 * 32 >= KC) continue;
+            const uint64_t rev = shfl64(ex[b2], 31 - lane);
+            uint64_t lo = ex[b2 - 1] < rev ? ex[b2 - 1] : rev;
+            uint64_t hi = ex[b2 - 1] < rev ? rev : ex[b2 - 1];
+#pragma unroll
+            for (int j = 16; j > 0; j >>= 1) {
+                const uint64_t ol = shfl_xor64(lo, j), oh = shfl_xor64(hi, j);
+                const bool lower = (lane & j) == 0;
+                lo = lower ? (lo < ol ? lo : ol) : (lo < ol ? ol : lo);
+                hi = lower ? (hi < oh ? hi : oh) : (hi < oh ? oh : hi);
+            }
+            ex[b2 - 1] = lo;
+            ex[b2] = hi;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t o = i * 32 + lane;
+        if (o < np) out_keys[(size_t)q * np + o] = ex[i];
+    }
+    // proof: every centroid outside the candidate set has approx d2 >= next_d2
+    uint64_t kth = KEY_NONE;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if ((int)((np - 1) >> 5) == i) kth = shfl64(ex[i], (int)((np - 1) & 31));
+    if (lane == 0) {
+        bool ok = true;
+        if (uncertain) ok = false;
+        else if (next_d2 != 0xFFFFFFFFu) {
+            const float a_next = __uint_as_float(next_d2);
+            const float cmax = sqrtf(__uint_as_float(*cmax_bits));
+            const float eps = 1.05f * 0.00390625f * sqrtf(qnorm[q]) * cmax + 3.1e-5f * a_next + 1e-30f;
+            ok = false;
+            if (kth != KEY_NONE) {
+                const float dk = key_dist(kth);
+                ok = (a_next - eps) > dk * dk * 1.000001f;
+            }
         }
         if (!ok) fb_idx[atomicAdd(fb_count, 1u)] = q;
     }
@@ -910,6 +1066,12 @@ struct TcScratchImpl {
     Buf<uint32_t> thr_g, list_cnt, pair_off, cursor, pair_q, pair_slot, n_items;
     Buf<ScanItem> items;
     Buf<uint64_t> partial, shortlist;
+    Buf<float> cnorm, dense;
+    Buf<uint64_t> coarse;
+    Buf<ScanItem> citems;
+    CUtensorMap tmap_cent;   // centroid table, box 32 floats x 64 rows
+    const float* tmap_cent_ptr = nullptr;
+    uint32_t tmap_cent_n = 0;
     CUtensorMap tmap_arena;  // box 32 floats x 128 rows (kernel R)
     CUtensorMap tmap_q;      // box 32 floats x 64 rows  (kernel Q)
     bool smem_attr_set_q = false;
@@ -926,6 +1088,7 @@ void tc_release(TcScratch& s) {
     m->xnorm.release(); m->qnorm.release(); m->misc.release(); m->thr_g.release(); m->list_cnt.release();
     m->pair_off.release(); m->cursor.release(); m->pair_q.release(); m->pair_slot.release(); m->n_items.release();
     m->items.release(); m->partial.release(); m->shortlist.release();
+    m->cnorm.release(); m->dense.release(); m->coarse.release(); m->citems.release();
     delete m;
     s.impl = nullptr;
 }
@@ -951,7 +1114,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     TCK(m->misc.ensure(16, dev_bytes));
     if (s.arena_dirty || m->tmap_rows != a.rows || m->tmap_n != a.n_rows) {
         TCK(m->xnorm.ensure(a.n_rows, dev_bytes));
-        TCK(cudaMemsetAsync(m->misc.p, 0, 16 * 4, st));
+        TCK(cudaMemsetAsync(m->misc.p, 0, 4, st));  // [0] = max |x|^2 bits; [4] = max |c|^2 bits (coarse)
         const uint32_t blocks = (uint32_t)std::min<uint64_t>((a.n_rows * 32 + 255) / 256, (uint64_t)a.sm_count * 16);
         row_norms_kernel<<<blocks, 256, 0, st>>>(a.rows, a.n_rows, D, m->xnorm.p, m->misc.p);
         TCK(cudaGetLastError());
@@ -1015,7 +1178,76 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         TCK(cudaGetLastError());
         (*launches) += 2;
     }
-    TCK(launch_probe_bucketing(a.coarse_keys, nq, np, a.list_off, a.nlist, tile_q, m->list_cnt.p, m->pair_off.p,
+    const uint64_t* coarse_keys = a.coarse_keys;
+    if (!coarse_keys) {
+        if (!use_q || np > TC_MAX_NPROBE_COARSE) { if (err) *err = "TC coarse step unsupported for this shape"; return FVDB_ERR_INVALID_ARG; }
+        // centroid norms + TMA descriptor of the centroid table
+        if (s.centroids_dirty || m->tmap_cent_ptr != a.centroids || m->tmap_cent_n != a.nlist) {
+            TCK(m->cnorm.ensure(a.nlist, dev_bytes));
+            TCK(cudaMemsetAsync(m->misc.p + 4, 0, 4, st));
+            const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)a.nlist * 32 + 255) / 256, (uint64_t)a.sm_count * 8);
+            row_norms_kernel<<<blocks, 256, 0, st>>>(a.centroids, a.nlist, D, m->cnorm.p, m->misc.p + 4);
+            TCK(cudaGetLastError());
+            (*launches)++;
+            EncodeTiledFn enc = get_encode_fn();
+            if (!enc) { if (err) *err = "cuTensorMapEncodeTiled unavailable"; return FVDB_ERR_CUDA; }
+            const cuuint64_t gdim[2] = {D, a.nlist};
+            const cuuint64_t gstride[1] = {(cuuint64_t)D * 4};
+            const cuuint32_t box[2] = {TC_KB_FLOATS, Q1_N};
+            const cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(&m->tmap_cent, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.centroids), gdim,
+                             gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled (centroids) failed"; return FVDB_ERR_CUDA; }
+            m->tmap_cent_ptr = a.centroids;
+            m->tmap_cent_n = a.nlist;
+            s.centroids_dirty = false;
+        }
+        const uint32_t ld = (a.nlist + 63) / 64 * 64;
+        const uint32_t n_qg = (nq + Q1_M - 1) / Q1_M;
+        const uint32_t tiles = ld / 64;
+        uint32_t n_chunks = std::max(1u, std::min(tiles, ((uint32_t)a.sm_count + n_qg - 1) / n_qg));
+        const uint32_t chunk_rows = ((tiles + n_chunks - 1) / n_chunks) * 64;
+        n_chunks = (ld + chunk_rows - 1) / chunk_rows;
+        const uint32_t n_citems = n_qg * n_chunks;
+        TCK(m->dense.ensure((size_t)nq * ld, dev_bytes));
+        TCK(m->coarse.ensure((size_t)nq * np, dev_bytes));
+        TCK(m->citems.ensure(n_citems, dev_bytes));
+        coarse_items_kernel<<<(n_citems + 127) / 128, 128, 0, st>>>(m->citems.p, nq, a.nlist, chunk_rows, n_chunks,
+                                                                     m->n_items.p + 2);
+        TCK(cudaGetLastError());
+        TcScanParams cp{};
+        cp.items = m->citems.p; cp.item_count = m->n_items.p + 2; cp.Q = a.Q; cp.qnorm = m->qnorm.p; cp.D = D; cp.KB = KB;
+        cp.xnorm = m->cnorm.p; cp.ids = nullptr; cp.P = 1; cp.partial = nullptr; cp.thr_g = nullptr;
+        cp.work_counter = m->n_items.p + 3;
+        TCK(cudaMemsetAsync(cp.work_counter, 0, 4, st));
+        cp.dense_out = m->dense.p; cp.dense_ld = ld;
+        uint32_t kbs = 1;
+        for (uint32_t c : {4u, 3u, 2u}) if (KB % c == 0) { kbs = c; break; }
+        uint32_t stages = 18;
+        while (stages > 2 && tc_scan_q_smem_bytes(stages, kbs) + 1024 > 232448) --stages;
+        cp.stages = stages; cp.kbs = kbs;
+        if (!m->smem_attr_set_q) {
+            TCK(cudaFuncSetAttribute(tc_scan_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+            m->smem_attr_set_q = true;
+        }
+        tc_scan_q_kernel<<<std::min<uint32_t>((uint32_t)a.sm_count, n_citems), TC_THREADS,
+                           tc_scan_q_smem_bytes(stages, kbs) + 1024, st>>>(m->tmap_cent, cp);
+        TCK(cudaGetLastError());
+        // candidate set: nprobe + 32 (the proof needs the next approx value to clear the exact
+        // nprobe-th by the TF32 bound; centroid distances are dense, so a generous margin)
+        const uint32_t KC = std::min(np + 32, 128u);
+        const size_t sel_smem = (size_t)4 * D * sizeof(float);
+        // 16 local entries per lane: P(one lane holds >= 16 of the KC nearest) is negligible
+            coarse_select_kernel<16><<<(nq + 3) / 4, 128, sel_smem, st>>>(m->dense.p, ld, a.centroids, a.Q, m->qnorm.p,
+                                                                          m->misc.p + 4, nq, a.nlist, D, np, KC,
+                                                                          m->coarse.p, a.d_fallback_count, a.d_fallback_idx);
+        TCK(cudaGetLastError());
+        (*launches) += 3;
+        coarse_keys = m->coarse.p;
+        if (a.coarse_out) TCK(cudaMemcpyAsync(a.coarse_out, m->coarse.p, (size_t)nq * np * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    TCK(launch_probe_bucketing(coarse_keys, nq, np, a.list_off, a.nlist, tile_q, m->list_cnt.p, m->pair_off.p,
                                m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st));
     (*launches) += 3;
     TCK(cudaMemsetAsync(m->partial.p, 0xFF, n_pairs * TC_KP * sizeof(uint64_t), st));
@@ -1069,7 +1301,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
 
     // ---- merge the per-(query, probe) shortlists, exact re-rank, proof ----
     TCK(launch_merge_partials(m->partial.p, nq, np, TC_KP, m->shortlist.p, st));
-    rerank_kernel<<<(nq + 3) / 4, 128, 0, st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k,
+    rerank_kernel<<<(nq + 3) / 4, 128, (size_t)4 * D * sizeof(float), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k,
                                                a.out_keys, a.d_fallback_count, a.d_fallback_idx);
     TCK(cudaGetLastError());
     (*launches) += 2;

@@ -23,6 +23,7 @@ struct TcScratch {
 
 constexpr uint32_t TC_MAX_K = 16;        // largest k served by the 32-entry shortlist
 constexpr uint32_t TC_MAX_NPROBE = 256;  // partial lists merged in one pass
+constexpr uint32_t TC_MAX_NPROBE_COARSE = 96;  // tensor-core coarse step (else exact coarse)
 constexpr uint32_t TC_TILE_Q = 64;       // queries per work item of the TC scan
 
 struct TcSearchArgs {
@@ -33,7 +34,10 @@ struct TcSearchArgs {
     uint32_t nlist;
     const float* Q;           // [nq x D]
     uint32_t nq, D, k, nprobe;
-    const uint64_t* coarse_keys;  // [nq][nprobe] exact coarse ranking (low 32 bits = list id)
+    const float* centroids;       // [nlist x D]
+    const uint64_t* coarse_keys;  // [nq][nprobe] exact coarse ranking (low 32 bits = list id), or
+                                  // nullptr: computed here on the tensor cores (nprobe <= 128)
+    uint64_t* coarse_out;         // when computed here: [nq][nprobe] exact keys (may be nullptr)
     const uint64_t* tomb;
     uint64_t tomb_bits;
     const uint64_t* filt;
