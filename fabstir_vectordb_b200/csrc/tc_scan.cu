@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "../../include/fvdb.h"
 #include "kernels.cuh"
@@ -60,9 +61,12 @@ struct TcScanParams {
     uint32_t* work_counter;  // dynamic tile scheduler: next unclaimed work item
     uint32_t stages;
     uint32_t kbs;            // kernel Q: k-blocks (128 B each) per pipeline stage
+    const float* rows_raw;   // layout experiment (debug bit 4): arena base for 1-D bulk copies
+    uint64_t rows_bytes;
     float* dense_out;        // kernel Q dense mode (coarse step): out[q * dense_ld + row] = approx d2
     uint32_t dense_ld;
     uint32_t debug;          // bit 0: skip the epilogue math (pipeline ceiling experiment)
+    unsigned long long* prof; // debug bit 7: [grid][3 roles][8] cycle counters (stopwatch laps per role)
 };
 constexpr int TC_SCHED = 4;          // depth of the in-CTA work-item ring
 constexpr uint32_t ITEM_END = 0xFFFFFFFFu;
@@ -396,6 +400,8 @@ constexpr int Q1_STAGE_BYTES = Q1_N * 128;      // 8 KB
 constexpr int Q1_POOL_LD = 65;                  // words per query: [0,32) sorted, [32,64) pending, +1 pad
 constexpr int Q1_TMEM_COLS = 512;
 constexpr int Q1_ACC_COL = 384;                 // accumulators at columns 384..511
+constexpr int Q1_NSLOT = 16;                    // ring of per-tile row-norm strips (see the producer)
+constexpr int Q1_XP_LD = 36;                    // floats per query row of the prologue transposition buffer
 
 struct QPool {
     uint32_t* d;  // [Q1_M][Q1_POOL_LD] approx d2 bits
@@ -437,6 +443,10 @@ __device__ __forceinline__ void q1_merge4(const QPool& pool, const uint32_t (&m)
     warp_merge32x4(lst, nw, lane);
 }
 
+// stopwatch lap: the cycles since the previous lap of this role are charged to category i
+#define Q1_LAP(i) do { if (p.prof) { const long long n_ = clock64(); lap[i] += (unsigned long long)(n_ - tl); tl = n_; } } while (0)
+#define Q1_LAP_DUMP(role) do { if (p.prof && lane == 0) { for (int i_ = 0; i_ < 8; ++i_) p.prof[((size_t)blockIdx.x * 3 + (role)) * 8 + i_] = lap[i_]; } } while (0)
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -450,9 +460,9 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
     QPool pool;
     pool.d = reinterpret_cast<uint32_t*>(ring + (size_t)STAGES * STAGE_BYTES);
     pool.p = pool.d + Q1_M * Q1_POOL_LD;
-    float* xn_w = reinterpret_cast<float*>(pool.p + Q1_M * Q1_POOL_LD);             // [4][2][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xn_w + 8 * Q1_N);
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5 + 2 * TC_SCHED);
+    float* xn_ring = reinterpret_cast<float*>(pool.p + Q1_M * Q1_POOL_LD);          // [Q1_NSLOT][64] tile row norms
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xn_ring + Q1_NSLOT * Q1_N);
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5 + 2 * TC_SCHED + Q1_NSLOT);
     uint32_t* sched_s = tmem_ptr_s + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -463,12 +473,14 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
     const uint32_t bar_qready = bar_tempty + 16;
     const uint32_t bar_sfull = bar_qready + 8;
     const uint32_t bar_sempty = bar_sfull + 8 * TC_SCHED;
+    const uint32_t bar_nfull = bar_sempty + 8 * TC_SCHED;   // [Q1_NSLOT] norms of a tile are in shared memory
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
+        for (int i = 0; i < Q1_NSLOT; ++i) mbar_init(bar_nfull + 8 * i, 1);
         mbar_init(bar_tfull, 1);
         mbar_init(bar_tfull + 8, 1);
         mbar_init(bar_tempty, 4);
@@ -491,14 +503,22 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
     const uint32_t n_items = *p.item_count;
+    unsigned long long lap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tl = clock64();
 
     if (warp == 0) {
         // ============ TMA producer + tile scheduler (whole warp converged, one lane issues) ============
-        uint32_t stage = 0, phase = 0, ss = 0, sphase = 0;
+        // It also stages the |x|^2 strip of every row tile (masked rows / rows past the list end
+        // = +inf) in a shared-memory ring, so the epilogue never waits on a global load.  Slot
+        // reuse needs no barrier: while this warp fills tile T the MMA warp has started a tile
+        // >= T - ceil(STAGES/NST) - 1, hence the epilogue has finished tile >= T - ceil(..) - 3;
+        // the launcher keeps ceil(STAGES/NST) + 3 < Q1_NSLOT.
+        uint32_t stage = 0, phase = 0, ss = 0, sphase = 0, tcount = 0;
         const uint64_t hint_first = 0x12F0000000000000ull;
         const uint64_t hint_normal = 0x1000000000000000ull;
         const uint32_t ring_base = smem_u32(ring);
         while (true) {
+            Q1_LAP(3);
             mbar_wait(bar_sempty + 8 * ss, sphase ^ 1);
             uint32_t item = 0;
             if (lane == 0) {
@@ -509,13 +529,36 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
             }
             item = __shfl_sync(0xffffffffu, item, 0);
             if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            Q1_LAP(0);
             if (item == ITEM_END) break;
             const ScanItem it = p.items[item];
             if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+            lap[6] += 1;
+            Q1_LAP(1);
             const uint64_t hint = (!it.identity && it.slot > 1) ? hint_normal : hint_first;
             for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
+                float xnv[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t pos = rt + h * 32 + lane;
+                    float xn = __uint_as_float(F32_INF_BITS);
+                    if (pos < it.row_end) {
+                        bool live = true;
+                        if (p.tomb || p.filt) {
+                            const uint32_t id = p.ids[pos];
+                            if (p.tomb && bit_test(p.tomb, p.tomb_bits, id)) live = false;
+                            else if (p.filt && !bit_test(p.filt, p.filt_bits, id)) live = false;
+                        }
+                        if (live) xn = __ldg(p.xnorm + pos);
+                    }
+                    xnv[h] = xn;
+                }
+                __syncwarp();
+                lap[7] += 1;
                 for (uint32_t st = 0; st < NST; ++st) {
+                    Q1_LAP(3);
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    Q1_LAP(2);
                     if (elect_one()) {
                         const uint32_t fb = bar_full + 8 * stage;
                         const uint32_t dst = ring_base + stage * STAGE_BYTES;
@@ -531,33 +574,50 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                {
+                    const uint32_t slot = tcount & (Q1_NSLOT - 1);
+                    xn_ring[slot * Q1_N + lane] = xnv[0];
+                    xn_ring[slot * Q1_N + 32 + lane] = xnv[1];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_nfull + 8 * slot);
+                    ++tcount;
+                }
             }
         }
+        Q1_LAP_DUMP(0);
     } else if (warp == 1) {
         // ============ MMA issuer (whole warp converged, one elected lane issues) ============
         uint32_t stage = 0, phase = 0, buf = 0, qphase = 0, ss = 0, sphase = 0, tph0 = 0, tph1 = 0;
         const uint32_t ring_base = smem_u32(ring);
-        const uint32_t idesc = umma_idesc_tf32(Q1_M, Q1_N);
+        const uint32_t idesc = umma_idesc_tf32(Q1_M, (p.debug >> 8) ? (p.debug >> 8) : Q1_N);  // debug: MMA N override
         while (true) {
+            Q1_LAP(4);
             mbar_wait(bar_sfull + 8 * ss, sphase);
             const uint32_t item = sched_s[ss];
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
             if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            Q1_LAP(0);
             if (item == ITEM_END) break;
             const ScanItem it = p.items[item];
             if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+            Q1_LAP(4);
             mbar_wait(bar_qready, qphase);
             qphase ^= 1;
             tc_fence_after();
+            Q1_LAP(1);
             for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
                 const uint32_t tph = buf ? tph1 : tph0;
+                Q1_LAP(4);
                 mbar_wait(bar_tempty + 8 * buf, tph ^ 1);
                 tc_fence_after();
+                Q1_LAP(2);
                 const uint32_t d_tmem = tmem_base + Q1_ACC_COL + buf * Q1_N;
                 for (uint32_t st = 0; st < NST; ++st) {
+                    Q1_LAP(4);
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
+                    Q1_LAP(3);
                     if (elect_one()) {
                         const uint32_t sbase = ring_base + stage * STAGE_BYTES;
                         if (!(p.debug & 8u)) {
@@ -565,8 +625,14 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                                 const uint64_t b0 = umma_desc_sw128(sbase + j * Q1_STAGE_BYTES);
                                 const uint32_t a0 = tmem_base + (st * KBS + j) * 32;
 #pragma unroll
-                                for (uint32_t k4 = 0; k4 < 4; ++k4)  // A: 8 tf32 = 8 TMEM columns per step
-                                    umma_tf32_ts(d_tmem, a0 + k4 * 8, b0 + 2 * k4, idesc, (st | j | k4) != 0 ? 1u : 0u);
+                                for (uint32_t k4 = 0; k4 < 4; ++k4) {  // A: 8 tf32 = 8 TMEM columns per step
+                                    // debug bits 5/6 (timing experiments, garbage math): rotate the
+                                    // accumulator per MMA to break the dependent-accumulate chain
+                                    uint32_t d = d_tmem;
+                                    if (p.debug & 32u) d = tmem_base + Q1_ACC_COL + (k4 & 1u) * 64u;
+                                    if (p.debug & 64u) d = tmem_base + Q1_ACC_COL + k4 * 32u;
+                                    umma_tf32_ts(d, a0 + k4 * 8, b0 + 2 * k4, idesc, (st | j | k4) != 0 ? 1u : 0u);
+                                }
                             }
                         }
                         umma_commit(bar_empty + 8 * stage);
@@ -579,102 +645,106 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 buf ^= 1;
             }
         }
+        Q1_LAP_DUMP(1);
     } else {
         // ================= epilogue: one thread = one query =================
         const int quarter = warp & 3;                 // TMEM lane quarter of this warp
         const uint32_t m = quarter * 32 + lane;       // TMEM lane == query row of the tile
         const uint32_t qslot_in_item = (uint32_t)lane * 4 + quarter;  // item query index held by this thread
         const uint32_t lane_taddr = (uint32_t)(quarter * 32) << 16;
-        float* xn_mine = xn_w + quarter * 2 * Q1_N;   // two strips: current tile / next tile
         const uint32_t D = p.D;
-        uint32_t buf = 0, ss = 0, sphase = 0, fph0 = 0, fph1 = 0;
-
-        // |x|^2 (+inf = masked / out of range) of rows pos and pos+32
-        auto load_xn = [&](uint32_t rt, uint32_t row_end, float (&out)[2]) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t pos = rt + h * 32 + lane;
-                float xn = __uint_as_float(F32_INF_BITS);
-                if (pos < row_end) {
-                    bool live = true;
-                    if (p.tomb || p.filt) {
-                        const uint32_t id = p.ids[pos];
-                        if (p.tomb && bit_test(p.tomb, p.tomb_bits, id)) live = false;
-                        else if (p.filt && !bit_test(p.filt, p.filt_bits, id)) live = false;
-                    }
-                    if (live) xn = __ldg(p.xnorm + pos);
-                }
-                out[h] = xn;
-            }
-        };
+        uint32_t buf = 0, ss = 0, sphase = 0, fph0 = 0, fph1 = 0, tcount = 0;
+        // prologue transposition buffers: this warp's (still empty) candidate pools
+        float* xp0 = reinterpret_cast<float*>(pool.d + quarter * 32 * Q1_POOL_LD);
+        float* xp1 = reinterpret_cast<float*>(pool.p + quarter * 32 * Q1_POOL_LD);
 
         while (true) {
+            Q1_LAP(4);
             mbar_wait(bar_sfull + 8 * ss, sphase);
             const uint32_t item = sched_s[ss];
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
             if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            Q1_LAP(0);
             if (item == ITEM_END) break;
             const ScanItem it = p.items[item];
             if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
-            // ---- item prologue: my query -> registers -> tensor memory ----
+            // ---- item prologue: the warp's 32 queries -> tensor memory ----
+            // Rows are read coalesced (8 lanes x 16 B = one 128-byte k-block of one query, four
+            // queries per load instruction), transposed through shared memory, and written by the
+            // owning thread (TMEM lane = query) with one 32-column tcgen05.st per k-block.
             const bool have = qslot_in_item < it.pair_count;
             uint32_t qi = ID_NONE, sl = 0;
             float qn = 0.f, thrp = -__uint_as_float(F32_INF_BITS);
+            uint32_t thr_pending = F32_INF_BITS;
             if (have) {
                 if (it.identity) { qi = it.pair_begin + qslot_in_item; sl = it.slot; }
                 else { qi = p.pair_q[it.pair_begin + qslot_in_item]; sl = p.pair_slot[it.pair_begin + qslot_in_item]; }
                 qn = p.qnorm[qi];
-                if (p.thr_g) thrp = __uint_as_float(*(volatile uint32_t*)(p.thr_g + qi)) - qn;
+                if (p.thr_g) {
+                    thr_pending = *(volatile uint32_t*)(p.thr_g + qi);
+                    thrp = __uint_as_float(thr_pending) - qn;
+                }
             }
-            float xnext[2];
-            load_xn(it.row_begin, it.row_end, xnext);   // first tile's norms, behind the query load
-            for (int i = 0; i < 32; ++i) pool.d[m * Q1_POOL_LD + i] = 0xFFFFFFFFu;  // empty shortlist
-            uint32_t cnt_new = 0;
             {
-                // two k-blocks of loads in flight per thread (software pipelined)
-                const float4* qrow = reinterpret_cast<const float4*>(p.Q + (size_t)(have ? qi : 0) * D);
-                float4 cur[8], nxt[8];
+                const float4* src[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) cur[i] = have ? __ldg(qrow + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t qs = __shfl_sync(0xffffffffu, qi, 4 * i + (lane >> 3));
+                    src[i] = (qs == ID_NONE) ? nullptr : reinterpret_cast<const float4*>(p.Q + (size_t)qs * D) + (lane & 7);
+                }
+                auto ldq = [&](uint32_t kb, float4 (&v)[8]) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        v[i] = src[i] ? __ldg(src[i] + kb * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+                };
+                float4 c0[8], c1[8], c2[8];
+                ldq(0, c0);
+                if (KB > 1) ldq(1, c1);
                 for (uint32_t kb = 0; kb < KB; ++kb) {
-                    if (kb + 1 < KB) {
+                    if (kb + 2 < KB) ldq(kb + 2, c2);
+                    float* xp = (kb & 1) ? xp1 : xp0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            nxt[i] = have ? __ldg(qrow + (kb + 1) * 8 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(xp + (4 * i + (lane >> 3)) * Q1_XP_LD + (lane & 7) * 4) = c0[i];
+                    __syncwarp();
                     uint32_t r[32];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        r[4 * i + 0] = __float_as_uint(cur[i].x); r[4 * i + 1] = __float_as_uint(cur[i].y);
-                        r[4 * i + 2] = __float_as_uint(cur[i].z); r[4 * i + 3] = __float_as_uint(cur[i].w);
+                        const float4 v = *reinterpret_cast<const float4*>(xp + lane * Q1_XP_LD + i * 4);
+                        r[4 * i + 0] = __float_as_uint(v.x); r[4 * i + 1] = __float_as_uint(v.y);
+                        r[4 * i + 2] = __float_as_uint(v.z); r[4 * i + 3] = __float_as_uint(v.w);
                     }
                     tmem_st32(tmem_base + lane_taddr + kb * 32, r);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+                    for (int i = 0; i < 8; ++i) { c0[i] = c1[i]; c1[i] = c2[i]; }
                 }
                 tmem_st_wait();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_qready);
+            for (int i = 0; i < 32; ++i) pool.d[m * Q1_POOL_LD + i] = 0xFFFFFFFFu;  // empty shortlist
+            uint32_t cnt_new = 0;
+            Q1_LAP(1);
 
             // ---- row tiles ----
-            uint32_t strip = 0;
             for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
-                float* xs = xn_mine + strip * Q1_N;
-                xs[lane] = xnext[0];
-                xs[32 + lane] = xnext[1];
-                __syncwarp();
-                if (rt + Q1_N < it.row_end) load_xn(rt + Q1_N, it.row_end, xnext);  // prefetch the next tile's norms
-                // thresholds tightened meanwhile by CTAs scanning other lists of the same query
-                uint32_t shared_thr = F32_INF_BITS;
-                if (have && p.thr_g) shared_thr = *(volatile uint32_t*)(p.thr_g + qi);
+                // thresholds tightened meanwhile by CTAs scanning other lists of the same query:
+                // the value loaded during the previous tile is applied now (no exposed latency)
+                if (have) thrp = fminf(thrp, __uint_as_float(thr_pending) - qn);
+                if (have && p.thr_g) thr_pending = *(volatile uint32_t*)(p.thr_g + qi);
+                const uint32_t slot = tcount & (Q1_NSLOT - 1);
+                Q1_LAP(3);
+                mbar_wait(bar_nfull + 8 * slot, (tcount / Q1_NSLOT) & 1u);
+                const float* xs = xn_ring + slot * Q1_N;
+                ++tcount;
+                Q1_LAP(5);
                 const uint32_t fph = buf ? fph1 : fph0;
                 mbar_wait(bar_tfull + 8 * buf, fph);
                 if (buf) fph1 ^= 1; else fph0 ^= 1;
                 tc_fence_after();
-                if (have) thrp = fminf(thrp, __uint_as_float(shared_thr) - qn);
+                Q1_LAP(2);
                 const uint32_t taddr = tmem_base + Q1_ACC_COL + buf * Q1_N + lane_taddr;
                 for (uint32_t c0 = 0; c0 < ((p.debug & 1u) ? 0u : (uint32_t)Q1_N); c0 += 16) {
                     uint32_t acc[16];
@@ -751,9 +821,9 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
                 buf ^= 1;
-                strip ^= 1;
             }
             // ---- item epilogue: final merge, publish the shortlists, tighten shared thresholds ----
+            Q1_LAP(3);
             unsigned todo = __ballot_sync(0xffffffffu, have && p.dense_out == nullptr);
             while (todo) {
                 uint32_t mm[4], nn[4], qis[4], sls[4];
@@ -780,7 +850,9 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 }
             }
             __syncwarp();
+            Q1_LAP(6);
         }
+        if (warp == 2) Q1_LAP_DUMP(2);
     }
     tc_fence_before();
     __syncthreads();
@@ -793,8 +865,17 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
 }
 
 size_t tc_scan_q_smem_bytes(uint32_t stages, uint32_t kbs) {
-    return (size_t)stages * kbs * Q1_STAGE_BYTES + (size_t)2 * Q1_M * Q1_POOL_LD * 4 + (size_t)8 * Q1_N * 4 +
-           (size_t)(2 * stages + 5 + 2 * TC_SCHED) * 8 + 16 + (size_t)TC_SCHED * 4;
+    return (size_t)stages * kbs * Q1_STAGE_BYTES + (size_t)2 * Q1_M * Q1_POOL_LD * 4 + (size_t)Q1_NSLOT * Q1_N * 4 +
+           (size_t)(2 * stages + 5 + 2 * TC_SCHED + Q1_NSLOT) * 8 + 16 + (size_t)TC_SCHED * 4;
+}
+
+// deepest ring that fits shared memory and keeps the norm-strip ring ahead of the epilogue
+// (ceil(stages / stages-per-tile) + 3 < Q1_NSLOT, see the producer)
+uint32_t q1_pick_stages(uint32_t KB, uint32_t kbs) {
+    const uint32_t nst = KB / kbs;
+    uint32_t stages = std::min<uint32_t>(18u, (uint32_t)(Q1_NSLOT - 4) * nst);
+    while (stages > 2 && tc_scan_q_smem_bytes(stages, kbs) + 1024 > 232448) --stages;
+    return stages;
 }
 
 size_t tc_scan_smem_bytes(uint32_t KB, uint32_t stages) {
@@ -1063,6 +1144,7 @@ struct Buf {
 struct TcScratchImpl {
     Buf<float> xnorm, qnorm;
     Buf<uint32_t> misc;  // [0] = max |x|^2 bits
+    Buf<unsigned long long> prof;
     Buf<uint32_t> thr_g, list_cnt, pair_off, cursor, pair_q, pair_slot, n_items;
     Buf<ScanItem> items;
     Buf<uint64_t> partial, shortlist;
@@ -1088,6 +1170,7 @@ void tc_release(TcScratch& s) {
     m->xnorm.release(); m->qnorm.release(); m->misc.release(); m->thr_g.release(); m->list_cnt.release();
     m->pair_off.release(); m->cursor.release(); m->pair_q.release(); m->pair_slot.release(); m->n_items.release();
     m->items.release(); m->partial.release(); m->shortlist.release();
+    m->prof.release();
     m->cnorm.release(); m->dense.release(); m->coarse.release(); m->citems.release();
     delete m;
     s.impl = nullptr;
@@ -1224,8 +1307,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         cp.dense_out = m->dense.p; cp.dense_ld = ld;
         uint32_t kbs = 1;
         for (uint32_t c : {4u, 3u, 2u}) if (KB % c == 0) { kbs = c; break; }
-        uint32_t stages = 18;
-        while (stages > 2 && tc_scan_q_smem_bytes(stages, kbs) + 1024 > 232448) --stages;
+        uint32_t stages = q1_pick_stages(KB, kbs);
         cp.stages = stages; cp.kbs = kbs;
         if (!m->smem_attr_set_q) {
             TCK(cudaFuncSetAttribute(tc_scan_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -1258,6 +1340,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = m->xnorm.p; p.ids = a.ids;
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
     p.P = np; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
+    p.rows_raw = a.rows; p.rows_bytes = a.n_rows * (uint64_t)D * 4;
     p.work_counter = m->n_items.p + 1;
     {
         const char* dbg = getenv("FVDB_TC_DEBUG");
@@ -1268,8 +1351,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         uint32_t kbs = 1;
         for (uint32_t c : {4u, 3u, 2u}) if (KB % c == 0) { kbs = c; break; }
         if (const char* e = getenv("FVDB_TC_KBS")) { const uint32_t v = (uint32_t)atoi(e); if (v && KB % v == 0) kbs = v; }
-        uint32_t stages = 18;
-        while (stages > 2 && tc_scan_q_smem_bytes(stages, kbs) + 1024 > 232448) --stages;
+        uint32_t stages = q1_pick_stages(KB, kbs);
         p.stages = stages;
         p.kbs = kbs;
         const size_t smem = tc_scan_q_smem_bytes(stages, kbs) + 1024;
@@ -1278,9 +1360,34 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             m->smem_attr_set_q = true;
         }
         const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
+        if (p.debug & 128u) {
+            TCK(m->prof.ensure((size_t)grid * 24, dev_bytes));
+            TCK(cudaMemsetAsync(m->prof.p, 0, (size_t)grid * 24 * 8, st));
+            p.prof = m->prof.p;
+        }
         if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
         tc_scan_q_kernel<<<grid, TC_THREADS, smem, st>>>(m->tmap_q, p);
         TCK(cudaGetLastError());
+        if (p.prof) {  // timing experiment only: per-role stopwatch laps, averaged over CTAs
+            std::vector<unsigned long long> hp((size_t)grid * 24);
+            TCK(cudaMemcpyAsync(hp.data(), m->prof.p, hp.size() * 8, cudaMemcpyDeviceToHost, st));
+            TCK(cudaStreamSynchronize(st));
+            static const char* names[3] = {"producer", "mma", "epilogue"};
+            for (int r = 0; r < 3; ++r) {
+                double avg[8] = {0}, mx[8] = {0};
+                for (uint32_t b = 0; b < grid; ++b)
+                    for (int i = 0; i < 8; ++i) {
+                        const double v = (double)hp[((size_t)b * 3 + r) * 8 + i];
+                        avg[i] += v / grid;
+                        mx[i] = std::max(mx[i], v);
+                    }
+                fprintf(stderr, "[q1 prof] %-8s avg:", names[r]);
+                for (int i = 0; i < 8; ++i) fprintf(stderr, " %9.0f", avg[i]);
+                fprintf(stderr, "  max:");
+                for (int i = 0; i < 8; ++i) fprintf(stderr, " %9.0f", mx[i]);
+                fprintf(stderr, "\n");
+            }
+        }
     } else {
         uint32_t stages = 8;
         while (stages > 2 && tc_scan_smem_bytes(KB, stages) > 227 * 1024) --stages;
