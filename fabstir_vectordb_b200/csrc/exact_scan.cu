@@ -352,7 +352,8 @@ __device__ __forceinline__ uint64_t block_excl_scan_u64(uint64_t v, uint64_t* wa
 // at least one query come first in the item order (their scan tightens that query's threshold
 // for every other list); items of one list stay adjacent so a re-read hits L2.
 __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __restrict__ list_cnt,
-                                  const uint32_t* __restrict__ list_off, uint32_t nlist,
+                                  const uint32_t* __restrict__ list_off,
+                                  const uint32_t* __restrict__ list_order, uint32_t nlist,
                                   uint32_t tile_q, uint32_t* __restrict__ pair_off,
                                   uint32_t* __restrict__ cursor, ScanItem* __restrict__ items,
                                   uint32_t* __restrict__ n_items, uint64_t* __restrict__ scanned_rows) {
@@ -362,9 +363,11 @@ __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __rest
     // pass A: totals of the nearest-first group
     uint64_t near_total = 0;
     for (uint32_t base = 0; base < nlist; base += 1024) {
-        const uint32_t l = base + t;
+        // list_order (longest list first) replaces the nearest-first grouping: the dynamic tile
+        // scheduler then ends with the cheapest items, which keeps the tail of the scan short
+        const uint32_t l = (base + t < nlist) ? (list_order ? list_order[base + t] : base + t) : nlist;
         uint64_t v = 0;
-        if (l < nlist) {
+        if (l < nlist && !list_order) {
             const uint32_t raw = list_cnt[l];
             const uint32_t c = (list_off[l + 1] != list_off[l]) ? (raw & ~NEAREST_BIT) : 0u;
             if ((raw & NEAREST_BIT) && c) v = ((uint64_t)((c + tile_q - 1) / tile_q) << 32) | c;
@@ -376,14 +379,14 @@ __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __rest
     // pass B: offsets
     uint64_t carry_near = 0, carry_far = near_total;
     for (uint32_t base = 0; base < nlist; base += 1024) {
-        const uint32_t l = base + t;
+        const uint32_t l = (base + t < nlist) ? (list_order ? list_order[base + t] : base + t) : nlist;
         uint32_t c = 0, len = 0;
         bool nearest = false;
         if (l < nlist) {
             const uint32_t raw = list_cnt[l];
             len = list_off[l + 1] - list_off[l];
             c = len ? (raw & ~NEAREST_BIT) : 0u;
-            nearest = (raw & NEAREST_BIT) != 0;
+            nearest = !list_order && (raw & NEAREST_BIT) != 0;
         }
         const uint32_t ni = (c + tile_q - 1) / tile_q;
         const uint64_t v = ((uint64_t)ni << 32) | c;
@@ -438,7 +441,8 @@ cudaError_t launch_probe_bucketing(const uint64_t* coarse_keys, uint32_t nq, uin
                                    const uint32_t* list_off, uint32_t nlist, uint32_t tile_q,
                                    uint32_t* list_cnt, uint32_t* pair_off, uint32_t* cursor,
                                    uint32_t* pair_q, uint32_t* pair_slot, ScanItem* items,
-                                   uint32_t* n_items, uint64_t* scanned_rows, cudaStream_t stream) {
+                                   uint32_t* n_items, uint64_t* scanned_rows, cudaStream_t stream,
+                                   const uint32_t* list_order) {
     const uint32_t n_pairs = nq * nprobe;
     cudaError_t e = cudaMemsetAsync(list_cnt, 0, sizeof(uint32_t) * nlist, stream);
     if (e != cudaSuccess) return e;
@@ -446,7 +450,7 @@ cudaError_t launch_probe_bucketing(const uint64_t* coarse_keys, uint32_t nq, uin
         return cudaMemsetAsync(n_items, 0, sizeof(uint32_t), stream);
     }
     probe_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, nprobe, list_cnt);
-    probe_scan_kernel<<<1, 1024, 0, stream>>>(list_cnt, list_off, nlist, tile_q, pair_off, cursor,
+    probe_scan_kernel<<<1, 1024, 0, stream>>>(list_cnt, list_off, list_order, nlist, tile_q, pair_off, cursor,
                                               items, n_items, scanned_rows);
     probe_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, nprobe,
                                                                    list_off, cursor, pair_q,

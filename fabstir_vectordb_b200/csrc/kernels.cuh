@@ -36,7 +36,8 @@ cudaError_t launch_probe_bucketing(const uint64_t* coarse_keys, uint32_t nq, uin
                                    const uint32_t* list_off, uint32_t nlist, uint32_t tile_q,
                                    uint32_t* list_cnt, uint32_t* pair_off, uint32_t* cursor,
                                    uint32_t* pair_q, uint32_t* pair_slot, ScanItem* items,
-                                   uint32_t* n_items, uint64_t* scanned_rows, cudaStream_t stream);
+                                   uint32_t* n_items, uint64_t* scanned_rows, cudaStream_t stream,
+                                   const uint32_t* list_order = nullptr);
 // one warp per (query, probed list): sparse batches (few queries per list)
 cudaError_t launch_exact_pair_scan(const uint64_t* coarse_keys, uint32_t nq, uint32_t nprobe, const uint32_t* list_off,
                                    const float* X, const uint32_t* ids, const float* Q, uint32_t D, uint32_t P,
@@ -44,6 +45,9 @@ cudaError_t launch_exact_pair_scan(const uint64_t* coarse_keys, uint32_t nq, uin
                                    uint64_t filt_bits, uint64_t* partial, cudaStream_t stream);
 cudaError_t launch_merge_partials(const uint64_t* in, uint32_t nq, uint32_t P, uint32_t k,
                                   uint64_t* out, cudaStream_t stream);
+// same for P rows of 32 keys each that may be unsorted or empty (tensor-core scan output)
+cudaError_t launch_merge_rows32(const uint64_t* in, uint32_t nq, uint32_t P, uint64_t* out,
+                                cudaStream_t stream);
 cudaError_t launch_finalize(const uint64_t* recent, const uint64_t* ivf, uint32_t nq, uint32_t k,
                             uint32_t* out_ids, float* out_dist, uint32_t* out_count,
                             cudaStream_t stream);

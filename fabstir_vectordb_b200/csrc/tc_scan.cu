@@ -30,15 +30,10 @@ namespace fvdb {
 
 namespace {
 
-constexpr int TC_ROWS = 128;                     // rows per tile (MMA M)
-constexpr int TC_NQ = (int)TC_TILE_Q;            // queries per item (MMA N max)
+constexpr int TC_ROWS = 128;                     // rows per tile of kernel R (MMA M)
 constexpr int TC_KB_FLOATS = 32;                 // one 128-byte swizzle atom
-constexpr int TC_STAGE_BYTES = TC_ROWS * 128;    // 16 KB
-constexpr int TC_QBLK_BYTES = TC_NQ * 128;       // 8 KB per k-block of the query tile
 constexpr int TC_KP = 32;                        // shortlist entries per (query, item)
-constexpr int TC_CAP = 128;                      // candidate slots per query per tile
-constexpr int TC_THREADS = 192;
-constexpr int TC_TMEM_COLS = 128;                // 2 accumulator buffers x 64 columns
+constexpr int TC_THREADS = 192;                  // kernel Q
 
 struct TcScanParams {
     const ScanItem* items;
@@ -73,313 +68,628 @@ constexpr uint32_t ITEM_END = 0xFFFFFFFFu;
 
 using namespace tcx;
 
-// ---- the scan kernel ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// ================================================================================================
+// Kernel R ("rows on lanes"): the scan kernel.  A 128-row tile of a posting list is the MMA A
+// operand (TMA -> 128B-swizzled shared-memory ring, one 16 KB stage per 128-byte k-block), the
+// <= 64 queries probing the list are the B operand (resident in shared memory for the whole
+// item), accumulators [128 rows x ncols] rotate through EIGHT 64-column TMEM buffers so the
+// MMA/TMA stream runs up to a whole list ahead of the epilogue.
+//
+// Warp roles (320 threads):
+//   warp 0      TMA producer + dynamic tile scheduler + per-tile |x|^2 strips (masked rows = +inf)
+//   warp 1      MMA issuer (one elected lane), TMEM owner
+//   warps 2-5   epilogue, one thread per row: v = |x|^2 - 2 x.q against the per-query threshold
+//               (shared memory, broadcast reads); the rare passing candidate is appended to the
+//               query's pending list with a shared-memory atomic.  After every tile the four warps
+//               meet at a named barrier; a query with > 16 pending candidates is merged into its
+//               sorted 32-entry shortlist by the warp that owns it, which tightens its threshold
+//               (also published to / refreshed from the global per-query bound thr_g that CTAs
+//               scanning other lists of the same query share).  A pending list that overflowed
+//               is replayed for exactly the rows that could not be stored.
+//   warps 6-9   query loaders: stage the NEXT item's query tile (coalesced reads, swizzled
+//               stores) as soon as the MMA warp has retired the current item.
+// ================================================================================================
+constexpr int R2_ROWS = 128;                     // rows per tile (MMA M = TMEM lanes)
+constexpr int R2_NQ = (int)TC_TILE_Q;            // queries per item (MMA N max)
+constexpr int R2_STAGE_BYTES = R2_ROWS * 128;    // 16 KB: 128 rows x one 128-byte k-block
+constexpr int R2_QBLK_BYTES = R2_NQ * 128;       // 8 KB per k-block of the query tile
+constexpr int R2_CAP = 32;                       // pending candidates per query
+constexpr int R2_FLUSH = 16;                     // merge a query once it holds more pending than this
+constexpr int R2_NBUF = 8;                       // accumulator buffers of R2_NQ columns
+constexpr int R2_NSLOT = 16;                     // |x|^2 strips in flight
+constexpr int R2_THREADS = 320;
+constexpr int R2_TMEM_COLS = 512;
+
+struct R2Smem {
+    unsigned char* q_tile;    // KB x 8 KB, 128B-swizzled K-major [query][32 floats]
+    unsigned char* ring;      // STAGES x 16 KB
+    uint64_t* sorted;         // [R2_NQ][TC_KP]  ascending approx keys of this item
+    uint64_t* pend;           // [R2_NQ][R2_CAP] unsorted pending candidates
+    float* xn_ring;           // [R2_NSLOT][R2_ROWS]
+    float* thrp;              // [R2_NQ] threshold - |q|^2   (-inf for padded columns)
+    uint32_t* pcnt;           // [R2_NQ] pending count (may exceed R2_CAP: overflow marker)
+    uint32_t* qidx;           // [2][R2_NQ]
+    uint32_t* qslot;          // [2][R2_NQ]
+    float* qn;                // [2][R2_NQ]
+    uint32_t* redo;           // [2] bitmask of queries to replay
+    uint64_t* bars;
+    uint32_t* tmem_ptr;
+    uint32_t* sched;          // [TC_SCHED]
+};
+
+__device__ __forceinline__ R2Smem r2_carve(unsigned char* smem, uint32_t KB, uint32_t STAGES) {
+    R2Smem m;
+    m.q_tile = smem;
+    m.ring = m.q_tile + (size_t)KB * R2_QBLK_BYTES;
+    m.sorted = reinterpret_cast<uint64_t*>(m.ring + (size_t)STAGES * R2_STAGE_BYTES);
+    m.pend = m.sorted + R2_NQ * TC_KP;
+    m.xn_ring = reinterpret_cast<float*>(m.pend + R2_NQ * R2_CAP);
+    m.thrp = m.xn_ring + R2_NSLOT * R2_ROWS;
+    m.pcnt = reinterpret_cast<uint32_t*>(m.thrp + R2_NQ);
+    m.qidx = m.pcnt + R2_NQ;
+    m.qslot = m.qidx + 2 * R2_NQ;
+    m.qn = reinterpret_cast<float*>(m.qslot + 2 * R2_NQ);
+    m.redo = reinterpret_cast<uint32_t*>(m.qn + 2 * R2_NQ);
+    m.bars = reinterpret_cast<uint64_t*>(m.redo + 4);
+    m.tmem_ptr = reinterpret_cast<uint32_t*>(m.bars + 2 * STAGES + 2 * R2_NBUF + R2_NSLOT + 2 * TC_SCHED + 3);
+    m.sched = m.tmem_ptr + 1;
+    return m;
+}
+
+size_t tc_scan_smem_bytes(uint32_t KB, uint32_t stages) {
+    return (size_t)KB * R2_QBLK_BYTES + (size_t)stages * R2_STAGE_BYTES + (size_t)R2_NQ * TC_KP * 8 +
+           (size_t)R2_NQ * R2_CAP * 8 + (size_t)R2_NSLOT * R2_ROWS * 4 + (size_t)R2_NQ * 8 * 4 + 16 +
+           (size_t)(2 * stages + 2 * R2_NBUF + R2_NSLOT + 2 * TC_SCHED + 3) * 8 + 16 + (size_t)TC_SCHED * 4;
+}
+
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+}
+__device__ __forceinline__ void epi_bar_n(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// Merge the pending candidates of up to four queries (owned by this warp) into their sorted
+// shortlists; lane i holds entry i.  n[g] pending entries (already clamped to R2_CAP).
+__device__ __forceinline__ void r2_merge4(const R2Smem& sm, const uint32_t (&qs)[4], const uint32_t (&n)[4],
+                                          const bool (&act)[4], uint64_t (&lst)[4], int lane) {
+    uint64_t nw[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        lst[g] = KEY_NONE;
+        nw[g] = KEY_NONE;
+        if (act[g]) {
+            lst[g] = sm.sorted[qs[g] * TC_KP + lane];
+            if ((uint32_t)lane < n[g]) nw[g] = sm.pend[qs[g] * R2_CAP + lane];
+        }
+    }
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+            uint64_t o[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) o[g] = shfl_xor64(nw[g], j);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint64_t mn = nw[g] < o[g] ? nw[g] : o[g], mx = nw[g] < o[g] ? o[g] : nw[g];
+                nw[g] = keep_min ? mn : mx;
+            }
+        }
+    }
+    warp_merge32x4(lst, nw, lane);
+}
+
+// stopwatch lap: the cycles since the previous lap of this role are charged to category i
+#define Q1_LAP(i) do { if (p.prof) { const long long n_ = clock64(); lap[i] += (unsigned long long)(n_ - tl); tl = n_; } } while (0)
+#define Q1_LAP_DUMP(role) do { if (p.prof && lane == 0) { for (int i_ = 0; i_ < 8; ++i_) p.prof[((size_t)blockIdx.x * 6 + (role)) * 8 + i_] = lap[i_]; } } while (0)
+
+__global__ void __launch_bounds__(R2_THREADS, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t KB = p.KB;
     const uint32_t STAGES = p.stages;
-    unsigned char* q_tile = smem;                                       // KB x 8 KB
-    unsigned char* ring = q_tile + (size_t)KB * TC_QBLK_BYTES;          // STAGES x 16 KB
-    uint32_t* cand_s = reinterpret_cast<uint32_t*>(ring + (size_t)STAGES * TC_STAGE_BYTES);  // [NQ][CAP]
-    uint64_t* list_s = reinterpret_cast<uint64_t*>(cand_s + TC_NQ * TC_CAP);                 // [NQ][KP]
-    float* thrp_s = reinterpret_cast<float*>(list_s + TC_NQ * TC_KP);   // [NQ] threshold - |q|^2
-    float* qn_s = thrp_s + TC_NQ;                                       // [NQ]
-    uint32_t* cnt_s = reinterpret_cast<uint32_t*>(qn_s + TC_NQ);        // [NQ]
-    uint32_t* qidx_s = cnt_s + TC_NQ;                                   // [NQ]
-    uint32_t* qslot_s = qidx_s + TC_NQ;                                 // [NQ]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(qslot_s + TC_NQ);      // full[S] empty[S] tfull[2] tempty[2] qready sfull[4] sempty[4]
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5 + 2 * TC_SCHED);
-    uint32_t* sched_s = tmem_ptr_s + 1;                                 // [TC_SCHED] claimed work items
+    const R2Smem sm = r2_carve(smem, KB, STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_full = smem_u32(sm.bars);
     const uint32_t bar_empty = bar_full + 8 * STAGES;
     const uint32_t bar_tfull = bar_empty + 8 * STAGES;
-    const uint32_t bar_tempty = bar_tfull + 16;
-    const uint32_t bar_qready = bar_tempty + 16;
-    const uint32_t bar_sfull = bar_qready + 8;
+    const uint32_t bar_tempty = bar_tfull + 8 * R2_NBUF;
+    const uint32_t bar_nfull = bar_tempty + 8 * R2_NBUF;
+    const uint32_t bar_sfull = bar_nfull + 8 * R2_NSLOT;
     const uint32_t bar_sempty = bar_sfull + 8 * TC_SCHED;
+    const uint32_t bar_qready = bar_sempty + 8 * TC_SCHED;  // query tile + item metadata staged
+    const uint32_t bar_qfree = bar_qready + 8;              // every MMA of the item has retired
+    const uint32_t bar_mfree = bar_qfree + 8;               // epilogue is done with an item's metadata
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        mbar_init(bar_tfull, 1);
-        mbar_init(bar_tfull + 8, 1);
-        mbar_init(bar_tempty, 4);
-        mbar_init(bar_tempty + 8, 4);
-        mbar_init(bar_qready, 1);
+        for (int i = 0; i < R2_NBUF; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 4);
+        }
+        for (int i = 0; i < R2_NSLOT; ++i) mbar_init(bar_nfull + 8 * i, 1);
         for (int i = 0; i < TC_SCHED; ++i) {
             mbar_init(bar_sfull + 8 * i, 1);
-            mbar_init(bar_sempty + 8 * i, 5);  // MMA lane + one lane of each epilogue warp
+            mbar_init(bar_sempty + 8 * i, 9);  // MMA lane + one lane of each epilogue and loader warp
         }
+        mbar_init(bar_qready, 128);
+        mbar_init(bar_qfree, 1);
+        mbar_init(bar_mfree, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
-                     "r"((uint32_t)TC_TMEM_COLS)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_ptr)),
+                     "r"((uint32_t)R2_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_s;
+    const uint32_t tmem_base = *sm.tmem_ptr;
     const uint32_t n_items = *p.item_count;
-    // Work items are claimed dynamically (atomic counter) by the producer lane and broadcast to
-    // the other roles through a small shared-memory ring, so all roles walk the same sequence.
+    unsigned long long lap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tl = clock64();
+    if (p.prof && threadIdx.x == 0) {  // wall-clock window of this CTA (role 3, slots 4..6)
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + 4] = gt;
+        p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + 6] = (unsigned long long)tl;
+    }
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, ss = 0, sphase = 0;
-            const uint64_t hint_first = 0x12F0000000000000ull;   // L2 evict-first: rows read once
-            const uint64_t hint_normal = 0x1000000000000000ull;  // list shared by several items
-            while (true) {
-                mbar_wait(bar_sempty + 8 * ss, sphase ^ 1);
-                uint32_t item = atomicAdd(p.work_counter, 1u);
+        // ============ TMA producer + tile scheduler (whole warp converged, one lane issues) ============
+        // Norm-strip slots need no "free" barrier: while this warp fills tile T the MMA warp has
+        // started a tile >= T - 1 - ceil(STAGES / KB), hence the epilogue has released a tile
+        // >= T - 1 - ceil(STAGES / KB) - R2_NBUF; the launcher keeps that window below R2_NSLOT.
+        uint32_t stage = 0, phase = 0, ss = 0, sphase = 0, tcount = 0;
+        const uint64_t hint_first = 0x12F0000000000000ull;   // L2 evict-first: rows read once
+        const uint64_t hint_normal = 0x1000000000000000ull;  // list shared by several items
+        const uint32_t ring_base = smem_u32(sm.ring);
+        while (true) {
+            Q1_LAP(3);
+            mbar_wait(bar_sempty + 8 * ss, sphase ^ 1);
+            uint32_t item = 0;
+            if (lane == 0) {
+                item = atomicAdd(p.work_counter, 1u);
                 if (item >= n_items) item = ITEM_END;
-                sched_s[ss] = item;
+                sm.sched[ss] = item;
                 mbar_arrive(bar_sfull + 8 * ss);
-                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
-                if (item == ITEM_END) break;
-                const ScanItem it = p.items[item];
-                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
-                const uint64_t hint = (!it.identity && it.slot > 1) ? hint_normal : hint_first;
-                for (uint32_t rt = it.row_begin; rt < it.row_end; rt += TC_ROWS) {
-                    for (uint32_t kb = 0; kb < KB; ++kb) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
-                        tma_load_2d(smem_u32(ring + (size_t)stage * TC_STAGE_BYTES), &tmap, bar_full + 8 * stage,
-                                    (int)(kb * TC_KB_FLOATS), (int)rt, hint);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            Q1_LAP(0);
+            if (item == ITEM_END) break;
+            const ScanItem it = p.items[item];
+            if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+            lap[6] += 1;
+            Q1_LAP(1);
+            const uint64_t hint = (!it.identity && it.slot > 1) ? hint_normal : hint_first;
+            for (uint32_t rt = it.row_begin; rt < it.row_end; rt += R2_ROWS) {
+                float xnv[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t pos = rt + h * 32 + lane;
+                    float xn = __uint_as_float(F32_INF_BITS);
+                    if (pos < it.row_end) {
+                        bool live = true;
+                        if (p.tomb || p.filt) {
+                            const uint32_t id = p.ids[pos];
+                            if (p.tomb && bit_test(p.tomb, p.tomb_bits, id)) live = false;
+                            else if (p.filt && !bit_test(p.filt, p.filt_bits, id)) live = false;
+                        }
+                        if (live) xn = __ldg(p.xnorm + pos);
                     }
+                    xnv[h] = xn;
                 }
+                __syncwarp();
+                lap[7] += 1;
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+                    Q1_LAP(3);
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    Q1_LAP(2);
+                    if (elect_one()) {
+                        const uint32_t fb = bar_full + 8 * stage;
+                        mbar_expect_tx(fb, R2_STAGE_BYTES);
+                        tma_load_2d(ring_base + stage * R2_STAGE_BYTES, &tmap, fb, (int)(kb * TC_KB_FLOATS), (int)rt, hint);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                const uint32_t slot = tcount & (R2_NSLOT - 1);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) sm.xn_ring[slot * R2_ROWS + h * 32 + lane] = xnv[h];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_nfull + 8 * slot);
+                ++tcount;
             }
         }
+        Q1_LAP_DUMP(0);
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, buf = 0, qphase = 0, ss = 0, sphase = 0;
-            uint32_t tphase[2] = {0, 0};
-            const uint32_t q_base = smem_u32(q_tile);
-            const uint32_t ring_base = smem_u32(ring);
-            while (true) {
-                mbar_wait(bar_sfull + 8 * ss, sphase);
-                const uint32_t item = sched_s[ss];
-                mbar_arrive(bar_sempty + 8 * ss);
-                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
-                if (item == ITEM_END) break;
-                const ScanItem it = p.items[item];
-                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
-                const uint32_t ncols = (it.pair_count + 15u) & ~15u;
-                const uint32_t idesc = umma_idesc_tf32(TC_ROWS, ncols);
-                mbar_wait(bar_qready, qphase);
-                qphase ^= 1;
+        // ============ MMA issuer (whole warp converged, one elected lane issues) ============
+        uint32_t stage = 0, phase = 0, ss = 0, sphase = 0, tile = 0, nit = 0;
+        const uint32_t q_base = smem_u32(sm.q_tile);
+        const uint32_t ring_base = smem_u32(sm.ring);
+        while (true) {
+            Q1_LAP(4);
+            mbar_wait(bar_sfull + 8 * ss, sphase);
+            const uint32_t item = sm.sched[ss];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
+            if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            Q1_LAP(0);
+            if (item == ITEM_END) break;
+            const ScanItem it = p.items[item];
+            if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+            const uint32_t ncols = (it.pair_count + 15u) & ~15u;
+            const uint32_t idesc = umma_idesc_tf32(R2_ROWS, ncols);
+            Q1_LAP(4);
+            mbar_wait(bar_qready, nit & 1u);
+            tc_fence_after();
+            Q1_LAP(1);
+            for (uint32_t rt = it.row_begin; rt < it.row_end; rt += R2_ROWS) {
+                const uint32_t buf = tile & (R2_NBUF - 1);
+                Q1_LAP(4);
+                mbar_wait(bar_tempty + 8 * buf, ((tile / R2_NBUF) & 1u) ^ 1u);
                 tc_fence_after();
-                for (uint32_t rt = it.row_begin; rt < it.row_end; rt += TC_ROWS) {
-                    mbar_wait(bar_tempty + 8 * buf, tphase[buf] ^ 1);
+                Q1_LAP(2);
+                const uint32_t d_tmem = tmem_base + buf * R2_NQ;
+                const bool last_tile = rt + R2_ROWS >= it.row_end;
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+                    Q1_LAP(4);
+                    mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * TC_NQ;
-                    for (uint32_t kb = 0; kb < KB; ++kb) {
-                        mbar_wait(bar_full + 8 * stage, phase);
-                        tc_fence_after();
-                        const uint64_t a0 = umma_desc_sw128(ring_base + stage * TC_STAGE_BYTES);
-                        const uint64_t b0 = umma_desc_sw128(q_base + kb * TC_QBLK_BYTES);
+                    Q1_LAP(3);
+                    if (elect_one()) {
+                        const uint64_t a0 = umma_desc_sw128(ring_base + stage * R2_STAGE_BYTES);
+                        const uint64_t b0 = umma_desc_sw128(q_base + kb * R2_QBLK_BYTES);
 #pragma unroll
                         for (uint32_t k4 = 0; k4 < 4; ++k4)  // UMMA_K = 8 tf32 = 32 bytes = +2 in the descriptor
                             umma_tf32(d_tmem, a0 + 2 * k4, b0 + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
                         umma_commit(bar_empty + 8 * stage);  // frees the ring slot once these MMAs retire
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (kb + 1 == KB) {
+                            umma_commit(bar_tfull + 8 * buf);   // accumulator ready for the epilogue
+                            if (last_tile) umma_commit(bar_qfree);  // query tile may be replaced
+                        }
                     }
-                    umma_commit(bar_tfull + 8 * buf);  // accumulator ready for the epilogue
-                    tphase[buf] ^= 1;
-                    buf ^= 1;
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                ++tile;
             }
+            ++nit;
         }
-    } else {
-        // ================= epilogue (128 threads) =================
-        const int ew = warp - 2;                 // 0..3: query stripe of this warp in the merge phase
-        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
-        const int trow = quarter * 32 + lane;    // row within the tile == TMEM lane
-        const int et = ew * 32 + lane;           // 0..127
+        Q1_LAP_DUMP(1);
+    } else if (warp >= 6) {
+        // ============ query loaders (128 threads) ============
+        const int lw = warp - 6;
+        const int lt = lw * 32 + lane;
         const uint32_t D = p.D;
-        uint32_t buf = 0, ss = 0, sphase = 0;
-        uint32_t fphase[2] = {0, 0};
-        const unsigned lt_mask = (1u << lane) - 1u;
+        uint32_t ss = 0, sphase = 0, nit = 0;
         while (true) {
+            Q1_LAP(3);
             mbar_wait(bar_sfull + 8 * ss, sphase);
-            const uint32_t item = sched_s[ss];
+            const uint32_t item = sm.sched[ss];
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
             if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            Q1_LAP(0);
             if (item == ITEM_END) break;
             const ScanItem it = p.items[item];
             if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
             const uint32_t cnt = it.pair_count;
             const uint32_t ncols = (cnt + 15u) & ~15u;
-            // ---- item prologue: query bookkeeping + query tile into swizzled shared memory ----
-            if (et < TC_NQ) {
-                uint32_t qi = ID_NONE, sl = 0;
-                float qn = 0.f, thr = __uint_as_float(F32_INF_BITS);
-                if ((uint32_t)et < cnt) {
-                    if (it.identity) { qi = it.pair_begin + et; sl = it.slot; }
-                    else { qi = p.pair_q[it.pair_begin + et]; sl = p.pair_slot[it.pair_begin + et]; }
-                    qn = p.qnorm[qi];
-                    thr = __uint_as_float(*(volatile uint32_t*)(p.thr_g + qi));
-                }
-                qidx_s[et] = qi;
-                qslot_s[et] = sl;
-                qn_s[et] = qn;
-                // padded query columns (et >= cnt) must never pass the filter: threshold -inf
-                thrp_s[et] = ((uint32_t)et < cnt) ? thr - qn : -__uint_as_float(F32_INF_BITS);
-                cnt_s[et] = 0;
+            // query indices of the item: lane l holds queries l and l + 32
+            uint32_t qi0 = ID_NONE, qi1 = ID_NONE, sl0 = 0, sl1 = 0;
+            if ((uint32_t)lane < cnt) {
+                if (it.identity) { qi0 = it.pair_begin + lane; sl0 = it.slot; }
+                else { qi0 = p.pair_q[it.pair_begin + lane]; sl0 = p.pair_slot[it.pair_begin + lane]; }
             }
-            for (int i = et; i < TC_NQ * TC_KP; i += 128) list_s[i] = KEY_NONE;
-            epi_bar(1);
+            if ((uint32_t)lane + 32 < cnt) {
+                if (it.identity) { qi1 = it.pair_begin + lane + 32; sl1 = it.slot; }
+                else { qi1 = p.pair_q[it.pair_begin + lane + 32]; sl1 = p.pair_slot[it.pair_begin + lane + 32]; }
+            }
+            // metadata buffer (nit & 1) was last used by item nit - 2
+            Q1_LAP(3);
+            if (nit >= 2) mbar_wait(bar_mfree, nit & 1u);
+            Q1_LAP(1);
+            if (lw == 0) {
+                const uint32_t mb = (nit & 1u) * R2_NQ;
+                sm.qidx[mb + lane] = qi0; sm.qidx[mb + 32 + lane] = qi1;
+                sm.qslot[mb + lane] = sl0; sm.qslot[mb + 32 + lane] = sl1;
+                sm.qn[mb + lane] = (qi0 != ID_NONE) ? p.qnorm[qi0] : 0.f;
+                sm.qn[mb + 32 + lane] = (qi1 != ID_NONE) ? p.qnorm[qi1] : 0.f;
+            }
+            // the query tile may be overwritten once every MMA of the previous item has retired
+            Q1_LAP(3);
+            if (nit >= 1) mbar_wait(bar_qfree, (nit - 1) & 1u);
+            Q1_LAP(2);
             {
-                // warp ew stages queries ew, ew+4, ...; a lane moves float4 columns lane, lane+32, ...
-                // Loads of four query rows are issued before any store so ~12 LDG.128 per lane
-                // are in flight (the loop was latency bound with one).
+                // warp lw stages queries lw, lw+4, ...; a lane moves float4 columns lane, lane+32, ...
+                // Loads of four query rows are issued before any store (12 LDG.128 per lane in flight).
                 const uint32_t f4_per_row = KB * 8;
-                for (uint32_t q0 = ew; q0 < ncols; q0 += 16) {
+                for (uint32_t q0 = lw; q0 < ncols; q0 += 16) {
+                    const float4* src[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t q = q0 + 4 * g;
+                        const uint32_t qa = __shfl_sync(0xffffffffu, qi0, q & 31), qb = __shfl_sync(0xffffffffu, qi1, q & 31);
+                        const uint32_t qi = (q < 32) ? qa : qb;
+                        src[g] = (q < ncols && qi != ID_NONE) ? reinterpret_cast<const float4*>(p.Q + (size_t)qi * D) : nullptr;
+                    }
                     for (uint32_t c = lane; c < f4_per_row; c += 32) {
                         float4 v[4];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint32_t q = q0 + 4 * g;
-                            v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (q < ncols) {
-                                const uint32_t qi = qidx_s[q];
-                                if (qi != ID_NONE) v[g] = __ldg(reinterpret_cast<const float4*>(p.Q + (size_t)qi * D) + c);
-                            }
-                        }
+                        for (int g = 0; g < 4; ++g) v[g] = src[g] ? __ldg(src[g] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                         const uint32_t kb = c >> 3, ch = c & 7;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const uint32_t q = q0 + 4 * g;
                             if (q < ncols)
-                                *reinterpret_cast<float4*>(q_tile + (size_t)kb * TC_QBLK_BYTES + q * 128 +
+                                *reinterpret_cast<float4*>(sm.q_tile + (size_t)kb * R2_QBLK_BYTES + q * 128 +
                                                            ((ch ^ (q & 7)) << 4)) = v[g];
                         }
                     }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
-            epi_bar(2);
-            if (et == 0) mbar_arrive(bar_qready);
+            mbar_arrive(bar_qready);
+            ++nit;
+            (void)lt;
+        }
+        if (warp == 6 && p.prof && lane == 0) { for (int i_ = 0; i_ < 4; ++i_) p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + i_] = lap[i_]; }
+    } else {
+        // ================= epilogue (warps 2-5): one thread = one row of the tile =================
+        const int ew = warp - 2;                 // owner stripe: this warp merges queries j with j % 4 == ew
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+        const int trow = quarter * 32 + lane;    // row within the tile == TMEM lane
+        const int et = ew * 32 + lane;           // 0..127
+        const uint32_t lane_taddr = (uint32_t)(quarter * 32) << 16;
+        uint32_t ss = 0, sphase = 0, tile = 0, nit = 0;
+        uint32_t st_app = 0, st_ovf = 0, st_merge = 0, st_replay = 0, st_chunks = 0;
+        // the query this lane owns in the merge phases (lanes 0..15): j = lane * 4 + ew
+        const uint32_t jown = (uint32_t)lane * 4u + (uint32_t)ew;
+        while (true) {
+            Q1_LAP(6);
+            mbar_wait(bar_sfull + 8 * ss, sphase);
+            const uint32_t item = sm.sched[ss];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
+            if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+            Q1_LAP(0);
+            if (item == ITEM_END) break;
+            const ScanItem it = p.items[item];
+            if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+            const uint32_t cnt = it.pair_count;
+            const uint32_t ncols = (cnt + 15u) & ~15u;
+            const uint32_t mb = (nit & 1u) * R2_NQ;
+            mbar_wait(bar_qready, nit & 1u);           // metadata of this item is staged
+            Q1_LAP(1);
+            if (nit >= 1) {                            // ... and only now release the previous item's
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_mfree);
+            }
+            // ---- item prologue: empty shortlists, thresholds from the shared bounds ----
+            if (et < R2_NQ) {
+                float thr = -__uint_as_float(F32_INF_BITS);  // padded columns never pass
+                if ((uint32_t)et < cnt) {
+                    const uint32_t g = p.thr_g ? *(volatile uint32_t*)(p.thr_g + sm.qidx[mb + et]) : (uint32_t)0x7f800000u;
+                    thr = __uint_as_float(g) - sm.qn[mb + et];
+                }
+                sm.thrp[et] = thr;
+                sm.pcnt[et] = 0;
+            }
+            if (et < 2) sm.redo[et] = 0;
+            for (int i = et; i < R2_NQ * TC_KP; i += 128) sm.sorted[i] = KEY_NONE;
+            const bool own = lane < 16 && jown < cnt;
+            const uint32_t qi_own = own ? sm.qidx[mb + jown] : 0u;
+            const float qn_own = own ? sm.qn[mb + jown] : 0.f;
+            uint32_t thr_pending = F32_INF_BITS;
+            epi_bar_n(1);
+            Q1_LAP(6);
+
+            // merge every owned query selected by `need` (warp-uniform mask over lanes 0..15)
+            auto merge_owned = [&](unsigned need) {
+                st_merge += __popc(need);
+                if (__popc(need) == 1) {
+                    // the common case: one query to fold -> a single 32-lane network (a quarter of
+                    // the instructions of the 4-way interleaved one)
+                    const int src = __ffs(need) - 1;
+                    const uint32_t q = (uint32_t)src * 4u + (uint32_t)ew;
+                    const uint32_t c = sm.pcnt[q];
+                    const uint32_t n = min(c, (uint32_t)R2_CAP);
+                    uint64_t nw = ((uint32_t)lane < n) ? sm.pend[q * R2_CAP + lane] : KEY_NONE;
+                    uint64_t lst = sm.sorted[q * TC_KP + lane];
+                    nw = warp_sort32(nw, lane);
+                    lst = warp_merge32(lst, nw, lane);
+                    sm.sorted[q * TC_KP + lane] = lst;
+                    const uint64_t last = shfl64(lst, 31);
+                    if (lane == src) {
+                        sm.pcnt[q] = 0;
+                        if (last != KEY_NONE) {
+                            sm.thrp[q] = fminf(sm.thrp[q], __uint_as_float((uint32_t)(last >> 32)) - qn_own);
+                            if (p.thr_g) atomicMin(p.thr_g + qi_own, (uint32_t)(last >> 32));
+                        }
+                        if (c > (uint32_t)R2_CAP) atomicOr(&sm.redo[q >> 5], 1u << (q & 31));
+                    }
+                    __syncwarp();
+                    return;
+                }
+                while (need) {
+                    uint32_t qs[4], nn[4], over = 0;
+                    bool act[4];
+                    int src[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        act[g] = need != 0;
+                        src[g] = act[g] ? (__ffs(need) - 1) : 0;
+                        if (act[g]) need &= need - 1;
+                        qs[g] = (uint32_t)src[g] * 4u + (uint32_t)ew;
+                        const uint32_t c = act[g] ? sm.pcnt[qs[g]] : 0u;
+                        nn[g] = min(c, (uint32_t)R2_CAP);
+                        if (c > (uint32_t)R2_CAP) over |= 1u << g;
+                    }
+                    uint64_t lst[4];
+                    r2_merge4(sm, qs, nn, act, lst, lane);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (!act[g]) continue;
+                        sm.sorted[qs[g] * TC_KP + lane] = lst[g];
+                        const uint64_t last = shfl64(lst[g], 31);
+                        if (lane == src[g]) {
+                            sm.pcnt[qs[g]] = 0;
+                            if (last != KEY_NONE) {
+                                sm.thrp[qs[g]] = fminf(sm.thrp[qs[g]], __uint_as_float((uint32_t)(last >> 32)) - qn_own);
+                                // any 32 rows below a value bound the global 32nd: share it at once
+                                if (p.thr_g) atomicMin(p.thr_g + qi_own, (uint32_t)(last >> 32));
+                            }
+                            if (over & (1u << g)) atomicOr(&sm.redo[qs[g] >> 5], 1u << (qs[g] & 31));
+                        }
+                    }
+                    __syncwarp();
+                }
+            };
 
             // ---- row tiles ----
-            for (uint32_t rt = it.row_begin; rt < it.row_end; rt += TC_ROWS) {
-                const uint32_t pos = rt + trow;
-                float xn = __uint_as_float(F32_INF_BITS);  // +inf => masked / out of range
-                if (pos < it.row_end) {
-                    bool live = true;
-                    if (p.tomb || p.filt) {
-                        const uint32_t id = p.ids[pos];
-                        if (p.tomb && bit_test(p.tomb, p.tomb_bits, id)) live = false;
-                        else if (p.filt && !bit_test(p.filt, p.filt_bits, id)) live = false;
-                    }
-                    if (live) xn = __ldg(p.xnorm + pos);
-                }
-                mbar_wait(bar_tfull + 8 * buf, fphase[buf]);
-                fphase[buf] ^= 1;
+            for (uint32_t rt = it.row_begin; rt < it.row_end; rt += R2_ROWS) {
+                const uint32_t slot = tile & (R2_NSLOT - 1);
+                Q1_LAP(4);
+                mbar_wait(bar_nfull + 8 * slot, (tile / R2_NSLOT) & 1u);
+                const float xn = sm.xn_ring[slot * R2_ROWS + trow];
+                const uint32_t buf = tile & (R2_NBUF - 1);
+                mbar_wait(bar_tfull + 8 * buf, (tile / R2_NBUF) & 1u);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + buf * TC_NQ + ((uint32_t)(quarter * 32) << 16);
+                Q1_LAP(2);
+                const uint32_t taddr = tmem_base + buf * R2_NQ + lane_taddr;
+                const uint32_t pos = rt + (uint32_t)trow;
+                uint64_t ovf = 0;  // queries whose pending list was full when this row passed
+
+                auto append = [&](uint32_t q, float v) {
+                    const uint32_t s = atomicAdd(&sm.pcnt[q], 1u);
+                    ++st_app;
+                    if (s < (uint32_t)R2_CAP)
+                        sm.pend[q * R2_CAP + s] =
+                            ((uint64_t)__float_as_uint(fmaxf(v + sm.qn[mb + q], 0.0f)) << 32) | (uint64_t)pos;
+                    else {
+                        ovf |= 1ull << q;
+                        ++st_ovf;
+                    }
+                };
+
                 for (uint32_t c0 = 0; c0 < ((p.debug & 1u) ? 0u : ncols); c0 += 16) {
                     uint32_t acc[16];
+                    ++st_chunks;
                     tmem_ld16(taddr + c0, acc);
                     float thr[16];
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(thrp_s + c0 + 4 * j4);
+                        const float4 t4 = *reinterpret_cast<const float4*>(sm.thrp + c0 + 4 * j4);
                         thr[4 * j4 + 0] = t4.x; thr[4 * j4 + 1] = t4.y; thr[4 * j4 + 2] = t4.z; thr[4 * j4 + 3] = t4.w;
                     }
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float v = fmaf(-2.0f, __uint_as_float(acc[j]), xn);  // |x|^2 - 2 x.q
-                        const bool pass = v < thr[j];
-                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                        if (bal) {  // warp-uniform: one shared-memory atomic per warp per query
-                            const uint32_t q = c0 + j;
-                            uint32_t base = 0;
-                            if (lane == 0) base = atomicAdd(&cnt_s[q], (uint32_t)__popc(bal));
-                            base = __shfl_sync(0xffffffffu, base, 0);
-                            if (pass) {
-                                const float d2 = fmaxf(v + qn_s[q], 0.0f);
-                                cand_s[q * TC_CAP + base + __popc(bal & lt_mask)] =
-                                    (__float_as_uint(d2) & ~127u) | (uint32_t)trow;
-                            }
+                        if (v < thr[j]) append(c0 + j, v);
+                    }
+                }
+                Q1_LAP(3);
+                epi_bar_n(2);  // every candidate of this tile is in the pending lists
+                // ---- merge phase: owners fold long pending lists, refresh shared thresholds ----
+                while (true) {
+                    if (own) {
+                        // bound tightened meanwhile by CTAs scanning other lists of the same query
+                        // (loaded during the previous tile: no exposed latency)
+                        sm.thrp[jown] = fminf(sm.thrp[jown], __uint_as_float(thr_pending) - qn_own);
+                        if (p.thr_g) thr_pending = *(volatile uint32_t*)(p.thr_g + qi_own);
+                    }
+                    const uint32_t pc = own ? sm.pcnt[jown] : 0u;
+                    merge_owned(__ballot_sync(0xffffffffu, pc > (uint32_t)R2_FLUSH));
+                    epi_bar_n(1);  // thresholds / pending counters settled
+                    const uint32_t r0 = sm.redo[0], r1 = sm.redo[1];
+                    if ((r0 | r1) == 0) break;
+                    ++st_replay;
+                    // replay: rows that met a full pending list are tested against the new thresholds
+                    epi_bar_n(2);
+                    if (et < 2) sm.redo[et] = 0;
+                    uint64_t rm = ((uint64_t)r1 << 32) | r0;
+                    while (rm) {
+                        const uint32_t q = (uint32_t)__ffsll((long long)rm) - 1u;
+                        rm &= rm - 1;
+                        uint32_t a;
+                        tmem_ld1(taddr + q, a);
+                        tmem_ld_wait();
+                        if ((ovf >> q) & 1ull) {
+                            ovf &= ~(1ull << q);
+                            const float v = fmaf(-2.0f, __uint_as_float(a), xn);
+                            if (v < sm.thrp[q]) append(q, v);
                         }
                     }
+                    epi_bar_n(1);
+                    // every replayed query is merged again (its pending list may have refilled)
+                    {
+                        const bool mine = own && (((jown < 32 ? r0 : r1) >> (jown & 31)) & 1u);
+                        merge_owned(__ballot_sync(0xffffffffu, mine && sm.pcnt[jown] > 0));
+                    }
+                    epi_bar_n(2);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);  // accumulator may be overwritten
-                epi_bar(1);
-                // ---- merge this tile's candidates into the per-query shortlists ----
-                for (uint32_t g0 = 0; g0 < (uint32_t)TC_NQ / 4; g0 += 4) {
-                    // this warp's queries: ew + 4*i; four at a time
-                    uint32_t qs[4], n[4];
-                    uint32_t nmax = 0;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        qs[g] = ew + 4 * (g0 + g);
-                        n[g] = (qs[g] < cnt) ? cnt_s[qs[g]] : 0u;
-                        nmax = max(nmax, n[g]);
+                ++tile;
+            }
+            // ---- item epilogue: fold what is pending, publish the shortlists ----
+            Q1_LAP(4);
+            {
+                // a query that never merged in this item (the usual case away from its nearest
+                // lists) publishes its few pending candidates UNSORTED; the shortlist merge that
+                // follows the scan sorts such rows.  Only queries holding both a sorted list and
+                // pending candidates need one more fold here.
+                const uint32_t pc = own ? sm.pcnt[jown] : 0u;
+                const bool has_sorted = own && sm.sorted[jown * TC_KP] != KEY_NONE;
+                merge_owned(__ballot_sync(0xffffffffu, pc > 0 && has_sorted));
+                __syncwarp();
+                for (uint32_t j = (uint32_t)ew; j < cnt; j += 4) {
+                    uint64_t mine = sm.sorted[j * TC_KP + lane];
+                    if (__shfl_sync(0xffffffffu, mine == KEY_NONE ? 1 : 0, 0)) {   // no sorted list: pending, as is
+                        const uint32_t n = sm.pcnt[j];
+                        if (n == 0) continue;                                      // partial is pre-filled
+                        mine = ((uint32_t)lane < n) ? sm.pend[j * R2_CAP + lane] : KEY_NONE;
                     }
-                    if (nmax == 0) continue;
-                    uint64_t lst[4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) lst[g] = list_s[qs[g] * TC_KP + lane];
-                    for (uint32_t b = 0; b < nmax; b += 32) {
-                        uint32_t c[4];
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            c[g] = (b + lane < n[g]) ? cand_s[qs[g] * TC_CAP + b + lane] : 0xFFFFFFFFu;
-                        warp_sort32x4_u32(c, lane);
-                        uint64_t key[4];
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            key[g] = (c[g] == 0xFFFFFFFFu) ? KEY_NONE
-                                                           : (((uint64_t)(c[g] & ~127u) << 32) | (uint64_t)(rt + (c[g] & 127u)));
-                        warp_merge32x4(lst, key, lane);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (n[g] == 0) continue;
-                        list_s[qs[g] * TC_KP + lane] = lst[g];
-                        if (lane == 31)
-                            thrp_s[qs[g]] = (lst[g] == KEY_NONE) ? __uint_as_float(F32_INF_BITS)
-                                                                 : __uint_as_float((uint32_t)(lst[g] >> 32)) - qn_s[qs[g]];
-                        if (lane == 0) cnt_s[qs[g]] = 0;
-                    }
+                    p.partial[((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * TC_KP + lane] = mine;
                 }
-                epi_bar(2);
-                buf ^= 1;
             }
-            // ---- item epilogue: publish shortlists and tighten the shared thresholds ----
-            for (uint32_t q = ew; q < cnt; q += 4) {
-                const uint64_t mine = list_s[q * TC_KP + lane];
-                const uint32_t qi = qidx_s[q];
-                p.partial[((size_t)qi * p.P + qslot_s[q]) * TC_KP + lane] = mine;
-                if (lane == 31 && mine != KEY_NONE) atomicMin(p.thr_g + qi, (uint32_t)(mine >> 32));
+            epi_bar_n(1);  // pools may be re-initialised for the next item
+            ++nit;
+            Q1_LAP(5);
+        }
+        if (warp == 2) Q1_LAP_DUMP(2);
+        if (p.prof && warp == 2) {
+            const uint32_t a = __reduce_add_sync(0xffffffffu, st_app), o = __reduce_add_sync(0xffffffffu, st_ovf);
+            if (lane == 0) {
+                unsigned long long* d = p.prof + ((size_t)blockIdx.x * 6 + 4) * 8;
+                d[0] = a; d[1] = o; d[2] = st_merge; d[3] = st_replay; d[4] = tile; d[5] = st_chunks;
             }
-            epi_bar(1);
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (p.prof && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + 5] = gt;
+        p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + 6] = (unsigned long long)clock64() - p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + 6];
+    }
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)TC_TMEM_COLS)
+                     "r"((uint32_t)R2_TMEM_COLS)
                      : "memory");
     }
 }
@@ -442,10 +752,6 @@ __device__ __forceinline__ void q1_merge4(const QPool& pool, const uint32_t (&m)
     }
     warp_merge32x4(lst, nw, lane);
 }
-
-// stopwatch lap: the cycles since the previous lap of this role are charged to category i
-#define Q1_LAP(i) do { if (p.prof) { const long long n_ = clock64(); lap[i] += (unsigned long long)(n_ - tl); tl = n_; } } while (0)
-#define Q1_LAP_DUMP(role) do { if (p.prof && lane == 0) { for (int i_ = 0; i_ < 8; ++i_) p.prof[((size_t)blockIdx.x * 3 + (role)) * 8 + i_] = lap[i_]; } } while (0)
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
@@ -878,12 +1184,6 @@ uint32_t q1_pick_stages(uint32_t KB, uint32_t kbs) {
     return stages;
 }
 
-size_t tc_scan_smem_bytes(uint32_t KB, uint32_t stages) {
-    return (size_t)KB * TC_QBLK_BYTES + (size_t)stages * TC_STAGE_BYTES + (size_t)TC_NQ * TC_CAP * 4 +
-           (size_t)TC_NQ * TC_KP * 8 + (size_t)TC_NQ * 5 * 4 + (size_t)(2 * stages + 5 + 2 * TC_SCHED) * 8 + 16 +
-           (size_t)TC_SCHED * 4;
-}
-
 
 // ---- small support kernels ----------------------------------------------------------------------
 __global__ void row_norms_kernel(const float* __restrict__ x, uint64_t n, uint32_t D, float* __restrict__ out,
@@ -1105,6 +1405,31 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restr
     }
 }
 
+// Shortlist merge after the scan: P rows of TC_KP approx keys per query (one per probed list), each
+// either empty, sorted (a list that was merged during the scan) or unsorted (pending candidates
+// published as they were).  One warp per query folds them into the query's best TC_KP.
+__global__ void __launch_bounds__(128) merge_rows32_kernel(const uint64_t* __restrict__ in, uint32_t nq, uint32_t P,
+                                                           uint64_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const uint64_t* base = in + (size_t)q * P * TC_KP;
+    uint64_t best = KEY_NONE;
+    for (uint32_t s0 = 0; s0 < P; s0 += 4) {
+        uint64_t row[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) row[g] = (s0 + g < P) ? base[(size_t)(s0 + g) * TC_KP + lane] : KEY_NONE;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (__ballot_sync(0xffffffffu, row[g] != KEY_NONE) == 0) continue;
+            const uint64_t up = shfl_up64(row[g], 1);
+            if (__ballot_sync(0xffffffffu, lane > 0 && up > row[g])) row[g] = warp_sort32(row[g], lane);
+            best = warp_merge32(best, row[g], lane);
+        }
+    }
+    out[(size_t)q * TC_KP + lane] = best;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1141,10 +1466,62 @@ struct Buf {
 
 }  // namespace
 
+// timing experiment only (FVDB_TC_DEBUG bit 7): per-role stopwatch laps, averaged over CTAs
+static cudaError_t dump_prof(const unsigned long long* d_prof, uint32_t grid, cudaStream_t st) {
+    std::vector<unsigned long long> hp((size_t)grid * 48);
+    cudaError_t e = cudaMemcpyAsync(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    {
+        unsigned long long t0 = ~0ull, t1 = 0;
+        double dur_avg = 0, dur_max = 0, cyc_avg = 0, start_max = 0;
+        for (uint32_t b = 0; b < grid; ++b) {
+            const unsigned long long* r = &hp[((size_t)b * 6 + 3) * 8];
+            if (r[4] == 0) continue;
+            t0 = std::min(t0, r[4]); t1 = std::max(t1, r[5]);
+        }
+        for (uint32_t b = 0; b < grid; ++b) {
+            const unsigned long long* r = &hp[((size_t)b * 6 + 3) * 8];
+            if (r[4] == 0) continue;
+            const double d = (double)(r[5] - r[4]);
+            dur_avg += d / grid; dur_max = std::max(dur_max, d); cyc_avg += (double)r[6] / grid;
+            start_max = std::max(start_max, (double)(r[4] - t0));
+        }
+        if (t1) fprintf(stderr, "[tc prof] wall: first start -> last end %.1f us; CTA duration avg %.1f max %.1f us; "
+                        "latest start +%.1f us; avg cycles %.0f => %.3f GHz\n", (t1 - t0) * 1e-3, dur_avg * 1e-3,
+                        dur_max * 1e-3, start_max * 1e-3, cyc_avg, cyc_avg / dur_avg);
+    }
+    static const char* names[5] = {"producer", "mma", "epilogue", "loader", "epistats"};
+    for (int r = 0; r < 5; ++r) {
+        double avg[8] = {0}, mx[8] = {0};
+        for (uint32_t b = 0; b < grid; ++b)
+            for (int i = 0; i < 8; ++i) {
+                const double v = (double)hp[((size_t)b * 6 + r) * 8 + i];
+                avg[i] += v / grid;
+                mx[i] = std::max(mx[i], v);
+            }
+        fprintf(stderr, "[tc prof] %-8s avg:", names[r]);
+        for (int i = 0; i < 8; ++i) fprintf(stderr, " %9.0f", avg[i]);
+        fprintf(stderr, "  max:");
+        for (int i = 0; i < 8; ++i) fprintf(stderr, " %9.0f", mx[i]);
+        fprintf(stderr, "\n");
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_merge_rows32(const uint64_t* in, uint32_t nq, uint32_t P, uint64_t* out, cudaStream_t stream) {
+    if (nq == 0) return cudaSuccess;
+    merge_rows32_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(in, nq, P, out);
+    return cudaGetLastError();
+}
+
 struct TcScratchImpl {
     Buf<float> xnorm, qnorm;
     Buf<uint32_t> misc;  // [0] = max |x|^2 bits
     Buf<unsigned long long> prof;
+    Buf<uint32_t> list_order;  // lists by descending length (tile-scheduler order)
+    uint32_t list_order_n = 0;
     Buf<uint32_t> thr_g, list_cnt, pair_off, cursor, pair_q, pair_slot, n_items;
     Buf<ScanItem> items;
     Buf<uint64_t> partial, shortlist;
@@ -1170,7 +1547,7 @@ void tc_release(TcScratch& s) {
     m->xnorm.release(); m->qnorm.release(); m->misc.release(); m->thr_g.release(); m->list_cnt.release();
     m->pair_off.release(); m->cursor.release(); m->pair_q.release(); m->pair_slot.release(); m->n_items.release();
     m->items.release(); m->partial.release(); m->shortlist.release();
-    m->prof.release();
+    m->prof.release(); m->list_order.release();
     m->cnorm.release(); m->dense.release(); m->coarse.release(); m->citems.release();
     delete m;
     s.impl = nullptr;
@@ -1229,6 +1606,20 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             if (err) *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
             return FVDB_ERR_CUDA;
         }
+        {
+            // longest-list-first order for the dynamic tile scheduler (once per arena layout)
+            std::vector<uint32_t> off(a.nlist + 1), order(a.nlist);
+            TCK(cudaMemcpyAsync(off.data(), a.list_off, (size_t)(a.nlist + 1) * 4, cudaMemcpyDeviceToHost, st));
+            TCK(cudaStreamSynchronize(st));
+            for (uint32_t l = 0; l < a.nlist; ++l) order[l] = l;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+                return off[x + 1] - off[x] > off[y + 1] - off[y];
+            });
+            TCK(m->list_order.ensure(a.nlist, dev_bytes));
+            TCK(cudaMemcpyAsync(m->list_order.p, order.data(), (size_t)a.nlist * 4, cudaMemcpyHostToDevice, st));
+            TCK(cudaStreamSynchronize(st));
+            m->list_order_n = a.nlist;
+        }
         m->tmap_rows = a.rows;
         m->tmap_n = a.n_rows;
         s.arena_dirty = false;
@@ -1239,7 +1630,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     // kernel Q (queries in tensor memory) needs D <= 384 TMEM columns for the query tile;
     // kernel R (rows on lanes, query tile in shared memory) covers 384 < D <= 512
     const char* kenv = getenv("FVDB_TC_KERNEL");
-    const bool use_q = (D <= 384) && !(kenv && kenv[0] == 'R');
+    const bool use_q = (D <= 384) && (kenv && kenv[0] == 'Q');
     const uint32_t tile_q = use_q ? (uint32_t)Q1_M : TC_TILE_Q;
     const size_t max_items = (size_t)a.nlist + (n_pairs + tile_q - 1) / tile_q + 1;
     TCK(m->qnorm.ensure(nq, dev_bytes));
@@ -1263,7 +1654,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     }
     const uint64_t* coarse_keys = a.coarse_keys;
     if (!coarse_keys) {
-        if (!use_q || np > TC_MAX_NPROBE_COARSE) { if (err) *err = "TC coarse step unsupported for this shape"; return FVDB_ERR_INVALID_ARG; }
+        if (D > 384 || np > TC_MAX_NPROBE_COARSE) { if (err) *err = "TC coarse step unsupported for this shape"; return FVDB_ERR_INVALID_ARG; }
         // centroid norms + TMA descriptor of the centroid table
         if (s.centroids_dirty || m->tmap_cent_ptr != a.centroids || m->tmap_cent_n != a.nlist) {
             TCK(m->cnorm.ensure(a.nlist, dev_bytes));
@@ -1330,7 +1721,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         if (a.coarse_out) TCK(cudaMemcpyAsync(a.coarse_out, m->coarse.p, (size_t)nq * np * 8, cudaMemcpyDeviceToDevice, st));
     }
     TCK(launch_probe_bucketing(coarse_keys, nq, np, a.list_off, a.nlist, tile_q, m->list_cnt.p, m->pair_off.p,
-                               m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st));
+                               m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st,
+                               (m->list_order_n == a.nlist && getenv("FVDB_TC_ORDER")) ? m->list_order.p : nullptr));
     (*launches) += 3;
     TCK(cudaMemsetAsync(m->partial.p, 0xFF, n_pairs * TC_KP * sizeof(uint64_t), st));
 
@@ -1361,36 +1753,18 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         }
         const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
         if (p.debug & 128u) {
-            TCK(m->prof.ensure((size_t)grid * 24, dev_bytes));
-            TCK(cudaMemsetAsync(m->prof.p, 0, (size_t)grid * 24 * 8, st));
+            TCK(m->prof.ensure((size_t)grid * 48, dev_bytes));
+            TCK(cudaMemsetAsync(m->prof.p, 0, (size_t)grid * 48 * 8, st));
             p.prof = m->prof.p;
         }
         if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
         tc_scan_q_kernel<<<grid, TC_THREADS, smem, st>>>(m->tmap_q, p);
         TCK(cudaGetLastError());
-        if (p.prof) {  // timing experiment only: per-role stopwatch laps, averaged over CTAs
-            std::vector<unsigned long long> hp((size_t)grid * 24);
-            TCK(cudaMemcpyAsync(hp.data(), m->prof.p, hp.size() * 8, cudaMemcpyDeviceToHost, st));
-            TCK(cudaStreamSynchronize(st));
-            static const char* names[3] = {"producer", "mma", "epilogue"};
-            for (int r = 0; r < 3; ++r) {
-                double avg[8] = {0}, mx[8] = {0};
-                for (uint32_t b = 0; b < grid; ++b)
-                    for (int i = 0; i < 8; ++i) {
-                        const double v = (double)hp[((size_t)b * 3 + r) * 8 + i];
-                        avg[i] += v / grid;
-                        mx[i] = std::max(mx[i], v);
-                    }
-                fprintf(stderr, "[q1 prof] %-8s avg:", names[r]);
-                for (int i = 0; i < 8; ++i) fprintf(stderr, " %9.0f", avg[i]);
-                fprintf(stderr, "  max:");
-                for (int i = 0; i < 8; ++i) fprintf(stderr, " %9.0f", mx[i]);
-                fprintf(stderr, "\n");
-            }
-        }
+        if (p.prof) TCK(dump_prof(m->prof.p, grid, st));
     } else {
-        uint32_t stages = 8;
-        while (stages > 2 && tc_scan_smem_bytes(KB, stages) > 227 * 1024) --stages;
+        // deepest ring that fits; the norm-strip window (see the producer) caps it at 6 tiles
+        uint32_t stages = std::min<uint32_t>(12u, 6u * KB);
+        while (stages > 2 && tc_scan_smem_bytes(KB, stages) + 1024 > 232448) --stages;
         p.stages = stages;
         const size_t smem = tc_scan_smem_bytes(KB, stages) + 1024;  // slack for the 1024-byte alignment
         if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
@@ -1399,15 +1773,21 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             m->smem_attr_set = true;
         }
         const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
+        if (p.debug & 128u) {
+            TCK(m->prof.ensure((size_t)grid * 48, dev_bytes));
+            TCK(cudaMemsetAsync(m->prof.p, 0, (size_t)grid * 48 * 8, st));
+            p.prof = m->prof.p;
+        }
         if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
-        tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(m->tmap_arena, p);
+        tc_scan_kernel<<<grid, R2_THREADS, smem, st>>>(m->tmap_arena, p);
         TCK(cudaGetLastError());
+        if (p.prof) TCK(dump_prof(m->prof.p, grid, st));
     }
     if (a.ev_scan1) TCK(cudaEventRecord(a.ev_scan1, st));
     (*launches)++;
 
     // ---- merge the per-(query, probe) shortlists, exact re-rank, proof ----
-    TCK(launch_merge_partials(m->partial.p, nq, np, TC_KP, m->shortlist.p, st));
+    TCK(launch_merge_rows32(m->partial.p, nq, np, m->shortlist.p, st));
     rerank_kernel<<<(nq + 3) / 4, 128, (size_t)4 * D * sizeof(float), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k,
                                                a.out_keys, a.d_fallback_count, a.d_fallback_idx);
     TCK(cudaGetLastError());
