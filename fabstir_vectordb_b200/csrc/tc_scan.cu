@@ -423,17 +423,27 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                         const uint32_t qi = (q < 32) ? qa : qb;
                         src[g] = (q < ncols && qi != ID_NONE) ? reinterpret_cast<const float4*>(p.Q + (size_t)qi * D) : nullptr;
                     }
-                    for (uint32_t c = lane; c < f4_per_row; c += 32) {
-                        float4 v[4];
+                    // three float4 columns x four query rows = 12 independent 16-byte loads per lane
+                    for (uint32_t c = lane; c < f4_per_row; c += 96) {
+                        float4 v[3][4];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) v[g] = src[g] ? __ldg(src[g] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const uint32_t kb = c >> 3, ch = c & 7;
+                        for (int u = 0; u < 3; ++u)
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint32_t q = q0 + 4 * g;
-                            if (q < ncols)
-                                *reinterpret_cast<float4*>(sm.q_tile + (size_t)kb * R2_QBLK_BYTES + q * 128 +
-                                                           ((ch ^ (q & 7)) << 4)) = v[g];
+                            for (int g = 0; g < 4; ++g)
+                                v[u][g] = (src[g] && c + 32 * u < f4_per_row) ? __ldg(src[g] + c + 32 * u)
+                                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            const uint32_t cc = c + 32 * u;
+                            if (cc >= f4_per_row) break;
+                            const uint32_t kb = cc >> 3, ch = cc & 7;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const uint32_t q = q0 + 4 * g;
+                                if (q < ncols)
+                                    *reinterpret_cast<float4*>(sm.q_tile + (size_t)kb * R2_QBLK_BYTES + q * 128 +
+                                                               ((ch ^ (q & 7)) << 4)) = v[u][g];
+                            }
                         }
                     }
                 }
@@ -1648,7 +1658,12 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)nq * 32 + 255) / 256, (uint64_t)a.sm_count * 8);
         row_norms_kernel<<<blocks, 256, 0, st>>>(a.Q, nq, D, m->qnorm.p, nullptr);
-        fill_u32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m->thr_g.p, nq, F32_INF_BITS);
+        {
+            // experiment (FVDB_TC_DEBUG bit 9): keep the previous batch's bounds = perfectly seeded thresholds
+            const char* dbg = getenv("FVDB_TC_DEBUG");
+            if (!(dbg && (atoi(dbg) & 512)))
+                fill_u32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m->thr_g.p, nq, F32_INF_BITS);
+        }
         TCK(cudaGetLastError());
         (*launches) += 2;
     }

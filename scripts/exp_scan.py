@@ -40,7 +40,7 @@ for arg in sys.argv[1:]:
     ms, tot = [], []
     try:
         for i in range(8):
-            sh.search(qsets[i % 4], bench.K, bench.NPROBE, tiers=L.TIER_HISTORICAL)
+            sh.search(qsets[0 if "ONESET" in envs else i % 4], bench.K, bench.NPROBE, tiers=L.TIER_HISTORICAL)
             torch.cuda.synchronize()
             st = eng.stats()
             if i >= 3:
