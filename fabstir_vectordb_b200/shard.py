@@ -93,9 +93,10 @@ class ShardedIndex:
                                b["ids"].data_ptr(), b["dist"].data_ptr(), b["cnt"].data_ptr(), stream)
         if self.world == 1:
             return b["ids"], b["dist"], b["cnt"]
-        dist.all_gather_into_tensor(b["g_ids"], b["ids"], group=self.group)
-        dist.all_gather_into_tensor(b["g_dist"], b["dist"], group=self.group)
-        dist.all_gather_into_tensor(b["g_cnt"], b["cnt"], group=self.group)
+        # [world][nq][k] == the rank-major concatenation along dim 0 (the form gloo insists on)
+        dist.all_gather_into_tensor(b["g_ids"].view(self.world * nq, k), b["ids"], group=self.group)
+        dist.all_gather_into_tensor(b["g_dist"].view(self.world * nq, k), b["dist"], group=self.group)
+        dist.all_gather_into_tensor(b["g_cnt"].view(self.world * nq), b["cnt"], group=self.group)
         self.eng.merge_topk_device(b["g_ids"].data_ptr(), b["g_dist"].data_ptr(), b["g_cnt"].data_ptr(),
                                    self.world, nq, k, b["o_ids"].data_ptr(), b["o_dist"].data_ptr(),
                                    b["o_cnt"].data_ptr(), stream)
