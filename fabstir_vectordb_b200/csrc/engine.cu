@@ -129,6 +129,7 @@ struct fvdb_index {
     DevBuf<double> s_f64;
     DevBuf<uint64_t> s_tmpbits;
     DevBuf<uint32_t> s_fb_idx;
+    DevBuf<uint32_t> s_fb_idx_flat;
     DevBuf<float> s_fb_q;
     DevBuf<uint64_t> s_fb_keys, s_fb_coarse;
     TcScratch tc;
@@ -690,11 +691,32 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             scan_timed = true;
         }
     }
+    bool flat_tc = false;
+    uint32_t* d_fb_count_flat = h->s_misc.p + 11;
     if (use_flat) {
         CK(h->s_flat_keys.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
         flat_keys = h->s_flat_keys.p;
-        RET(scan_all_exact(h, h->flat_rows.p, h->flat_ids.p, h->flat_n, d_q, nq, k, tomb, h->tomb_bits,
-                           filt, filter_bits, flat_keys, st));
+        // recent tier: exhaustive scan instead of the HNSW walk (src/hnsw/core.rs:398-467); on the
+        // tensor cores when the batch is large enough to amortise the item set-up
+        flat_tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D) && k <= TC_MAX_K &&
+                  (uint64_t)h->flat_n * nq >= (4ull << 20) && !getenv("FVDB_FLAT_EXACT");
+        if (flat_tc) {
+            CK(h->s_fb_idx_flat.ensure((size_t)2 * nq, 0, st, &h->dev_bytes));
+            TcFlatArgs fa{};
+            fa.rows = h->flat_rows.p; fa.ids = h->flat_ids.p; fa.n_rows = h->flat_n;
+            fa.Q = d_q; fa.nq = nq; fa.D = D; fa.k = k;
+            fa.tomb = tomb; fa.tomb_bits = h->tomb_bits; fa.filt = filt; fa.filt_bits = filter_bits;
+            fa.out_keys = flat_keys;
+            fa.d_fallback_count = d_fb_count_flat; fa.d_fallback_idx = h->s_fb_idx_flat.p;
+            fa.sm_count = h->sm_count;
+            uint32_t launches = 0;
+            int r = tc_flat_search(h->tc, fa, st, &h->dev_bytes, &launches, &h->err);
+            if (r != FVDB_OK) return r;
+            h->stats.last_launches += launches;
+        } else {
+            RET(scan_all_exact(h, h->flat_rows.p, h->flat_ids.p, h->flat_n, d_q, nq, k, tomb, h->tomb_bits,
+                               filt, filter_bits, flat_keys, st));
+        }
     }
     CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
     h->stats.last_launches += 1;
@@ -716,6 +738,20 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         if (cudaEventElapsedTime(&sms, h->ev_s0, h->ev_s1) == cudaSuccess) h->stats.last_scan_ms = sms;
         else cudaGetLastError();
     }
+    const uint32_t n_fb_flat = flat_tc ? std::min(host_misc[11], 2 * nq) : 0;
+    if (n_fb_flat) {
+        // flat-tier proof failures: exact scan of the recent tier for exactly those queries
+        CK(h->s_fb_q.ensure((size_t)n_fb_flat * D, 0, st, &h->dev_bytes));
+        CK(h->s_fb_keys.ensure((size_t)n_fb_flat * k, 0, st, &h->dev_bytes));
+        CK(launch_gather_rows(d_q, nq, nullptr, h->s_fb_idx_flat.p, n_fb_flat, D, h->s_fb_q.p, st));
+        RET(scan_all_exact(h, h->flat_rows.p, h->flat_ids.p, h->flat_n, h->s_fb_q.p, n_fb_flat, k, tomb, h->tomb_bits,
+                           filt, filter_bits, h->s_fb_keys.p, st));
+        CK(launch_scatter_keys(h->s_fb_keys.p, h->s_fb_idx_flat.p, n_fb_flat, k, flat_keys, st));
+        CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
+        CK(cudaStreamSynchronize(st));
+        h->stats.last_launches += 3;
+        h->stats.last_fallback_queries += n_fb_flat;
+    }
     const uint32_t n_fb = used_tc ? std::min(host_misc[10], 2 * nq) : 0;
     if (n_fb) {
         // the tensor-core proof failed for n_fb queries: re-run exactly those on the exact path
@@ -732,7 +768,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
         CK(cudaStreamSynchronize(st));
         h->stats.last_launches += 3;
-        h->stats.last_fallback_queries = n_fb;
+        h->stats.last_fallback_queries += n_fb;
     }
     uint64_t rows = scanned + (use_flat ? h->flat_n : 0);
     h->stats.last_scanned_rows = rows;

@@ -270,7 +270,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
             if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
             lap[6] += 1;
             Q1_LAP(1);
-            const uint64_t hint = (!it.identity && it.slot > 1) ? hint_normal : hint_first;
+            // rows shared by several items (a list with > 64 probing queries, a flat-tier chunk) stay in L2
+            const uint64_t hint = (it.identity == 2 || (!it.identity && it.slot > 1)) ? hint_normal : hint_first;
             for (uint32_t rt = it.row_begin; rt < it.row_end; rt += R2_ROWS) {
                 float xnv[4];
 #pragma unroll
@@ -1295,6 +1296,27 @@ __global__ void coarse_items_kernel(ScanItem* items, uint32_t nq, uint32_t nlist
     items[i] = it;
 }
 
+// identity work items of the flat-tier scan: (query group of TC_TILE_Q) x (row chunk); `slot` = chunk
+// index = the partial slot the item's shortlists are published to
+__global__ void flat_items_kernel(ScanItem* items, uint32_t nq, uint32_t n_rows, uint32_t chunk_rows,
+                                  uint32_t n_chunks, uint32_t* n_items) {
+    const uint32_t n_qg = (nq + TC_TILE_Q - 1) / TC_TILE_Q;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_items = n_qg * n_chunks;
+    if (i >= n_qg * n_chunks) return;
+    // chunk-major order: the query groups of one chunk are adjacent, so its re-reads hit L2
+    const uint32_t c = i / n_qg, g = i % n_qg;
+    ScanItem it;
+    it.row_begin = c * chunk_rows;
+    it.row_end = min(n_rows, (c + 1) * chunk_rows);
+    it.pair_begin = g * TC_TILE_Q;
+    it.pair_count = min((uint32_t)TC_TILE_Q, nq - g * TC_TILE_Q);
+    it.slot = c;
+    it.identity = n_qg > 1 ? 2 : 1;   // 2: the chunk is read by several query groups (keep it in L2)
+    if (it.row_begin >= it.row_end) it.pair_count = 0;
+    items[i] = it;
+}
+
 template <int T>
 __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restrict__ dense, uint32_t ld,
                                                             const float* __restrict__ centroids,
@@ -1531,6 +1553,11 @@ struct TcScratchImpl {
     Buf<uint32_t> misc;  // [0] = max |x|^2 bits
     Buf<unsigned long long> prof;
     Buf<uint32_t> list_order;  // lists by descending length (tile-scheduler order)
+    Buf<float> fxnorm;         // flat tier: |x|^2 per row
+    Buf<ScanItem> fitems;
+    CUtensorMap tmap_flat;     // flat tier, box 32 floats x 128 rows
+    const float* tmap_flat_rows = nullptr;
+    uint64_t tmap_flat_n = 0;
     uint32_t list_order_n = 0;
     Buf<uint32_t> thr_g, list_cnt, pair_off, cursor, pair_q, pair_slot, n_items;
     Buf<ScanItem> items;
@@ -1557,7 +1584,7 @@ void tc_release(TcScratch& s) {
     m->xnorm.release(); m->qnorm.release(); m->misc.release(); m->thr_g.release(); m->list_cnt.release();
     m->pair_off.release(); m->cursor.release(); m->pair_q.release(); m->pair_slot.release(); m->n_items.release();
     m->items.release(); m->partial.release(); m->shortlist.release();
-    m->prof.release(); m->list_order.release();
+    m->prof.release(); m->list_order.release(); m->fxnorm.release(); m->fitems.release();
     m->cnorm.release(); m->dense.release(); m->coarse.release(); m->citems.release();
     delete m;
     s.impl = nullptr;
@@ -1807,6 +1834,85 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
                                                a.out_keys, a.d_fallback_count, a.d_fallback_idx);
     TCK(cudaGetLastError());
     (*launches) += 2;
+    return FVDB_OK;
+}
+
+int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* dev_bytes, uint32_t* launches,
+                   std::string* err) {
+    if (!s.impl) s.impl = new TcScratchImpl();
+    TcScratchImpl* m = s.impl;
+    const uint32_t D = a.D, KB = D / 32, nq = a.nq;
+    if (a.n_rows >= 0x7FFFFFFFull) { if (err) *err = "flat tier too large for the TC path"; return FVDB_ERR_INVALID_ARG; }
+    TCK(m->misc.ensure(16, dev_bytes));
+    // ---- per-tier state: row norms, max norm ([8] of misc), TMA descriptor ----
+    if (s.flat_dirty || m->tmap_flat_rows != a.rows || m->tmap_flat_n != a.n_rows) {
+        TCK(m->fxnorm.ensure(a.n_rows, dev_bytes));
+        TCK(cudaMemsetAsync(m->misc.p + 8, 0, 4, st));
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((a.n_rows * 32 + 255) / 256, (uint64_t)a.sm_count * 16);
+        row_norms_kernel<<<blocks, 256, 0, st>>>(a.rows, a.n_rows, D, m->fxnorm.p, m->misc.p + 8);
+        TCK(cudaGetLastError());
+        (*launches)++;
+        EncodeTiledFn enc = get_encode_fn();
+        if (!enc) { if (err) *err = "cuTensorMapEncodeTiled unavailable"; return FVDB_ERR_CUDA; }
+        const cuuint64_t gdim[2] = {D, a.n_rows};
+        const cuuint64_t gstride[1] = {(cuuint64_t)D * 4};
+        const cuuint32_t box[2] = {TC_KB_FLOATS, TC_ROWS};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&m->tmap_flat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.rows), gdim, gstride,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled (flat tier) failed"; return FVDB_ERR_CUDA; }
+        m->tmap_flat_rows = a.rows;
+        m->tmap_flat_n = a.n_rows;
+        s.flat_dirty = false;
+    }
+    // ---- work items: every 64-query group against every row chunk ----
+    const uint32_t n_qg = (nq + TC_TILE_Q - 1) / TC_TILE_Q;
+    const uint32_t tiles = (uint32_t)((a.n_rows + TC_ROWS - 1) / TC_ROWS);
+    uint32_t n_chunks = std::max(1u, std::min(std::min(tiles, 128u), ((uint32_t)a.sm_count * 4 + n_qg - 1) / n_qg));
+    const uint32_t chunk_rows = ((tiles + n_chunks - 1) / n_chunks) * TC_ROWS;
+    n_chunks = (uint32_t)((a.n_rows + chunk_rows - 1) / chunk_rows);
+    const uint32_t n_items = n_qg * n_chunks;
+    TCK(m->qnorm.ensure(nq, dev_bytes));
+    TCK(m->thr_g.ensure(nq, dev_bytes));
+    TCK(m->n_items.ensure(8, dev_bytes));
+    TCK(m->fitems.ensure(n_items, dev_bytes));
+    TCK(m->partial.ensure((size_t)nq * n_chunks * TC_KP, dev_bytes));
+    TCK(m->shortlist.ensure((size_t)nq * TC_KP, dev_bytes));
+    {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)nq * 32 + 255) / 256, (uint64_t)a.sm_count * 8);
+        row_norms_kernel<<<blocks, 256, 0, st>>>(a.Q, nq, D, m->qnorm.p, nullptr);
+        fill_u32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m->thr_g.p, nq, F32_INF_BITS);
+        flat_items_kernel<<<(n_items + 127) / 128, 128, 0, st>>>(m->fitems.p, nq, (uint32_t)a.n_rows, chunk_rows, n_chunks,
+                                                                m->n_items.p + 4);
+        TCK(cudaGetLastError());
+        (*launches) += 3;
+    }
+    TCK(cudaMemsetAsync(m->partial.p, 0xFF, (size_t)nq * n_chunks * TC_KP * sizeof(uint64_t), st));
+    TcScanParams p{};
+    p.items = m->fitems.p; p.item_count = m->n_items.p + 4; p.pair_q = nullptr; p.pair_slot = nullptr;
+    p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = m->fxnorm.p; p.ids = a.ids;
+    p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
+    p.P = n_chunks; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
+    p.work_counter = m->n_items.p + 5;
+    TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
+    uint32_t stages = std::min<uint32_t>(12u, 6u * KB);
+    while (stages > 2 && tc_scan_smem_bytes(KB, stages) + 1024 > 232448) --stages;
+    p.stages = stages;
+    const size_t smem = tc_scan_smem_bytes(KB, stages) + 1024;
+    if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
+    if (!m->smem_attr_set) {
+        TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        m->smem_attr_set = true;
+    }
+    tc_scan_kernel<<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(m->tmap_flat, p);
+    TCK(cudaGetLastError());
+    TCK(launch_merge_rows32(m->partial.p, nq, n_chunks, m->shortlist.p, st));
+    rerank_kernel<<<(nq + 3) / 4, 128, (size_t)4 * D * sizeof(float), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p,
+                                                                         m->misc.p + 8, nq, D, a.k, a.out_keys,
+                                                                         a.d_fallback_count, a.d_fallback_idx);
+    TCK(cudaGetLastError());
+    (*launches) += 3;
     return FVDB_OK;
 }
 

@@ -50,6 +50,23 @@ struct TcSearchArgs {
     int sm_count;
 };
 
+// Tensor-core scan of the recent ("HNSW") tier: every query against every flat row.
+struct TcFlatArgs {
+    const float* rows;        // flat tier [n_rows x D]
+    const uint32_t* ids;      // [n_rows]
+    uint64_t n_rows;
+    const float* Q;           // [nq x D]
+    uint32_t nq, D, k;
+    const uint64_t* tomb;
+    uint64_t tomb_bits;
+    const uint64_t* filt;
+    uint64_t filt_bits;
+    uint64_t* out_keys;           // [nq][k] exact keys, sorted
+    uint32_t* d_fallback_count;   // device: queries whose proof failed
+    uint32_t* d_fallback_idx;     // device [nq]
+    int sm_count;
+};
+
 // dim % 32 == 0 (one 128-byte swizzle atom per k-block), dim <= 512 (query tile in smem)
 bool tc_supported(uint32_t D);
 
@@ -58,6 +75,10 @@ bool tc_supported(uint32_t D);
 // be re-run on the exact path by the caller.
 int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* dev_bytes,
                   uint32_t* launches, std::string* err);
+// Same machinery for the flat tier (replaces HNSWIndex::search, src/hnsw/core.rs:398-467, by an
+// exhaustive scan): work items = (64-query group) x (row chunk), shortlist + exact re-rank + proof.
+int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* dev_bytes, uint32_t* launches,
+                   std::string* err);
 void tc_release(TcScratch& s);
 
 }  // namespace fvdb

@@ -137,6 +137,32 @@ def test_flat_tier_is_exact_scan(mode):
     _assert_same(*got, *want)
 
 
+@pytest.mark.parametrize("d", [384, 64])
+def test_flat_tier_tensor_core_path(d):
+    # large enough (rows x queries >= 4M) for the tensor-core flat scan: several row chunks and
+    # query groups, a ragged last tile, tombstones and a filter bitmap; must stay bit-exact
+    n, nq, k = 21_003, 210, 10
+    x = _data(n, d, 23)
+    ids = (np.arange(n, dtype=np.uint32) * 2 + 1).astype(np.uint32)
+    eng = Engine(d, k_max=16)
+    _set_mode(eng, "tc")
+    eng.flat_add(x, ids)
+    q = _queries(nq, d, n, 23)
+    got = eng.search(q, k, 0, tiers=L.TIER_RECENT)
+    want = O.hybrid_batch_search(None, x, ids, q, k, 0, tiers=1)
+    _assert_same(*got, *want)
+    dele = ids[::17].copy()
+    eng.set_deleted(dele, True)
+    nbits = int(ids.max()) + 1
+    keep = ids[(ids % 3) != 0]
+    fbits = O.make_bitmap((nbits + 63) // 64 * 64, keep)
+    got = eng.search(q, k, 0, tiers=L.TIER_RECENT, filter_bits=fbits)
+    want = O.hybrid_batch_search(None, x, ids, q, k, 0, tiers=1,
+                                 deleted=O.make_bitmap((nbits + 63) // 64 * 64, dele), filter_bits=fbits)
+    _assert_same(*got, *want)
+    eng.close()
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_hybrid_merge_ties_and_no_dedup(mode):
     # the same vectors live in both tiers under different ids: distance ties, recent first
