@@ -89,6 +89,8 @@ struct fvdb_index {
     uint32_t scan_mode = FVDB_SCAN_EXACT;
     uint32_t shortlist = 0;
     uint32_t kmeans_tc = 0;
+    uint64_t centroids_version = 0;     // bumped whenever the centroid table changes
+    uint64_t assign_fallback_rows = 0;  // rows re-assigned exactly after a failed tensor-core proof
     size_t dev_bytes = 0;
 
     uint32_t nlist = 0;
@@ -334,8 +336,48 @@ int assign_device(fvdb_index* h, const float* d_x, uint64_t n, uint32_t* d_assig
     if (n == 0) return FVDB_OK;
     if (n >= 0xFFFFFFFFull) return h->fail(FVDB_ERR_INVALID_ARG, "batch exceeds u32 rows");
     CK(h->s_ivf_keys.ensure(n, 0, st, &h->dev_bytes));
-    RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_x, (uint32_t)n, 1, nullptr, 0,
-                       nullptr, 0, h->s_ivf_keys.p, st));
+    // Large batches (k-means iterations, bulk insert / load): the rows play the "queries", the
+    // centroid table the scanned row set of the tensor-core flat scan; the four approximately
+    // nearest centroids are re-ranked in the reference's arithmetic and the fifth bounds the rest
+    // (proof as in tc_scan.cu); rows whose proof fails are re-assigned by the exact kernel.
+    const bool tc = h->scan_mode == FVDB_SCAN_TC && tc_supported(h->dim) && h->nlist >= 256 &&
+                    n * (uint64_t)h->nlist >= (64ull << 20) && !getenv("FVDB_ASSIGN_EXACT");
+    if (tc) {
+        const uint64_t CH = 1u << 18;   // rows per pass: bounds the shortlist scratch (256 B per row)
+        CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
+        uint32_t* d_fb = h->s_misc.p + 12;
+        for (uint64_t r0 = 0; r0 < n; r0 += CH) {
+            const uint32_t m = (uint32_t)std::min<uint64_t>(CH, n - r0);
+            CK(h->s_fb_idx_flat.ensure((size_t)2 * m, 0, st, &h->dev_bytes));
+            CK(cudaMemsetAsync(d_fb, 0, 4, st));
+            TcFlatArgs fa{};
+            fa.rows = h->centroids.p; fa.ids = nullptr; fa.n_rows = h->nlist;
+            fa.Q = d_x + r0 * h->dim; fa.nq = m; fa.D = h->dim; fa.k = 1;
+            fa.out_keys = h->s_ivf_keys.p + r0;
+            fa.d_fallback_count = d_fb; fa.d_fallback_idx = h->s_fb_idx_flat.p;
+            fa.sm_count = h->sm_count;
+            fa.state = 1; fa.version = h->centroids_version; fa.rerank_r = 4;
+            uint32_t launches = 0;
+            int r = tc_flat_search(h->tc, fa, st, &h->dev_bytes, &launches, &h->err);
+            if (r != FVDB_OK) return r;
+            uint32_t n_fb = 0;
+            CK(cudaMemcpyAsync(&n_fb, d_fb, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            n_fb = std::min(n_fb, 2 * m);
+            if (n_fb) {
+                CK(h->s_fb_q.ensure((size_t)n_fb * h->dim, 0, st, &h->dev_bytes));
+                CK(h->s_fb_keys.ensure((size_t)n_fb, 0, st, &h->dev_bytes));
+                CK(launch_gather_rows(d_x + r0 * h->dim, m, nullptr, h->s_fb_idx_flat.p, n_fb, h->dim, h->s_fb_q.p, st));
+                RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, h->s_fb_q.p, n_fb, 1, nullptr, 0, nullptr, 0,
+                                   h->s_fb_keys.p, st));
+                CK(launch_scatter_keys(h->s_fb_keys.p, h->s_fb_idx_flat.p, n_fb, 1, h->s_ivf_keys.p + r0, st));
+            }
+            h->assign_fallback_rows += n_fb;
+        }
+    } else {
+        RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_x, (uint32_t)n, 1, nullptr, 0,
+                           nullptr, 0, h->s_ivf_keys.p, st));
+    }
     CK(launch_extract_assign(h->s_ivf_keys.p, n, d_assign, d_dist, prev, d_changed, st));
     return FVDB_OK;
 }
@@ -460,7 +502,7 @@ int train_device_impl(fvdb_index* h, const float* d_data, uint64_t n, uint32_t n
     CK(h->centroids.ensure((size_t)nlist * D, 0, st, &h->dev_bytes));
     h->nlist = nlist;
     h->trained = false;
-    h->tc.centroids_dirty = true;
+    h->tc.centroids_dirty = true; ++h->centroids_version;
     if (d_init) {
         RET(check_nan_device(h, d_init, (size_t)nlist * D, st));
         CK(cudaMemcpyAsync(h->centroids.p, d_init, (size_t)nlist * D * 4, cudaMemcpyDeviceToDevice, st));
@@ -522,7 +564,7 @@ int train_device_impl(fvdb_index* h, const float* d_data, uint64_t n, uint32_t n
         CK(launch_stable_group(assign.p, n, nlist, h->s_u32c.p, h->s_perm.p, h->s_group.p, st));
         CK(launch_centroid_update(d_data, D, h->s_u32c.p, h->s_perm.p, nlist, h->centroids.p, st));
         CK(cudaStreamSynchronize(st));
-        h->tc.centroids_dirty = true;
+        h->tc.centroids_dirty = true; ++h->centroids_version;
         if (iterations >= max_iterations) break;
         float current_error = 0.f;
         RET(compute_error_device(h, d_data, n, assign.p, &current_error));
@@ -902,7 +944,7 @@ int fvdb_ivf_set_centroids(fvdb_index* h, const float* centroids, uint32_t nlist
     RET(h2d(h, h->centroids.p, centroids, (size_t)nlist * h->dim * 4));
     h->nlist = nlist;
     h->trained = true;
-    h->tc.centroids_dirty = true;
+    h->tc.centroids_dirty = true; ++h->centroids_version;
     clear_lists(h);
     CK(h->list_off.ensure(nlist + 2, 0, h->stream, &h->dev_bytes));
     CK(cudaMemsetAsync(h->list_off.p, 0, (nlist + 2) * 4, h->stream));
@@ -1248,7 +1290,7 @@ int fvdb_kmeans_apply_device(fvdb_index* h, const float* d_sums, const uint32_t*
     if (!h->nlist || !h->centroids.p) return h->fail(FVDB_ERR_NOT_TRAINED, "centroids not set");
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     CK(launch_apply_means(d_sums, d_counts, h->nlist, h->dim, h->centroids.p, st));
-    h->tc.centroids_dirty = true;
+    h->tc.centroids_dirty = true; ++h->centroids_version;
     return FVDB_OK;
 }
 

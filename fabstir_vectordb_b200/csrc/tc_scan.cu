@@ -1234,8 +1234,10 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
                                                      const float* __restrict__ rows, const uint32_t* __restrict__ ids,
                                                      const float* __restrict__ Q, const float* __restrict__ qnorm,
                                                      const uint32_t* __restrict__ xmax_bits, uint32_t nq, uint32_t D,
-                                                     uint32_t k, uint64_t* __restrict__ out_keys,
+                                                     uint32_t k, uint32_t R, uint64_t* __restrict__ out_keys,
                                                      uint32_t* __restrict__ fb_count, uint32_t* __restrict__ fb_idx) {
+    // R = shortlist entries that are re-ranked (TC_KP for search; a handful for nearest-centroid
+    // assignment, where entry R — the best approximate value NOT re-ranked — is the proof bound)
     extern __shared__ __align__(16) float q_sm[];  // [4][D]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * 4 + w;
@@ -1244,15 +1246,16 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
     for (uint32_t d = lane; d < D; d += 32) q_s[d] = __ldg(Q + (size_t)q * D + d);
     __syncwarp();
     const uint64_t akey = shortlist[(size_t)q * TC_KP + lane];
-    const bool have = akey != KEY_NONE;
+    const bool have = akey != KEY_NONE && (uint32_t)lane < R;
     const uint32_t pos = have ? (uint32_t)akey : 0u;
-    const float dist = exact_l2_lane(q_s, rows + (size_t)pos * D, D);
+    float dist = 0.f;
+    if (R >= 16 || have) dist = exact_l2_lane(q_s, rows + (size_t)pos * D, D);
     uint64_t ekey = KEY_NONE;
-    if (have) ekey = make_key(dist, ids[pos]);
+    if (have) ekey = make_key(dist, ids ? ids[pos] : pos);
     ekey = warp_sort32(ekey, lane);
     if ((uint32_t)lane < k) out_keys[(size_t)q * k + lane] = ekey;
     // proof
-    const uint64_t a_last_key = shfl64(akey, 31);
+    const uint64_t a_last_key = shfl64(akey, (int)min(R, 31u));
     const uint64_t kth = shfl64(ekey, (int)k - 1);
     if (lane == 0 && a_last_key != KEY_NONE) {
         const float a_last = __uint_as_float((uint32_t)(a_last_key >> 32));
@@ -1553,11 +1556,13 @@ struct TcScratchImpl {
     Buf<uint32_t> misc;  // [0] = max |x|^2 bits
     Buf<unsigned long long> prof;
     Buf<uint32_t> list_order;  // lists by descending length (tile-scheduler order)
-    Buf<float> fxnorm;         // flat tier: |x|^2 per row
+    struct RowSet {            // cached per scanned row matrix: |x|^2, TMA descriptor (box 32 x 128)
+        Buf<float> xnorm;
+        CUtensorMap tmap;
+        const float* rows = nullptr;
+        uint64_t n = 0, version = ~0ull;
+    } rs[2];                   // [0] recent tier, [1] centroid table (assignment)
     Buf<ScanItem> fitems;
-    CUtensorMap tmap_flat;     // flat tier, box 32 floats x 128 rows
-    const float* tmap_flat_rows = nullptr;
-    uint64_t tmap_flat_n = 0;
     uint32_t list_order_n = 0;
     Buf<uint32_t> thr_g, list_cnt, pair_off, cursor, pair_q, pair_slot, n_items;
     Buf<ScanItem> items;
@@ -1584,7 +1589,7 @@ void tc_release(TcScratch& s) {
     m->xnorm.release(); m->qnorm.release(); m->misc.release(); m->thr_g.release(); m->list_cnt.release();
     m->pair_off.release(); m->cursor.release(); m->pair_q.release(); m->pair_slot.release(); m->n_items.release();
     m->items.release(); m->partial.release(); m->shortlist.release();
-    m->prof.release(); m->list_order.release(); m->fxnorm.release(); m->fitems.release();
+    m->prof.release(); m->list_order.release(); m->rs[0].xnorm.release(); m->rs[1].xnorm.release(); m->fitems.release();
     m->cnorm.release(); m->dense.release(); m->coarse.release(); m->citems.release();
     delete m;
     s.impl = nullptr;
@@ -1830,7 +1835,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
 
     // ---- merge the per-(query, probe) shortlists, exact re-rank, proof ----
     TCK(launch_merge_rows32(m->partial.p, nq, np, m->shortlist.p, st));
-    rerank_kernel<<<(nq + 3) / 4, 128, (size_t)4 * D * sizeof(float), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k,
+    rerank_kernel<<<(nq + 3) / 4, 128, (size_t)4 * D * sizeof(float), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k, (uint32_t)TC_KP,
                                                a.out_keys, a.d_fallback_count, a.d_fallback_idx);
     TCK(cudaGetLastError());
     (*launches) += 2;
@@ -1844,12 +1849,15 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
     const uint32_t D = a.D, KB = D / 32, nq = a.nq;
     if (a.n_rows >= 0x7FFFFFFFull) { if (err) *err = "flat tier too large for the TC path"; return FVDB_ERR_INVALID_ARG; }
     TCK(m->misc.ensure(16, dev_bytes));
-    // ---- per-tier state: row norms, max norm ([8] of misc), TMA descriptor ----
-    if (s.flat_dirty || m->tmap_flat_rows != a.rows || m->tmap_flat_n != a.n_rows) {
-        TCK(m->fxnorm.ensure(a.n_rows, dev_bytes));
-        TCK(cudaMemsetAsync(m->misc.p + 8, 0, 4, st));
+    // ---- per-row-set state: row norms, max norm (misc[8] / misc[12]), TMA descriptor ----
+    TcScratchImpl::RowSet& rs = m->rs[a.state ? 1 : 0];
+    uint32_t* xmax_bits = m->misc.p + (a.state ? 12 : 8);
+    const bool stale = a.state ? (rs.version != a.version) : s.flat_dirty;
+    if (stale || rs.rows != a.rows || rs.n != a.n_rows) {
+        TCK(rs.xnorm.ensure(a.n_rows, dev_bytes));
+        TCK(cudaMemsetAsync(xmax_bits, 0, 4, st));
         const uint32_t blocks = (uint32_t)std::min<uint64_t>((a.n_rows * 32 + 255) / 256, (uint64_t)a.sm_count * 16);
-        row_norms_kernel<<<blocks, 256, 0, st>>>(a.rows, a.n_rows, D, m->fxnorm.p, m->misc.p + 8);
+        row_norms_kernel<<<blocks, 256, 0, st>>>(a.rows, a.n_rows, D, rs.xnorm.p, xmax_bits);
         TCK(cudaGetLastError());
         (*launches)++;
         EncodeTiledFn enc = get_encode_fn();
@@ -1858,13 +1866,14 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
         const cuuint64_t gstride[1] = {(cuuint64_t)D * 4};
         const cuuint32_t box[2] = {TC_KB_FLOATS, TC_ROWS};
         const cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&m->tmap_flat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.rows), gdim, gstride,
+        CUresult r = enc(&rs.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.rows), gdim, gstride,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled (flat tier) failed"; return FVDB_ERR_CUDA; }
-        m->tmap_flat_rows = a.rows;
-        m->tmap_flat_n = a.n_rows;
-        s.flat_dirty = false;
+        if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled (row set) failed"; return FVDB_ERR_CUDA; }
+        rs.rows = a.rows;
+        rs.n = a.n_rows;
+        rs.version = a.version;
+        if (!a.state) s.flat_dirty = false;
     }
     // ---- work items: every 64-query group against every row chunk ----
     const uint32_t n_qg = (nq + TC_TILE_Q - 1) / TC_TILE_Q;
@@ -1891,7 +1900,7 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
     TCK(cudaMemsetAsync(m->partial.p, 0xFF, (size_t)nq * n_chunks * TC_KP * sizeof(uint64_t), st));
     TcScanParams p{};
     p.items = m->fitems.p; p.item_count = m->n_items.p + 4; p.pair_q = nullptr; p.pair_slot = nullptr;
-    p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = m->fxnorm.p; p.ids = a.ids;
+    p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = rs.xnorm.p; p.ids = a.ids;
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
     p.P = n_chunks; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
     p.work_counter = m->n_items.p + 5;
@@ -1905,11 +1914,12 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
         TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         m->smem_attr_set = true;
     }
-    tc_scan_kernel<<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(m->tmap_flat, p);
+    tc_scan_kernel<<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(rs.tmap, p);
     TCK(cudaGetLastError());
     TCK(launch_merge_rows32(m->partial.p, nq, n_chunks, m->shortlist.p, st));
     rerank_kernel<<<(nq + 3) / 4, 128, (size_t)4 * D * sizeof(float), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p,
-                                                                         m->misc.p + 8, nq, D, a.k, a.out_keys,
+                                                                         xmax_bits, nq, D, a.k,
+                                                                         a.rerank_r ? a.rerank_r : (uint32_t)TC_KP, a.out_keys,
                                                                          a.d_fallback_count, a.d_fallback_idx);
     TCK(cudaGetLastError());
     (*launches) += 3;

@@ -65,6 +65,12 @@ struct TcFlatArgs {
     uint32_t* d_fallback_count;   // device: queries whose proof failed
     uint32_t* d_fallback_idx;     // device [nq]
     int sm_count;
+    // which cached row set (norms + TMA descriptor): 0 = the recent tier (invalidated by
+    // TcScratch::flat_dirty), 1 = the centroid table scanned by batched nearest-centroid
+    // assignment (invalidated when `version` changes)
+    uint32_t state = 0;
+    uint64_t version = 0;
+    uint32_t rerank_r = 0;        // shortlist entries re-ranked exactly (0 = all 32)
 };
 
 // dim % 32 == 0 (one 128-byte swizzle atom per k-block), dim <= 512 (query tile in smem)

@@ -138,6 +138,25 @@ def test_flat_tier_is_exact_scan(mode):
 
 
 @pytest.mark.parametrize("d", [384, 64])
+def test_bulk_assignment_tensor_core_path(d):
+    # rows x lists >= 64M: find_nearest_centroid (src/ivf/core.rs:373-386) runs as a tensor-core scan
+    # of the centroid table with exact re-rank + proof; every assignment must equal the oracle's
+    n, nlist = 65_536, 1024
+    x = _data(n, d, 29, n_comp=512)
+    cents = x[:: n // nlist][:nlist].copy()
+    cents[7] = cents[3]                     # duplicate centroid: the lower id must win
+    eng = Engine(d, k_max=16)
+    _set_mode(eng, "tc")
+    eng.set_centroids(cents)
+    got = eng.assign(x)
+    sample = np.arange(0, n, 16 if d == 384 else 2)
+    want = O.assign(x[sample], cents)
+    assert got[sample].tolist() == want.tolist()
+    assert 7 not in set(got.tolist())
+    eng.close()
+
+
+@pytest.mark.parametrize("d", [384, 64])
 def test_flat_tier_tensor_core_path(d):
     # large enough (rows x queries >= 4M) for the tensor-core flat scan: several row chunks and
     # query groups, a ragged last tile, tombstones and a filter bitmap; must stay bit-exact
