@@ -172,7 +172,7 @@ def ground_truth(torch, lib, q, n_total, n_comp, rank, world, k):
     from fabstir_vectordb_b200 import Engine, _lib as L
     from fabstir_vectordb_b200.shard import ShardedIndex
     dev = q.device
-    eng = Engine(DIM, k_max=max(16, k))
+    eng = Engine(DIM, k_max=max(16, k), device=torch.cuda.current_device())
     eng.set_option(L.OPT_SCAN_MODE, L.SCAN_EXACT)
     CH = 1 << 18
     buf = torch.empty((CH, DIM), dtype=torch.float32, device=dev)
@@ -341,6 +341,8 @@ def main():
     truth = ground_truth(torch, lib, rq, n_total, n_comp, rank, world, K)
     recall = recall_of(found[0], found[2], truth[0], truth[2], K)
     log(f"recall@{K} = {recall:.4f} over {RECALL_QUERIES} queries (fallback queries {fallback_q})")
+    if os.environ.get("FVDB_BENCH_DEBUG"):
+        log(f"found[0]={found[0][0].tolist()} cnt={found[2][:4].tolist()} truth[0]={truth[0][0].tolist()} cnt={truth[2][:4].tolist()}")
 
     # ---- timed region: HBM-resident inputs ---------------------------------------------------
     sampler = ClockSampler(local_rank)  # samples clocks through warm-up + timed region

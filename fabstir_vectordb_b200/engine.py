@@ -90,6 +90,13 @@ _u32p = C.POINTER(C.c_uint32)
 _u64p = C.POINTER(C.c_uint64)
 
 
+def _stream(stream: int):
+    """cudaStream_t argument.  0 is torch's (legacy) default stream, but NULL means "the handle's
+    own stream" in the C ABI, so 0 is passed as cudaStreamLegacy (0x1): the work is then ordered
+    with whatever the caller enqueued on the default stream (NCCL collectives, copies)."""
+    return C.c_void_p(stream if stream else 1)
+
+
 class Engine:
     def __init__(self, dim: int, k_max: int = 128, device: int = 0):
         self._lib = L.load()
@@ -225,13 +232,13 @@ class Engine:
         """Device-pointer variant (ints are raw device addresses, e.g. tensor.data_ptr())."""
         self._ck(self._lib.fvdb_search_device(self._h, d_q, nq, k, nprobe, tiers, d_filter or None,
                                               filter_nbits, d_out_ids, d_out_dist, d_out_count,
-                                              stream or None))
+                                              _stream(stream)))
 
     def merge_topk_device(self, d_ids: int, d_dist: int, d_count: int, parts: int, nq: int, k: int,
                           d_out_ids: int, d_out_dist: int, d_out_count: int, stream: int = 0):
         self._ck(self._lib.fvdb_merge_topk_device(self._h, d_ids, d_dist, d_count, parts, nq, k,
                                                   d_out_ids, d_out_dist, d_out_count,
-                                                  stream or None))
+                                                  _stream(stream)))
 
     def ivf_add_device(self, d_x: int, d_ids: int, n: int, mod: int = 1, rem: int = 0) -> int:
         kept = C.c_uint64()
@@ -253,7 +260,7 @@ class Engine:
                                  stream=0):
         self._ck(self._lib.fvdb_kmeans_accumulate_device(self._h, d_data, n, d_sums, d_counts,
                                                          d_sqerr, d_assign, d_changed,
-                                                         stream or None))
+                                                         _stream(stream)))
 
     def kmeans_apply_device(self, d_sums, d_counts, stream=0):
-        self._ck(self._lib.fvdb_kmeans_apply_device(self._h, d_sums, d_counts, stream or None))
+        self._ck(self._lib.fvdb_kmeans_apply_device(self._h, d_sums, d_counts, _stream(stream)))

@@ -232,9 +232,12 @@ class IVF:
             self._h = lib().fo_ivf_build_assigned(pc, self.nlist, self.dim, px, pi, pa, n)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().fo_ivf_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().fo_ivf_free(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
     def list_len(self, l) -> int:
         return int(lib().fo_ivf_list_len(self._h, l))
