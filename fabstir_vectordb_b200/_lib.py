@@ -80,6 +80,9 @@ SIGNATURES = {
                               C.c_uint64, _u32p, _f32p, _u32p]),
     "fvdb_search_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
                                      C.c_uint64, _vp, _vp, _vp, _vp]),
+    "fvdb_coarse_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "fvdb_search_device_coarse": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
+                                            C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     "fvdb_merge_topk_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32,
                                          _vp, _vp, _vp, _vp]),
     "fvdb_ivf_add_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _u64p]),

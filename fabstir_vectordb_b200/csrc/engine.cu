@@ -657,10 +657,55 @@ int ivf_scan_exact(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uin
     return FVDB_OK;
 }
 
+// Coarse ranking only (src/ivf/core.rs:646-656) for nq queries: keys [nq][np] (distance bits << 32 |
+// list id), ascending, ties to the lower list id.  Tensor cores + exact verify when possible;
+// queries whose proof fails are re-ranked by the exact kernel.
+int coarse_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t np, uint64_t* d_out_keys,
+                       cudaStream_t st) {
+    const uint32_t D = h->dim;
+    if (nq == 0) return FVDB_OK;
+    CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
+    int* d_nan = reinterpret_cast<int*>(h->s_misc.p);
+    uint32_t* d_fb_count = h->s_misc.p + 10;
+    CK(cudaMemsetAsync(h->s_misc.p, 0, 64, st));
+    CK(launch_nan_check(d_q, (size_t)nq * D, d_nan, st));
+    const bool tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D) && D <= 384 && np <= TC_MAX_NPROBE_COARSE &&
+                    !getenv("FVDB_EXACT_COARSE");
+    if (tc) {
+        CK(h->s_fb_idx.ensure((size_t)2 * nq, 0, st, &h->dev_bytes));
+        TcSearchArgs ta{};
+        ta.nlist = h->nlist; ta.Q = d_q; ta.nq = nq; ta.D = D; ta.k = 1; ta.nprobe = np;
+        ta.centroids = h->centroids.p; ta.coarse_keys = nullptr; ta.coarse_out = d_out_keys; ta.coarse_only = true;
+        ta.d_fallback_count = d_fb_count; ta.d_fallback_idx = h->s_fb_idx.p;
+        ta.sm_count = h->sm_count;
+        uint32_t launches = 0;
+        int r = tc_ivf_search(h->tc, ta, st, &h->dev_bytes, &launches, &h->err);
+        if (r != FVDB_OK) return r;
+    } else {
+        RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_q, nq, np, nullptr, 0, nullptr, 0, d_out_keys, st));
+    }
+    uint32_t host_misc[16] = {0};
+    CK(cudaMemcpyAsync(host_misc, h->s_misc.p, sizeof(host_misc), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (host_misc[0])
+        return h->fail(FVDB_ERR_NAN, "NaN in query (the reference panics on partial_cmp().unwrap())");
+    const uint32_t n_fb = tc ? std::min(host_misc[10], 2 * nq) : 0;
+    if (n_fb) {
+        CK(h->s_fb_q.ensure((size_t)n_fb * D, 0, st, &h->dev_bytes));
+        CK(h->s_fb_coarse.ensure((size_t)n_fb * np, 0, st, &h->dev_bytes));
+        CK(launch_gather_rows(d_q, nq, nullptr, h->s_fb_idx.p, n_fb, D, h->s_fb_q.p, st));
+        RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, h->s_fb_q.p, n_fb, np, nullptr, 0, nullptr, 0,
+                           h->s_fb_coarse.p, st));
+        CK(launch_scatter_keys(h->s_fb_coarse.p, h->s_fb_idx.p, n_fb, np, d_out_keys, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return FVDB_OK;
+}
+
 int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,
                        uint32_t tiers, const uint64_t* d_filter, uint64_t filter_bits,
                        uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count,
-                       cudaStream_t st) {
+                       cudaStream_t st, const uint64_t* ext_coarse = nullptr) {
     if (k == 0) return h->fail(FVDB_ERR_INVALID_ARG, "k must be >= 1");
     if (k > h->k_max) return h->fail(FVDB_ERR_K_TOO_LARGE, "k exceeds k_max given at fvdb_create");
     h->stats.last_nq = nq;
@@ -702,11 +747,17 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         used_tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D) && k <= TC_MAX_K && np <= TC_MAX_NPROBE;
         // coarse step: all centroid distances, nearest np lists (src/ivf/core.rs:646-656); exact
         // CUDA-core scan, or (TC mode, D <= 384, np <= 128) tensor-core distances + exact verify
-        const bool tc_coarse = used_tc && D <= 384 && np <= TC_MAX_NPROBE_COARSE && !getenv("FVDB_EXACT_COARSE");
-        CK(h->s_coarse.ensure((size_t)nq * np, 0, st, &h->dev_bytes));
-        if (!tc_coarse)
-            RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_q, nq, np, nullptr, 0, nullptr, 0,
-                               h->s_coarse.p, st));
+        // (or handed in: the multi-GPU driver ranks a slice of the batch per GPU and all-gathers)
+        const bool tc_coarse = !ext_coarse && used_tc && D <= 384 && np <= TC_MAX_NPROBE_COARSE &&
+                               !getenv("FVDB_EXACT_COARSE");
+        const uint64_t* coarse_in = ext_coarse;
+        if (!ext_coarse) {
+            CK(h->s_coarse.ensure((size_t)nq * np, 0, st, &h->dev_bytes));
+            coarse_in = h->s_coarse.p;
+            if (!tc_coarse)
+                RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_q, nq, np, nullptr, 0, nullptr, 0,
+                                   h->s_coarse.p, st));
+        }
         if (used_tc) {
             CK(h->s_fb_idx.ensure((size_t)2 * nq, 0, st, &h->dev_bytes));
             TcSearchArgs ta{};
@@ -714,7 +765,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             ta.list_off = h->list_off.p; ta.nlist = h->nlist;
             ta.Q = d_q; ta.nq = nq; ta.D = D; ta.k = k; ta.nprobe = np;
             ta.centroids = h->centroids.p;
-            ta.coarse_keys = tc_coarse ? nullptr : h->s_coarse.p;
+            ta.coarse_keys = tc_coarse ? nullptr : coarse_in;
             ta.coarse_out = nullptr;
             ta.tomb = tomb; ta.tomb_bits = h->tomb_bits; ta.filt = filt; ta.filt_bits = filter_bits;
             ta.out_keys = ivf_keys;
@@ -728,7 +779,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             h->stats.last_launches += launches;
             scan_timed = true;
         } else {
-            RET(ivf_scan_exact(h, d_q, nq, k, np, h->s_coarse.p, tomb, filt, filter_bits, ivf_keys,
+            RET(ivf_scan_exact(h, d_q, nq, k, np, coarse_in, tomb, filt, filter_bits, ivf_keys,
                                d_scanned, true, st));
             scan_timed = true;
         }
@@ -1214,6 +1265,28 @@ int fvdb_search_device(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return search_device_impl(h, d_q, nq, k, nprobe, tiers, d_filter_bits, filter_nbits, d_out_ids,
                               d_out_dist, d_out_count, st);
+}
+
+int fvdb_coarse_device(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t nprobe, uint64_t* d_out_keys,
+                       void* stream) {
+    ENTER(h);
+    if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");
+    if (nprobe == 0 || nprobe > h->nlist || nprobe > 512)
+        return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_coarse_device needs 1 <= nprobe <= min(nlist, 512)");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return coarse_device_impl(h, d_q, nq, nprobe, d_out_keys, st);
+}
+
+int fvdb_search_device_coarse(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,
+                              uint32_t tiers, const uint64_t* d_filter_bits, uint64_t filter_nbits,
+                              const uint64_t* d_coarse_keys, uint32_t* d_out_ids, float* d_out_dist,
+                              uint32_t* d_out_count, void* stream) {
+    ENTER(h);
+    if (d_coarse_keys && nprobe > h->nlist)
+        return h->fail(FVDB_ERR_INVALID_ARG, "coarse keys are [nq x nprobe]: nprobe must not exceed nlist");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return search_device_impl(h, d_q, nq, k, nprobe, tiers, d_filter_bits, filter_nbits, d_out_ids,
+                              d_out_dist, d_out_count, st, d_coarse_keys);
 }
 
 int fvdb_search(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t nprobe, uint32_t tiers,

@@ -1614,7 +1614,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
 
     // ---- per-arena state: row norms, max norm, TMA descriptor ----
     TCK(m->misc.ensure(16, dev_bytes));
-    if (s.arena_dirty || m->tmap_rows != a.rows || m->tmap_n != a.n_rows) {
+    if (!a.coarse_only && (s.arena_dirty || m->tmap_rows != a.rows || m->tmap_n != a.n_rows)) {
         TCK(m->xnorm.ensure(a.n_rows, dev_bytes));
         TCK(cudaMemsetAsync(m->misc.p, 0, 4, st));  // [0] = max |x|^2 bits; [4] = max |c|^2 bits (coarse)
         const uint32_t blocks = (uint32_t)std::min<uint64_t>((a.n_rows * 32 + 255) / 256, (uint64_t)a.sm_count * 16);
@@ -1767,6 +1767,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         coarse_keys = m->coarse.p;
         if (a.coarse_out) TCK(cudaMemcpyAsync(a.coarse_out, m->coarse.p, (size_t)nq * np * 8, cudaMemcpyDeviceToDevice, st));
     }
+    if (a.coarse_only) return FVDB_OK;
     TCK(launch_probe_bucketing(coarse_keys, nq, np, a.list_off, a.nlist, tile_q, m->list_cnt.p, m->pair_off.p,
                                m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st,
                                (m->list_order_n == a.nlist && getenv("FVDB_TC_ORDER")) ? m->list_order.p : nullptr));

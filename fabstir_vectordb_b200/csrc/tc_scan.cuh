@@ -38,6 +38,7 @@ struct TcSearchArgs {
     const uint64_t* coarse_keys;  // [nq][nprobe] exact coarse ranking (low 32 bits = list id), or
                                   // nullptr: computed here on the tensor cores (nprobe <= 128)
     uint64_t* coarse_out;         // when computed here: [nq][nprobe] exact keys (may be nullptr)
+    bool coarse_only = false;     // stop after the coarse step (keys in coarse_out); the arena is not touched
     const uint64_t* tomb;
     uint64_t tomb_bits;
     const uint64_t* filt;

@@ -8,6 +8,7 @@ The collective is torch.distributed (NCCL on GPUs; gloo in the CPU tests of the 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -56,6 +57,7 @@ class ShardedIndex:
         self.rank = rank
         self.world = world
         self.group = group
+        self.shard_coarse = os.environ.get("FVDB_SHARD_COARSE", "1") != "0"
         self._bufs = {}
 
     def add_rows_device(self, x, row_ids) -> int:
@@ -88,11 +90,32 @@ class ShardedIndex:
         nq = q.shape[0]
         b = self._buffers(nq, k, q.device)
         stream = torch.cuda.current_stream().cuda_stream
-        self.eng.search_device(q.data_ptr(), nq, k, nprobe, tiers,
-                               filter_bits.data_ptr() if filter_bits is not None else 0, filter_nbits,
-                               b["ids"].data_ptr(), b["dist"].data_ptr(), b["cnt"].data_ptr(), stream)
+        f_ptr = filter_bits.data_ptr() if filter_bits is not None else 0
         if self.world == 1:
+            self.eng.search_device(q.data_ptr(), nq, k, nprobe, tiers, f_ptr, filter_nbits,
+                                   b["ids"].data_ptr(), b["dist"].data_ptr(), b["cnt"].data_ptr(), stream)
             return b["ids"], b["dist"], b["cnt"]
+        coarse = 0
+        if (tiers & L.TIER_HISTORICAL) and nprobe > 0 and self.shard_coarse:
+            # the coarse step is sharded by QUERY: each rank ranks its slice of the batch against the
+            # (replicated) centroid table, one small all-gather hands every rank the whole ranking
+            np_ = min(nprobe, self.eng.stats().nlist)
+            per = (nq + self.world - 1) // self.world
+            key = ("coarse", nq, np_)
+            if key not in self._bufs:
+                self._bufs[key] = (torch.empty((per, np_), dtype=torch.int64, device=q.device),
+                                   torch.empty((self.world * per, np_), dtype=torch.int64, device=q.device))
+            mine, allk = self._bufs[key]
+            lo = min(nq, self.rank * per)
+            n_mine = max(0, min(nq, lo + per) - lo)
+            if n_mine < per:
+                mine.fill_(-1)                                   # 0xFF..FF keys: "probe nothing"
+            if n_mine:
+                self.eng.coarse_device(q[lo:lo + n_mine].data_ptr(), n_mine, np_, mine.data_ptr(), stream)
+            dist.all_gather_into_tensor(allk, mine, group=self.group)
+            coarse, nprobe = allk.data_ptr(), np_
+        self.eng.search_device_coarse(q.data_ptr(), nq, k, nprobe, tiers, f_ptr, filter_nbits, coarse,
+                                      b["ids"].data_ptr(), b["dist"].data_ptr(), b["cnt"].data_ptr(), stream)
         # [world][nq][k] == the rank-major concatenation along dim 0 (the form gloo insists on)
         dist.all_gather_into_tensor(b["g_ids"].view(self.world * nq, k), b["ids"], group=self.group)
         dist.all_gather_into_tensor(b["g_dist"].view(self.world * nq, k), b["dist"], group=self.group)

@@ -205,6 +205,21 @@ int fvdb_search_device(fvdb_index *h, const float *d_q, uint32_t nq, uint32_t k,
                        uint64_t filter_nbits, uint32_t *d_out_ids, float *d_out_dist,
                        uint32_t *d_out_count, void *stream);
 
+/* The coarse step alone (src/ivf/core.rs:646-656) for nq device-resident queries:
+ * d_out_keys [nq x nprobe] = (f32 bits of the exact centroid distance << 32) | list id, ascending,
+ * ties to the lower list id (the reference's stable sort).  1 <= nprobe <= nlist.  Used by the
+ * multi-GPU driver: each GPU ranks a slice of the batch against the replicated centroids and the
+ * slices are all-gathered, so the coarse cost per GPU does not grow with the number of GPUs. */
+int fvdb_coarse_device(fvdb_index *h, const float *d_q, uint32_t nq, uint32_t nprobe,
+                       uint64_t *d_out_keys, void *stream);
+/* fvdb_search_device with the coarse ranking handed in (d_coarse_keys [nq x nprobe] as written
+ * by fvdb_coarse_device; rows of 0xFF..FF keys = "probe nothing"; NULL = compute it here). */
+int fvdb_search_device_coarse(fvdb_index *h, const float *d_q, uint32_t nq, uint32_t k,
+                              uint32_t nprobe, uint32_t tiers, const uint64_t *d_filter_bits,
+                              uint64_t filter_nbits, const uint64_t *d_coarse_keys,
+                              uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count,
+                              void *stream);
+
 /* K-way merge of `parts` per-query partial results laid out [parts][nq][k] (ids, dist) with
  * counts [parts][nq] into [nq][k]: the `sort_by(distance); truncate(k)` of
  * src/hybrid/core.rs:482-483 applied across GPUs after the all-gather.  Ties: lower part first,

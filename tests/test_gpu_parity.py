@@ -341,3 +341,31 @@ def test_kmeanspp_seeded_training_quality():
         assert res["final_error"] >= 0.99 * min(errs)
         assert res["final_error"] < res["initial_error"]
         assert eng.get_centroids().shape == (nlist, d)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_coarse_entry_and_search_with_given_coarse(mode):
+    # fvdb_coarse_device == the oracle's coarse ranking (src/ivf/core.rs:646-656) bit for bit, and
+    # fvdb_search_device_coarse fed with it == fvdb_search (the multi-GPU driver's two-step path)
+    import torch
+    d, n, nlist, nq, k, nprobe = 384, 12000, 96, 70, 10, 12
+    eng, ivf, x, cents, _, _ = _build(n, d, nlist, 53, mode)
+    q = _queries(nq, d, n, 53)
+    dq = torch.from_numpy(q).cuda()
+    keys = torch.empty((nq, nprobe), dtype=torch.int64, device="cuda")
+    eng.coarse_device(dq.data_ptr(), nq, nprobe, keys.data_ptr())
+    torch.cuda.synchronize()
+    hk = keys.cpu().numpy().view(np.uint64)
+    for i in range(nq):
+        ol, od = ivf.coarse(q[i], nprobe)
+        assert (hk[i] & np.uint64(0xFFFFFFFF)).astype(np.uint32).tolist() == ol.tolist()
+        assert (hk[i] >> np.uint64(32)).astype(np.uint32).tolist() == od.view(np.uint32).tolist()
+    o_ids = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    o_dst = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    o_cnt = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    eng.search_device_coarse(dq.data_ptr(), nq, k, nprobe, L.TIER_HISTORICAL, 0, 0, keys.data_ptr(),
+                             o_ids.data_ptr(), o_dst.data_ptr(), o_cnt.data_ptr())
+    torch.cuda.synchronize()
+    want = O.hybrid_batch_search(ivf, None, None, q, k, nprobe, tiers=2)
+    _assert_same(o_ids.cpu().numpy().view(np.uint32), o_dst.cpu().numpy(), o_cnt.cpu().numpy().view(np.uint32), *want)
+    eng.close()
