@@ -347,8 +347,13 @@ def main():
     # ---- timed region: HBM-resident inputs ---------------------------------------------------
     sampler = ClockSampler(local_rank)  # samples clocks through warm-up + timed region
     sampler.start()
-    for w in range(args.warmup):
+    # at least W warm-up steps, and at least ~0.6 s of them so that the clock sampler (one
+    # nvidia-smi call per ~0.1 s) sees the GPU under this very load before and during the timed steps
+    t_w = time.perf_counter()
+    w = 0
+    while w < args.warmup or (time.perf_counter() - t_w < 0.6 and w < 5000):
         step(w)
+        w += 1
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -411,8 +416,14 @@ def main():
     scan_bytes = scan_rows * DIM * 4 + scan_rows * 4  # rows + row norms/ids touched once
     mean_scan_ms = float(np.mean(scan_ms)) if scan_ms else 0.0
     achieved = scan_bytes / (mean_scan_ms * 1e-3) / 1e9 if mean_scan_ms > 0 else 0.0
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, one ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as fh:
+            traffic = float(json.load(fh)["dram_bytes_per_launch"]) if world == 1 else None
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
+                "frac": achieved / peak if peak else None, "traffic": traffic,
                 "kernel": "ivf posting-list scan", "kernel_ms": mean_scan_ms,
                 "algorithmic_bytes_per_launch": scan_bytes, "peak_source": peak_src,
                 "share_of_step": mean_scan_ms / (elapsed_ms / args.steps) if elapsed_ms else None}
