@@ -1770,7 +1770,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     if (a.coarse_only) return FVDB_OK;
     TCK(launch_probe_bucketing(coarse_keys, nq, np, a.list_off, a.nlist, tile_q, m->list_cnt.p, m->pair_off.p,
                                m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st,
-                               (m->list_order_n == a.nlist && getenv("FVDB_TC_ORDER")) ? m->list_order.p : nullptr));
+                               (m->list_order_n == a.nlist && !getenv("FVDB_TC_NO_ORDER")) ? m->list_order.p : nullptr));
     (*launches) += 3;
     TCK(cudaMemsetAsync(m->partial.p, 0xFF, n_pairs * TC_KP * sizeof(uint64_t), st));
 
