@@ -11,7 +11,7 @@ Layout:
 from . import _lib  # noqa: F401
 from .engine import (DimensionMismatch, DuplicateVector, Engine, FvdbError,  # noqa: F401
                      InconsistentDimensions, InsufficientTrainingData, InvalidConfig, NanInput,
-                     NoDevice, NotTrained, VectorNotFound)
+                     NoDevice, NotTrained, PinnedArray, VectorNotFound)
 from .index import (HNSWConfig, HNSWIndex, HybridConfig, HybridIndex,  # noqa: F401
                     HybridSearchConfig, IVFConfig, IVFIndex, MetadataFilter, NotInitialized,
                     SearchConfig, SearchResult, TrainResult)

@@ -78,6 +78,8 @@ SIGNATURES = {
     "fvdb_vacuum": (C.c_int, [_vp, _u64p]),
     "fvdb_search": (C.c_int, [_vp, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u64p,
                               C.c_uint64, _u32p, _f32p, _u32p]),
+    "fvdb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "fvdb_host_free": (None, [_vp]),
     "fvdb_search_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
                                      C.c_uint64, _vp, _vp, _vp, _vp]),
     "fvdb_coarse_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),

@@ -702,10 +702,32 @@ int coarse_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t np
     return FVDB_OK;
 }
 
+// Pinned host destinations of a batch's results: the device -> host copies ride in front of the
+// batch's single synchronisation point (the NaN flag / fallback counter read-back).
+struct HostOut {
+    void* ids;
+    void* dist;
+    void* cnt;
+    size_t ob, cb;  // bytes of ids / dist, of cnt
+};
+cudaError_t copy_out(const HostOut* ho, const uint32_t* d_ids, const float* d_dist, const uint32_t* d_cnt,
+                     cudaStream_t st) {
+    cudaError_t e = cudaMemcpyAsync(ho->ids, d_ids, ho->ob, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ho->dist, d_dist, ho->ob, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ho->cnt, d_cnt, ho->cb, cudaMemcpyDeviceToHost, st);
+    return e;
+}
+// page-locked host memory (fvdb_host_alloc, cudaHostAlloc, cudaHostRegister): DMA without staging
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,
                        uint32_t tiers, const uint64_t* d_filter, uint64_t filter_bits,
                        uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count,
-                       cudaStream_t st, const uint64_t* ext_coarse = nullptr) {
+                       cudaStream_t st, const uint64_t* ext_coarse = nullptr, const HostOut* ho = nullptr) {
     if (k == 0) return h->fail(FVDB_ERR_INVALID_ARG, "k must be >= 1");
     if (k > h->k_max) return h->fail(FVDB_ERR_K_TOO_LARGE, "k exceeds k_max given at fvdb_create");
     h->stats.last_nq = nq;
@@ -814,6 +836,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
     CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
     h->stats.last_launches += 1;
     CK(cudaEventRecord(h->ev_b, st));
+    if (ho) CK(copy_out(ho, d_out_ids, d_out_dist, d_out_count, st));
 
     // one synchronisation point per batch: NaN flag + counters
     uint32_t host_misc[16] = {0};
@@ -841,6 +864,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
                            filt, filter_bits, h->s_fb_keys.p, st));
         CK(launch_scatter_keys(h->s_fb_keys.p, h->s_fb_idx_flat.p, n_fb_flat, k, flat_keys, st));
         CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
+        if (ho) CK(copy_out(ho, d_out_ids, d_out_dist, d_out_count, st));
         CK(cudaStreamSynchronize(st));
         h->stats.last_launches += 3;
         h->stats.last_fallback_queries += n_fb_flat;
@@ -859,6 +883,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
                            h->s_fb_keys.p, nullptr, false, st));
         CK(launch_scatter_keys(h->s_fb_keys.p, h->s_fb_idx.p, n_fb, k, ivf_keys, st));
         CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
+        if (ho) CK(copy_out(ho, d_out_ids, d_out_dist, d_out_count, st));
         CK(cudaStreamSynchronize(st));
         h->stats.last_launches += 3;
         h->stats.last_fallback_queries += n_fb;
@@ -1304,10 +1329,13 @@ int fvdb_search(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t
     CK(h->s_out_ids.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
     CK(h->s_out_dist.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
     CK(h->s_out_cnt.ensure(nq, 0, st, &h->dev_bytes));
-    // pinned staging: queries in, results out, one async copy each way
-    CK(h->ensure_pin(std::max(qb, 2 * ob + cb)));
-    std::memcpy(h->pin, q, qb);
-    CK(cudaMemcpyAsync(h->s_q.p, h->pin, qb, cudaMemcpyHostToDevice, st));
+    // Queries in, results out, one async copy each way.  Page-locked caller buffers (fvdb_host_alloc)
+    // are handed to the copy engine as they are; pageable ones go through the handle's pinned staging.
+    const bool q_pinned = is_pinned_host(q);
+    const bool out_pinned = is_pinned_host(out_ids) && is_pinned_host(out_dist) && is_pinned_host(out_count);
+    CK(h->ensure_pin(std::max(q_pinned ? (size_t)0 : qb, out_pinned ? (size_t)0 : 2 * ob + cb)));
+    if (!q_pinned) std::memcpy(h->pin, q, qb);
+    CK(cudaMemcpyAsync(h->s_q.p, q_pinned ? (const void*)q : (const void*)h->pin, qb, cudaMemcpyHostToDevice, st));
     const uint64_t* d_filter = nullptr;
     if (filter_bits && filter_nbits) {
         const size_t words = (filter_nbits + 63) / 64;
@@ -1322,17 +1350,35 @@ int fvdb_search(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t
         d_filter = h->s_filter.p;
         filter_nbits = 0;
     }
-    RET(search_device_impl(h, h->s_q.p, nq, k, nprobe, tiers, d_filter, filter_nbits, h->s_out_ids.p,
-                           h->s_out_dist.p, h->s_out_cnt.p, st));
+    if (!out_pinned) CK(h->ensure_pin(2 * ob + cb));
     char* pin = (char*)h->pin;
-    CK(cudaMemcpyAsync(pin, h->s_out_ids.p, ob, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(pin + ob, h->s_out_dist.p, ob, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(pin + 2 * ob, h->s_out_cnt.p, cb, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    std::memcpy(out_ids, pin, ob);
-    std::memcpy(out_dist, pin + ob, ob);
-    std::memcpy(out_count, pin + 2 * ob, cb);
+    HostOut ho{out_pinned ? (void*)out_ids : (void*)pin, out_pinned ? (void*)out_dist : (void*)(pin + ob),
+               out_pinned ? (void*)out_count : (void*)(pin + 2 * ob), ob, cb};
+    // the result copies are enqueued in front of the batch's one synchronisation point
+    RET(search_device_impl(h, h->s_q.p, nq, k, nprobe, tiers, d_filter, filter_nbits, h->s_out_ids.p,
+                           h->s_out_dist.p, h->s_out_cnt.p, st, nullptr, &ho));
+    if (!out_pinned) {
+        std::memcpy(out_ids, pin, ob);
+        std::memcpy(out_dist, pin + ob, ob);
+        std::memcpy(out_count, pin + 2 * ob, cb);
+    }
     return FVDB_OK;
+}
+
+int fvdb_host_alloc(size_t bytes, void** out) {
+    if (!out) return FVDB_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (bytes == 0) return FVDB_OK;
+    if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return FVDB_ERR_OOM;
+    }
+    return FVDB_OK;
+}
+
+void fvdb_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
 }
 
 int fvdb_merge_topk_device(fvdb_index* h, const uint32_t* d_ids, const float* d_dist, const uint32_t* d_count,

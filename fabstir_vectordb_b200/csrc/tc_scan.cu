@@ -60,7 +60,7 @@ struct TcScanParams {
     uint64_t rows_bytes;
     float* dense_out;        // kernel Q dense mode (coarse step): out[q * dense_ld + row] = approx d2
     uint32_t dense_ld;
-    uint32_t debug;          // bit 0: skip the epilogue math (pipeline ceiling experiment)
+    uint32_t debug;          // timing experiments. bit 0: skip the epilogue math; 3: no MMAs; 4: a quarter of the MMAs; 5: N = 16
     unsigned long long* prof; // debug bit 7: [grid][3 roles][8] cycle counters (stopwatch laps per role)
 };
 constexpr int TC_SCHED = 4;          // depth of the in-CTA work-item ring
@@ -329,7 +329,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
             const ScanItem it = p.items[item];
             if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
             const uint32_t ncols = (it.pair_count + 15u) & ~15u;
-            const uint32_t idesc = umma_idesc_tf32(R2_ROWS, ncols);
+            const uint32_t idesc = umma_idesc_tf32(R2_ROWS, (p.debug & 32u) ? 16u : ncols);   // debug: narrow MMAs (timing only)
             Q1_LAP(4);
             mbar_wait(bar_qready, nit & 1u);
             tc_fence_after();
@@ -352,7 +352,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                         const uint64_t b0 = umma_desc_sw128(q_base + kb * R2_QBLK_BYTES);
 #pragma unroll
                         for (uint32_t k4 = 0; k4 < 4; ++k4)  // UMMA_K = 8 tf32 = 32 bytes = +2 in the descriptor
-                            umma_tf32(d_tmem, a0 + 2 * k4, b0 + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+                            if (!(p.debug & 8u) && (!(p.debug & 16u) || k4 == 0))   // timing experiments: no / a quarter of the MMAs
+                                umma_tf32(d_tmem, a0 + 2 * k4, b0 + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
                         umma_commit(bar_empty + 8 * stage);  // frees the ring slot once these MMAs retire
                         if (kb + 1 == KB) {
                             umma_commit(bar_tfull + 8 * buf);   // accumulator ready for the epilogue

@@ -9,6 +9,30 @@ import numpy as np
 from . import _lib as L
 
 
+class PinnedArray:
+    """numpy view of a page-locked host buffer from fvdb_host_alloc (freed with the object).  Passed
+    to Engine.search(..., out=...) or as the query matrix, the copy engines read / write it
+    directly (no staging memcpy)."""
+
+    def __init__(self, shape, dtype):
+        lib = L.load()
+        self.shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._ptr = C.c_void_p()
+        rc = lib.fvdb_host_alloc(max(n, 1), C.byref(self._ptr))
+        if rc != 0:
+            raise MemoryError(f"fvdb_host_alloc({n}) failed with code {rc}")
+        self._lib = lib
+        buf = (C.c_char * max(n, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def __del__(self):
+        p, self._ptr = getattr(self, "_ptr", None), None
+        if p is not None and p.value:
+            self._lib.fvdb_host_free(p)
+
+
 class FvdbError(Exception):
     """Base of the error enums of the reference (IVFError src/ivf/core.rs:14-39, HNSWError,
     HybridError src/hybrid/core.rs:16-35)."""
@@ -204,17 +228,25 @@ class Engine:
         return removed.value
 
     # -- search ---------------------------------------------------------------------------
-    def search(self, queries, k: int, nprobe: int, tiers: int = L.TIER_BOTH, filter_bits=None):
-        """Returns (ids [nq,k] u32, dist [nq,k] f32, count [nq] u32); host buffers both ways."""
+    def search(self, queries, k: int, nprobe: int, tiers: int = L.TIER_BOTH, filter_bits=None, out=None):
+        """Returns (ids [nq,k] u32, dist [nq,k] f32, count [nq] u32); host buffers both ways.
+        `out` = (ids, dist, count) arrays to fill (e.g. PinnedArray(...).array views)."""
         q = _f32(queries)
         if q.ndim == 1:
             q = q.reshape(1, -1)
         if q.shape[1] != self.dim:
             raise DimensionMismatch(self.dim, q.shape[1])
         nq = q.shape[0]
-        ids = np.empty((nq, k), dtype=np.uint32)
-        dist = np.empty((nq, k), dtype=np.float32)
-        cnt = np.zeros(nq, dtype=np.uint32)
+        if out is not None:
+            ids, dist, cnt = out
+            if ids.shape != (nq, k) or dist.shape != (nq, k) or cnt.shape != (nq,) or ids.dtype != np.uint32 \
+                    or dist.dtype != np.float32 or cnt.dtype != np.uint32:
+                raise ValueError("out must be (u32 [nq,k], f32 [nq,k], u32 [nq])")
+            cnt[:] = 0
+        else:
+            ids = np.empty((nq, k), dtype=np.uint32)
+            dist = np.empty((nq, k), dtype=np.float32)
+            cnt = np.zeros(nq, dtype=np.uint32)
         fp, fn = None, 0
         if filter_bits is not None:
             fb = np.ascontiguousarray(filter_bits, dtype=np.uint64)

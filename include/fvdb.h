@@ -195,6 +195,14 @@ int fvdb_search(fvdb_index *h, const float *q, uint32_t nq, uint32_t k, uint32_t
                 uint32_t tiers, const uint64_t *filter_bits, uint64_t filter_nbits,
                 uint32_t *out_ids, float *out_dist, uint32_t *out_count);
 
+/* Page-locked host buffers for the host-buffer entry points (replaces the `Vec<f32>` the Rust
+ * callers of HybridIndex::search hand in, src/hybrid/core.rs:425).  Query and result buffers
+ * allocated here are copied by the GPU's copy engines directly; pageable buffers remain legal
+ * everywhere and are staged through the handle's own pinned buffer (one extra memcpy each way).
+ * No handle is needed; returns FVDB_ERR_OOM when the allocation fails. */
+int fvdb_host_alloc(size_t bytes, void **out);
+void fvdb_host_free(void *p);
+
 /* Same, with every buffer already resident in device memory of the handle's GPU and the
  * work enqueued on `stream` (a cudaStream_t; NULL = the handle's own stream).  Used for
  * HBM-resident throughput measurement and by the multi-GPU shard driver, which all-gathers

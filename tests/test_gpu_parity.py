@@ -369,3 +369,30 @@ def test_coarse_entry_and_search_with_given_coarse(mode):
     want = O.hybrid_batch_search(ivf, None, None, q, k, nprobe, tiers=2)
     _assert_same(o_ids.cpu().numpy().view(np.uint32), o_dst.cpu().numpy(), o_cnt.cpu().numpy().view(np.uint32), *want)
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", MODES)
+def test_page_locked_buffers_same_results(mode):
+    """fvdb_search with page-locked caller buffers (fvdb_host_alloc: no staging copy, result copies
+    in front of the batch's single synchronisation point) returns the bits of the pageable path
+    and of the oracle; mixing one pinned and one pageable side is legal too."""
+    from fabstir_vectordb_b200 import PinnedArray
+    n, d, nlist, nprobe, k, nq = 4000, 384, 32, 8, 10, 70
+    eng, ivf, x, cents, _, _ = _build(n, d, nlist, 23, mode)
+    q = _queries(nq, d, n, 23)
+    ref = eng.search(q, k, nprobe, tiers=L.TIER_HISTORICAL)
+    pq = PinnedArray(q.shape, np.float32)
+    pq.array[...] = q
+    po = (PinnedArray((nq, k), np.uint32), PinnedArray((nq, k), np.float32), PinnedArray((nq,), np.uint32))
+    out = tuple(a.array for a in po)
+    ids, dist, cnt = eng.search(pq.array, k, nprobe, tiers=L.TIER_HISTORICAL, out=out)
+    assert ids is out[0] and dist is out[1] and cnt is out[2]
+    for a, b in zip((ids, dist.view(np.uint32), cnt), (ref[0], ref[1].view(np.uint32), ref[2])):
+        assert np.array_equal(a, b)
+    o = O.hybrid_batch_search(ivf, None, None, q, k, nprobe, tiers=2)
+    _assert_same(ids, dist, cnt, *o)
+    mixed = eng.search(pq.array, k, nprobe, tiers=L.TIER_HISTORICAL)          # pinned in, pageable out
+    assert np.array_equal(mixed[0], ref[0]) and np.array_equal(mixed[2], ref[2])
+    out2 = eng.search(q, k, nprobe, tiers=L.TIER_HISTORICAL, out=out)          # pageable in, pinned out
+    assert np.array_equal(out2[0], ref[0]) and np.array_equal(out2[1].view(np.uint32), ref[1].view(np.uint32))
