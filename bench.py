@@ -349,9 +349,11 @@ def main():
     sampler.start()
     # at least W warm-up steps, and at least ~0.6 s of them so that the clock sampler (one
     # nvidia-smi call per ~0.1 s) sees the GPU under this very load before and during the timed steps
+    # (N > 1: a FIXED count — every step is a collective, so all ranks must run the same number)
     t_w = time.perf_counter()
     w = 0
-    while w < args.warmup or (time.perf_counter() - t_w < 0.6 and w < 5000):
+    n_fixed = max(args.warmup, 300) if world > 1 else 0
+    while (w < n_fixed) if world > 1 else (w < args.warmup or (time.perf_counter() - t_w < 0.6 and w < 5000)):
         step(w)
         w += 1
     torch.cuda.synchronize()

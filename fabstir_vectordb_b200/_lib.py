@@ -87,6 +87,10 @@ SIGNATURES = {
                                             C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     "fvdb_merge_topk_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32,
                                          _vp, _vp, _vp, _vp]),
+    "fvdb_bounds_export": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "fvdb_bounds_import": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32]),
+    "fvdb_bounds_begin_batch": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "fvdb_merge_topk_packed_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]),
     "fvdb_ivf_add_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _u64p]),
     "fvdb_flat_add_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
     "fvdb_ivf_train_device": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp,

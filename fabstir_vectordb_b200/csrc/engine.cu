@@ -135,6 +135,10 @@ struct fvdb_index {
     DevBuf<float> s_fb_q;
     DevBuf<uint64_t> s_fb_keys, s_fb_coarse;
     TcScratch tc;
+    // multi-GPU bound sharing (fvdb_bounds_*): [2][bounds_cap] u32, one half per batch parity
+    uint32_t* bounds = nullptr;
+    uint32_t bounds_cap = 0, bounds_parity = 0, bounds_armed_nq = 0;
+    std::vector<uint32_t*> peer_bounds;   // peers' arrays (cudaIpcOpenMemHandle)
 
     // pinned staging
     void* pin = nullptr;
@@ -795,6 +799,13 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             ta.d_fallback_count = d_fb_count; ta.d_fallback_idx = h->s_fb_idx.p;
             ta.ev_scan0 = h->ev_s0; ta.ev_scan1 = h->ev_s1;
             ta.sm_count = h->sm_count;
+            if (h->bounds_armed_nq == nq && h->bounds) {   // fvdb_bounds_begin_batch was called for this batch
+                ta.thr_ext = h->bounds + (size_t)h->bounds_parity * h->bounds_cap;
+                ta.n_peers = (uint32_t)std::min<size_t>(h->peer_bounds.size(), TC_MAX_PEERS);
+                for (uint32_t r = 0; r < ta.n_peers; ++r)
+                    ta.thr_peers[r] = h->peer_bounds[r] + (size_t)h->bounds_parity * h->bounds_cap;
+            }
+            h->bounds_armed_nq = 0;
             uint32_t launches = 0;
             int r = tc_ivf_search(h->tc, ta, st, &h->dev_bytes, &launches, &h->err);
             if (r != FVDB_OK) return r;
@@ -967,6 +978,8 @@ void fvdb_destroy(fvdb_index* h) {
     if (h->ev_b) cudaEventDestroy(h->ev_b);
     if (h->ev_s0) cudaEventDestroy(h->ev_s0);
     if (h->ev_s1) cudaEventDestroy(h->ev_s1);
+    for (uint32_t* pb : h->peer_bounds) cudaIpcCloseMemHandle(pb);
+    if (h->bounds) cudaFree(h->bounds);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1379,6 +1392,64 @@ int fvdb_host_alloc(size_t bytes, void** out) {
 
 void fvdb_host_free(void* p) {
     if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
+}
+
+int fvdb_bounds_export(fvdb_index* h, uint32_t nq_cap, void* handle_out) {
+    ENTER(h);
+    if (!handle_out || nq_cap == 0) return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_bounds_export needs a handle buffer and nq_cap > 0");
+    for (uint32_t* pb : h->peer_bounds) cudaIpcCloseMemHandle(pb);
+    h->peer_bounds.clear();
+    if (h->bounds) { CK(cudaStreamSynchronize(h->stream)); cudaFree(h->bounds); h->bounds = nullptr; }
+    CK(cudaMalloc(&h->bounds, (size_t)2 * nq_cap * sizeof(uint32_t)));
+    CK(cudaMemset(h->bounds, 0x7f, (size_t)2 * nq_cap * sizeof(uint32_t)));
+    h->bounds_cap = nq_cap;
+    h->bounds_parity = 0;
+    h->bounds_armed_nq = 0;
+    cudaIpcMemHandle_t ih;
+    CK(cudaIpcGetMemHandle(&ih, h->bounds));
+    static_assert(sizeof(cudaIpcMemHandle_t) == FVDB_BOUNDS_HANDLE_BYTES, "handle size");
+    std::memcpy(handle_out, &ih, sizeof(ih));
+    return FVDB_OK;
+}
+
+int fvdb_bounds_import(fvdb_index* h, const void* handles, uint32_t n_ranks, uint32_t my_rank) {
+    ENTER(h);
+    if (!h->bounds) return h->fail(FVDB_ERR_INVALID_ARG, "call fvdb_bounds_export first");
+    if (!handles || my_rank >= n_ranks || n_ranks - 1 > TC_MAX_PEERS)
+        return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_bounds_import: 2..8 ranks, my_rank < n_ranks");
+    for (uint32_t* pb : h->peer_bounds) cudaIpcCloseMemHandle(pb);
+    h->peer_bounds.clear();
+    for (uint32_t r = 0; r < n_ranks; ++r) {
+        if (r == my_rank) continue;
+        cudaIpcMemHandle_t ih;
+        std::memcpy(&ih, (const char*)handles + (size_t)r * sizeof(ih), sizeof(ih));
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_bounds.push_back(static_cast<uint32_t*>(ptr));
+    }
+    return FVDB_OK;
+}
+
+int fvdb_bounds_begin_batch(fvdb_index* h, uint32_t nq, void* stream) {
+    ENTER(h);
+    if (!h->bounds || nq > h->bounds_cap) { h->bounds_armed_nq = 0; return FVDB_OK; }   // not shared: the scan uses its own array
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->bounds_parity ^= 1u;
+    // +inf bits 0x7f800000: two passes of memset cannot write it, so a tiny fill kernel
+    CK(launch_fill_u32(h->bounds + (size_t)h->bounds_parity * h->bounds_cap, nq, 0x7f800000u, st));
+    h->bounds_armed_nq = nq;
+    return FVDB_OK;
+}
+
+int fvdb_merge_topk_packed_device(fvdb_index* h, const uint32_t* d_pack, uint32_t parts, uint32_t nq, uint32_t k,
+                                  uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count, void* stream) {
+    ENTER(h);
+    if (parts == 0 || parts > 64) return h->fail(FVDB_ERR_INVALID_ARG, "parts must be in 1..64");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const size_t nk = (size_t)nq * k, chunk = 2 * nk + nq;
+    CK(launch_merge_parts(d_pack, reinterpret_cast<const float*>(d_pack + nk), d_pack + 2 * nk, parts, nq, k,
+                          d_out_ids, d_out_dist, d_out_count, st, chunk, chunk));
+    return FVDB_OK;
 }
 
 int fvdb_merge_topk_device(fvdb_index* h, const uint32_t* d_ids, const float* d_dist, const uint32_t* d_count,

@@ -654,9 +654,10 @@ cudaError_t launch_finalize(const uint64_t* recent, const uint64_t* ivf, uint32_
 // Cross-GPU merge after the all-gather (fvdb_merge_topk_device): parts x [nq][k] (ids, dist,
 // count) -> [nq][k].  Order: (distance, part, position) — each part is already sorted, lower
 // part first on ties.  One thread per query (k and parts are small).
+// part p's block starts at p * stride_kv (ids, dist; elements) and p * stride_c (counts).
 __global__ void merge_parts_kernel(const uint32_t* __restrict__ ids, const float* __restrict__ dist,
                                    const uint32_t* __restrict__ cnt, uint32_t parts, uint32_t nq,
-                                   uint32_t k, uint32_t* __restrict__ out_ids,
+                                   uint32_t k, size_t stride_kv, size_t stride_c, uint32_t* __restrict__ out_ids,
                                    float* __restrict__ out_dist, uint32_t* __restrict__ out_count) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
@@ -668,14 +669,14 @@ __global__ void merge_parts_kernel(const uint32_t* __restrict__ ids, const float
         float best = 0.f;
         int bp = -1;
         for (uint32_t p = 0; p < parts; ++p) {
-            const uint32_t c = min(cnt[(size_t)p * nq + q], k);
+            const uint32_t c = min(cnt[(size_t)p * stride_c + q], k);
             if (pos[p] < c) {
-                const float d = dist[((size_t)p * nq + q) * k + pos[p]];
+                const float d = dist[(size_t)p * stride_kv + (size_t)q * k + pos[p]];
                 if (bp < 0 || d < best) { best = d; bp = (int)p; }
             }
         }
         if (bp < 0) break;
-        out_ids[(size_t)q * k + o] = ids[((size_t)bp * nq + q) * k + pos[bp]];
+        out_ids[(size_t)q * k + o] = ids[(size_t)bp * stride_kv + (size_t)q * k + pos[bp]];
         out_dist[(size_t)q * k + o] = best;
         pos[bp]++;
     }
@@ -688,11 +689,14 @@ __global__ void merge_parts_kernel(const uint32_t* __restrict__ ids, const float
 
 cudaError_t launch_merge_parts(const uint32_t* ids, const float* dist, const uint32_t* cnt,
                                uint32_t parts, uint32_t nq, uint32_t k, uint32_t* out_ids,
-                               float* out_dist, uint32_t* out_count, cudaStream_t stream) {
+                               float* out_dist, uint32_t* out_count, cudaStream_t stream,
+                               size_t stride_kv, size_t stride_c) {
     if (nq == 0) return cudaSuccess;
     if (parts > 64) return cudaErrorInvalidValue;
-    merge_parts_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(ids, dist, cnt, parts, nq, k, out_ids,
-                                                            out_dist, out_count);
+    if (stride_kv == 0) stride_kv = (size_t)nq * k;
+    if (stride_c == 0) stride_c = nq;
+    merge_parts_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(ids, dist, cnt, parts, nq, k, stride_kv, stride_c,
+                                                            out_ids, out_dist, out_count);
     return cudaGetLastError();
 }
 

@@ -53,6 +53,8 @@ struct TcScanParams {
     uint32_t P;
     uint64_t* partial;  // [nq][P][TC_KP] approx keys: (approx d2 bits << 32) | arena row
     uint32_t* thr_g;    // [nq] running upper bound of the query's TC_KP-th approx d2 (f32 bits)
+    uint32_t* thr_peer[TC_MAX_PEERS];  // the same array on the peer GPUs (NVLink peer memory)
+    uint32_t n_peer;
     uint32_t* work_counter;  // dynamic tile scheduler: next unclaimed work item
     uint32_t stages;
     uint32_t kbs;            // kernel Q: k-blocks (128 B each) per pipeline stage
@@ -177,6 +179,14 @@ __device__ __forceinline__ void r2_merge4(const R2Smem& sm, const uint32_t (&qs)
         }
     }
     warp_merge32x4(lst, nw, lane);
+}
+
+// Publish a tightened bound of query qi: the local array first; when that improved it, the
+// peer GPUs' arrays too (fire-and-forget reductions over NVLink).
+__device__ __forceinline__ void publish_bound(const TcScanParams& p, uint32_t qi, uint32_t bits) {
+    const uint32_t old = atomicMin(p.thr_g + qi, bits);
+    if (bits < old)
+        for (uint32_t r = 0; r < p.n_peer; ++r) atomicMin(p.thr_peer[r] + qi, bits);
 }
 
 // stopwatch lap: the cycles since the previous lap of this role are charged to category i
@@ -526,7 +536,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                         sm.pcnt[q] = 0;
                         if (last != KEY_NONE) {
                             sm.thrp[q] = fminf(sm.thrp[q], __uint_as_float((uint32_t)(last >> 32)) - qn_own);
-                            if (p.thr_g) atomicMin(p.thr_g + qi_own, (uint32_t)(last >> 32));
+                            if (p.thr_g) publish_bound(p, qi_own, (uint32_t)(last >> 32));
                         }
                         if (c > (uint32_t)R2_CAP) atomicOr(&sm.redo[q >> 5], 1u << (q & 31));
                     }
@@ -559,7 +569,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                             if (last != KEY_NONE) {
                                 sm.thrp[qs[g]] = fminf(sm.thrp[qs[g]], __uint_as_float((uint32_t)(last >> 32)) - qn_own);
                                 // any 32 rows below a value bound the global 32nd: share it at once
-                                if (p.thr_g) atomicMin(p.thr_g + qi_own, (uint32_t)(last >> 32));
+                                if (p.thr_g) publish_bound(p, qi_own, (uint32_t)(last >> 32));
                             }
                             if (over & (1u << g)) atomicOr(&sm.redo[qs[g] >> 5], 1u << (qs[g] & 31));
                         }
@@ -1546,6 +1556,12 @@ static cudaError_t dump_prof(const unsigned long long* d_prof, uint32_t grid, cu
     return cudaSuccess;
 }
 
+cudaError_t launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    fill_u32_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, stream>>>(p, n, v);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_merge_rows32(const uint64_t* in, uint32_t nq, uint32_t P, uint64_t* out, cudaStream_t stream) {
     if (nq == 0) return cudaSuccess;
     merge_rows32_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(in, nq, P, out);
@@ -1694,7 +1710,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         {
             // experiment (FVDB_TC_DEBUG bit 9): keep the previous batch's bounds = perfectly seeded thresholds
             const char* dbg = getenv("FVDB_TC_DEBUG");
-            if (!(dbg && (atoi(dbg) & 512)))
+            if (!(dbg && (atoi(dbg) & 512)) && !a.thr_ext)   // a shared array was reset by the caller
                 fill_u32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m->thr_g.p, nq, F32_INF_BITS);
         }
         TCK(cudaGetLastError());
@@ -1780,7 +1796,9 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     p.items = m->items.p; p.item_count = m->n_items.p; p.pair_q = m->pair_q.p; p.pair_slot = m->pair_slot.p;
     p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = m->xnorm.p; p.ids = a.ids;
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
-    p.P = np; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
+    p.P = np; p.partial = m->partial.p; p.thr_g = a.thr_ext ? a.thr_ext : m->thr_g.p;
+    p.n_peer = a.thr_ext ? std::min(a.n_peers, TC_MAX_PEERS) : 0u;
+    for (uint32_t r = 0; r < p.n_peer; ++r) p.thr_peer[r] = a.thr_peers[r];
     p.rows_raw = a.rows; p.rows_bytes = a.n_rows * (uint64_t)D * 4;
     p.work_counter = m->n_items.p + 1;
     {

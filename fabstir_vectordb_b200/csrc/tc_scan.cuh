@@ -25,6 +25,7 @@ constexpr uint32_t TC_MAX_K = 16;        // largest k served by the 32-entry sho
 constexpr uint32_t TC_MAX_NPROBE = 256;  // partial lists merged in one pass
 constexpr uint32_t TC_MAX_NPROBE_COARSE = 96;  // tensor-core coarse step (else exact coarse)
 constexpr uint32_t TC_TILE_Q = 64;       // queries per work item of the TC scan
+constexpr uint32_t TC_MAX_PEERS = 7;     // peer GPUs whose bound arrays one scan can push to
 
 struct TcSearchArgs {
     const float* rows;        // IVF arena [n_rows x D]
@@ -49,6 +50,13 @@ struct TcSearchArgs {
     uint32_t* d_fallback_idx;     // device [nq]: their indices
     cudaEvent_t ev_scan0, ev_scan1;
     int sm_count;
+    // multi-GPU bound sharing (optional): the per-query bound array of this batch lives in memory
+    // the peer GPUs can reach (already reset to +inf by the caller); a bound tightened here is
+    // also pushed into the peers' arrays with NVLink atomics, so that a shard which does not hold
+    // a query's nearest lists still scans with that query's tight threshold
+    uint32_t* thr_ext = nullptr;
+    uint32_t* thr_peers[TC_MAX_PEERS] = {};
+    uint32_t n_peers = 0;
 };
 
 // Tensor-core scan of the recent ("HNSW") tier: every query against every flat row.
@@ -87,5 +95,6 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
 int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* dev_bytes, uint32_t* launches,
                    std::string* err);
 void tc_release(TcScratch& s);
+cudaError_t launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t stream);
 
 }  // namespace fvdb

@@ -283,6 +283,23 @@ class Engine:
                                                   d_out_ids, d_out_dist, d_out_count,
                                                   _stream(stream)))
 
+    def bounds_export(self, nq_cap: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self._lib.fvdb_bounds_export(self._h, nq_cap, buf))
+        return buf.raw
+
+    def bounds_import(self, handles: bytes, n_ranks: int, my_rank: int):
+        self._ck(self._lib.fvdb_bounds_import(self._h, C.c_char_p(handles), n_ranks, my_rank))
+
+    def bounds_begin_batch(self, nq: int, stream: int = 0):
+        self._ck(self._lib.fvdb_bounds_begin_batch(self._h, nq, _stream(stream)))
+
+    def merge_topk_packed_device(self, d_pack: int, parts: int, nq: int, k: int, d_out_ids: int, d_out_dist: int,
+                                 d_out_count: int, stream: int = 0):
+        """parts x [ids nq*k | dist nq*k | count nq] 32-bit words (see shard.pack_layout)."""
+        self._ck(self._lib.fvdb_merge_topk_packed_device(self._h, d_pack, parts, nq, k, d_out_ids, d_out_dist,
+                                                         d_out_count, _stream(stream)))
+
     def ivf_add_device(self, d_x: int, d_ids: int, n: int, mod: int = 1, rem: int = 0) -> int:
         kept = C.c_uint64()
         self._ck(self._lib.fvdb_ivf_add_device(self._h, d_x, d_ids, n, mod, rem, C.byref(kept)))

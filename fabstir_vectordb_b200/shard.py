@@ -1,7 +1,7 @@
 """Multi-GPU list-sharded search: one process per GPU, torch.distributed for the
 plumbing.  IVF list l lives on rank (l % world); centroids are replicated, so every rank runs
 the same coarse step, scans only the probed lists it owns (the others are empty in its arena)
-and emits a local top-k.  One exchange step: all-gather of the per-rank [nq x k] results, then
+and emits a local top-k.  One exchange step: all-gather of the packed per-rank results (ids | dist | count), then
 the k-way merge of src/hybrid/core.rs:482-483 (`fvdb_merge_topk_device`).
 
 The collective is torch.distributed (NCCL on GPUs; gloo in the CPU tests of the layout logic).
@@ -26,6 +26,14 @@ def gather_layout(nq: int, k: int, world: int) -> Tuple[Tuple[int, ...], Tuple[i
     """Shapes of the all-gathered buffers consumed by fvdb_merge_topk_device:
     ids/dist [world][nq][k], count [world][nq]."""
     return (world, nq, k), (world, nq)
+
+
+def pack_layout(nq: int, k: int) -> Tuple[int, int, int, int]:
+    """One rank's chunk of the single-collective exchange, in 32-bit words:
+    (offset of ids [nq x k], offset of dist [nq x k], offset of count [nq], chunk length).
+    Must match fvdb_merge_topk_packed_device."""
+    nk = nq * k
+    return 0, nk, 2 * nk, 2 * nk + nq
 
 
 def merge_parts_reference(ids: np.ndarray, dist: np.ndarray, cnt: np.ndarray, k: int):
@@ -58,7 +66,19 @@ class ShardedIndex:
         self.world = world
         self.group = group
         self.shard_coarse = os.environ.get("FVDB_SHARD_COARSE", "1") != "0"
+        self.share_bounds = os.environ.get("FVDB_SHARE_BOUNDS", "1") != "0"
+        self._bounds_cap = 0
         self._bufs = {}
+
+    def _setup_bound_sharing(self, nq: int, device):
+        """Exchange the inter-process handles of the per-query bound arrays (once per capacity)."""
+        import torch
+        import torch.distributed as dist
+        mine = torch.frombuffer(bytearray(self.eng.bounds_export(nq)), dtype=torch.uint8).to(device)
+        allh = torch.empty((self.world * 64,), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        self.eng.bounds_import(bytes(allh.cpu().numpy().tobytes()), self.world, self.rank)
+        self._bounds_cap = nq
 
     def add_rows_device(self, x, row_ids) -> int:
         """Assign rows to lists and keep those this rank owns."""
@@ -68,13 +88,15 @@ class ShardedIndex:
         import torch
         key = (nq, k)
         if key not in self._bufs:
+            o_ids, o_dist, o_cnt, chunk = pack_layout(nq, k)
+            # this rank's results are written straight into the three sections of its packed chunk
+            pack = torch.empty((chunk,), dtype=torch.int32, device=device)
             self._bufs[key] = dict(
-                ids=torch.empty((nq, k), dtype=torch.int32, device=device),
-                dist=torch.empty((nq, k), dtype=torch.float32, device=device),
-                cnt=torch.empty((nq,), dtype=torch.int32, device=device),
-                g_ids=torch.empty((self.world, nq, k), dtype=torch.int32, device=device),
-                g_dist=torch.empty((self.world, nq, k), dtype=torch.float32, device=device),
-                g_cnt=torch.empty((self.world, nq), dtype=torch.int32, device=device),
+                pack=pack,
+                ids=pack[o_ids:o_ids + nq * k].view(nq, k),
+                dist=pack[o_dist:o_dist + nq * k].view(torch.float32).view(nq, k),
+                cnt=pack[o_cnt:o_cnt + nq],
+                g_pack=torch.empty((self.world, chunk), dtype=torch.int32, device=device),
                 o_ids=torch.empty((nq, k), dtype=torch.int32, device=device),
                 o_dist=torch.empty((nq, k), dtype=torch.float32, device=device),
                 o_cnt=torch.empty((nq,), dtype=torch.int32, device=device),
@@ -100,6 +122,12 @@ class ShardedIndex:
             # the coarse step is sharded by QUERY: each rank ranks its slice of the batch against the
             # (replicated) centroid table, one small all-gather hands every rank the whole ranking
             np_ = min(nprobe, self.eng.stats().nlist)
+            if self.share_bounds and q.is_cuda and self.world <= 8:
+                # NVLink bound sharing: reset this rank's bound array BEFORE the coarse all-gather
+                # (which orders the reset before any peer's scan of this batch)
+                if nq > self._bounds_cap:
+                    self._setup_bound_sharing(nq, q.device)
+                self.eng.bounds_begin_batch(nq, stream)
             per = (nq + self.world - 1) // self.world
             key = ("coarse", nq, np_)
             if key not in self._bufs:
@@ -116,11 +144,8 @@ class ShardedIndex:
             coarse, nprobe = allk.data_ptr(), np_
         self.eng.search_device_coarse(q.data_ptr(), nq, k, nprobe, tiers, f_ptr, filter_nbits, coarse,
                                       b["ids"].data_ptr(), b["dist"].data_ptr(), b["cnt"].data_ptr(), stream)
-        # [world][nq][k] == the rank-major concatenation along dim 0 (the form gloo insists on)
-        dist.all_gather_into_tensor(b["g_ids"].view(self.world * nq, k), b["ids"], group=self.group)
-        dist.all_gather_into_tensor(b["g_dist"].view(self.world * nq, k), b["dist"], group=self.group)
-        dist.all_gather_into_tensor(b["g_cnt"].view(self.world * nq), b["cnt"], group=self.group)
-        self.eng.merge_topk_device(b["g_ids"].data_ptr(), b["g_dist"].data_ptr(), b["g_cnt"].data_ptr(),
-                                   self.world, nq, k, b["o_ids"].data_ptr(), b["o_dist"].data_ptr(),
-                                   b["o_cnt"].data_ptr(), stream)
+        # ONE exchange step: all-gather of the packed per-rank chunks (ids | dist | count), then the merge
+        dist.all_gather_into_tensor(b["g_pack"].view(-1), b["pack"], group=self.group)
+        self.eng.merge_topk_packed_device(b["g_pack"].data_ptr(), self.world, nq, k, b["o_ids"].data_ptr(),
+                                          b["o_dist"].data_ptr(), b["o_cnt"].data_ptr(), stream)
         return b["o_ids"], b["o_dist"], b["o_cnt"]

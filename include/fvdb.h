@@ -228,6 +228,33 @@ int fvdb_search_device_coarse(fvdb_index *h, const float *d_q, uint32_t nq, uint
                               uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count,
                               void *stream);
 
+/* Multi-GPU bound sharing over NVLink peer memory (one process per GPU, lists sharded by
+ * l % world as above).  During the posting-list scan every query carries a running upper bound of
+ * its 32nd-nearest approximate distance; rows above it are dropped in the epilogue.  A shard that
+ * does not hold a query's nearest lists would scan with a loose bound: these calls let the shards
+ * push their bounds into each other's arrays with NVLink atomics while they scan.
+ *   fvdb_bounds_export      allocates this handle's [2][nq_cap] bound array and writes its
+ *                           FVDB_BOUNDS_HANDLE_BYTES-byte inter-process handle (all-gather these);
+ *   fvdb_bounds_import      opens the arrays of the other ranks (handles of ALL ranks, rank-major);
+ *   fvdb_bounds_begin_batch flips the batch parity and resets this rank's half to +inf on `stream`.
+ * Protocol (every rank, every batch): begin_batch -> fvdb_coarse_device on a slice -> all-gather of
+ * the coarse keys -> fvdb_search_device_coarse.  The all-gather orders every rank's reset before
+ * any peer's scan of that batch, and the parity keeps a rank that is one batch ahead out of the
+ * array a slower peer still reads.  Results are independent of the sharing (bounds only ever drop
+ * rows that cannot be among a query's 32 nearest); without these calls each rank uses a private array. */
+#define FVDB_BOUNDS_HANDLE_BYTES 64
+int fvdb_bounds_export(fvdb_index *h, uint32_t nq_cap, void *handle_out);
+int fvdb_bounds_import(fvdb_index *h, const void *handles, uint32_t n_ranks, uint32_t my_rank);
+int fvdb_bounds_begin_batch(fvdb_index *h, uint32_t nq, void *stream);
+
+/* The same merge over ONE packed buffer per part — [ids nq*k | dist nq*k | count nq] 32-bit words,
+ * parts back to back — so that the exchange step is a single all-gather: a rank lets
+ * fvdb_search_device write its results into the three sections of its own chunk and gathers the
+ * chunks.  Device pointers. */
+int fvdb_merge_topk_packed_device(fvdb_index *h, const uint32_t *d_pack, uint32_t parts, uint32_t nq,
+                                  uint32_t k, uint32_t *d_out_ids, float *d_out_dist,
+                                  uint32_t *d_out_count, void *stream);
+
 /* K-way merge of `parts` per-query partial results laid out [parts][nq][k] (ids, dist) with
  * counts [parts][nq] into [nq][k]: the `sort_by(distance); truncate(k)` of
  * src/hybrid/core.rs:482-483 applied across GPUs after the all-gather.  Ties: lower part first,

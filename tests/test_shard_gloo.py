@@ -14,7 +14,7 @@ import torch.multiprocessing as mp  # noqa: E402
 
 import oracle as O  # noqa: E402
 from fabstir_vectordb_b200 import synth  # noqa: E402
-from fabstir_vectordb_b200.shard import gather_layout, merge_parts_reference, owner_of_list  # noqa: E402
+from fabstir_vectordb_b200.shard import gather_layout, merge_parts_reference, owner_of_list, pack_layout  # noqa: E402
 
 N, D, NLIST, NQ, K, NPROBE = 4000, 32, 16, 24, 10, 6
 
@@ -45,15 +45,20 @@ def _worker(rank, world, port, out_dir):
         mine = np.array([owner_of_list(int(l), world) == rank for l in full.assign])
         shard = O.IVF(cents, x[mine], np.arange(N, dtype=np.uint32)[mine], assign_=full.assign[mine])
         ids, dst, cnt = O.hybrid_batch_search(shard, None, None, q, K, NPROBE, tiers=2)
+        # the product's exchange step: ONE all-gather of the packed chunk [ids | dist | count]
+        o_i, o_d, o_c, chunk = pack_layout(NQ, K)
+        pack = np.empty(chunk, dtype=np.int32)
+        pack[o_i:o_i + NQ * K] = ids.astype(np.uint32).view(np.int32).ravel()
+        pack[o_d:o_d + NQ * K] = dst.astype(np.float32).view(np.int32).ravel()
+        pack[o_c:o_c + NQ] = cnt.astype(np.uint32).view(np.int32)
+        g_pack = torch.empty((world, chunk), dtype=torch.int32)
+        dist.all_gather_into_tensor(g_pack.view(-1), torch.from_numpy(pack))
+        g = g_pack.numpy()
         (gs, cs) = gather_layout(NQ, K, world)
-        g_ids = torch.empty(gs, dtype=torch.int64)
-        g_dst = torch.empty(gs, dtype=torch.float32)
-        g_cnt = torch.empty(cs, dtype=torch.int64)
-        dist.all_gather_into_tensor(g_ids.view(world * NQ, K), torch.from_numpy(ids.astype(np.int64)))
-        dist.all_gather_into_tensor(g_dst.view(world * NQ, K), torch.from_numpy(dst.copy()))
-        dist.all_gather_into_tensor(g_cnt.view(world * NQ), torch.from_numpy(cnt.astype(np.int64)))
-        m_ids, m_dst, m_cnt = merge_parts_reference(g_ids.numpy().astype(np.uint32), g_dst.numpy(),
-                                                    g_cnt.numpy().astype(np.uint32), K)
+        g_ids = g[:, o_i:o_i + NQ * K].copy().view(np.uint32).reshape(gs)
+        g_dst = g[:, o_d:o_d + NQ * K].copy().view(np.float32).reshape(gs)
+        g_cnt = g[:, o_c:o_c + NQ].copy().view(np.uint32).reshape(cs)
+        m_ids, m_dst, m_cnt = merge_parts_reference(g_ids, g_dst, g_cnt, K)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=m_ids, dst=m_dst, cnt=m_cnt)
     finally:
         dist.destroy_process_group()
