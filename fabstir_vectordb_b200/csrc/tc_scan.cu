@@ -181,12 +181,15 @@ __device__ __forceinline__ void r2_merge4(const R2Smem& sm, const uint32_t (&qs)
     warp_merge32x4(lst, nw, lane);
 }
 
-// Publish a tightened bound of query qi: the local array first; when that improved it, the
-// peer GPUs' arrays too (fire-and-forget reductions over NVLink).
-__device__ __forceinline__ void publish_bound(const TcScanParams& p, uint32_t qi, uint32_t bits) {
-    const uint32_t old = atomicMin(p.thr_g + qi, bits);
-    if (bits < old)
+// Publish a tightened bound of query qi: a fire-and-forget reduction on the local array, and —
+// when it beats what this lane last sent by ~1 % (2^16 in the bit pattern of a positive float) —
+// on the peer GPUs' arrays over NVLink.
+__device__ __forceinline__ void publish_bound(const TcScanParams& p, uint32_t qi, uint32_t bits, uint32_t& peer_sent) {
+    atomicMin(p.thr_g + qi, bits);
+    if (p.n_peer && bits + 0x10000u < peer_sent) {
+        peer_sent = bits;
         for (uint32_t r = 0; r < p.n_peer; ++r) atomicMin(p.thr_peer[r] + qi, bits);
+    }
 }
 
 // stopwatch lap: the cycles since the previous lap of this role are charged to category i
@@ -513,6 +516,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
             const uint32_t qi_own = own ? sm.qidx[mb + jown] : 0u;
             const float qn_own = own ? sm.qn[mb + jown] : 0.f;
             uint32_t thr_pending = F32_INF_BITS;
+            uint32_t peer_sent = F32_INF_BITS;   // last bound of the owned query pushed to the peer GPUs
             epi_bar_n(1);
             Q1_LAP(6);
 
@@ -536,7 +540,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                         sm.pcnt[q] = 0;
                         if (last != KEY_NONE) {
                             sm.thrp[q] = fminf(sm.thrp[q], __uint_as_float((uint32_t)(last >> 32)) - qn_own);
-                            if (p.thr_g) publish_bound(p, qi_own, (uint32_t)(last >> 32));
+                            if (p.thr_g) publish_bound(p, qi_own, (uint32_t)(last >> 32), peer_sent);
                         }
                         if (c > (uint32_t)R2_CAP) atomicOr(&sm.redo[q >> 5], 1u << (q & 31));
                     }
@@ -569,7 +573,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                             if (last != KEY_NONE) {
                                 sm.thrp[qs[g]] = fminf(sm.thrp[qs[g]], __uint_as_float((uint32_t)(last >> 32)) - qn_own);
                                 // any 32 rows below a value bound the global 32nd: share it at once
-                                if (p.thr_g) publish_bound(p, qi_own, (uint32_t)(last >> 32));
+                                if (p.thr_g) publish_bound(p, qi_own, (uint32_t)(last >> 32), peer_sent);
                             }
                             if (over & (1u << g)) atomicOr(&sm.redo[qs[g] >> 5], 1u << (qs[g] & 31));
                         }
