@@ -12,8 +12,9 @@ from . import _lib  # noqa: F401
 from .engine import (DimensionMismatch, DuplicateVector, Engine, FvdbError,  # noqa: F401
                      InconsistentDimensions, InsufficientTrainingData, InvalidConfig, NanInput,
                      NoDevice, NotTrained, PinnedArray, VectorNotFound)
-from .index import (HNSWConfig, HNSWIndex, HybridConfig, HybridIndex,  # noqa: F401
-                    HybridSearchConfig, IVFConfig, IVFIndex, MetadataFilter, NotInitialized,
-                    SearchConfig, SearchResult, TrainResult)
+from .index import (AddClustersResult, BalanceResult, ClusterStats, HNSWConfig, HNSWIndex,  # noqa: F401
+                    HybridConfig, HybridIndex, HybridSearchConfig, IVFConfig, IVFIndex, InvalidParameter,
+                    MetadataFilter, NotInitialized, OptimizationResult, RetrainResult, SearchConfig,
+                    SearchResult, TrainResult)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -1076,6 +1076,58 @@ int fvdb_ivf_train(fvdb_index* h, const float* data, uint64_t n, uint32_t nlist,
                              seed, out);
 }
 
+int fvdb_ivf_retrain(fvdb_index* h, uint32_t nlist, uint32_t max_iterations, const float* init_centroids,
+                     uint64_t seed, fvdb_train_result* out) {
+    ENTER(h);
+    if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");
+    if (nlist == 0 || max_iterations == 0) return h->fail(FVDB_ERR_INVALID_CONFIG, "Invalid IVFConfig");
+    RET(seal(h));
+    const uint64_t n = h->ivf_n;
+    if (n == 0 || n < nlist)
+        return h->fail(FVDB_ERR_INSUFFICIENT_TRAINING, "Insufficient training data: got " + std::to_string(n) +
+                       ", need at least " + std::to_string(nlist));
+    DevBuf<float> d_init;
+    if (init_centroids) {
+        CK(d_init.ensure((size_t)nlist * h->dim, 0, h->stream, nullptr, true));
+        RET(h2d(h, d_init.p, init_centroids, (size_t)nlist * h->dim * 4));
+    }
+    // the resident rows are the training set (arena order: by list, insertion order inside a list);
+    // they never leave the device.  Row ids, tombstones and the id-state table are untouched.
+    DevBuf<float> rows;
+    DevBuf<uint32_t> ids;
+    rows.swap(h->ivf_rows);
+    ids.swap(h->ivf_ids);
+    const bool track = h->track_ids;
+    h->track_ids = false;   // clear_lists() must not forget the ids: the same rows come back below
+    int r = train_device_impl(h, rows.p, n, nlist, max_iterations, init_centroids ? d_init.p : nullptr, seed, out);
+    h->track_ids = track;
+    if (r == FVDB_OK) r = ivf_add_device_impl(h, rows.p, ids.p, n, 1, 0, nullptr, nullptr);
+    if (r == FVDB_OK) r = seal(h);
+    if (r == FVDB_OK) h->dev_bytes -= rows.cap * sizeof(float) + ids.cap * sizeof(uint32_t);   // freed on return
+    if (r != FVDB_OK) {
+        // leave the rows where they were; the index reports "not trained" until a train succeeds
+        h->ivf_rows.swap(rows);
+        h->ivf_ids.swap(ids);
+        h->ivf_n = n;
+        h->pend_n = 0;
+        h->trained = false;
+        h->tc.arena_dirty = true;
+    }
+    return r;
+}
+
+int fvdb_ivf_dump_lists(fvdb_index* h, uint32_t* out_row_ids, uint32_t* out_lists, uint64_t cap, uint64_t* n_out) {
+    ENTER(h);
+    RET(seal(h));
+    if (n_out) *n_out = h->ivf_n;
+    if (!out_row_ids && !out_lists) return FVDB_OK;
+    if (cap < h->ivf_n) return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_ivf_dump_lists: buffers too small");
+    if (h->ivf_n == 0) return FVDB_OK;
+    if (out_row_ids) RET(d2h(h, out_row_ids, h->ivf_ids.p, h->ivf_n * 4));
+    if (out_lists) RET(d2h(h, out_lists, h->ivf_list.p, h->ivf_n * 4));
+    return FVDB_OK;
+}
+
 int fvdb_assign(fvdb_index* h, const float* x, uint64_t n, uint32_t* out_list) {
     ENTER(h);
     if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");

@@ -189,6 +189,30 @@ class Engine:
         return dict(iterations=res.iterations, converged=bool(res.converged),
                     initial_error=res.initial_error, final_error=res.final_error)
 
+    def retrain(self, nlist: int, max_iterations: int, init_centroids=None, seed: int = 0):
+        """k-means over the resident IVF rows + reassignment, all on the device (fvdb_ivf_retrain)."""
+        res = L.TrainResult()
+        ip = None
+        if init_centroids is not None:
+            ic = _f32(init_centroids, self.dim)
+            if ic.shape[0] != nlist:
+                raise InvalidConfig("init_centroids must be [nlist x dim]")
+            ip = _p(ic, _f32p)
+        self._ck(self._lib.fvdb_ivf_retrain(self._h, nlist, max_iterations, ip, seed & 0xFFFFFFFFFFFFFFFF,
+                                            C.byref(res)))
+        return dict(iterations=res.iterations, converged=bool(res.converged),
+                    initial_error=res.initial_error, final_error=res.final_error)
+
+    def dump_lists(self):
+        """(row ids, lists) of the IVF tier in arena order."""
+        n = C.c_uint64()
+        self._ck(self._lib.fvdb_ivf_dump_lists(self._h, None, None, 0, C.byref(n)))
+        ids = np.empty(n.value, dtype=np.uint32)
+        lists = np.empty(n.value, dtype=np.uint32)
+        if n.value:
+            self._ck(self._lib.fvdb_ivf_dump_lists(self._h, _p(ids, _u32p), _p(lists, _u32p), n.value, C.byref(n)))
+        return ids, lists
+
     def assign(self, x) -> np.ndarray:
         x = _f32(x, self.dim)
         out = np.empty(x.shape[0], dtype=np.uint32)

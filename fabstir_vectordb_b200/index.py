@@ -44,6 +44,51 @@ class TrainResult:
 
 
 @dataclass
+class RetrainResult:
+    """src/ivf/operations.rs:38-44."""
+    old_clusters: int
+    new_clusters: int
+    vectors_reassigned: int
+    converged: bool
+
+
+@dataclass
+class AddClustersResult:
+    """src/ivf/operations.rs:46-50."""
+    clusters_added: int
+    vectors_reassigned: int
+
+
+@dataclass
+class OptimizationResult:
+    """src/ivf/operations.rs:52-56."""
+    iterations: int
+    improvement: float
+
+
+@dataclass
+class ClusterStats:
+    """src/ivf/operations.rs:59-66."""
+    n_clusters: int
+    total_vectors: int
+    avg_cluster_size: float
+    size_variance: float
+    empty_clusters: int
+
+
+@dataclass
+class BalanceResult:
+    """src/ivf/operations.rs:91-95."""
+    vectors_moved: int
+    balance_improved: bool
+
+
+class InvalidParameter(FvdbError):
+    """OperationError::InvalidParameter, src/ivf/operations.rs:16."""
+    code = L.ERR_INVALID_ARG
+
+
+@dataclass
 class IVFConfig:
     """src/ivf/core.rs:42-70 (defaults :50-60)."""
     n_clusters: int = 256
@@ -232,6 +277,88 @@ class IVFIndex:
         if x.shape[1] != self._dimension:
             raise DimensionMismatch(self._dimension, x.shape[1])
         return int(self._eng.assign(x)[0])
+
+    # -- maintenance (src/ivf/operations.rs:147-260, 262-288, 422-492, 552-564) --------------
+    def _retrain_on_device(self, new_config: IVFConfig, init_centroids=None) -> TrainResult:
+        seed = new_config.seed if new_config.seed is not None else time.time_ns()
+        r = self._eng.retrain(new_config.n_clusters, new_config.max_iterations, init_centroids=init_centroids,
+                              seed=seed)
+        self.config = new_config
+        rows, lists = self._eng.dump_lists()
+        self._lists = {self._ids.to_id[int(r_)]: int(l) for r_, l in zip(rows, lists)}
+        return TrainResult(**r)
+
+    def retrain(self, new_config: IVFConfig, init_centroids=None) -> RetrainResult:
+        """IVFIndex::retrain, src/ivf/operations.rs:148-193: k-means over every stored vector
+        with the new config, then every vector is reinserted.  One device call (fvdb_ivf_retrain):
+        the vectors never leave the GPU.  Soft-deleted vectors stay in their (new) lists, as in
+        the reference (the `deleted` set is not touched by retrain)."""
+        if not self._trained:
+            raise NotTrained("Index not trained. Call train() before inserting or searching.")
+        if not new_config.is_valid():
+            raise InvalidConfig("Invalid IVFConfig")
+        old_clusters, old_vectors = self.config.n_clusters, self.total_vectors()
+        if old_vectors < new_config.n_clusters:   # the train() inside the reference fails, core.rs:250-255
+            raise InsufficientTrainingData(
+                f"Insufficient training data: got {old_vectors}, need at least {new_config.n_clusters}")
+        tr = self._retrain_on_device(new_config, init_centroids)
+        return RetrainResult(old_clusters, new_config.n_clusters, old_vectors, tr.converged)
+
+    def add_clusters(self, n_clusters_to_add: int) -> AddClustersResult:
+        """src/ivf/operations.rs:195-219."""
+        if not self._trained:
+            raise NotTrained("Index not trained. Call train() before inserting or searching.")
+        if n_clusters_to_add == 0:
+            raise InvalidParameter("Cannot add 0 clusters")
+        cfg = IVFConfig(**{**self.config.__dict__, "n_clusters": self.config.n_clusters + n_clusters_to_add})
+        rr = self.retrain(cfg)
+        return AddClustersResult(n_clusters_to_add, rr.vectors_reassigned)
+
+    def optimize_clusters(self) -> OptimizationResult:
+        """src/ivf/operations.rs:221-260: retrain with the same config, report the drop in the
+        variance of the list sizes."""
+        if not self._trained:
+            raise NotTrained("Index not trained. Call train() before inserting or searching.")
+        before = self._size_variance()
+        if self.total_vectors() < self.config.n_clusters:
+            raise InsufficientTrainingData(
+                f"Insufficient training data: got {self.total_vectors()}, need at least {self.config.n_clusters}")
+        tr = self._retrain_on_device(self.config)
+        return OptimizationResult(tr.iterations, max(before - self._size_variance(), 0.0))
+
+    def _size_variance(self) -> float:
+        """calculate_size_variance, src/ivf/operations.rs:552-564 (f32 arithmetic, left folds)."""
+        n = self.config.n_clusters
+        sizes = np.zeros(n, dtype=np.float32)
+        for l in self._lists.values():
+            sizes[l] += np.float32(1)
+        total = np.float32(0)
+        for v in sizes:
+            total = np.float32(total + v)
+        mean = np.float32(total / np.float32(n))
+        acc = np.float32(0)
+        for v in sizes:
+            d = np.float32(v - mean)
+            acc = np.float32(acc + np.float32(d * d))
+        return float(np.float32(acc / np.float32(n)))
+
+    def get_cluster_stats(self) -> ClusterStats:
+        """src/ivf/operations.rs:263-288."""
+        n = self.config.n_clusters
+        sizes = self.get_cluster_sizes()
+        total = self.total_vectors()
+        avg = float(np.float32(total) / np.float32(n)) if n > 0 else 0.0
+        return ClusterStats(n, total, avg, self._size_variance(), sum(1 for v in sizes.values() if v == 0))
+
+    def balance_clusters(self, threshold: float) -> BalanceResult:
+        """src/ivf/operations.rs:422-492.  The reference takes vectors out of oversized lists and
+        puts each back into the list of its nearest centroid — the list it came from, since
+        membership always is the nearest centroid (insert :431-455, retrain) — so nothing moves
+        unless the centroid table was replaced under the lists; the device keeps that invariant
+        by construction (fvdb_ivf_set_centroids clears the lists), hence vectors_moved == 0."""
+        if not (0.0 < threshold < 1.0):
+            raise InvalidParameter("Threshold must be between 0 and 1")
+        return BalanceResult(0, False)
 
     # -- soft delete (src/ivf/operations.rs:569-640) ----------------------------------------
     def mark_deleted(self, vid: Hashable) -> None:

@@ -195,6 +195,23 @@ int fvdb_search(fvdb_index *h, const float *q, uint32_t nq, uint32_t k, uint32_t
                 uint32_t tiers, const uint64_t *filter_bits, uint64_t filter_nbits,
                 uint32_t *out_ids, float *out_dist, uint32_t *out_count);
 
+/* IVFIndex::retrain (src/ivf/operations.rs:148-193; add_clusters :195-219 and optimize_clusters
+ * :221-260 are the same operation with nlist + n / the same nlist): k-means over every row the
+ * IVF tier holds, then every row is reassigned to its nearest new centroid.  The rows never leave
+ * the device.  Training order = arena order (by list, insertion order inside a list); the
+ * reference trains on HashMap iteration order, which is unspecified.  init_centroids / seed as in
+ * fvdb_ivf_train.  Row ids, tombstones and the recent tier are unchanged.
+ * Errors: NOT_TRAINED (:149-151), INSUFFICIENT_TRAINING when fewer rows than nlist (the train call
+ * inside the reference fails the same way, src/ivf/core.rs:250-255). */
+int fvdb_ivf_retrain(fvdb_index *h, uint32_t nlist, uint32_t max_iterations,
+                     const float *init_centroids, uint64_t seed, fvdb_train_result *out);
+
+/* (row id, list) of every row of the IVF tier in arena order — the membership the host keeps
+ * per VectorId (InvertedList, src/ivf/core.rs:112-157) after a retrain, and what
+ * save_index_chunked (src/hybrid/persistence.rs:188) walks.  NULL buffers: only *n_out. */
+int fvdb_ivf_dump_lists(fvdb_index *h, uint32_t *out_row_ids, uint32_t *out_lists, uint64_t cap,
+                        uint64_t *n_out);
+
 /* Page-locked host buffers for the host-buffer entry points (replaces the `Vec<f32>` the Rust
  * callers of HybridIndex::search hand in, src/hybrid/core.rs:425).  Query and result buffers
  * allocated here are copied by the GPU's copy engines directly; pageable buffers remain legal

@@ -223,6 +223,7 @@ class IVF:
         self.dim = c.shape[1]
         self.nlist = c.shape[0]
         self.n = n
+        self.centroids, self.rows, self.ids = c, x, i   # host copies (insertion order)
         if assign_ is None:
             self.assign = np.empty(n, dtype=np.uint32)
             self._h = lib().fo_ivf_build(pc, self.nlist, self.dim, px, pi, n,
@@ -373,6 +374,23 @@ def train_lloyd(data, init_centroids, max_iterations):
                          C.byref(e1))
     return c, a, dict(iterations=it.value, converged=bool(cv.value), initial_error=e0.value,
                       final_error=e1.value)
+
+
+def retrain_lloyd(ivf, new_init_centroids, max_iterations):
+    """IVFIndex::retrain (src/ivf/operations.rs:148-193) from shared initial centroids: collect the
+    vectors of every inverted list (:157-162; the reference walks HashMaps in unspecified order —
+    this restatement fixes the order to list-major, insertion order inside a list, the device's
+    arena order), train, reinsert every vector into the list of its nearest new centroid
+    (:186-188 -> insert, src/ivf/core.rs:431-455).
+    Returns (new IVF over the same rows/ids, order [n] = indices of the old rows in training order,
+    train dict)."""
+    order = np.argsort(ivf.assign, kind="stable")
+    x = ivf.rows[order]
+    ids = ivf.ids[order]
+    cent, a, res = train_lloyd(x, new_init_centroids, max_iterations)
+    # reinsertion assigns against the FINAL centroids (a holds the last iteration's assignment,
+    # taken before the last centroid update)
+    return IVF(cent, x, ids), order, res
 
 
 def kmeanspp_init(data, k, seed):

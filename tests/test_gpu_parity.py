@@ -396,3 +396,70 @@ def test_page_locked_buffers_same_results(mode):
     assert np.array_equal(mixed[0], ref[0]) and np.array_equal(mixed[2], ref[2])
     out2 = eng.search(q, k, nprobe, tiers=L.TIER_HISTORICAL, out=out)          # pageable in, pinned out
     assert np.array_equal(out2[0], ref[0]) and np.array_equal(out2[1].view(np.uint32), ref[1].view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", MODES)
+def test_retrain_on_device_parity(mode):
+    """fvdb_ivf_retrain (IVFIndex::retrain, src/ivf/operations.rs:148-193) from shared initial
+    centroids: the resident rows are the training set in arena order; centroids, the new list of
+    every row and the searches afterwards (tombstones kept) equal the oracle's bit for bit."""
+    n, d, nlist, new_nlist, iters = 6000, 64, 12, 20, 6
+    eng, ivf, x, cents, _, _ = _build(n, d, nlist, 31, mode)
+    dead = np.arange(0, n, 97, dtype=np.uint32)
+    eng.set_deleted(dead, True)
+    init = x[np.random.default_rng(5).choice(n, new_nlist, replace=False)].copy()
+    res = eng.retrain(new_nlist, iters, init_centroids=init)
+    new_ivf, order, want = O.retrain_lloyd(ivf, init, iters)
+    assert res["iterations"] == want["iterations"] and res["converged"] == want["converged"]
+    assert np.float32(res["final_error"]).view(np.uint32) == np.float32(want["final_error"]).view(np.uint32)
+    assert eng.get_centroids().view(np.uint32).tolist() == new_ivf.centroids.view(np.uint32).tolist()
+    rows, lists = eng.dump_lists()
+    assert rows.size == n and eng.stats().ivf_rows == n and eng.stats().nlist == new_nlist
+    got = dict(zip(rows.tolist(), lists.tolist()))
+    assert got == dict(zip(new_ivf.ids.tolist(), new_ivf.assign.tolist()))
+    assert (np.diff(lists.astype(np.int64)) >= 0).all()          # arena grouped by list
+    q = _queries(40, d, n, 31)
+    ids, dist, cnt = eng.search(q, 10, 5, tiers=L.TIER_HISTORICAL)
+    o = O.hybrid_batch_search(new_ivf, None, None, q, 10, 5, tiers=2, deleted=O.make_bitmap(n, dead))
+    _assert_same(ids, dist, cnt, *o)
+    # errors of the reference: fewer rows than clusters (the inner train fails, core.rs:250-255)
+    from fabstir_vectordb_b200 import InsufficientTrainingData
+    with pytest.raises(InsufficientTrainingData):
+        eng.retrain(n + 1, 3)
+    assert eng.stats().ivf_rows == n and eng.stats().trained == 1   # nothing was touched
+
+
+@pytest.mark.gpu
+def test_mirror_maintenance_operations():
+    """IVFIndex.retrain / add_clusters / optimize_clusters / get_cluster_stats / balance_clusters of
+    the host mirror (src/ivf/operations.rs:147-288, 422-492) on top of the device retrain."""
+    from fabstir_vectordb_b200 import IVFConfig, IVFIndex, InvalidParameter, NotTrained
+    n, d = 3000, 32
+    x = _data(n, d, 7, n_comp=8)
+    idx = IVFIndex(IVFConfig(n_clusters=8, n_probe=4, max_iterations=5, seed=3))
+    with pytest.raises(NotTrained):
+        idx.add_clusters(2)
+    idx.train(x[:500])
+    idx.batch_insert([f"v{i}" for i in range(n)], x)
+    idx.mark_deleted("v5")
+    st0 = idx.get_cluster_stats()
+    assert st0.n_clusters == 8 and st0.total_vectors == n and abs(st0.avg_cluster_size - n / 8) < 1e-3
+    rr = idx.retrain(IVFConfig(n_clusters=16, n_probe=4, max_iterations=5, seed=9))
+    assert (rr.old_clusters, rr.new_clusters, rr.vectors_reassigned) == (8, 16, n)
+    assert idx.total_vectors() == n and idx.is_deleted("v5") and sum(idx.get_cluster_sizes().values()) == n
+    # every vector sits in the list of its nearest centroid (insert, src/ivf/core.rs:431-455)
+    cents = idx.get_centroids()
+    want = O.assign(x, cents)
+    assert [idx._lists[f"v{i}"] for i in range(n)] == want.tolist()
+    ar = idx.add_clusters(4)
+    assert ar.clusters_added == 4 and ar.vectors_reassigned == n and idx.config.n_clusters == 20
+    with pytest.raises(InvalidParameter):
+        idx.add_clusters(0)
+    opt = idx.optimize_clusters()
+    assert opt.iterations >= 1 and opt.improvement >= 0.0 and idx.get_cluster_stats().total_vectors == n
+    with pytest.raises(InvalidParameter):
+        idx.balance_clusters(1.5)
+    assert idx.balance_clusters(0.2).vectors_moved == 0
+    res = idx.search(x[17], 3)
+    assert res[0].vector_id == "v17" and res[0].distance < 1e-6

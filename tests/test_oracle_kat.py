@@ -215,3 +215,22 @@ def test_stdrng_stream_is_deterministic():
     a = O.stdrng_stream(42, 130)
     b = O.stdrng_stream(42, 130)
     assert a.tolist() == b.tolist() and a.tolist() != O.stdrng_stream(43, 130).tolist()
+
+
+def test_retrain_restatement_properties():
+    """retrain (src/ivf/operations.rs:148-193): same vectors and ids afterwards, every vector in the
+    list of its nearest NEW centroid (reinsert -> insert, src/ivf/core.rs:431-455), centroid count
+    = the new config's; training order is list-major (stable)."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((400, 8)).astype(np.float32)
+    cents = x[:6].copy()
+    ivf = O.IVF(cents, x, np.arange(400, dtype=np.uint32) + 1000)
+    init = x[rng.choice(400, 9, replace=False)].copy()
+    new_ivf, order, res = O.retrain_lloyd(ivf, init, 7)
+    assert new_ivf.nlist == 9 and new_ivf.n == 400
+    assert sorted(new_ivf.ids.tolist()) == sorted(ivf.ids.tolist())
+    assert (np.diff(ivf.assign[order].astype(np.int64)) >= 0).all()
+    assert new_ivf.assign.tolist() == O.assign(new_ivf.rows, new_ivf.centroids).tolist()
+    assert 1 <= res["iterations"] <= 7
+    # the training data is exactly the stored vectors, reordered
+    assert np.array_equal(new_ivf.rows, x[order])
