@@ -35,6 +35,7 @@ SCAN_TC = 1
 OPT_SCAN_MODE = 1
 OPT_SHORTLIST = 2
 OPT_KMEANS_TC = 3
+OPT_COALESCE = 4
 
 
 class TrainResult(C.Structure):
@@ -50,7 +51,7 @@ class Stats(C.Structure):
                 ("last_fallback_queries", C.c_uint32), ("last_scanned_rows", C.c_uint64),
                 ("last_algorithmic_bytes", C.c_uint64), ("last_device_ms", C.c_float),
                 ("last_scan_ms", C.c_float), ("last_launches", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("last_batch_calls", C.c_uint32)]
 
 
 _f32p = C.POINTER(C.c_float)

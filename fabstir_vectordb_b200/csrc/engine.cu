@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -77,6 +79,18 @@ struct SplitMix {
 
 }  // namespace
 
+// One fvdb_search call waiting in the handle's submission queue (see fvdb_search).
+struct SearchReq {
+    const float* q;
+    uint32_t nq, k, nprobe, tiers;
+    uint32_t* out_ids;
+    float* out_dist;
+    uint32_t* out_count;
+    int rc = FVDB_OK;
+    enum State { WAITING, LEAD, DONE } state = WAITING;
+    std::condition_variable cv;
+};
+
 struct fvdb_index {
     int device = 0;
     uint32_t dim = 0, k_max = 0;
@@ -135,6 +149,12 @@ struct fvdb_index {
     DevBuf<float> s_fb_q;
     DevBuf<uint64_t> s_fb_keys, s_fb_coarse;
     TcScratch tc;
+    // submission queue of fvdb_search: concurrent host-buffer calls are coalesced into one batch
+    std::mutex qmu;
+    std::deque<SearchReq*> queue;
+    bool leader_active = false;
+    uint32_t coalesce = 1;
+    uint32_t last_batch_calls = 0;
     // multi-GPU bound sharing (fvdb_bounds_*): [2][bounds_cap] u32, one half per batch parity
     uint32_t* bounds = nullptr;
     uint32_t bounds_cap = 0, bounds_parity = 0, bounds_armed_nq = 0;
@@ -1005,6 +1025,9 @@ int fvdb_set_option(fvdb_index* h, int option, uint64_t value) {
         case FVDB_OPT_KMEANS_TC:
             h->kmeans_tc = value ? 1u : 0u;
             return FVDB_OK;
+        case FVDB_OPT_COALESCE:
+            h->coalesce = value ? 1u : 0u;
+            return FVDB_OK;
         default:
             return h->fail(FVDB_ERR_INVALID_ARG, "unknown option");
     }
@@ -1020,6 +1043,7 @@ int fvdb_get_stats(fvdb_index* h, fvdb_stats* out) {
     h->stats.flat_rows = h->flat_n;
     h->stats.deleted_rows = h->deleted_count;
     h->stats.device_bytes = h->dev_bytes;
+    h->stats.last_batch_calls = h->last_batch_calls;
     *out = h->stats;
     return FVDB_OK;
 }
@@ -1379,14 +1403,14 @@ int fvdb_search_device_coarse(fvdb_index* h, const float* d_q, uint32_t nq, uint
                               d_out_dist, d_out_count, st, d_coarse_keys);
 }
 
-int fvdb_search(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t nprobe, uint32_t tiers,
-                const uint64_t* filter_bits, uint64_t filter_nbits, uint32_t* out_ids, float* out_dist,
-                uint32_t* out_count) {
-    ENTER(h);
-    if (k == 0) return h->fail(FVDB_ERR_INVALID_ARG, "k must be >= 1");
-    if (k > h->k_max) return h->fail(FVDB_ERR_K_TOO_LARGE, "k exceeds k_max given at fvdb_create");
-    if (nq == 0) return FVDB_OK;
-    if (!q || !out_ids || !out_dist || !out_count) return h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+namespace {
+
+// One host-buffer batch: queries in, results out, one async copy each way.  Page-locked caller
+// buffers (fvdb_host_alloc) are handed to the copy engine as they are; pageable ones go through
+// the handle's pinned staging.  Caller holds h->mu.
+int search_host_locked(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t nprobe, uint32_t tiers,
+                       const uint64_t* filter_bits, uint64_t filter_nbits, uint32_t* out_ids, float* out_dist,
+                       uint32_t* out_count) {
     cudaStream_t st = h->stream;
     const uint32_t D = h->dim;
     const size_t qb = (size_t)nq * D * 4, ob = (size_t)nq * k * 4, cb = (size_t)nq * 4;
@@ -1394,8 +1418,6 @@ int fvdb_search(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t
     CK(h->s_out_ids.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
     CK(h->s_out_dist.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
     CK(h->s_out_cnt.ensure(nq, 0, st, &h->dev_bytes));
-    // Queries in, results out, one async copy each way.  Page-locked caller buffers (fvdb_host_alloc)
-    // are handed to the copy engine as they are; pageable ones go through the handle's pinned staging.
     const bool q_pinned = is_pinned_host(q);
     const bool out_pinned = is_pinned_host(out_ids) && is_pinned_host(out_dist) && is_pinned_host(out_count);
     CK(h->ensure_pin(std::max(q_pinned ? (size_t)0 : qb, out_pinned ? (size_t)0 : 2 * ob + cb)));
@@ -1428,6 +1450,142 @@ int fvdb_search(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t
         std::memcpy(out_count, pin + 2 * ob, cb);
     }
     return FVDB_OK;
+}
+
+// Several queued calls with the same (k, nprobe, tiers) as ONE device batch: the queries are
+// concatenated in the pinned staging buffer, the results scattered back to each caller's buffers.
+// A NaN anywhere fails the whole device batch; then every call is run on its own so that only
+// the offending caller sees the error.  Caller holds h->mu.
+void run_coalesced(fvdb_index* h, std::vector<SearchReq*>& batch) {
+    h->last_batch_calls = (uint32_t)batch.size();
+    if (batch.size() == 1) {
+        SearchReq* r = batch[0];
+        r->rc = search_host_locked(h, r->q, r->nq, r->k, r->nprobe, r->tiers, nullptr, 0, r->out_ids, r->out_dist,
+                                   r->out_count);
+        return;
+    }
+    const uint32_t D = h->dim, k = batch[0]->k;
+    uint64_t total = 0;
+    for (SearchReq* r : batch) total += r->nq;
+    const size_t qb = (size_t)total * D * 4, ob = (size_t)total * k * 4, cb = (size_t)total * 4;
+    int rc = FVDB_OK;
+    cudaStream_t st = h->stream;
+    auto stage = [&]() -> int {
+        CK(h->s_q.ensure((size_t)total * D, 0, st, &h->dev_bytes));
+        CK(h->s_out_ids.ensure((size_t)total * k, 0, st, &h->dev_bytes));
+        CK(h->s_out_dist.ensure((size_t)total * k, 0, st, &h->dev_bytes));
+        CK(h->s_out_cnt.ensure(total, 0, st, &h->dev_bytes));
+        CK(h->ensure_pin(std::max(qb, 2 * ob + cb)));
+        size_t off = 0;
+        for (SearchReq* r : batch) {
+            std::memcpy((char*)h->pin + off, r->q, (size_t)r->nq * D * 4);
+            off += (size_t)r->nq * D * 4;
+        }
+        CK(cudaMemcpyAsync(h->s_q.p, h->pin, qb, cudaMemcpyHostToDevice, st));
+        char* pin = (char*)h->pin;
+        HostOut ho{pin, pin + ob, pin + 2 * ob, ob, cb};
+        RET(search_device_impl(h, h->s_q.p, (uint32_t)total, k, batch[0]->nprobe, batch[0]->tiers, nullptr, 0,
+                               h->s_out_ids.p, h->s_out_dist.p, h->s_out_cnt.p, st, nullptr, &ho));
+        size_t row = 0;
+        for (SearchReq* r : batch) {
+            std::memcpy(r->out_ids, pin + row * k * 4, (size_t)r->nq * k * 4);
+            std::memcpy(r->out_dist, pin + ob + row * k * 4, (size_t)r->nq * k * 4);
+            std::memcpy(r->out_count, pin + 2 * ob + row * 4, (size_t)r->nq * 4);
+            row += r->nq;
+        }
+        return FVDB_OK;
+    };
+    rc = stage();
+    if (rc == FVDB_ERR_NAN) {
+        for (SearchReq* r : batch)
+            r->rc = search_host_locked(h, r->q, r->nq, r->k, r->nprobe, r->tiers, nullptr, 0, r->out_ids, r->out_dist,
+                                       r->out_count);
+        return;
+    }
+    for (SearchReq* r : batch) r->rc = rc;
+}
+
+constexpr uint64_t COALESCE_MAX_QUERIES = 8192;   // one device batch of coalesced calls
+
+}  // namespace
+
+int fvdb_search(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t nprobe, uint32_t tiers,
+                const uint64_t* filter_bits, uint64_t filter_nbits, uint32_t* out_ids, float* out_dist,
+                uint32_t* out_count) {
+    if (!h) return FVDB_ERR_INVALID_ARG;
+    if (filter_bits || !h->coalesce) {
+        // a filter bitmap belongs to one call: no coalescing
+        ENTER(h);
+        if (k == 0) return h->fail(FVDB_ERR_INVALID_ARG, "k must be >= 1");
+        if (k > h->k_max) return h->fail(FVDB_ERR_K_TOO_LARGE, "k exceeds k_max given at fvdb_create");
+        if (nq == 0) return FVDB_OK;
+        if (!q || !out_ids || !out_dist || !out_count) return h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+        h->last_batch_calls = 1;
+        return search_host_locked(h, q, nq, k, nprobe, tiers, filter_bits, filter_nbits, out_ids, out_dist, out_count);
+    }
+    // Submission queue (the reference allows many concurrent `&self` searches, src/hybrid/core.rs:
+    // 202-213, and its callers search one query at a time, src/ivf/operations.rs:139): a call
+    // queues its request; the first caller becomes the leader, takes every queued request with its
+    // own (k, nprobe, tiers) and runs them as ONE device batch, then hands the lead to the next
+    // waiting caller.  Without concurrency this is exactly one call = one batch.
+    SearchReq r{q, nq, k, nprobe, tiers, out_ids, out_dist, out_count};
+    std::unique_lock<std::mutex> ql(h->qmu);
+    h->queue.push_back(&r);
+    if (h->leader_active) {
+        r.cv.wait(ql, [&] { return r.state != SearchReq::WAITING; });
+        if (r.state == SearchReq::DONE) return r.rc;
+    } else {
+        h->leader_active = true;
+    }
+    ql.unlock();
+    {
+        std::lock_guard<std::mutex> guard(h->mu);
+        h->err.clear();
+        std::vector<SearchReq*> batch;
+        ql.lock();
+        {
+            // own request first, then every compatible one in arrival order
+            uint64_t total = r.nq;
+            batch.push_back(&r);
+            for (auto it = h->queue.begin(); it != h->queue.end();) {
+                SearchReq* o = *it;
+                if (o == &r) { it = h->queue.erase(it); continue; }
+                if (o->k == r.k && o->nprobe == r.nprobe && o->tiers == r.tiers && total + o->nq <= COALESCE_MAX_QUERIES) {
+                    total += o->nq;
+                    batch.push_back(o);
+                    it = h->queue.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+        }
+        ql.unlock();
+        int early = FVDB_OK;
+        if (cudaSetDevice(h->device) != cudaSuccess) early = h->fail(FVDB_ERR_CUDA, "cudaSetDevice failed");
+        // per-call argument checks (a bad call must not fail the calls it was batched with)
+        std::vector<SearchReq*> good;
+        for (SearchReq* o : batch) {
+            if (early != FVDB_OK) o->rc = early;
+            else if (o->k == 0) o->rc = h->fail(FVDB_ERR_INVALID_ARG, "k must be >= 1");
+            else if (o->k > h->k_max) o->rc = h->fail(FVDB_ERR_K_TOO_LARGE, "k exceeds k_max given at fvdb_create");
+            else if (o->nq == 0) o->rc = FVDB_OK;
+            else if (!o->q || !o->out_ids || !o->out_dist || !o->out_count) o->rc = h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+            else good.push_back(o);
+        }
+        if (!good.empty()) run_coalesced(h, good);
+        ql.lock();
+        for (SearchReq* o : batch)
+            if (o != &r) { o->state = SearchReq::DONE; o->cv.notify_one(); }
+        if (!h->queue.empty()) {
+            SearchReq* nx = h->queue.front();
+            nx->state = SearchReq::LEAD;
+            nx->cv.notify_one();
+        } else {
+            h->leader_active = false;
+        }
+        ql.unlock();
+    }
+    return r.rc;
 }
 
 int fvdb_host_alloc(size_t bytes, void** out) {

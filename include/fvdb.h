@@ -83,7 +83,8 @@ typedef enum fvdb_metric {
 typedef enum fvdb_option {
     FVDB_OPT_SCAN_MODE = 1,   /* FVDB_SCAN_EXACT | FVDB_SCAN_TC (default TC when dim%32==0) */
     FVDB_OPT_SHORTLIST = 2,   /* shortlist length k' of the TC mode (default max(32, ..)) */
-    FVDB_OPT_KMEANS_TC = 3    /* 1: k-means assignment on tensor cores with exact verify */
+    FVDB_OPT_KMEANS_TC = 3,   /* 1: k-means assignment on tensor cores with exact verify */
+    FVDB_OPT_COALESCE = 4     /* 1 (default): concurrent fvdb_search calls are coalesced into one device batch */
 } fvdb_option;
 
 /* TrainResult, src/ivf/core.rs:103-109. */
@@ -111,7 +112,7 @@ typedef struct fvdb_stats {
     float last_device_ms;           /* device time of the last search (CUDA events) */
     float last_scan_ms;             /* device time of the posting-list scan kernel alone */
     uint32_t last_launches;         /* kernels launched by the last search */
-    uint32_t reserved;
+    uint32_t last_batch_calls;      /* fvdb_search calls served by the last device batch (submission queue) */
 } fvdb_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
@@ -190,7 +191,13 @@ int fvdb_vacuum(fvdb_index *h, uint64_t *removed);
  *                (src/hybrid/core.rs:513-549) is reproduced by the host mirror on top of this.
  *   out_ids      [nq x k], out_dist [nq x k], out_count [nq] (<= k valid entries per query;
  *                fewer than k is legal, src/ivf/core.rs:386-398 of the tests).
- * Empty index or untrained+no recent rows: counts are 0 (Ok(vec![]) :431-434). */
+ * Empty index or untrained+no recent rows: counts are 0 (Ok(vec![]) :431-434).
+ * Concurrency: may be called from many OS threads at once (the reference's `&self` searches behind
+ * an RwLock, src/hybrid/core.rs:202-213).  Calls without a filter bitmap pass through a submission
+ * queue: the first caller leads, takes every queued call with the same (k, nprobe, tiers) and runs
+ * them as ONE device batch (results are those of the separate calls, bit for bit — every query of a
+ * batch is independent), then hands the lead to the next waiting caller.  FVDB_OPT_COALESCE = 0
+ * serialises the calls instead. */
 int fvdb_search(fvdb_index *h, const float *q, uint32_t nq, uint32_t k, uint32_t nprobe,
                 uint32_t tiers, const uint64_t *filter_bits, uint64_t filter_nbits,
                 uint32_t *out_ids, float *out_dist, uint32_t *out_count);

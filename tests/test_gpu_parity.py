@@ -463,3 +463,69 @@ def test_mirror_maintenance_operations():
     assert idx.balance_clusters(0.2).vectors_moved == 0
     res = idx.search(x[17], 3)
     assert res[0].vector_id == "v17" and res[0].distance < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", MODES)
+def test_concurrent_single_query_calls_are_coalesced(mode):
+    """Many OS threads calling fvdb_search with one query each (the reference's usage: `&self`
+    searches behind an RwLock, one query per call): the submission queue runs queued calls as one
+    device batch; every caller gets exactly the result of its own separate call (= the oracle's)."""
+    import threading
+    n, d, nlist, nprobe, k = 4000, 384, 32, 8, 10
+    eng, ivf, x, cents, _, _ = _build(n, d, nlist, 41, mode)
+    n_threads, per = 12, 25
+    q = _queries(n_threads * per, d, n, 41)
+    want = O.hybrid_batch_search(ivf, None, None, q, k, nprobe, tiers=2)
+    got = [None] * (n_threads * per)
+    seen_batch = []
+    errors = []
+
+    def worker(t):
+        try:
+            for j in range(per):
+                i = t * per + j
+                got[i] = eng.search(q[i], k, nprobe, tiers=L.TIER_HISTORICAL)
+                if j % 8 == 0:
+                    seen_batch.append(eng.stats().last_batch_calls)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    ids = np.concatenate([g[0] for g in got])
+    dist = np.concatenate([g[1] for g in got])
+    cnt = np.concatenate([g[2] for g in got])
+    _assert_same(ids, dist, cnt, *want)
+    assert max(seen_batch) >= 1
+    # a bad call must not fail the calls it is batched with, and sees its own error
+    from fabstir_vectordb_b200 import NanInput
+    bad = q[0].copy()
+    bad[3] = np.nan
+    res = {}
+
+    def good_call():
+        res["good"] = eng.search(q[1], k, nprobe, tiers=L.TIER_HISTORICAL)
+
+    def bad_call():
+        try:
+            eng.search(bad, k, nprobe, tiers=L.TIER_HISTORICAL)
+            res["bad"] = "no error"
+        except NanInput:
+            res["bad"] = "nan"
+
+    ts = [threading.Thread(target=f) for f in (good_call, bad_call, good_call)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert res["bad"] == "nan"
+    assert np.array_equal(res["good"][0], got[1][0]) and np.array_equal(res["good"][1].view(np.uint32), got[1][1].view(np.uint32))
+    # serialised mode gives the same bits
+    eng.set_option(L.OPT_COALESCE, 0)
+    one = eng.search(q[2], k, nprobe, tiers=L.TIER_HISTORICAL)
+    assert np.array_equal(one[0], got[2][0]) and eng.stats().last_batch_calls == 1
