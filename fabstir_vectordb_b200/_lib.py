@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libfvdb_b200.so")
+# FVDB_LIB selects an experiment build of the same library (fabstir_vectordb_b200/build.py variants)
+SO_PATH = os.environ.get("FVDB_LIB") or os.path.join(_HERE, "libfvdb_b200.so")
 
 # fvdb_status (include/fvdb.h)
 OK = 0

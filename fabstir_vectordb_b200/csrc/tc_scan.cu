@@ -95,10 +95,24 @@ constexpr int R2_ROWS = 128;                     // rows per tile (MMA M = TMEM 
 constexpr int R2_NQ = (int)TC_TILE_Q;            // queries per item (MMA N max)
 constexpr int R2_STAGE_BYTES = R2_ROWS * 128;    // 16 KB: 128 rows x one 128-byte k-block
 constexpr int R2_QBLK_BYTES = R2_NQ * 128;       // 8 KB per k-block of the query tile
-constexpr int R2_CAP = 32;                       // pending candidates per query
-constexpr int R2_FLUSH = 16;                     // merge a query once it holds more pending than this
+#ifndef FVDB_R2_CAP
+#define FVDB_R2_CAP 32
+#endif
+#ifndef FVDB_R2_FLUSH
+#define FVDB_R2_FLUSH (FVDB_R2_CAP / 2)
+#endif
+#ifndef FVDB_R2_NSLOT
+#define FVDB_R2_NSLOT 16
+#endif
+#ifndef FVDB_R2_SLACK
+#define FVDB_R2_SLACK 1024
+#endif
+constexpr int R2_CAP = FVDB_R2_CAP;              // pending candidates per query (<= 32: one sorting network)
+constexpr int R2_FLUSH = FVDB_R2_FLUSH;          // merge a query once it holds more pending than this
 constexpr int R2_NBUF = 8;                       // accumulator buffers of R2_NQ columns
-constexpr int R2_NSLOT = 16;                     // |x|^2 strips in flight
+constexpr int R2_NSLOT = FVDB_R2_NSLOT;          // |x|^2 strips in flight
+constexpr int R2_SLACK = FVDB_R2_SLACK;          // bytes reserved for aligning the dynamic shared memory to 1024 (0: trap if it is not)
+static_assert(R2_CAP <= 32 && R2_FLUSH < R2_CAP && R2_NSLOT > R2_NBUF + 2, "kernel R pools");
 constexpr int R2_THREADS = 320;
 constexpr int R2_TMEM_COLS = 512;
 
@@ -201,6 +215,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    if (R2_SLACK < 1024 && smem != smem_raw) __trap();   // built without slack: the declared alignment must hold
     const uint32_t KB = p.KB;
     const uint32_t STAGES = p.stages;
     const R2Smem sm = r2_carve(smem, KB, STAGES);
@@ -316,7 +331,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                const uint32_t slot = tcount & (R2_NSLOT - 1);
+                const uint32_t slot = tcount % R2_NSLOT;
 #pragma unroll
                 for (int h = 0; h < 4; ++h) sm.xn_ring[slot * R2_ROWS + h * 32 + lane] = xnv[h];
                 __syncwarp();
@@ -584,7 +599,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
 
             // ---- row tiles ----
             for (uint32_t rt = it.row_begin; rt < it.row_end; rt += R2_ROWS) {
-                const uint32_t slot = tile & (R2_NSLOT - 1);
+                const uint32_t slot = tile % R2_NSLOT;
                 Q1_LAP(4);
                 mbar_wait(bar_nfull + 8 * slot, (tile / R2_NSLOT) & 1u);
                 const float xn = sm.xn_ring[slot * R2_ROWS + trow];
@@ -619,10 +634,22 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
                         thr[4 * j4 + 0] = t4.x; thr[4 * j4 + 1] = t4.y; thr[4 * j4 + 2] = t4.z; thr[4 * j4 + 3] = t4.w;
                     }
                     tmem_ld_wait();
+                    // branch-free compare of the 16 columns into a bit mask, then one divergent loop over
+                    // the set bits: the warp pays max-over-lanes(passing columns) append latencies per
+                    // chunk (2-3) instead of one per column in which ANY lane passes (~11 of 16)
+                    uint32_t pass = 0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float v = fmaf(-2.0f, __uint_as_float(acc[j]), xn);  // |x|^2 - 2 x.q
-                        if (v < thr[j]) append(c0 + j, v);
+                        pass |= (v < thr[j]) ? (1u << j) : 0u;
+                    }
+                    while (pass) {
+                        const uint32_t b = (uint32_t)__ffs((int)pass) - 1u;
+                        pass &= pass - 1u;
+                        uint32_t a = acc[0];
+#pragma unroll
+                        for (int j = 1; j < 16; ++j) a = (b == (uint32_t)j) ? acc[j] : a;
+                        append(c0 + b, fmaf(-2.0f, __uint_as_float(a), xn));
                     }
                 }
                 Q1_LAP(3);
@@ -720,6 +747,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     }
 }
 
+
+#include "tc_scan_pair.cuh"
 
 // ================================================================================================
 // Kernel Q ("queries on lanes"): the query tile is the MMA A operand and lives in TENSOR MEMORY
@@ -1600,6 +1629,7 @@ struct TcScratchImpl {
     const float* tmap_rows = nullptr;
     uint64_t tmap_n = 0;
     bool smem_attr_set = false;
+    bool smem_attr_set_pair = false;
 };
 
 bool tc_supported(uint32_t D) { return D % 32 == 0 && D >= 32 && D <= 512; }
@@ -1694,7 +1724,11 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     // kernel R (rows on lanes, query tile in shared memory) covers 384 < D <= 512
     const char* kenv = getenv("FVDB_TC_KERNEL");
     const bool use_q = (D <= 384) && (kenv && kenv[0] == 'Q');
-    const uint32_t tile_q = use_q ? (uint32_t)Q1_M : TC_TILE_Q;
+    // kernel P (CTA pairs, 128-query items): needs an even grid and the pair's shared-memory budget
+    const bool use_pair = !use_q && (kenv && kenv[0] == 'P') && a.sm_count >= 2 &&
+                          tc_scan_pair_smem_bytes(KB, 2) + 1024 <= 232448;
+    const uint32_t tile_q = use_q ? (uint32_t)Q1_M : use_pair ? (uint32_t)P2_NQ : TC_TILE_Q;
+    const uint32_t prows = use_pair ? 2u : 1u;   // shortlist rows per (query, probe)
     const size_t max_items = (size_t)a.nlist + (n_pairs + tile_q - 1) / tile_q + 1;
     TCK(m->qnorm.ensure(nq, dev_bytes));
     TCK(m->thr_g.ensure(nq, dev_bytes));
@@ -1705,7 +1739,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     TCK(m->pair_slot.ensure(n_pairs, dev_bytes));
     TCK(m->n_items.ensure(4, dev_bytes));
     TCK(m->items.ensure(max_items, dev_bytes));
-    TCK(m->partial.ensure(n_pairs * TC_KP, dev_bytes));
+    TCK(m->partial.ensure(n_pairs * prows * TC_KP, dev_bytes));
     TCK(m->shortlist.ensure((size_t)nq * TC_KP, dev_bytes));
 
     {
@@ -1793,7 +1827,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
                                m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st,
                                (m->list_order_n == a.nlist && !getenv("FVDB_TC_NO_ORDER")) ? m->list_order.p : nullptr));
     (*launches) += 3;
-    TCK(cudaMemsetAsync(m->partial.p, 0xFF, n_pairs * TC_KP * sizeof(uint64_t), st));
+    TCK(cudaMemsetAsync(m->partial.p, 0xFF, n_pairs * prows * TC_KP * sizeof(uint64_t), st));
 
     // ---- the scan ----
     TcScanParams p{};
@@ -1832,12 +1866,44 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         tc_scan_q_kernel<<<grid, TC_THREADS, smem, st>>>(m->tmap_q, p);
         TCK(cudaGetLastError());
         if (p.prof) TCK(dump_prof(m->prof.p, grid, st));
+    } else if (use_pair) {
+        uint32_t stages = std::min<uint32_t>(12u, 6u * KB);
+        while (stages > 2 && tc_scan_pair_smem_bytes(KB, stages) + 1024 > 232448) --stages;
+        if (const char* e = getenv("FVDB_TC_STAGES")) { const uint32_t v = (uint32_t)atoi(e); if (v >= 2 && v < stages) stages = v; }
+        p.stages = stages;
+        const size_t smem = tc_scan_pair_smem_bytes(KB, stages) + 1024;
+        if (!m->smem_attr_set_pair) {
+            TCK(cudaFuncSetAttribute(tc_scan_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+            m->smem_attr_set_pair = true;
+        }
+        const uint32_t grid = (uint32_t)a.sm_count & ~1u;   // whole pairs; idle pairs exit at once
+        if (p.debug & 128u) {
+            TCK(m->prof.ensure((size_t)grid * 48, dev_bytes));
+            TCK(cudaMemsetAsync(m->prof.p, 0, (size_t)grid * 48 * 8, st));
+            p.prof = m->prof.p;
+        }
+        if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(R2_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TCK(cudaLaunchKernelEx(&cfg, tc_scan_pair_kernel, m->tmap_arena, p));
+        if (p.prof) TCK(dump_prof(m->prof.p, grid, st));
     } else {
         // deepest ring that fits; the norm-strip window (see the producer) caps it at 6 tiles
-        uint32_t stages = std::min<uint32_t>(12u, 6u * KB);
-        while (stages > 2 && tc_scan_smem_bytes(KB, stages) + 1024 > 232448) --stages;
+        uint32_t stages = std::min<uint32_t>(12u, (uint32_t)(R2_NSLOT - 2 - R2_NBUF) * KB);
+        while (stages > 2 && tc_scan_smem_bytes(KB, stages) + R2_SLACK > 232448) --stages;
+        if (const char* e = getenv("FVDB_TC_STAGES")) { const uint32_t v = (uint32_t)atoi(e); if (v >= 2 && v < stages) stages = v; }
         p.stages = stages;
-        const size_t smem = tc_scan_smem_bytes(KB, stages) + 1024;  // slack for the 1024-byte alignment
+        const size_t smem = tc_scan_smem_bytes(KB, stages) + R2_SLACK;  // slack for the 1024-byte alignment
         if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
         if (!m->smem_attr_set) {
             TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -1858,7 +1924,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     (*launches)++;
 
     // ---- merge the per-(query, probe) shortlists, exact re-rank, proof ----
-    TCK(launch_merge_rows32(m->partial.p, nq, np, m->shortlist.p, st));
+    TCK(launch_merge_rows32(m->partial.p, nq, np * prows, m->shortlist.p, st));
     rerank_kernel<<<(nq + 3) / 4, 128, (size_t)4 * D * sizeof(float), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k, (uint32_t)TC_KP,
                                                a.out_keys, a.d_fallback_count, a.d_fallback_idx);
     TCK(cudaGetLastError());
