@@ -38,6 +38,19 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (test_wait never suspends the thread; try_wait may, for a system-dependent
+// time): for a role that polls two barriers in turn.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;  // fast path: no clock read
     const long long t0 = clock64();

@@ -113,6 +113,11 @@ constexpr int R2_NBUF = 8;                       // accumulator buffers of R2_NQ
 constexpr int R2_NSLOT = FVDB_R2_NSLOT;          // |x|^2 strips in flight
 constexpr int R2_SLACK = FVDB_R2_SLACK;          // bytes reserved for aligning the dynamic shared memory to 1024 (0: trap if it is not)
 static_assert(R2_CAP <= 32 && R2_FLUSH < R2_CAP && R2_NSLOT > R2_NBUF + 2, "kernel R pools");
+// offloaded merges (tc_scan_kernel_t<true>): the pending pool is split into two halves that alternate by
+// tile, so the merge warps fold tile t while the epilogue warps compare tile t + 1
+constexpr int RO_CAP = R2_CAP / 2;               // pending candidates per query and half
+constexpr int RO_FLUSH = RO_CAP / 2;
+static_assert(2 * RO_CAP <= 32, "the final fold sorts both halves in one 32-lane network");
 constexpr int R2_THREADS = 320;
 constexpr int R2_TMEM_COLS = 512;
 
@@ -123,11 +128,11 @@ struct R2Smem {
     uint64_t* pend;           // [R2_NQ][R2_CAP] unsorted pending candidates
     float* xn_ring;           // [R2_NSLOT][R2_ROWS]
     float* thrp;              // [R2_NQ] threshold - |q|^2   (-inf for padded columns)
-    uint32_t* pcnt;           // [R2_NQ] pending count (may exceed R2_CAP: overflow marker)
+    uint32_t* pcnt;           // [2][R2_NQ] pending count (may exceed the capacity: overflow marker)
     uint32_t* qidx;           // [2][R2_NQ]
     uint32_t* qslot;          // [2][R2_NQ]
     float* qn;                // [2][R2_NQ]
-    uint32_t* redo;           // [2] bitmask of queries to replay
+    uint32_t* redo;           // [8] bitmask of queries to replay ([half][round parity][2] with offloaded merges)
     uint64_t* bars;
     uint32_t* tmem_ptr;
     uint32_t* sched;          // [TC_SCHED]
@@ -142,20 +147,20 @@ __device__ __forceinline__ R2Smem r2_carve(unsigned char* smem, uint32_t KB, uin
     m.xn_ring = reinterpret_cast<float*>(m.pend + R2_NQ * R2_CAP);
     m.thrp = m.xn_ring + R2_NSLOT * R2_ROWS;
     m.pcnt = reinterpret_cast<uint32_t*>(m.thrp + R2_NQ);
-    m.qidx = m.pcnt + R2_NQ;
+    m.qidx = m.pcnt + 2 * R2_NQ;
     m.qslot = m.qidx + 2 * R2_NQ;
     m.qn = reinterpret_cast<float*>(m.qslot + 2 * R2_NQ);
     m.redo = reinterpret_cast<uint32_t*>(m.qn + 2 * R2_NQ);
-    m.bars = reinterpret_cast<uint64_t*>(m.redo + 4);
-    m.tmem_ptr = reinterpret_cast<uint32_t*>(m.bars + 2 * STAGES + 2 * R2_NBUF + R2_NSLOT + 2 * TC_SCHED + 3);
+    m.bars = reinterpret_cast<uint64_t*>(m.redo + 8);
+    m.tmem_ptr = reinterpret_cast<uint32_t*>(m.bars + 2 * STAGES + 2 * R2_NBUF + R2_NSLOT + 2 * TC_SCHED + 8);
     m.sched = m.tmem_ptr + 1;
     return m;
 }
 
 size_t tc_scan_smem_bytes(uint32_t KB, uint32_t stages) {
     return (size_t)KB * R2_QBLK_BYTES + (size_t)stages * R2_STAGE_BYTES + (size_t)R2_NQ * TC_KP * 8 +
-           (size_t)R2_NQ * R2_CAP * 8 + (size_t)R2_NSLOT * R2_ROWS * 4 + (size_t)R2_NQ * 8 * 4 + 16 +
-           (size_t)(2 * stages + 2 * R2_NBUF + R2_NSLOT + 2 * TC_SCHED + 3) * 8 + 16 + (size_t)TC_SCHED * 4;
+           (size_t)R2_NQ * R2_CAP * 8 + (size_t)R2_NSLOT * R2_ROWS * 4 + (size_t)R2_NQ * 9 * 4 + 32 +
+           (size_t)(2 * stages + 2 * R2_NBUF + R2_NSLOT + 2 * TC_SCHED + 8) * 8 + 16 + (size_t)TC_SCHED * 4;
 }
 
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
@@ -166,7 +171,9 @@ __device__ __forceinline__ void epi_bar_n(int id) { asm volatile("bar.sync %0, 1
 // Merge the pending candidates of up to four queries (owned by this warp) into their sorted
 // shortlists; lane i holds entry i.  n[g] pending entries (already clamped to R2_CAP).
 __device__ __forceinline__ void r2_merge4(const R2Smem& sm, const uint32_t (&qs)[4], const uint32_t (&n)[4],
-                                          const bool (&act)[4], uint64_t (&lst)[4], int lane) {
+                                          const bool (&act)[4], uint64_t (&lst)[4], int lane,
+                                          const uint64_t* pend = nullptr, uint32_t cap = R2_CAP) {
+    if (!pend) pend = sm.pend;
     uint64_t nw[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -174,7 +181,7 @@ __device__ __forceinline__ void r2_merge4(const R2Smem& sm, const uint32_t (&qs)
         nw[g] = KEY_NONE;
         if (act[g]) {
             lst[g] = sm.sorted[qs[g] * TC_KP + lane];
-            if ((uint32_t)lane < n[g]) nw[g] = sm.pend[qs[g] * R2_CAP + lane];
+            if ((uint32_t)lane < n[g]) nw[g] = pend[qs[g] * cap + lane];
         }
     }
 #pragma unroll
@@ -206,12 +213,53 @@ __device__ __forceinline__ void publish_bound(const TcScanParams& p, uint32_t qi
     }
 }
 
+// Stage the query tile of an item: warp lw stages queries lw, lw+4, ...; a lane moves float4 columns
+// lane, lane+32, ...; loads of four query rows are issued before any store (12 LDG.128 per lane in
+// flight).  Lane l of every loader warp holds the indices of queries l and l + 32 in qi0 / qi1.
+__device__ __forceinline__ void r2_load_queries(const R2Smem& sm, const TcScanParams& p, uint32_t qi0, uint32_t qi1,
+                                                uint32_t ncols, int lw, int lane, uint32_t KB, uint32_t D) {
+    const uint32_t f4_per_row = KB * 8;
+    for (uint32_t q0 = lw; q0 < ncols; q0 += 16) {
+        const float4* src[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t q = q0 + 4 * g;
+            const uint32_t qa = __shfl_sync(0xffffffffu, qi0, q & 31), qb = __shfl_sync(0xffffffffu, qi1, q & 31);
+            const uint32_t qi = (q < 32) ? qa : qb;
+            src[g] = (q < ncols && qi != ID_NONE) ? reinterpret_cast<const float4*>(p.Q + (size_t)qi * D) : nullptr;
+        }
+        for (uint32_t c = lane; c < f4_per_row; c += 96) {
+            float4 v[3][4];
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    v[u][g] = (src[g] && c + 32 * u < f4_per_row) ? __ldg(src[g] + c + 32 * u)
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const uint32_t cc = c + 32 * u;
+                if (cc >= f4_per_row) break;
+                const uint32_t kb = cc >> 3, ch = cc & 7;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t q = q0 + 4 * g;
+                    if (q < ncols)
+                        *reinterpret_cast<float4*>(sm.q_tile + (size_t)kb * R2_QBLK_BYTES + q * 128 +
+                                                   ((ch ^ (q & 7)) << 4)) = v[u][g];
+                }
+            }
+        }
+    }
+}
+
 // stopwatch lap: the cycles since the previous lap of this role are charged to category i
 #define Q1_LAP(i) do { if (p.prof) { const long long n_ = clock64(); lap[i] += (unsigned long long)(n_ - tl); tl = n_; } } while (0)
 #define Q1_LAP_DUMP(role) do { if (p.prof && lane == 0) { for (int i_ = 0; i_ < 8; ++i_) p.prof[((size_t)blockIdx.x * 6 + (role)) * 8 + i_] = lap[i_]; } } while (0)
 
+template <bool OFF>   // OFF: the loader warps also fold the pending candidates (merges off the epilogue's path)
 __global__ void __launch_bounds__(R2_THREADS, 1)
-tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
+tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -231,8 +279,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     const uint32_t bar_qready = bar_sempty + 8 * TC_SCHED;  // query tile + item metadata staged
     const uint32_t bar_qfree = bar_qready + 8;              // every MMA of the item has retired
     const uint32_t bar_mfree = bar_qfree + 8;               // epilogue is done with an item's metadata
+    const uint32_t bar_pfull = bar_mfree + 8;               // [2] OFF: every candidate of a round is in the pending half
+    const uint32_t bar_pfree = bar_pfull + 16;              // [2] OFF: the merge warps are done with the half
+    const uint32_t bar_idone = bar_pfree + 16;              // OFF: the item's shortlists are published
 
     if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_pfull + 8 * i, 4);
+            mbar_init(bar_pfree + 8 * i, 4);
+        }
+        mbar_init(bar_idone, 4);
+        for (int i = 0; i < 8; ++i) sm.redo[i] = 0;
         for (uint32_t s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
@@ -401,6 +458,225 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
         const int lw = warp - 6;
         const int lt = lw * 32 + lane;
         const uint32_t D = p.D;
+        if constexpr (OFF) {
+            // ===== loader + MERGE warps.  Job n = the n-th non-empty item of this CTA.  Load side: as in the
+            // classic variant.  Merge side: for every tile of the job, in rounds on the pending half
+            // (tile & 1): wait for the epilogue's `pfull`, fold the owned queries (j % 4 == lw) that hold
+            // more than RO_FLUSH pending, tighten / share their bounds, arrive on `pfree`.  A round that
+            // saw an overflow (redo mask) is followed by another round on the same half (the epilogue
+            // replays the rows it could not store).  Every wait of the load side services merge rounds.
+            const uint32_t jown = (uint32_t)lane * 4u + (uint32_t)lw;
+            uint32_t j_load = 0, j_done = 0;
+            uint32_t job_cnt0 = 0, job_cnt1 = 0, job_tiles0 = 0, job_tiles1 = 0;
+            uint32_t mt = 0, g_tile = 0, mround0 = 0, mround1 = 0, st_merge = 0;
+            bool job_open = false, own = false;
+            uint32_t qi_own = 0, thr_pending = F32_INF_BITS, peer_sent = F32_INF_BITS;
+            float qn_own = 0.f;
+
+            auto merge_owned = [&](unsigned need, uint32_t b) {
+                const uint64_t* pend = sm.pend + (size_t)b * R2_NQ * RO_CAP;
+                uint32_t* pcnt = sm.pcnt + b * R2_NQ;
+                st_merge += __popc(need);
+                if (__popc(need) == 1) {
+                    const int src = __ffs(need) - 1;
+                    const uint32_t q = (uint32_t)src * 4u + (uint32_t)lw;
+                    const uint32_t n = min(pcnt[q], (uint32_t)RO_CAP);
+                    uint64_t nw = ((uint32_t)lane < n) ? pend[q * RO_CAP + lane] : KEY_NONE;
+                    uint64_t lst = sm.sorted[q * TC_KP + lane];
+                    nw = warp_sort32(nw, lane);
+                    lst = warp_merge32(lst, nw, lane);
+                    sm.sorted[q * TC_KP + lane] = lst;
+                    const uint64_t last = shfl64(lst, 31);
+                    __syncwarp();
+                    if (lane == src) {
+                        pcnt[q] = 0;
+                        if (last != KEY_NONE) {
+                            sm.thrp[q] = fminf(sm.thrp[q], __uint_as_float((uint32_t)(last >> 32)) - qn_own);
+                            if (p.thr_g) publish_bound(p, qi_own, (uint32_t)(last >> 32), peer_sent);
+                        }
+                    }
+                    __syncwarp();
+                    return;
+                }
+                while (need) {
+                    uint32_t qs[4], nn[4];
+                    bool act[4];
+                    int src[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        act[g] = need != 0;
+                        src[g] = act[g] ? (__ffs(need) - 1) : 0;
+                        if (act[g]) need &= need - 1;
+                        qs[g] = (uint32_t)src[g] * 4u + (uint32_t)lw;
+                        nn[g] = act[g] ? min(pcnt[qs[g]], (uint32_t)RO_CAP) : 0u;
+                    }
+                    uint64_t lst[4];
+                    r2_merge4(sm, qs, nn, act, lst, lane, pend, (uint32_t)RO_CAP);
+                    __syncwarp();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (!act[g]) continue;
+                        sm.sorted[qs[g] * TC_KP + lane] = lst[g];
+                        const uint64_t last = shfl64(lst[g], 31);
+                        if (lane == src[g]) {
+                            pcnt[qs[g]] = 0;
+                            if (last != KEY_NONE) {
+                                sm.thrp[qs[g]] = fminf(sm.thrp[qs[g]], __uint_as_float((uint32_t)(last >> 32)) - qn_own);
+                                if (p.thr_g) publish_bound(p, qi_own, (uint32_t)(last >> 32), peer_sent);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            };
+
+            // one merge round if the epilogue has posted one; false when there is nothing to do right now
+            auto service = [&]() -> bool {
+                if (j_done == j_load) return false;
+                const uint32_t b = g_tile & 1u;
+                const uint32_t mr = b ? mround1 : mround0;
+                if (!__all_sync(0xffffffffu, mbar_test(bar_pfull + 8 * b, mr & 1u) ? 1 : 0)) return false;
+                const uint32_t jb = j_done & 1u;
+                const uint32_t cnt = jb ? job_cnt1 : job_cnt0;
+                const uint32_t mb = jb * R2_NQ;
+                if (!job_open) {
+                    for (uint32_t j = (uint32_t)lw; j < (uint32_t)R2_NQ; j += 4) sm.sorted[j * TC_KP + lane] = KEY_NONE;
+                    own = lane < R2_NQ / 4 && jown < cnt;
+                    qi_own = own ? sm.qidx[mb + jown] : 0u;
+                    qn_own = own ? sm.qn[mb + jown] : 0.f;
+                    thr_pending = F32_INF_BITS;
+                    peer_sent = F32_INF_BITS;
+                    job_open = true;
+                    mt = 0;
+                    __syncwarp();
+                }
+                const uint32_t par = mr & 1u;
+                const uint32_t r0 = sm.redo[b * 4 + par * 2], r1 = sm.redo[b * 4 + par * 2 + 1];
+                __syncwarp();
+                if (lw == 0 && lane < 2) sm.redo[b * 4 + (par ^ 1u) * 2 + lane] = 0;   // the next round's mask
+                if (own) {
+                    // bound tightened meanwhile by CTAs scanning other lists of the same query
+                    sm.thrp[jown] = fminf(sm.thrp[jown], __uint_as_float(thr_pending) - qn_own);
+                    if (p.thr_g) thr_pending = *(volatile uint32_t*)(p.thr_g + qi_own);
+                }
+                const uint32_t pc = own ? sm.pcnt[b * R2_NQ + jown] : 0u;
+                merge_owned(__ballot_sync(0xffffffffu, pc > (uint32_t)RO_FLUSH), b);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pfree + 8 * b);
+                if (b) ++mround1; else ++mround0;
+                if ((r0 | r1) == 0) {      // the tile is complete
+                    ++g_tile;
+                    ++mt;
+                    if (mt == (jb ? job_tiles1 : job_tiles0)) {
+                        // ---- job epilogue: fold what is pending in both halves, publish the shortlists.  A
+                        // query that never merged publishes its pending candidates UNSORTED (the shortlist
+                        // merge after the scan sorts such rows).
+                        for (uint32_t j = (uint32_t)lw; j < cnt; j += 4) {
+                            const uint32_t n0 = min(sm.pcnt[j], (uint32_t)RO_CAP), n1 = min(sm.pcnt[R2_NQ + j], (uint32_t)RO_CAP);
+                            const uint64_t lst = sm.sorted[j * TC_KP + lane];
+                            const bool has_sorted = __shfl_sync(0xffffffffu, lst != KEY_NONE ? 1 : 0, 0) != 0;
+                            if (n0 + n1 == 0 && !has_sorted) continue;      // partial is pre-filled
+                            uint64_t nw = KEY_NONE;
+                            if (lane < RO_CAP) { if ((uint32_t)lane < n0) nw = sm.pend[j * RO_CAP + lane]; }
+                            else if ((uint32_t)(lane - RO_CAP) < n1) nw = sm.pend[(size_t)(R2_NQ + j) * RO_CAP + (lane - RO_CAP)];
+                            uint64_t out = nw;
+                            if (has_sorted) {
+                                out = lst;
+                                if (n0 + n1) {
+                                    nw = warp_sort32(nw, lane);
+                                    out = warp_merge32(lst, nw, lane);
+                                    if (p.thr_g && lane == 31 && out != KEY_NONE) atomicMin(p.thr_g + sm.qidx[mb + j], (uint32_t)(out >> 32));
+                                }
+                            }
+                            p.partial[((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * TC_KP + lane] = out;
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_idone);
+                        ++j_done;
+                        job_open = false;
+                    }
+                }
+                return true;
+            };
+            // wait on a barrier of the load side, folding pending candidates meanwhile
+            auto wait_serv = [&](uint32_t bar, uint32_t parity) {
+                long long t0 = 0;
+                bool timed = false;
+                while (!__all_sync(0xffffffffu, mbar_test(bar, parity) ? 1 : 0)) {
+                    if (service()) { timed = false; continue; }
+                    if (!timed) { t0 = clock64(); timed = true; }
+                    else if (clock64() - t0 > 4000000000ll) __trap();
+                }
+            };
+            auto drain_until = [&](uint32_t jobs_done) {
+                long long t0 = 0;
+                bool timed = false;
+                while (j_done < jobs_done) {
+                    if (service()) { timed = false; continue; }
+                    if (!timed) { t0 = clock64(); timed = true; }
+                    else if (clock64() - t0 > 4000000000ll) __trap();
+                }
+            };
+
+            uint32_t ss = 0, sphase = 0, nit = 0;
+            while (true) {
+                Q1_LAP(3);
+                wait_serv(bar_sfull + 8 * ss, sphase);
+                const uint32_t item = sm.sched[ss];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
+                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+                Q1_LAP(0);
+                if (item == ITEM_END) break;
+                const ScanItem it = p.items[item];
+                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+                const uint32_t cnt = it.pair_count;
+                const uint32_t ncols = (cnt + 15u) & ~15u;
+                uint32_t qi0 = ID_NONE, qi1 = ID_NONE, sl0 = 0, sl1 = 0;
+                if ((uint32_t)lane < cnt) {
+                    if (it.identity) { qi0 = it.pair_begin + lane; sl0 = it.slot; }
+                    else { qi0 = p.pair_q[it.pair_begin + lane]; sl0 = p.pair_slot[it.pair_begin + lane]; }
+                }
+                if ((uint32_t)lane + 32 < cnt) {
+                    if (it.identity) { qi1 = it.pair_begin + lane + 32; sl1 = it.slot; }
+                    else { qi1 = p.pair_q[it.pair_begin + lane + 32]; sl1 = p.pair_slot[it.pair_begin + lane + 32]; }
+                }
+                // metadata buffer and job slot (nit & 1) were last used by job nit - 2: the epilogue has
+                // released it (mfree) and this warp has published it
+                Q1_LAP(3);
+                if (nit >= 2) {
+                    drain_until(nit - 1);
+                    // ... and so have the other merge warps (they read the same metadata).  Job nit - 1 of
+                    // this warp done => the epilogue started item nit - 1 => it saw `idone` of job nit - 2;
+                    // otherwise wait for it here (nothing to service meanwhile: the epilogue posts no
+                    // round of job nit - 1 before that barrier completes, so the phase cannot be lapped)
+                    if (j_done == nit - 1) mbar_wait(bar_idone, nit & 1u);
+                    wait_serv(bar_mfree, nit & 1u);
+                }
+                Q1_LAP(1);
+                if (lw == 0) {
+                    const uint32_t mb = (nit & 1u) * R2_NQ;
+                    sm.qidx[mb + lane] = qi0; sm.qidx[mb + 32 + lane] = qi1;
+                    sm.qslot[mb + lane] = sl0; sm.qslot[mb + 32 + lane] = sl1;
+                    sm.qn[mb + lane] = (qi0 != ID_NONE) ? p.qnorm[qi0] : 0.f;
+                    sm.qn[mb + 32 + lane] = (qi1 != ID_NONE) ? p.qnorm[qi1] : 0.f;
+                }
+                {
+                    const uint32_t ntiles = (it.row_end - it.row_begin + R2_ROWS - 1) / R2_ROWS;
+                    if (nit & 1u) { job_cnt1 = cnt; job_tiles1 = ntiles; } else { job_cnt0 = cnt; job_tiles0 = ntiles; }
+                    j_load = nit + 1;
+                }
+                Q1_LAP(3);
+                if (nit >= 1) wait_serv(bar_qfree, (nit - 1) & 1u);
+                Q1_LAP(2);
+                r2_load_queries(sm, p, qi0, qi1, ncols, lw, lane, KB, D);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+                mbar_arrive(bar_qready);
+                ++nit;
+            }
+            drain_until(j_load);
+            lap[7] = st_merge;
+        } else {
         uint32_t ss = 0, sphase = 0, nit = 0;
         while (true) {
             Q1_LAP(3);
@@ -483,7 +759,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
             ++nit;
             (void)lt;
         }
-        if (warp == 6 && p.prof && lane == 0) { for (int i_ = 0; i_ < 4; ++i_) p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + i_] = lap[i_]; }
+        }
+        if (warp == 6 && p.prof && lane == 0) {
+            for (int i_ = 0; i_ < 4; ++i_) p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + i_] = lap[i_];
+            p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + 7] = lap[7];
+        }
     } else {
         // ================= epilogue (warps 2-5): one thread = one row of the tile =================
         const int ew = warp - 2;                 // owner stripe: this warp merges queries j with j % 4 == ew
@@ -495,6 +775,136 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
         uint32_t st_app = 0, st_ovf = 0, st_merge = 0, st_replay = 0, st_chunks = 0;
         // the query this lane owns in the merge phases (lanes 0..15): j = lane * 4 + ew
         const uint32_t jown = (uint32_t)lane * 4u + (uint32_t)ew;
+        if constexpr (OFF) {
+            // ===== compare-only epilogue: candidates go to the pending half (tile & 1); the merge warps
+            // fold it while this role compares the next tile.  Only an overflow (a query that met a
+            // full pending list) couples the two roles: wait for the fold, replay the rows concerned.
+            uint32_t round0 = 0, round1 = 0;     // rounds posted on each half (both roles count them alike)
+            while (true) {
+                Q1_LAP(6);
+                mbar_wait(bar_sfull + 8 * ss, sphase);
+                const uint32_t item = sm.sched[ss];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
+                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
+                Q1_LAP(0);
+                if (item == ITEM_END) break;
+                const ScanItem it = p.items[item];
+                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
+                const uint32_t cnt = it.pair_count;
+                const uint32_t ncols = (cnt + 15u) & ~15u;
+                const uint32_t mb = (nit & 1u) * R2_NQ;
+                mbar_wait(bar_qready, nit & 1u);           // metadata of this item is staged
+                if (nit >= 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_mfree);
+                    mbar_wait(bar_idone, (nit - 1) & 1u);  // the previous item's pending pools are drained
+                }
+                Q1_LAP(1);
+                if (et < R2_NQ) {
+                    float thr = -__uint_as_float(F32_INF_BITS);  // padded columns never pass
+                    if ((uint32_t)et < cnt) {
+                        const uint32_t g = p.thr_g ? *(volatile uint32_t*)(p.thr_g + sm.qidx[mb + et]) : (uint32_t)0x7f800000u;
+                        thr = __uint_as_float(g) - sm.qn[mb + et];
+                    }
+                    sm.thrp[et] = thr;
+                    sm.pcnt[et] = 0;
+                    sm.pcnt[R2_NQ + et] = 0;
+                }
+                epi_bar_n(1);
+                Q1_LAP(6);
+                for (uint32_t rt = it.row_begin; rt < it.row_end; rt += R2_ROWS) {
+                    const uint32_t slot = tile % R2_NSLOT;
+                    Q1_LAP(4);
+                    mbar_wait(bar_nfull + 8 * slot, (tile / R2_NSLOT) & 1u);
+                    const float xn = sm.xn_ring[slot * R2_ROWS + trow];
+                    const uint32_t buf = tile & (R2_NBUF - 1);
+                    mbar_wait(bar_tfull + 8 * buf, (tile / R2_NBUF) & 1u);
+                    tc_fence_after();
+                    Q1_LAP(2);
+                    const uint32_t b = tile & 1u;
+                    uint32_t rnd = b ? round1 : round0;
+                    if (rnd) mbar_wait(bar_pfree + 8 * b, (rnd - 1) & 1u);   // the half is folded
+                    Q1_LAP(5);
+                    const uint32_t taddr = tmem_base + buf * R2_NQ + lane_taddr;
+                    const uint32_t pos = rt + (uint32_t)trow;
+                    uint64_t* pend = sm.pend + (size_t)b * R2_NQ * RO_CAP;
+                    uint32_t* pcnt = sm.pcnt + b * R2_NQ;
+                    uint64_t ovf = 0;  // queries whose pending list was full when this row passed
+
+                    auto append = [&](uint32_t q, float v) {
+                        const uint32_t s = atomicAdd(&pcnt[q], 1u);
+                        ++st_app;
+                        if (s < (uint32_t)RO_CAP)
+                            pend[q * RO_CAP + s] = ((uint64_t)__float_as_uint(fmaxf(v + sm.qn[mb + q], 0.0f)) << 32) | (uint64_t)pos;
+                        else {
+                            ovf |= 1ull << q;
+                            atomicOr(&sm.redo[b * 4 + (rnd & 1u) * 2 + (q >> 5)], 1u << (q & 31));
+                            ++st_ovf;
+                        }
+                    };
+
+                    for (uint32_t c0 = 0; c0 < ((p.debug & 1u) ? 0u : ncols); c0 += 16) {
+                        uint32_t acc[16];
+                        ++st_chunks;
+                        tmem_ld16(taddr + c0, acc);
+                        float thr[16];
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(sm.thrp + c0 + 4 * j4);
+                            thr[4 * j4 + 0] = t4.x; thr[4 * j4 + 1] = t4.y; thr[4 * j4 + 2] = t4.z; thr[4 * j4 + 3] = t4.w;
+                        }
+                        tmem_ld_wait();
+                        uint32_t pass = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float v = fmaf(-2.0f, __uint_as_float(acc[j]), xn);  // |x|^2 - 2 x.q
+                            pass |= (v < thr[j]) ? (1u << j) : 0u;
+                        }
+                        while (pass) {
+                            const uint32_t bb = (uint32_t)__ffs((int)pass) - 1u;
+                            pass &= pass - 1u;
+                            uint32_t a = acc[0];
+#pragma unroll
+                            for (int j = 1; j < 16; ++j) a = (bb == (uint32_t)j) ? acc[j] : a;
+                            append(c0 + bb, fmaf(-2.0f, __uint_as_float(a), xn));
+                        }
+                    }
+                    Q1_LAP(3);
+                    while (true) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_pfull + 8 * b);
+                        mbar_wait(bar_pfull + 8 * b, rnd & 1u);      // every candidate of the round is stored
+                        const uint32_t r0 = sm.redo[b * 4 + (rnd & 1u) * 2], r1 = sm.redo[b * 4 + (rnd & 1u) * 2 + 1];
+                        ++rnd;
+                        if ((r0 | r1) == 0) break;
+                        ++st_replay;
+                        mbar_wait(bar_pfree + 8 * b, (rnd - 1) & 1u);  // folded: thresholds tightened, lists emptied
+                        // replay: rows that met a full pending list are tested against the new thresholds
+                        uint64_t rm = ((uint64_t)r1 << 32) | r0;
+                        while (rm) {
+                            const uint32_t q = (uint32_t)__ffsll((long long)rm) - 1u;
+                            rm &= rm - 1;
+                            uint32_t a;
+                            tmem_ld1(taddr + q, a);
+                            tmem_ld_wait();
+                            if ((ovf >> q) & 1ull) {
+                                ovf &= ~(1ull << q);
+                                const float v = fmaf(-2.0f, __uint_as_float(a), xn);
+                                if (v < sm.thrp[q]) append(q, v);
+                            }
+                        }
+                    }
+                    if (b) round1 = rnd; else round0 = rnd;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);  // accumulator may be overwritten
+                    ++tile;
+                    Q1_LAP(4);
+                }
+                ++nit;
+            }
+        } else {
         while (true) {
             Q1_LAP(6);
             mbar_wait(bar_sfull + 8 * ss, sphase);
@@ -721,6 +1131,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
             epi_bar_n(1);  // pools may be re-initialised for the next item
             ++nit;
             Q1_LAP(5);
+        }
         }
         if (warp == 2) Q1_LAP_DUMP(2);
         if (p.prof && warp == 2) {
@@ -1268,6 +1679,74 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t v
     for (; i < n; i += stride) p[i] = v;
 }
 
+// ---- row gather for the exact re-rank steps ------------------------------------------------------
+// Each lane computes the exact distance of ITS OWN row (one candidate per lane), but the rows are
+// fetched by the warp together.  A lane walking its own row makes every load instruction touch 32
+// different cache lines, and the L1 tag stage (one line per cycle per SM) then bounds the kernel
+// (ncu: 6.5 M sector requests, 47 us for 100 MB of centroid rows that sit in L2).  Here eight lanes
+// fetch the 128-byte segment of one row (four lines per instruction) with cp.async into shared
+// memory, up to GATHER_STAGES segments per row in flight and no registers held; 16-byte chunk c of
+// row r sits at (c ^ (r & 7)), so both the cooperative writes and the lane-private reads are
+// conflict-free.  The accumulation is the strictly sequential f32 chain of euclidean_distance_scalar
+// (src/core/vector_ops.rs:51-57): same bits as exact_l2_lane.  All 32 lanes must call (row may be null).
+constexpr int GATHER_STAGES_ROWS = 6;      // re-rank: rows come from HBM
+constexpr int GATHER_STAGES_CENT = 4;      // coarse step: centroids come from L2
+__host__ __device__ constexpr int gather_warp_bytes(int stages) { return stages * 32 * 128; }
+template <int GATHER_STAGES>
+__device__ __forceinline__ float exact_l2_lane_gather(const float* __restrict__ q_s, const float* __restrict__ row,
+                                                      uint32_t KB, uint32_t warp_stage_base, int lane) {
+    // instruction j of a stage: this lane fetches chunk (lane & 7) of the row owned by lane 4 j + lane / 8
+    const char* src[8];
+    uint32_t dst[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int r = 4 * j + (lane >> 3);
+        const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)row, r);
+        src[j] = rp ? reinterpret_cast<const char*>((uintptr_t)rp) + (lane & 7) * 16 : nullptr;
+        dst[j] = warp_stage_base + (uint32_t)r * 128u + ((uint32_t)((lane & 7) ^ (r & 7)) << 4);
+    }
+    auto issue = [&](uint32_t kb) {
+        if (kb < KB) {
+            const uint32_t so = (kb % GATHER_STAGES) * 4096u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (src[j])
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst[j] + so), "l"(src[j] + (size_t)kb * 128) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (uint32_t s2 = 0; s2 + 1 < GATHER_STAGES; ++s2) issue(s2);
+    const float4* q4 = reinterpret_cast<const float4*>(q_s);
+    const uint32_t mine = warp_stage_base + (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)lane & 7u;
+    float acc = 0.0f;
+    for (uint32_t kb = 0; kb < KB; ++kb) {
+        issue(kb + GATHER_STAGES - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(GATHER_STAGES - 1) : "memory");
+        __syncwarp();   // the segment of this lane's row was copied by eight other lanes
+        if (row) {
+            const uint32_t st = mine + (kb % GATHER_STAGES) * 4096u;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+                float4 x;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                             : "r"(st + ((j ^ sw) << 4)));
+                const float4 qq = q4[kb * 8 + j];
+                float t;
+                t = __fsub_rn(qq.x, x.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                t = __fsub_rn(qq.y, x.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                t = __fsub_rn(qq.z, x.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                t = __fsub_rn(qq.w, x.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+            }
+        }
+        __syncwarp();   // the stage may be overwritten by the next iteration's copies
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    return __fsqrt_rn(acc);
+}
+
 // Exact re-rank + proof.  One warp per query, lane = shortlist entry.  Distances are recomputed
 // as euclidean_distance_scalar does (sequential f32, (q - x)^2, no FMA, sqrt), so the returned
 // keys are bit-identical to the exact path.  Proof: every row outside the shortlist has
@@ -1282,18 +1761,19 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
                                                      uint32_t* __restrict__ fb_count, uint32_t* __restrict__ fb_idx) {
     // R = shortlist entries that are re-ranked (TC_KP for search; a handful for nearest-centroid
     // assignment, where entry R — the best approximate value NOT re-ranked — is the proof bound)
-    extern __shared__ __align__(16) float q_sm[];  // [4][D]
+    constexpr int GWB = gather_warp_bytes(GATHER_STAGES_ROWS);
+    extern __shared__ __align__(128) unsigned char rr_sm[];  // [4] gather stages, then [4][D] queries
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * 4 + w;
     if (q >= nq) return;
-    float* q_s = q_sm + (size_t)w * D;
+    float* q_s = reinterpret_cast<float*>(rr_sm + 4 * GWB) + (size_t)w * D;
     for (uint32_t d = lane; d < D; d += 32) q_s[d] = __ldg(Q + (size_t)q * D + d);
     __syncwarp();
     const uint64_t akey = shortlist[(size_t)q * TC_KP + lane];
     const bool have = akey != KEY_NONE && (uint32_t)lane < R;
     const uint32_t pos = have ? (uint32_t)akey : 0u;
-    float dist = 0.f;
-    if (R >= 16 || have) dist = exact_l2_lane(q_s, rows + (size_t)pos * D, D);
+    const float dist = exact_l2_lane_gather<GATHER_STAGES_ROWS>(q_s, have ? rows + (size_t)pos * D : nullptr, D / 32,
+                                                                smem_u32(rr_sm) + (uint32_t)w * GWB, lane);
     uint64_t ekey = KEY_NONE;
     if (have) ekey = make_key(dist, ids ? ids[pos] : pos);
     ekey = warp_sort32(ekey, lane);
@@ -1364,7 +1844,10 @@ __global__ void flat_items_kernel(ScanItem* items, uint32_t nq, uint32_t n_rows,
     items[i] = it;
 }
 
-template <int T>
+// One block (four warps) per query: at 1024 queries one warp per query leaves fewer than two warps per
+// scheduler and the kernel runs at the latency of its ~10K dependent instructions (ncu: 8.5 cycles
+// per issued instruction, 47 us).
+template <int T>   // approximate values kept per thread
 __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restrict__ dense, uint32_t ld,
                                                             const float* __restrict__ centroids,
                                                             const float* __restrict__ Q, const float* __restrict__ qnorm,
@@ -1372,73 +1855,123 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restr
                                                             uint32_t nlist, uint32_t D, uint32_t np, uint32_t KC,
                                                             uint64_t* __restrict__ out_keys,
                                                             uint32_t* __restrict__ fb_count, uint32_t* __restrict__ fb_idx) {
-    extern __shared__ __align__(16) float q_sm[];  // [4][D]
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t q = blockIdx.x * 4 + w;
-    if (q >= nq) return;
-    float* q_s = q_sm + (size_t)w * D;
-    for (uint32_t d = lane; d < D; d += 32) q_s[d] = __ldg(Q + (size_t)q * D + d);
-    // lane-local sorted top-T of this lane's strided share: (approx d2 bits, list id) pairs
+    constexpr int GWB = gather_warp_bytes(GATHER_STAGES_CENT);
+    // [nw] gather stages (nw = warps that hold candidates), [D] query, [128] candidate ids, [32] scratch, [128] keys
+    extern __shared__ __align__(128) unsigned char cs_sm[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t q = blockIdx.x;
+    const uint32_t nw = (KC + 31) / 32;
+    float* q_s = reinterpret_cast<float*>(cs_sm + (size_t)nw * GWB);
+    uint32_t* cand_s = reinterpret_cast<uint32_t*>(q_s + D);
+    uint32_t* red_s = cand_s + 128;
+    uint64_t* key_s = reinterpret_cast<uint64_t*>(red_s + 32);
+    for (uint32_t d = tid; d < D; d += 128) q_s[d] = __ldg(Q + (size_t)q * D + d);
+    // thread-local sorted top-T of this thread's strided share: (approx d2 bits, list id) pairs; the
+    // approximate distances are fetched eight per thread at a time BEFORE the insertions
     uint32_t ld2[T], lid[T];
 #pragma unroll
     for (int i = 0; i < T; ++i) { ld2[i] = 0xFFFFFFFFu; lid[i] = 0xFFFFFFFFu; }
     const float* row = dense + (size_t)q * ld;
-    for (uint32_t c = lane; c < nlist; c += 32) {
-        uint32_t kd = __float_as_uint(fmaxf(row[c], 0.0f)), ki = c;
-        if (kd < ld2[T - 1]) {  // ids ascend within a lane, so equal d2 keeps the earlier (lower) id first
+    for (uint32_t base = 0; base < nlist; base += 1024) {
+        float v[8];
 #pragma unroll
-            for (int i = 0; i < T; ++i) {
-                const bool sw = kd < ld2[i];
-                const uint32_t td = sw ? ld2[i] : kd, ti = sw ? lid[i] : ki;
-                ld2[i] = sw ? kd : ld2[i];
-                lid[i] = sw ? ki : lid[i];
-                kd = td; ki = ti;
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t c = base + (uint32_t)i * 128u + (uint32_t)tid;
+            v[i] = (c < nlist) ? __ldg(row + c) : 0.0f;
+        }
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) {
+            const uint32_t c = base + (uint32_t)i2 * 128u + (uint32_t)tid;
+            uint32_t kd = __float_as_uint(fmaxf(v[i2], 0.0f)), ki = c;
+            if (c < nlist && kd < ld2[T - 1]) {  // ids ascend within a thread, so equal d2 keeps the earlier (lower) id first
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    const bool sw = kd < ld2[i];
+                    const uint32_t td = sw ? ld2[i] : kd, ti = sw ? lid[i] : ki;
+                    ld2[i] = sw ? kd : ld2[i];
+                    lid[i] = sw ? ki : lid[i];
+                    kd = td; ki = ti;
+                }
             }
         }
     }
-    __syncwarp();
-    // extract the KC smallest (d2, id) across lanes with two REDUX per round; round r's winner is
-    // kept by lane r % 32 in slot r / 32
-    uint32_t cand[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    uint32_t taken = 0, next_d2 = 0xFFFFFFFFu;
-    for (uint32_t r = 0; r <= KC; ++r) {
-        const uint32_t md = __reduce_min_sync(0xffffffffu, ld2[0]);
-        if (r == KC) { next_d2 = md; break; }
-        if (md == 0xFFFFFFFFu) break;
-        const uint32_t mi = __reduce_min_sync(0xffffffffu, ld2[0] == md ? lid[0] : 0xFFFFFFFFu);
-        if (ld2[0] == md && lid[0] == mi) {
+    // block-wide sum of one value per thread (scratch slots double-buffered by `par`: one barrier per call)
+    auto block_sum = [&](uint32_t x, uint32_t par) -> uint32_t {
+        const uint32_t ws = __reduce_add_sync(0xffffffffu, x);
+        if (lane == 0) red_s[par * 4 + w] = ws;
+        __syncthreads();
+        return red_s[par * 4] + red_s[par * 4 + 1] + red_s[par * 4 + 2] + red_s[par * 4 + 3];
+    };
+    // block-wide exclusive prefix (slots 8..15, one barrier per call, alternate `par`)
+    auto block_excl = [&](uint32_t x, uint32_t par) -> uint32_t {
+        uint32_t inc = x;
 #pragma unroll
-            for (int i = 0; i + 1 < T; ++i) { ld2[i] = ld2[i + 1]; lid[i] = lid[i + 1]; }
-            ld2[T - 1] = 0xFFFFFFFFu; lid[T - 1] = 0xFFFFFFFFu;
-            ++taken;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
         }
-        if ((r & 31) == (uint32_t)lane) {
-            if ((r >> 5) == 0) cand[0] = mi;
-            else if ((r >> 5) == 1) cand[1] = mi;
-            else if ((r >> 5) == 2) cand[2] = mi;
-            else cand[3] = mi;
-        }
+        if (lane == 31) red_s[8 + par * 4 + w] = inc;
+        __syncthreads();
+        uint32_t before = 0;
+        for (int i = 0; i < w; ++i) before += red_s[8 + par * 4 + i];
+        return before + inc - x;
+    };
+    // the KC smallest over the block: bitwise search for the KC-th smallest d2 value t (the largest t with
+    // fewer than KC entries below it); every entry below t plus as many entries equal to t as are still
+    // needed (in thread order) are the candidates
+    uint32_t n_valid = 0;
+#pragma unroll
+    for (int i = 0; i < T; ++i) n_valid += (ld2[i] != 0xFFFFFFFFu) ? 1u : 0u;
+    const uint32_t KCe = min(KC, block_sum(n_valid, 1));   // (scratch parity alternates from call to call)
+    uint32_t t = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t tc = t | (1u << bit);
+        uint32_t below = 0;
+#pragma unroll
+        for (int i = 0; i < T; ++i) below += (ld2[i] < tc) ? 1u : 0u;
+        if (block_sum(below, (uint32_t)(bit & 1) ^ 1u) < KCe) t = tc;
     }
-    // a lane whose T local entries were all consumed may have dropped keys below next_d2
-    const bool uncertain = __any_sync(0xffffffffu, taken == (uint32_t)T && nlist > (uint32_t)T * 32u);
-    // exact distances of the candidates (reference operation order), then sort by (distance, id)
+    uint32_t n_lt = 0, n_eq = 0;
+#pragma unroll
+    for (int i = 0; i < T; ++i) { n_lt += (ld2[i] < t) ? 1u : 0u; n_eq += (ld2[i] == t) ? 1u : 0u; }
+    const uint32_t need_eq = KCe - block_sum(n_lt, 0);
+    const uint32_t eq_before = block_excl(n_eq, 0);
+    const uint32_t sel = n_lt + min(n_eq, need_eq > eq_before ? need_eq - eq_before : 0u);
+    const uint32_t off = block_excl(sel, 1);
+    uint32_t my_next = 0xFFFFFFFFu;   // smallest approximate value this thread did NOT hand in
+#pragma unroll
+    for (int i = 0; i < T; ++i) {
+        if ((uint32_t)i < sel) cand_s[off + i] = lid[i];
+        if ((uint32_t)i == sel) my_next = ld2[i];
+    }
+    {
+        const uint32_t wm = __reduce_min_sync(0xffffffffu, my_next);
+        if (lane == 0) red_s[16 + w] = wm;
+    }
+    // a thread whose T local entries were all consumed may have dropped keys below next_d2
+    const bool uncertain = __syncthreads_or((sel == (uint32_t)T && nlist > (uint32_t)T * 128u) ? 1 : 0) != 0;
+    const uint32_t next_d2 = min(min(red_s[16], red_s[17]), min(red_s[18], red_s[19]));
+    // exact distances of the candidates (reference operation order): one candidate per thread
+    {
+        uint64_t key = KEY_NONE;
+        if ((uint32_t)w < nw) {   // warp-uniform
+            const bool h = (uint32_t)tid < KCe;
+            const uint32_t c = h ? cand_s[tid] : 0u;
+            const float d = exact_l2_lane_gather<GATHER_STAGES_CENT>(q_s, h ? centroids + (size_t)c * D : nullptr, D / 32,
+                                                                     smem_u32(cs_sm) + (uint32_t)w * GWB, lane);
+            if (h) key = make_key(d, c);
+        }
+        key_s[tid] = key;
+    }
+    __syncthreads();
+    if (w != 0) return;
+    // sort by (distance, id): four sorted 32-chunks, then merge-split passes
     uint64_t ex[4];
 #pragma unroll
-    for (int ch = 0; ch < 4; ch += 2) {
+    for (int ch = 0; ch < 4; ++ch) {
         ex[ch] = KEY_NONE;
-        ex[ch + 1] = KEY_NONE;
-        if ((uint32_t)ch * 32 < KC) {  // warp-uniform; two candidate rows per lane in one pass (ILP)
-            const bool h0 = cand[ch] != 0xFFFFFFFFu, h1 = cand[ch + 1] != 0xFFFFFFFFu;
-            const uint32_t c0 = h0 ? cand[ch] : 0u, c1 = h1 ? cand[ch + 1] : 0u;
-            float d0, d1;
-            exact_l2_lane2(q_s, centroids + (size_t)c0 * D, centroids + (size_t)c1 * D, D, d0, d1);
-            if (h0) ex[ch] = make_key(d0, c0);
-            if (h1) ex[ch + 1] = make_key(d1, c1);
-            ex[ch] = warp_sort32(ex[ch], lane);
-            ex[ch + 1] = warp_sort32(ex[ch + 1], lane);
-        }
+        if ((uint32_t)ch * 32 < KC) ex[ch] = warp_sort32(key_s[ch * 32 + lane], lane);
     }
-    // merge-split passes over the sorted 32-chunks: afterwards ex[0] <= ex[1] <= ... globally
 #pragma unroll
     for (int a2 = 0; a2 < 3; ++a2) {
 #pragma unroll
@@ -1489,15 +2022,17 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restr
 // published as they were).  One warp per query folds them into the query's best TC_KP.
 __global__ void __launch_bounds__(128) merge_rows32_kernel(const uint64_t* __restrict__ in, uint32_t nq, uint32_t P,
                                                            uint64_t* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t q = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (q >= nq) return;
+    // one block per query: warp w folds rows w, w + 4, ... (a chain of P / 4 dependent merges instead of
+    // P, and four times the warps in flight), warp 0 folds the four results
+    __shared__ uint64_t part[3][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x;
     const uint64_t* base = in + (size_t)q * P * TC_KP;
     uint64_t best = KEY_NONE;
-    for (uint32_t s0 = 0; s0 < P; s0 += 4) {
+    for (uint32_t s0 = (uint32_t)w; s0 < P; s0 += 16) {
         uint64_t row[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) row[g] = (s0 + g < P) ? base[(size_t)(s0 + g) * TC_KP + lane] : KEY_NONE;
+        for (int g = 0; g < 4; ++g) row[g] = (s0 + 4 * g < P) ? base[(size_t)(s0 + 4 * g) * TC_KP + lane] : KEY_NONE;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (__ballot_sync(0xffffffffu, row[g] != KEY_NONE) == 0) continue;
@@ -1506,6 +2041,11 @@ __global__ void __launch_bounds__(128) merge_rows32_kernel(const uint64_t* __res
             best = warp_merge32(best, row[g], lane);
         }
     }
+    if (w) part[w - 1][lane] = best;
+    __syncthreads();
+    if (w) return;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) best = warp_merge32(best, part[i][lane], lane);
     out[(size_t)q * TC_KP + lane] = best;
 }
 
@@ -1597,7 +2137,7 @@ cudaError_t launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t st
 
 cudaError_t launch_merge_rows32(const uint64_t* in, uint32_t nq, uint32_t P, uint64_t* out, cudaStream_t stream) {
     if (nq == 0) return cudaSuccess;
-    merge_rows32_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(in, nq, P, out);
+    merge_rows32_kernel<<<nq, 128, 0, stream>>>(in, nq, P, out);
     return cudaGetLastError();
 }
 
@@ -1630,9 +2170,28 @@ struct TcScratchImpl {
     uint64_t tmap_n = 0;
     bool smem_attr_set = false;
     bool smem_attr_set_pair = false;
+    bool smem_attr_set_rerank = false;
 };
 
 bool tc_supported(uint32_t D) { return D % 32 == 0 && D >= 32 && D <= 512; }
+
+static size_t rerank_smem_bytes(uint32_t D) { return (size_t)4 * gather_warp_bytes(GATHER_STAGES_ROWS) + (size_t)4 * D * sizeof(float); }
+static size_t coarse_select_smem_bytes(uint32_t D, uint32_t KC) {
+    return (size_t)((KC + 31) / 32) * gather_warp_bytes(GATHER_STAGES_CENT) + (size_t)D * sizeof(float) + (128 + 32) * 4 + 128 * 8;
+}
+static cudaError_t rerank_prepare(TcScratchImpl* m) {
+    if (m->smem_attr_set_rerank) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rerank_smem_bytes(512));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(coarse_select_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_select_smem_bytes(512, 128));
+    if (e == cudaSuccess) m->smem_attr_set_rerank = true;
+    return e;
+}
+
+// kernel R variant: FVDB_TC_MERGE=E keeps the merges in the epilogue warps (the classic variant)
+static bool tc_offload_merges() {
+    const char* e = getenv("FVDB_TC_MERGE");
+    return e && e[0] == 'O';
+}
 
 void tc_release(TcScratch& s) {
     if (!s.impl) return;
@@ -1812,11 +2371,12 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         // candidate set: nprobe + 32 (the proof needs the next approx value to clear the exact
         // nprobe-th by the TF32 bound; centroid distances are dense, so a generous margin)
         const uint32_t KC = std::min(np + 32, 128u);
-        const size_t sel_smem = (size_t)4 * D * sizeof(float);
-        // 16 local entries per lane: P(one lane holds >= 16 of the KC nearest) is negligible
-            coarse_select_kernel<16><<<(nq + 3) / 4, 128, sel_smem, st>>>(m->dense.p, ld, a.centroids, a.Q, m->qnorm.p,
-                                                                          m->misc.p + 4, nq, a.nlist, D, np, KC,
-                                                                          m->coarse.p, a.d_fallback_count, a.d_fallback_idx);
+        const size_t sel_smem = coarse_select_smem_bytes(D, KC);
+        TCK(rerank_prepare(m));
+        // 8 local entries per thread: P(one thread holds >= 8 of the KC nearest) is negligible
+        coarse_select_kernel<8><<<nq, 128, sel_smem, st>>>(m->dense.p, ld, a.centroids, a.Q, m->qnorm.p,
+                                                          m->misc.p + 4, nq, a.nlist, D, np, KC,
+                                                          m->coarse.p, a.d_fallback_count, a.d_fallback_idx);
         TCK(cudaGetLastError());
         (*launches) += 3;
         coarse_keys = m->coarse.p;
@@ -1906,7 +2466,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         const size_t smem = tc_scan_smem_bytes(KB, stages) + R2_SLACK;  // slack for the 1024-byte alignment
         if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
         if (!m->smem_attr_set) {
-            TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+            TCK(cudaFuncSetAttribute(tc_scan_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+            TCK(cudaFuncSetAttribute(tc_scan_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
             m->smem_attr_set = true;
         }
         const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
@@ -1916,7 +2477,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             p.prof = m->prof.p;
         }
         if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
-        tc_scan_kernel<<<grid, R2_THREADS, smem, st>>>(m->tmap_arena, p);
+        if (tc_offload_merges()) tc_scan_kernel_t<true><<<grid, R2_THREADS, smem, st>>>(m->tmap_arena, p);
+        else tc_scan_kernel_t<false><<<grid, R2_THREADS, smem, st>>>(m->tmap_arena, p);
         TCK(cudaGetLastError());
         if (p.prof) TCK(dump_prof(m->prof.p, grid, st));
     }
@@ -1925,7 +2487,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
 
     // ---- merge the per-(query, probe) shortlists, exact re-rank, proof ----
     TCK(launch_merge_rows32(m->partial.p, nq, np * prows, m->shortlist.p, st));
-    rerank_kernel<<<(nq + 3) / 4, 128, (size_t)4 * D * sizeof(float), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k, (uint32_t)TC_KP,
+    TCK(rerank_prepare(m));
+    rerank_kernel<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k, (uint32_t)TC_KP,
                                                a.out_keys, a.d_fallback_count, a.d_fallback_idx);
     TCK(cudaGetLastError());
     (*launches) += 2;
@@ -2001,13 +2564,16 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
     const size_t smem = tc_scan_smem_bytes(KB, stages) + 1024;
     if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
     if (!m->smem_attr_set) {
-        TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TCK(cudaFuncSetAttribute(tc_scan_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        TCK(cudaFuncSetAttribute(tc_scan_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         m->smem_attr_set = true;
     }
-    tc_scan_kernel<<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(rs.tmap, p);
+    if (tc_offload_merges()) tc_scan_kernel_t<true><<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(rs.tmap, p);
+    else tc_scan_kernel_t<false><<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(rs.tmap, p);
     TCK(cudaGetLastError());
     TCK(launch_merge_rows32(m->partial.p, nq, n_chunks, m->shortlist.p, st));
-    rerank_kernel<<<(nq + 3) / 4, 128, (size_t)4 * D * sizeof(float), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p,
+    TCK(rerank_prepare(m));
+    rerank_kernel<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p,
                                                                          xmax_bits, nq, D, a.k,
                                                                          a.rerank_r ? a.rerank_r : (uint32_t)TC_KP, a.out_keys,
                                                                          a.d_fallback_count, a.d_fallback_idx);
