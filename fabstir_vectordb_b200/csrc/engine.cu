@@ -777,12 +777,17 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
     uint64_t* d_scanned = reinterpret_cast<uint64_t*>(h->s_misc.p + 2);
     uint32_t* d_fb_count = h->s_misc.p + 10;
     CK(cudaMemsetAsync(h->s_misc.p, 0, 64, st));
-    CK(launch_nan_check(d_q, (size_t)nq * D, d_nan, st));
-    h->stats.last_launches += 1;
+    // the tensor-core IVF path looks at every query element anyway (query norms): it raises the flag
+    const bool tc_ivf = use_ivf && (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D) && k <= TC_MAX_K &&
+                        std::min(nprobe, h->nlist) <= TC_MAX_NPROBE;
+    if (!tc_ivf) {
+        CK(launch_nan_check(d_q, (size_t)nq * D, d_nan, st));
+        h->stats.last_launches += 1;
+    }
 
     uint64_t* ivf_keys = nullptr;
     uint64_t* flat_keys = nullptr;
-    bool scan_timed = false, used_tc = false;
+    bool scan_timed = false, used_tc = false, fused_finalize = false;
     uint32_t np = 0;
 
     if (use_ivf) {
@@ -819,6 +824,11 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             ta.d_fallback_count = d_fb_count; ta.d_fallback_idx = h->s_fb_idx.p;
             ta.ev_scan0 = h->ev_s0; ta.ev_scan1 = h->ev_s1;
             ta.sm_count = h->sm_count;
+            ta.d_nan = d_nan;
+            if (!use_flat) {   // the only tier: the re-rank writes the result arrays itself
+                ta.fin_ids = d_out_ids; ta.fin_dist = d_out_dist; ta.fin_count = d_out_count;
+                fused_finalize = true;
+            }
             if (h->bounds_armed_nq == nq && h->bounds) {   // fvdb_bounds_begin_batch was called for this batch
                 ta.thr_ext = h->bounds + (size_t)h->bounds_parity * h->bounds_cap;
                 ta.n_peers = (uint32_t)std::min<size_t>(h->peer_bounds.size(), TC_MAX_PEERS);
@@ -864,8 +874,10 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
                                filt, filter_bits, flat_keys, st));
         }
     }
-    CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
-    h->stats.last_launches += 1;
+    if (!fused_finalize) {
+        CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
+        h->stats.last_launches += 1;
+    }
     CK(cudaEventRecord(h->ev_b, st));
     if (ho) CK(copy_out(ho, d_out_ids, d_out_dist, d_out_count, st));
 

@@ -1652,8 +1652,12 @@ uint32_t q1_pick_stages(uint32_t KB, uint32_t kbs) {
 
 
 // ---- small support kernels ----------------------------------------------------------------------
+// optional riders of the query-norm pass: fill[r] = fill_value (the per-query bound reset) and the
+// NaN flag of the batch (a sum of squares is NaN exactly when an element is: no subtraction, and
+// inf * inf = inf)
 __global__ void row_norms_kernel(const float* __restrict__ x, uint64_t n, uint32_t D, float* __restrict__ out,
-                                 uint32_t* __restrict__ max_bits) {
+                                 uint32_t* __restrict__ max_bits, uint32_t* __restrict__ fill = nullptr,
+                                 uint32_t fill_value = 0, int* __restrict__ nan_flag = nullptr) {
     const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -1667,7 +1671,11 @@ __global__ void row_norms_kernel(const float* __restrict__ x, uint64_t n, uint32
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) out[r] = s;
+        if (lane == 0) {
+            out[r] = s;
+            if (fill) fill[r] = fill_value;
+            if (nan_flag && isnan(s)) *nan_flag = 1;
+        }
         mx = fmaxf(mx, s);
     }
     if (max_bits && lane == 0 && mx > 0.f) atomicMax(max_bits, __float_as_uint(mx));
@@ -1758,7 +1766,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
                                                      const float* __restrict__ Q, const float* __restrict__ qnorm,
                                                      const uint32_t* __restrict__ xmax_bits, uint32_t nq, uint32_t D,
                                                      uint32_t k, uint32_t R, uint64_t* __restrict__ out_keys,
-                                                     uint32_t* __restrict__ fb_count, uint32_t* __restrict__ fb_idx) {
+                                                     uint32_t* __restrict__ fb_count, uint32_t* __restrict__ fb_idx,
+                                                     uint32_t* __restrict__ fin_ids = nullptr, float* __restrict__ fin_dist = nullptr,
+                                                     uint32_t* __restrict__ fin_count = nullptr) {
     // R = shortlist entries that are re-ranked (TC_KP for search; a handful for nearest-centroid
     // assignment, where entry R — the best approximate value NOT re-ranked — is the proof bound)
     constexpr int GWB = gather_warp_bytes(GATHER_STAGES_ROWS);
@@ -1778,6 +1788,15 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
     if (have) ekey = make_key(dist, ids ? ids[pos] : pos);
     ekey = warp_sort32(ekey, lane);
     if ((uint32_t)lane < k) out_keys[(size_t)q * k + lane] = ekey;
+    if (fin_ids) {
+        // the caller-facing arrays as finalize_kernel writes them when this tier is the only one
+        if ((uint32_t)lane < k) {
+            fin_ids[(size_t)q * k + lane] = ekey != KEY_NONE ? key_id(ekey) : ID_NONE;
+            fin_dist[(size_t)q * k + lane] = ekey != KEY_NONE ? key_dist(ekey) : __uint_as_float(0x7f800000u);
+        }
+        const uint32_t found = __popc(__ballot_sync(0xffffffffu, ekey != KEY_NONE && (uint32_t)lane < k));
+        if (lane == 0) fin_count[q] = found;
+    }
     // proof
     const uint64_t a_last_key = shfl64(akey, (int)min(R, 31u));
     const uint64_t kth = shfl64(ekey, (int)k - 1);
@@ -2303,15 +2322,15 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
 
     {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)nq * 32 + 255) / 256, (uint64_t)a.sm_count * 8);
-        row_norms_kernel<<<blocks, 256, 0, st>>>(a.Q, nq, D, m->qnorm.p, nullptr);
-        {
-            // experiment (FVDB_TC_DEBUG bit 9): keep the previous batch's bounds = perfectly seeded thresholds
-            const char* dbg = getenv("FVDB_TC_DEBUG");
-            if (!(dbg && (atoi(dbg) & 512)) && !a.thr_ext)   // a shared array was reset by the caller
-                fill_u32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m->thr_g.p, nq, F32_INF_BITS);
-        }
+        // query norms; the same pass resets the per-query bounds (unless the caller shares an array it
+        // has reset itself) and raises the batch's NaN flag
+        // experiment (FVDB_TC_DEBUG bit 9): keep the previous batch's bounds = perfectly seeded thresholds
+        const char* dbg = getenv("FVDB_TC_DEBUG");
+        const bool reset_bounds = !(dbg && (atoi(dbg) & 512)) && !a.thr_ext;
+        row_norms_kernel<<<blocks, 256, 0, st>>>(a.Q, nq, D, m->qnorm.p, nullptr, reset_bounds ? m->thr_g.p : nullptr,
+                                                 F32_INF_BITS, a.d_nan);
         TCK(cudaGetLastError());
-        (*launches) += 2;
+        (*launches) += 1;
     }
     const uint64_t* coarse_keys = a.coarse_keys;
     if (!coarse_keys) {
@@ -2489,7 +2508,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     TCK(launch_merge_rows32(m->partial.p, nq, np * prows, m->shortlist.p, st));
     TCK(rerank_prepare(m));
     rerank_kernel<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k, (uint32_t)TC_KP,
-                                               a.out_keys, a.d_fallback_count, a.d_fallback_idx);
+                                               a.out_keys, a.d_fallback_count, a.d_fallback_idx, a.fin_ids, a.fin_dist, a.fin_count);
     TCK(cudaGetLastError());
     (*launches) += 2;
     return FVDB_OK;

@@ -57,6 +57,11 @@ struct TcSearchArgs {
     uint32_t* thr_ext = nullptr;
     uint32_t* thr_peers[TC_MAX_PEERS] = {};
     uint32_t n_peers = 0;
+    // optional fusions with the caller's steps (both save a launch per batch):
+    int* d_nan = nullptr;             // set to 1 when Q holds a NaN (the query-norm pass sees every element)
+    uint32_t* fin_ids = nullptr;      // when given, the re-rank also writes the caller-facing result
+    float* fin_dist = nullptr;        //   arrays [nq][k] / [nq] (what finalize_kernel derives from
+    uint32_t* fin_count = nullptr;    //   out_keys when no other tier takes part)
 };
 
 // Tensor-core scan of the recent ("HNSW") tier: every query against every flat row.
