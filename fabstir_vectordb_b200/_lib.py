@@ -60,7 +60,13 @@ _u32p = C.POINTER(C.c_uint32)
 _u64p = C.POINTER(C.c_uint64)
 _vp = C.c_void_p
 
-# symbol -> (restype, argtypes); every symbol include/fvdb.h and include/fvdb_synth.h declare
+class ChunkInfo(C.Structure):
+    """fvdb_chunk_info (include/fvdb_chunk.h)."""
+    _fields_ = [("chunk_id", C.c_char * 128), ("start_idx", C.c_uint64), ("end_idx", C.c_uint64),
+                ("n_vectors", C.c_uint64), ("dim", C.c_uint32)]
+
+
+# symbol -> (restype, argtypes); every symbol include/fvdb.h, fvdb_synth.h and fvdb_chunk.h declare
 SIGNATURES = {
     "fvdb_abi_version": (C.c_int, []),
     "fvdb_create": (C.c_int, [C.c_int, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(_vp)]),
@@ -101,6 +107,10 @@ SIGNATURES = {
                                         C.c_uint64, C.POINTER(TrainResult)]),
     "fvdb_kmeans_accumulate_device": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fvdb_kmeans_apply_device": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "fvdb_chunk_decode": (C.c_int, [_vp, C.c_size_t, C.POINTER(ChunkInfo), _vp, _vp, C.c_uint64]),
+    "fvdb_chunk_encode": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, _vp, _vp, C.c_uint64, C.c_uint32,
+                                    _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "fvdb_chunk_last_error": (C.c_char_p, []),
     "fvdb_synth_rows_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
                                          C.c_float, C.c_uint64, _vp]),
     "fvdb_synth_rows_strided_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,

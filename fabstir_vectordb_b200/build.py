@@ -22,7 +22,7 @@ _TAG = ("." + VARIANT) if VARIANT else ""
 SO = os.path.join(HERE, f"libfvdb_b200{_TAG}.so")
 STAMP = os.path.join(HERE, f".libfvdb_b200{_TAG}.stamp")
 
-SOURCES = ["engine.cu", "exact_scan.cu", "layout.cu", "kmeans.cu", "tc_scan.cu", "synth.cu"]
+SOURCES = ["engine.cu", "exact_scan.cu", "layout.cu", "kmeans.cu", "tc_scan.cu", "synth.cu", "chunk_codec.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "tc_scan.cuh", "tc_ptx.cuh", "tc_scan_pair.cuh"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -40,7 +40,7 @@ def _digest() -> str:
     for f in SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
-    for f in ("fvdb.h", "fvdb_synth.h"):
+    for f in ("fvdb.h", "fvdb_synth.h", "fvdb_chunk.h"):
         with open(os.path.join(ROOT, "include", f), "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(FLAGS + DEFINES).encode())

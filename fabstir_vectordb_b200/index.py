@@ -269,6 +269,18 @@ class IVFIndex:
         for v, l in zip(ids, lists):
             self._lists[v] = int(l)
 
+    def load_chunk(self, cbor: bytes) -> int:
+        """Bulk load of one stored VectorChunk: what `load_index_chunked` does per chunk
+        (src/hybrid/persistence.rs:610-653: decode, then `find_cluster` for every vector inside a
+        loop over clusters) as one decode into dense arrays and ONE assignment launch.  Vector ids
+        are the 32 VectorId bytes.  Returns the number of vectors added."""
+        from .chunk import decode_vector_chunk
+        ch = decode_vector_chunk(cbor, pinned=True)
+        if len(ch) == 0:
+            return 0
+        self.batch_insert([bytes(b) for b in ch.ids], ch.rows)
+        return len(ch)
+
     def find_cluster(self, vector) -> int:
         """src/ivf/core.rs:493-499."""
         if not self._trained:

@@ -17,15 +17,15 @@ def _declared(header):
 
 def test_library_exports_every_declared_symbol(built_lib):
     lib = C.CDLL(built_lib)
-    names = _declared("fvdb.h") + _declared("fvdb_synth.h")
-    assert len(names) >= 25
+    names = _declared("fvdb.h") + _declared("fvdb_synth.h") + _declared("fvdb_chunk.h")
+    assert len(names) >= 28
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ but not exported"
 
 
 def test_binding_covers_header(built_lib):
     from fabstir_vectordb_b200 import _lib
-    declared = set(_declared("fvdb.h") + _declared("fvdb_synth.h"))
+    declared = set(_declared("fvdb.h") + _declared("fvdb_synth.h") + _declared("fvdb_chunk.h"))
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load()
     assert lib.fvdb_abi_version() == 1
@@ -33,7 +33,7 @@ def test_binding_covers_header(built_lib):
 
 def test_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "fvdb.h"\n#include "fvdb_synth.h"\nint main(void){return FVDB_OK;}\n')
+    src.write_text('#include "fvdb.h"\n#include "fvdb_synth.h"\n#include "fvdb_chunk.h"\nint main(void){return FVDB_OK;}\n')
     import subprocess
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I",
                            os.path.join(ROOT, "include"), "-c", str(src), "-o",

@@ -529,3 +529,33 @@ def test_concurrent_single_query_calls_are_coalesced(mode):
     eng.set_option(L.OPT_COALESCE, 0)
     one = eng.search(q[2], k, nprobe, tiers=L.TIER_HISTORICAL)
     assert np.array_equal(one[0], got[2][0]) and eng.stats().last_batch_calls == 1
+
+
+def test_load_chunk_bulk_path():
+    """SURVEY §8f rows 1-2: a stored VectorChunk (CBOR) goes through ONE decode and ONE assignment launch;
+    list membership and searches equal the oracle's per-vector `find_cluster` + insert
+    (src/hybrid/persistence.rs:626-653)."""
+    from fabstir_vectordb_b200 import IVFConfig, IVFIndex, encode_vector_chunk
+    rng = np.random.default_rng(21)
+    n, d, nlist = 3000, 64, 16
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x[rng.random((n, d)) < 0.05] = 0.5           # some half-float-exact values in the chunk
+    cents = x[rng.choice(n, nlist, replace=False)].copy()
+    ids = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    idx = IVFIndex(IVFConfig(n_clusters=nlist, n_probe=4))
+    idx.set_trained(cents, d)
+    added = 0
+    for c0 in range(0, n, 1000):                 # three chunks
+        added += idx.load_chunk(encode_vector_chunk(f"chunk-{c0 // 1000}", c0, c0 + 999, ids[c0:c0 + 1000], x[c0:c0 + 1000]))
+    assert added == n and idx.total_vectors() == n
+    want_lists = O.assign(x, cents)
+    got = np.array([idx._lists[bytes(b)] for b in ids])
+    assert np.array_equal(got, want_lists)
+    o = O.IVF(cents, x)                         # oracle ids = row numbers
+    q = x[:16] + np.float32(0.01)
+    for i in range(16):
+        want_ids, want_dist = o.search(q[i], 5, 4)
+        res = idx.search_with_config(q[i], 5, 4)
+        assert [r.vector_id for r in res] == [bytes(ids[j]) for j in want_ids]
+        assert np.array_equal(np.array([r.distance for r in res], np.float32).view(np.uint32),
+                              np.asarray(want_dist, np.float32).view(np.uint32))
