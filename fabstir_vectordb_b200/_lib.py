@@ -135,6 +135,8 @@ def load():
             "(there is no CPU fallback)")
     lib = C.CDLL(SO_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("FVDB_LIB") and not hasattr(lib, name):
+            continue  # an experiment build of an older source tree may lack newer entry points
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args

@@ -1914,15 +1914,19 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restr
             }
         }
     }
-    // block-wide sum of one value per thread (scratch slots double-buffered by `par`: one barrier per call)
-    auto block_sum = [&](uint32_t x, uint32_t par) -> uint32_t {
+    // block-wide sum of one value per thread (scratch slots double-buffered, alternating from call to
+    // call: one barrier per call)
+    uint32_t sum_par = 0, excl_par = 0;
+    auto block_sum = [&](uint32_t x) -> uint32_t {
+        const uint32_t par = (sum_par ^= 1u);
         const uint32_t ws = __reduce_add_sync(0xffffffffu, x);
         if (lane == 0) red_s[par * 4 + w] = ws;
         __syncthreads();
         return red_s[par * 4] + red_s[par * 4 + 1] + red_s[par * 4 + 2] + red_s[par * 4 + 3];
     };
-    // block-wide exclusive prefix (slots 8..15, one barrier per call, alternate `par`)
-    auto block_excl = [&](uint32_t x, uint32_t par) -> uint32_t {
+    // block-wide exclusive prefix (slots 8..15, one barrier per call)
+    auto block_excl = [&](uint32_t x) -> uint32_t {
+        const uint32_t par = (excl_par ^= 1u);
         uint32_t inc = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1941,22 +1945,22 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restr
     uint32_t n_valid = 0;
 #pragma unroll
     for (int i = 0; i < T; ++i) n_valid += (ld2[i] != 0xFFFFFFFFu) ? 1u : 0u;
-    const uint32_t KCe = min(KC, block_sum(n_valid, 1));   // (scratch parity alternates from call to call)
+    uint32_t KCe = min(KC, block_sum(n_valid));
     uint32_t t = 0;
     for (int bit = 31; bit >= 0; --bit) {
         const uint32_t tc = t | (1u << bit);
         uint32_t below = 0;
 #pragma unroll
         for (int i = 0; i < T; ++i) below += (ld2[i] < tc) ? 1u : 0u;
-        if (block_sum(below, (uint32_t)(bit & 1) ^ 1u) < KCe) t = tc;
+        if (block_sum(below) < KCe) t = tc;
     }
     uint32_t n_lt = 0, n_eq = 0;
 #pragma unroll
     for (int i = 0; i < T; ++i) { n_lt += (ld2[i] < t) ? 1u : 0u; n_eq += (ld2[i] == t) ? 1u : 0u; }
-    const uint32_t need_eq = KCe - block_sum(n_lt, 0);
-    const uint32_t eq_before = block_excl(n_eq, 0);
+    const uint32_t need_eq = KCe - block_sum(n_lt);
+    const uint32_t eq_before = block_excl(n_eq);
     const uint32_t sel = n_lt + min(n_eq, need_eq > eq_before ? need_eq - eq_before : 0u);
-    const uint32_t off = block_excl(sel, 1);
+    const uint32_t off = block_excl(sel);
     uint32_t my_next = 0xFFFFFFFFu;   // smallest approximate value this thread did NOT hand in
 #pragma unroll
     for (int i = 0; i < T; ++i) {
@@ -1968,8 +1972,44 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restr
         if (lane == 0) red_s[16 + w] = wm;
     }
     // a thread whose T local entries were all consumed may have dropped keys below next_d2
-    const bool uncertain = __syncthreads_or((sel == (uint32_t)T && nlist > (uint32_t)T * 128u) ? 1 : 0) != 0;
-    const uint32_t next_d2 = min(min(red_s[16], red_s[17]), min(red_s[18], red_s[19]));
+    bool uncertain = __syncthreads_or((sel == (uint32_t)T && nlist > (uint32_t)T * 128u) ? 1 : 0) != 0;
+    uint32_t next_d2 = min(min(red_s[16], red_s[17]), min(red_s[18], red_s[19]));
+    if (uncertain) {
+        // Rare (centroids that are near-duplicates of one another AND share a residue mod 128 — e.g.
+        // a k-means initialised from clumped seeds): select again straight from the dense row, without
+        // the thread-local lists.  32 passes over the row (it sits in L2), exact for any nlist.
+        KCe = min(KC, nlist);
+        t = 0;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t tc = t | (1u << bit);
+            uint32_t below = 0;
+            for (uint32_t c = tid; c < nlist; c += 128) below += (__float_as_uint(fmaxf(__ldg(row + c), 0.0f)) < tc) ? 1u : 0u;
+            if (block_sum(below) < KCe) t = tc;
+        }
+        uint32_t lt = 0, eq = 0;
+        for (uint32_t c = tid; c < nlist; c += 128) {
+            const uint32_t b = __float_as_uint(fmaxf(__ldg(row + c), 0.0f));
+            lt += (b < t) ? 1u : 0u;
+            eq += (b == t) ? 1u : 0u;
+        }
+        const uint32_t need2 = KCe - block_sum(lt);
+        const uint32_t eqb = block_excl(eq);
+        uint32_t take = min(eq, need2 > eqb ? need2 - eqb : 0u);
+        uint32_t o2 = block_excl(lt + take);
+        uint32_t nx = 0xFFFFFFFFu;
+        for (uint32_t c = tid; c < nlist; c += 128) {
+            const uint32_t b = __float_as_uint(fmaxf(__ldg(row + c), 0.0f));
+            bool pick = b < t;
+            if (b == t && take) { pick = true; --take; }
+            if (pick) cand_s[o2++] = c;
+            else nx = min(nx, b);
+        }
+        nx = __reduce_min_sync(0xffffffffu, nx);
+        if (lane == 0) red_s[20 + w] = nx;
+        __syncthreads();
+        next_d2 = min(min(red_s[20], red_s[21]), min(red_s[22], red_s[23]));
+        uncertain = false;
+    }
     // exact distances of the candidates (reference operation order): one candidate per thread
     {
         uint64_t key = KEY_NONE;
@@ -2032,6 +2072,10 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restr
                 ok = (a_next - eps) > dk * dk * 1.000001f;
             }
         }
+#ifdef FVDB_CS_DEBUG
+        if (!ok) printf("coarse_select q %u uncertain %d next_d2 %08x (%f) kth %f KCe %u t %08x\n", q, (int)uncertain, next_d2,
+                        __uint_as_float(next_d2), kth != KEY_NONE ? key_dist(kth) * key_dist(kth) : -1.f, KCe, t);
+#endif
         if (!ok) fb_idx[atomicAdd(fb_count, 1u)] = q;
     }
 }

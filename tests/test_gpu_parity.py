@@ -559,3 +559,31 @@ def test_load_chunk_bulk_path():
         assert [r.vector_id for r in res] == [bytes(ids[j]) for j in want_ids]
         assert np.array_equal(np.array([r.distance for r in res], np.float32).view(np.uint32),
                               np.asarray(want_dist, np.float32).view(np.uint32))
+
+
+@pytest.mark.parametrize("nlist", [2048, 4096])
+def test_coarse_selection_with_clumped_centroid_ids(nlist):
+    """Centroids whose ids share a residue mod 128 are near-duplicates of one another (what a k-means
+    initialised from clumped seeds leaves behind): all of a query's nearest centroids then sit in ONE
+    thread's share of the coarse selection.  The kernel must notice and re-select exactly: same
+    results as the oracle, and the queries are NOT handed to the exact fallback path wholesale (before
+    the in-kernel re-selection every one of them was)."""
+    rng = np.random.default_rng(nlist)
+    d, n, nprobe, k, nq = 64, 20000, 16, 10, 96
+
+    def unit(a):
+        return (a / np.linalg.norm(a, axis=1, keepdims=True)).astype(np.float32)
+
+    seeds = unit(rng.standard_normal((128, d)))
+    cents = unit(seeds[np.arange(nlist) % 128] + 0.01 * rng.standard_normal((nlist, d)))
+    x = unit(cents[rng.integers(0, nlist, n)] + 0.05 * rng.standard_normal((n, d)))
+    q = unit(seeds[rng.integers(0, 128, nq)] + 0.02 * rng.standard_normal((nq, d)))
+    eng = Engine(d, k_max=32)
+    _set_mode(eng, "tc")
+    eng.set_centroids(cents)
+    eng.ivf_add(x, np.arange(n, dtype=np.uint32))
+    ivf = O.IVF(cents, x)
+    ids, dist, cnt = eng.search(q, k, nprobe, tiers=L.TIER_HISTORICAL)
+    o = O.hybrid_batch_search(ivf, None, None, q, k, nprobe, tiers=2)
+    _assert_same(ids, dist, cnt, *o)
+    assert eng.stats().last_fallback_queries < nq // 2
