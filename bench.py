@@ -134,7 +134,16 @@ def build_index(torch, eng, rank, world, log):
                                             stream)
     assert rc == 0
     torch.cuda.synchronize()
-    init = train[torch.arange(nlist, device=dev) * (n_train // nlist)].contiguous()
+    # initial centroids: one training row per list, each from a DIFFERENT mixture component.  (Taking
+    # the first row of every 64-row block picks rows 64*stride*j, whose components (row mod n_comp)
+    # collapse onto n_comp/64 values: 16 seeds per component, a clumped k-means — FVDB_BENCH_CLUMPED_INIT=1
+    # reproduces that earlier set-up.)
+    blk = torch.arange(nlist, device=dev)
+    per = n_train // nlist
+    if os.environ.get("FVDB_BENCH_CLUMPED_INIT") or per != 64:
+        init = train[blk * per].contiguous()
+    else:
+        init = train[blk * 64 + (blk // max(1, nlist // 16)) % 64].contiguous()
     res = eng.train_device(train.data_ptr(), n_train, nlist, TRAIN_ITERS, init.data_ptr(), SEED)
     torch.cuda.synchronize()
     t1 = time.time()

@@ -42,6 +42,7 @@ struct ScanItem {
     uint32_t pair_count;  // queries in this item (<= TQ)
     uint32_t slot;        // partial slot when identity
     uint32_t identity;    // 1: query = pair_begin + i, slot = slot; 0: via pair arrays
+    uint32_t sub;         // row-range index when a long posting list is split into several items (else 0)
 };
 
 struct DeviceError {

@@ -277,6 +277,7 @@ __global__ void build_identity_items_kernel(ScanItem* items, uint32_t nq, uint32
     it.pair_count = min((uint32_t)TQ, nq - qt * TQ);
     it.slot = sp;
     it.identity = 1;
+    it.sub = 0;
     if (it.row_begin >= it.row_end) it.pair_count = 0;
     items[i] = it;
 }
@@ -356,7 +357,8 @@ __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __rest
                                   const uint32_t* __restrict__ list_order, uint32_t nlist,
                                   uint32_t tile_q, uint32_t* __restrict__ pair_off,
                                   uint32_t* __restrict__ cursor, ScanItem* __restrict__ items,
-                                  uint32_t* __restrict__ n_items, uint64_t* __restrict__ scanned_rows) {
+                                  uint32_t* __restrict__ n_items, uint64_t* __restrict__ scanned_rows,
+                                  bool order_near, uint32_t rows_cap) {
     __shared__ uint64_t warp_tot[33];
     const int t = threadIdx.x;
     uint64_t my_rows = 0;
@@ -368,7 +370,11 @@ __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __rest
         if (l < nlist) {
             const uint32_t raw = list_cnt[l];
             const uint32_t c = (list_off[l + 1] != list_off[l]) ? (raw & ~NEAREST_BIT) : 0u;
-            if ((raw & NEAREST_BIT) && c) v = ((uint64_t)((c + tile_q - 1) / tile_q) << 32) | c;
+            if ((raw & NEAREST_BIT) && c) {
+                const uint32_t len = list_off[l + 1] - list_off[l];
+                const uint32_t ns = (rows_cap && len > rows_cap) ? (len + rows_cap - 1) / rows_cap : 1u;
+                v = ((uint64_t)(((c + tile_q - 1) / tile_q) * ns) << 32) | c;
+            }
         }
         uint64_t tot;
         block_excl_scan_u64(v, warp_tot, &tot);
@@ -382,7 +388,7 @@ __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __rest
     uint64_t carry = 0;
     for (int g = 0; g < 2; ++g) {
         for (uint32_t base = 0; base < nlist; base += 1024) {
-            const uint32_t l = (base + t < nlist) ? ((g && list_order) ? list_order[base + t] : base + t) : nlist;
+            const uint32_t l = (base + t < nlist) ? (((g || order_near) && list_order) ? list_order[base + t] : base + t) : nlist;
             uint32_t c = 0, len = 0;
             if (l < nlist) {
                 const uint32_t raw = list_cnt[l];
@@ -391,7 +397,13 @@ __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __rest
                 if (((raw & NEAREST_BIT) != 0) != (g == 0)) c = 0;   // not this group's list
             }
             const uint32_t ni = (c + tile_q - 1) / tile_q;
-            const uint64_t v = ((uint64_t)ni << 32) | c;
+            // a long list is cut into ns row ranges of at most rows_cap rows: ns items per query group,
+            // each with its own shortlist slot (ScanItem::sub), so that no single item is a long tail.
+            // Nearest-first group: only the FIRST range here, the others follow below.  Other lists
+            // (bounds already tight when they start): all ranges, adjacent.
+            const uint32_t ns = (rows_cap && len > rows_cap) ? (len + rows_cap - 1) / rows_cap : 1u;
+            const uint32_t ns_here = g ? ns : 1u;
+            const uint64_t v = ((uint64_t)(ni * ns_here) << 32) | c;
             uint64_t tot;
             const uint64_t ex = block_excl_scan_u64(v, warp_tot, &tot);
             if (c > 0) {
@@ -400,18 +412,61 @@ __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __rest
                 pair_off[l] = p_excl;
                 cursor[l] = p_excl;
                 for (uint32_t j = 0; j < ni; ++j) {
-                    ScanItem it;
-                    it.row_begin = list_off[l];
-                    it.row_end = list_off[l + 1];
-                    it.pair_begin = p_excl + j * tile_q;
-                    it.pair_count = min(tile_q, c - j * tile_q);
-                    it.slot = ni;  // items sharing this list (the TC scan keeps such lists in L2)
-                    it.identity = 0;
-                    items[i_excl + j] = it;
+                    for (uint32_t sb = 0; sb < ns_here; ++sb) {
+                        ScanItem it;
+                        it.row_begin = list_off[l] + (ns > 1 ? sb * rows_cap : 0u);
+                        it.row_end = (ns > 1) ? min(list_off[l + 1], it.row_begin + rows_cap) : list_off[l + 1];
+                        it.pair_begin = p_excl + j * tile_q;
+                        it.pair_count = min(tile_q, c - j * tile_q);
+                        it.slot = ni;  // query groups sharing this list (the TC scan keeps such lists in L2)
+                        it.identity = 0;
+                        it.sub = sb;
+                        items[i_excl + j * ns_here + sb] = it;
+                    }
                 }
                 my_rows += len;
             }
             carry += tot;
+        }
+        if (g == 0 && rows_cap) {
+            // the further row ranges of the nearest-first lists, range by range, behind every first
+            // range: by the time range s of a list starts, its range s - 1 has been scanned for a while
+            // and has published the queries' bounds (ranges that start together all start cold:
+            // measured 5 % more work).  The cheap far lists still come last.
+            for (uint32_t sb = 1; sb < 64; ++sb) {
+                uint32_t any = 0;
+                for (uint32_t base = 0; base < nlist; base += 1024) {
+                    const uint32_t l = (base + t < nlist) ? ((order_near && list_order) ? list_order[base + t] : base + t) : nlist;
+                    uint32_t c = 0, len = 0;
+                    if (l < nlist) {
+                        const uint32_t raw = list_cnt[l];
+                        len = list_off[l + 1] - list_off[l];
+                        c = (len && (raw & NEAREST_BIT)) ? (raw & ~NEAREST_BIT) : 0u;
+                    }
+                    const uint32_t ns = (len > rows_cap) ? (len + rows_cap - 1) / rows_cap : 1u;
+                    const uint32_t ni = (c && sb < ns) ? (c + tile_q - 1) / tile_q : 0u;
+                    uint64_t tot;
+                    const uint64_t ex = block_excl_scan_u64(ni, warp_tot, &tot);
+                    if (ni) {
+                        const uint32_t p_excl = pair_off[l];
+                        const uint32_t i0 = (uint32_t)(carry >> 32) + (uint32_t)ex;
+                        for (uint32_t j = 0; j < ni; ++j) {
+                            ScanItem it;
+                            it.row_begin = list_off[l] + sb * rows_cap;
+                            it.row_end = min(list_off[l + 1], it.row_begin + rows_cap);
+                            it.pair_begin = p_excl + j * tile_q;
+                            it.pair_count = min(tile_q, c - j * tile_q);
+                            it.slot = ni;
+                            it.identity = 0;
+                            it.sub = sb;
+                            items[i0 + j] = it;
+                        }
+                    }
+                    carry += tot << 32;
+                    any += (uint32_t)tot;
+                }
+                if (any == 0) break;   // block-uniform: no list has this many ranges
+            }
         }
     }
     const uint64_t carry_far = carry;
@@ -445,7 +500,7 @@ cudaError_t launch_probe_bucketing(const uint64_t* coarse_keys, uint32_t nq, uin
                                    uint32_t* list_cnt, uint32_t* pair_off, uint32_t* cursor,
                                    uint32_t* pair_q, uint32_t* pair_slot, ScanItem* items,
                                    uint32_t* n_items, uint64_t* scanned_rows, cudaStream_t stream,
-                                   const uint32_t* list_order) {
+                                   const uint32_t* list_order, bool order_near, uint32_t rows_cap) {
     const uint32_t n_pairs = nq * nprobe;
     cudaError_t e = cudaMemsetAsync(list_cnt, 0, sizeof(uint32_t) * nlist, stream);
     if (e != cudaSuccess) return e;
@@ -454,7 +509,7 @@ cudaError_t launch_probe_bucketing(const uint64_t* coarse_keys, uint32_t nq, uin
     }
     probe_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, nprobe, list_cnt);
     probe_scan_kernel<<<1, 1024, 0, stream>>>(list_cnt, list_off, list_order, nlist, tile_q, pair_off, cursor,
-                                              items, n_items, scanned_rows);
+                                              items, n_items, scanned_rows, order_near, rows_cap);
     probe_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, nprobe,
                                                                    list_off, cursor, pair_q,
                                                                    pair_slot);

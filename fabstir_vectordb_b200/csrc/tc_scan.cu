@@ -51,7 +51,8 @@ struct TcScanParams {
     const uint64_t* filt;
     uint64_t filt_bits;
     uint32_t P;
-    uint64_t* partial;  // [nq][P][TC_KP] approx keys: (approx d2 bits << 32) | arena row
+    uint64_t* partial;  // [nq][P][S][TC_KP] approx keys: (approx d2 bits << 32) | arena row
+    uint32_t S;         // shortlist slots per (query, probe): row ranges a long list is split into (0 = 1)
     uint32_t* thr_g;    // [nq] running upper bound of the query's TC_KP-th approx d2 (f32 bits)
     uint32_t* thr_peer[TC_MAX_PEERS];  // the same array on the peer GPUs (NVLink peer memory)
     uint32_t n_peer;
@@ -119,6 +120,8 @@ constexpr int RO_CAP = R2_CAP / 2;               // pending candidates per query
 constexpr int RO_FLUSH = RO_CAP / 2;
 static_assert(2 * RO_CAP <= 32, "the final fold sorts both halves in one 32-lane network");
 constexpr int R2_THREADS = 320;
+constexpr uint32_t TC_SPLIT_MAX = 4;          // row ranges a long posting list is split into, at most
+constexpr uint32_t TC_SPLIT_MIN_ROWS = 2048;  // lists up to this length are never split
 constexpr int R2_TMEM_COLS = 512;
 
 struct R2Smem {
@@ -467,7 +470,7 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
             // replays the rows it could not store).  Every wait of the load side services merge rounds.
             const uint32_t jown = (uint32_t)lane * 4u + (uint32_t)lw;
             uint32_t j_load = 0, j_done = 0;
-            uint32_t job_cnt0 = 0, job_cnt1 = 0, job_tiles0 = 0, job_tiles1 = 0;
+            uint32_t job_cnt0 = 0, job_cnt1 = 0, job_tiles0 = 0, job_tiles1 = 0, job_sub0 = 0, job_sub1 = 0;
             uint32_t mt = 0, g_tile = 0, mround0 = 0, mround1 = 0, st_merge = 0;
             bool job_open = false, own = false;
             uint32_t qi_own = 0, thr_pending = F32_INF_BITS, peer_sent = F32_INF_BITS;
@@ -588,7 +591,7 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                                     if (p.thr_g && lane == 31 && out != KEY_NONE) atomicMin(p.thr_g + sm.qidx[mb + j], (uint32_t)(out >> 32));
                                 }
                             }
-                            p.partial[((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * TC_KP + lane] = out;
+                            p.partial[(((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * (p.S ? p.S : 1u) + (jb ? job_sub1 : job_sub0)) * TC_KP + lane] = out;
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_idone);
@@ -663,7 +666,7 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 }
                 {
                     const uint32_t ntiles = (it.row_end - it.row_begin + R2_ROWS - 1) / R2_ROWS;
-                    if (nit & 1u) { job_cnt1 = cnt; job_tiles1 = ntiles; } else { job_cnt0 = cnt; job_tiles0 = ntiles; }
+                    if (nit & 1u) { job_cnt1 = cnt; job_tiles1 = ntiles; job_sub1 = it.sub; } else { job_cnt0 = cnt; job_tiles0 = ntiles; job_sub0 = it.sub; }
                     j_load = nit + 1;
                 }
                 Q1_LAP(3);
@@ -1125,7 +1128,7 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                         if (n == 0) continue;                                      // partial is pre-filled
                         mine = ((uint32_t)lane < n) ? sm.pend[j * R2_CAP + lane] : KEY_NONE;
                     }
-                    p.partial[((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * TC_KP + lane] = mine;
+                    p.partial[(((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * (p.S ? p.S : 1u) + it.sub) * TC_KP + lane] = mine;
                 }
             }
             epi_bar_n(1);  // pools may be re-initialised for the next item
@@ -1838,6 +1841,7 @@ __global__ void coarse_items_kernel(ScanItem* items, uint32_t nq, uint32_t nlist
     it.pair_count = min((uint32_t)Q1_M, nq - g * Q1_M);
     it.slot = it.row_begin;
     it.identity = 1;
+    it.sub = 0;
     if (it.row_begin >= it.row_end) it.pair_count = 0;
     items[i] = it;
 }
@@ -1859,6 +1863,7 @@ __global__ void flat_items_kernel(ScanItem* items, uint32_t nq, uint32_t n_rows,
     it.pair_count = min((uint32_t)TC_TILE_Q, nq - g * TC_TILE_Q);
     it.slot = c;
     it.identity = n_qg > 1 ? 2 : 1;   // 2: the chunk is read by several query groups (keep it in L2)
+    it.sub = 0;
     if (it.row_begin >= it.row_end) it.pair_count = 0;
     items[i] = it;
 }
@@ -2217,6 +2222,7 @@ struct TcScratchImpl {
     } rs[2];                   // [0] recent tier, [1] centroid table (assignment)
     Buf<ScanItem> fitems;
     uint32_t list_order_n = 0;
+    uint32_t max_list_len = 0;
     Buf<uint32_t> thr_g, list_cnt, pair_off, cursor, pair_q, pair_slot, n_items;
     Buf<ScanItem> items;
     Buf<uint64_t> partial, shortlist;
@@ -2326,6 +2332,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             std::vector<uint32_t> off(a.nlist + 1), order(a.nlist);
             TCK(cudaMemcpyAsync(off.data(), a.list_off, (size_t)(a.nlist + 1) * 4, cudaMemcpyDeviceToHost, st));
             TCK(cudaStreamSynchronize(st));
+            m->max_list_len = 0;
+            for (uint32_t l = 0; l < a.nlist; ++l) m->max_list_len = std::max(m->max_list_len, off[l + 1] - off[l]);
             for (uint32_t l = 0; l < a.nlist; ++l) order[l] = l;
             std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
                 return off[x + 1] - off[x] > off[y + 1] - off[y];
@@ -2350,8 +2358,22 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     const bool use_pair = !use_q && (kenv && kenv[0] == 'P') && a.sm_count >= 2 &&
                           tc_scan_pair_smem_bytes(KB, 2) + 1024 <= 232448;
     const uint32_t tile_q = use_q ? (uint32_t)Q1_M : use_pair ? (uint32_t)P2_NQ : TC_TILE_Q;
-    const uint32_t prows = use_pair ? 2u : 1u;   // shortlist rows per (query, probe)
-    const size_t max_items = (size_t)a.nlist + (n_pairs + tile_q - 1) / tile_q + 1;
+    // Long posting lists are cut into row ranges (one work item and one shortlist slot each): a hub
+    // list of 9 K rows probed by 64 queries is otherwise ONE item of 71 tiles — a third of the whole
+    // scan on one SM, and the tail every other SM waits for.  At most TC_SPLIT_MAX ranges per list.
+    uint32_t n_split = 1, rows_cap = 0;
+    if (!use_q) {
+        uint32_t want = TC_SPLIT_MAX;
+        if (const char* e = getenv("FVDB_TC_SPLIT")) want = std::min<uint32_t>(std::max(1, atoi(e)), 16u);
+        const uint32_t unit = use_pair ? 2u * R2_ROWS : (uint32_t)R2_ROWS;
+        if (want > 1 && m->max_list_len > TC_SPLIT_MIN_ROWS) {
+            rows_cap = std::max<uint32_t>(TC_SPLIT_MIN_ROWS / 2, ((m->max_list_len + want - 1) / want + unit - 1) / unit * unit);
+            n_split = (m->max_list_len + rows_cap - 1) / rows_cap;
+            if (n_split <= 1) { n_split = 1; rows_cap = 0; }
+        }
+    }
+    const uint32_t prows = (use_pair ? 2u : 1u) * n_split;   // shortlist rows per (query, probe)
+    const size_t max_items = ((size_t)a.nlist + (n_pairs + tile_q - 1) / tile_q) * n_split + 1;
     TCK(m->qnorm.ensure(nq, dev_bytes));
     TCK(m->thr_g.ensure(nq, dev_bytes));
     TCK(m->list_cnt.ensure(a.nlist + 1, dev_bytes));
@@ -2448,7 +2470,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     if (a.coarse_only) return FVDB_OK;
     TCK(launch_probe_bucketing(coarse_keys, nq, np, a.list_off, a.nlist, tile_q, m->list_cnt.p, m->pair_off.p,
                                m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st,
-                               (m->list_order_n == a.nlist && !getenv("FVDB_TC_NO_ORDER")) ? m->list_order.p : nullptr));
+                               (m->list_order_n == a.nlist && !getenv("FVDB_TC_NO_ORDER")) ? m->list_order.p : nullptr,
+                               getenv("FVDB_TC_ORDER_NEAR") != nullptr, rows_cap));
     (*launches) += 3;
     TCK(cudaMemsetAsync(m->partial.p, 0xFF, n_pairs * prows * TC_KP * sizeof(uint64_t), st));
 
@@ -2457,7 +2480,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     p.items = m->items.p; p.item_count = m->n_items.p; p.pair_q = m->pair_q.p; p.pair_slot = m->pair_slot.p;
     p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = m->xnorm.p; p.ids = a.ids;
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
-    p.P = np; p.partial = m->partial.p; p.thr_g = a.thr_ext ? a.thr_ext : m->thr_g.p;
+    p.P = np; p.S = n_split; p.partial = m->partial.p; p.thr_g = a.thr_ext ? a.thr_ext : m->thr_g.p;
     p.n_peer = a.thr_ext ? std::min(a.n_peers, TC_MAX_PEERS) : 0u;
     for (uint32_t r = 0; r < p.n_peer; ++r) p.thr_peer[r] = a.thr_peers[r];
     p.rows_raw = a.rows; p.rows_bytes = a.n_rows * (uint64_t)D * 4;
