@@ -362,25 +362,7 @@ __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __rest
     __shared__ uint64_t warp_tot[33];
     const int t = threadIdx.x;
     uint64_t my_rows = 0;
-    // pass A: totals of the nearest-first group
-    uint64_t near_total = 0;
-    for (uint32_t base = 0; base < nlist; base += 1024) {
-        const uint32_t l = base + t;
-        uint64_t v = 0;
-        if (l < nlist) {
-            const uint32_t raw = list_cnt[l];
-            const uint32_t c = (list_off[l + 1] != list_off[l]) ? (raw & ~NEAREST_BIT) : 0u;
-            if ((raw & NEAREST_BIT) && c) {
-                const uint32_t len = list_off[l + 1] - list_off[l];
-                const uint32_t ns = (rows_cap && len > rows_cap) ? (len + rows_cap - 1) / rows_cap : 1u;
-                v = ((uint64_t)(((c + tile_q - 1) / tile_q) * ns) << 32) | c;
-            }
-        }
-        uint64_t tot;
-        block_excl_scan_u64(v, warp_tot, &tot);
-        near_total += tot;
-    }
-    // pass B: offsets and items.  g = 0: the nearest-first group in list order; g = 1: the other
+    // offsets and items.  g = 0: the nearest-first group in list order; g = 1: the other
     // lists, longest first when list_order is given — the dynamic tile scheduler then ends with
     // the cheapest items, which keeps the tail of the scan short.  (Ordering the nearest group by
     // length as well starts every CTA on the most popular lists with cold thresholds: measured
@@ -470,7 +452,6 @@ __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __rest
         }
     }
     const uint64_t carry_far = carry;
-    (void)near_total;
     uint64_t rows_total;
     block_excl_scan_u64(my_rows, warp_tot, &rows_total);
     if (t == 0) {
