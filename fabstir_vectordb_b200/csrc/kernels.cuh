@@ -48,7 +48,7 @@ cudaError_t launch_merge_partials(const uint64_t* in, uint32_t nq, uint32_t P, u
                                   uint64_t* out, cudaStream_t stream);
 // same for P rows of 32 keys each that may be unsorted or empty (tensor-core scan output)
 cudaError_t launch_merge_rows32(const uint64_t* in, uint32_t nq, uint32_t P, uint64_t* out,
-                                cudaStream_t stream);
+                                cudaStream_t stream, const uint32_t* row_stamp, uint32_t stamp);
 cudaError_t launch_finalize(const uint64_t* recent, const uint64_t* ivf, uint32_t nq, uint32_t k,
                             uint32_t* out_ids, float* out_dist, uint32_t* out_count,
                             cudaStream_t stream);

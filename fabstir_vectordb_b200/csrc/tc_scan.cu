@@ -53,6 +53,8 @@ struct TcScanParams {
     uint32_t P;
     uint64_t* partial;  // [nq][P][S][TC_KP] approx keys: (approx d2 bits << 32) | arena row
     uint32_t S;         // shortlist slots per (query, probe): row ranges a long list is split into (0 = 1)
+    uint32_t* row_stamp; // [nq][P][S]: a shortlist row written by THIS launch carries `stamp` (rows that no item
+    uint32_t stamp;      // touched keep an older one and are skipped by the merge: no memset of `partial`)
     uint32_t* thr_g;    // [nq] running upper bound of the query's TC_KP-th approx d2 (f32 bits)
     uint32_t* thr_peer[TC_MAX_PEERS];  // the same array on the peer GPUs (NVLink peer memory)
     uint32_t n_peer;
@@ -591,7 +593,9 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                                     if (p.thr_g && lane == 31 && out != KEY_NONE) atomicMin(p.thr_g + sm.qidx[mb + j], (uint32_t)(out >> 32));
                                 }
                             }
-                            p.partial[(((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * (p.S ? p.S : 1u) + (jb ? job_sub1 : job_sub0)) * TC_KP + lane] = out;
+                            const size_t prow = ((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * (p.S ? p.S : 1u) + (jb ? job_sub1 : job_sub0);
+                            p.partial[prow * TC_KP + lane] = out;
+                            if (lane == 0) p.row_stamp[prow] = p.stamp;
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_idone);
@@ -1128,7 +1132,9 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                         if (n == 0) continue;                                      // partial is pre-filled
                         mine = ((uint32_t)lane < n) ? sm.pend[j * R2_CAP + lane] : KEY_NONE;
                     }
-                    p.partial[(((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * (p.S ? p.S : 1u) + it.sub) * TC_KP + lane] = mine;
+                    const size_t prow = ((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * (p.S ? p.S : 1u) + it.sub;
+                    p.partial[prow * TC_KP + lane] = mine;
+                    if (lane == 0) p.row_stamp[prow] = p.stamp;
                 }
             }
             epi_bar_n(1);  // pools may be re-initialised for the next item
@@ -1621,6 +1627,7 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 for (int g = 0; g < 4; ++g) {
                     if (!act[g]) continue;
                     p.partial[((size_t)qis[g] * p.P + sls[g]) * TC_KP + lane] = lst[g];
+                    if (lane == 0) p.row_stamp[(size_t)qis[g] * p.P + sls[g]] = p.stamp;
                     if (lane == 31 && lst[g] != KEY_NONE) atomicMin(p.thr_g + qis[g], (uint32_t)(lst[g] >> 32));
                 }
             }
@@ -2089,7 +2096,8 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restr
 // either empty, sorted (a list that was merged during the scan) or unsorted (pending candidates
 // published as they were).  One warp per query folds them into the query's best TC_KP.
 __global__ void __launch_bounds__(128) merge_rows32_kernel(const uint64_t* __restrict__ in, uint32_t nq, uint32_t P,
-                                                           uint64_t* __restrict__ out) {
+                                                           uint64_t* __restrict__ out,
+                                                           const uint32_t* __restrict__ row_stamp, uint32_t stamp) {
     // one block per query: warp w folds rows w, w + 4, ... (a chain of P / 4 dependent merges instead of
     // P, and four times the warps in flight), warp 0 folds the four results
     __shared__ uint64_t part[3][32];
@@ -2100,7 +2108,11 @@ __global__ void __launch_bounds__(128) merge_rows32_kernel(const uint64_t* __res
     for (uint32_t s0 = (uint32_t)w; s0 < P; s0 += 16) {
         uint64_t row[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) row[g] = (s0 + 4 * g < P) ? base[(size_t)(s0 + 4 * g) * TC_KP + lane] : KEY_NONE;
+        for (int g = 0; g < 4; ++g) {
+            // only rows this launch wrote (the others hold whatever an earlier batch left there)
+            const bool live = s0 + 4 * g < P && row_stamp[(size_t)q * P + s0 + 4 * g] == stamp;
+            row[g] = live ? base[(size_t)(s0 + 4 * g) * TC_KP + lane] : KEY_NONE;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (__ballot_sync(0xffffffffu, row[g] != KEY_NONE) == 0) continue;
@@ -2203,9 +2215,10 @@ cudaError_t launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t st
     return cudaGetLastError();
 }
 
-cudaError_t launch_merge_rows32(const uint64_t* in, uint32_t nq, uint32_t P, uint64_t* out, cudaStream_t stream) {
+cudaError_t launch_merge_rows32(const uint64_t* in, uint32_t nq, uint32_t P, uint64_t* out, cudaStream_t stream,
+                                const uint32_t* row_stamp, uint32_t stamp) {
     if (nq == 0) return cudaSuccess;
-    merge_rows32_kernel<<<nq, 128, 0, stream>>>(in, nq, P, out);
+    merge_rows32_kernel<<<nq, 128, 0, stream>>>(in, nq, P, out, row_stamp, stamp);
     return cudaGetLastError();
 }
 
@@ -2226,6 +2239,21 @@ struct TcScratchImpl {
     Buf<uint32_t> thr_g, list_cnt, pair_off, cursor, pair_q, pair_slot, n_items;
     Buf<ScanItem> items;
     Buf<uint64_t> partial, shortlist;
+    Buf<uint32_t> row_stamp;   // one stamp per shortlist row of `partial`
+    uint32_t stamp = 0;        // launch counter; a fresh or wrapped counter clears the stamps
+    // stamps for `rows` shortlist rows of the next scan launch: returns the launch's stamp
+    cudaError_t next_stamp(size_t rows, size_t* dev_bytes, cudaStream_t st, uint32_t* out) {
+        const size_t before = row_stamp.cap;
+        cudaError_t e = row_stamp.ensure(rows, dev_bytes);
+        if (e != cudaSuccess) return e;
+        if (row_stamp.cap != before || stamp == 0xFFFFFFFFu) {
+            e = cudaMemsetAsync(row_stamp.p, 0, row_stamp.cap * sizeof(uint32_t), st);
+            if (e != cudaSuccess) return e;
+            stamp = 0;
+        }
+        *out = ++stamp;
+        return cudaSuccess;
+    }
     Buf<float> cnorm, dense;
     Buf<uint64_t> coarse;
     Buf<ScanItem> citems;
@@ -2267,7 +2295,7 @@ void tc_release(TcScratch& s) {
     TcScratchImpl* m = s.impl;
     m->xnorm.release(); m->qnorm.release(); m->misc.release(); m->thr_g.release(); m->list_cnt.release();
     m->pair_off.release(); m->cursor.release(); m->pair_q.release(); m->pair_slot.release(); m->n_items.release();
-    m->items.release(); m->partial.release(); m->shortlist.release();
+    m->items.release(); m->partial.release(); m->shortlist.release(); m->row_stamp.release();
     m->prof.release(); m->list_order.release(); m->rs[0].xnorm.release(); m->rs[1].xnorm.release(); m->fitems.release();
     m->cnorm.release(); m->dense.release(); m->coarse.release(); m->citems.release();
     delete m;
@@ -2473,7 +2501,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
                                (m->list_order_n == a.nlist && !getenv("FVDB_TC_NO_ORDER")) ? m->list_order.p : nullptr,
                                getenv("FVDB_TC_ORDER_NEAR") != nullptr, rows_cap));
     (*launches) += 3;
-    TCK(cudaMemsetAsync(m->partial.p, 0xFF, n_pairs * prows * TC_KP * sizeof(uint64_t), st));
+    uint32_t stamp = 0;
+    TCK(m->next_stamp(n_pairs * prows, dev_bytes, st, &stamp));
 
     // ---- the scan ----
     TcScanParams p{};
@@ -2481,6 +2510,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = m->xnorm.p; p.ids = a.ids;
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
     p.P = np; p.S = n_split; p.partial = m->partial.p; p.thr_g = a.thr_ext ? a.thr_ext : m->thr_g.p;
+    p.row_stamp = m->row_stamp.p; p.stamp = stamp;
     p.n_peer = a.thr_ext ? std::min(a.n_peers, TC_MAX_PEERS) : 0u;
     for (uint32_t r = 0; r < p.n_peer; ++r) p.thr_peer[r] = a.thr_peers[r];
     p.rows_raw = a.rows; p.rows_bytes = a.n_rows * (uint64_t)D * 4;
@@ -2572,7 +2602,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     (*launches)++;
 
     // ---- merge the per-(query, probe) shortlists, exact re-rank, proof ----
-    TCK(launch_merge_rows32(m->partial.p, nq, np * prows, m->shortlist.p, st));
+    TCK(launch_merge_rows32(m->partial.p, nq, np * prows, m->shortlist.p, st, m->row_stamp.p, stamp));
     TCK(rerank_prepare(m));
     rerank_kernel<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k, (uint32_t)TC_KP,
                                                a.out_keys, a.d_fallback_count, a.d_fallback_idx, a.fin_ids, a.fin_dist, a.fin_count);
@@ -2636,12 +2666,14 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
         TCK(cudaGetLastError());
         (*launches) += 3;
     }
-    TCK(cudaMemsetAsync(m->partial.p, 0xFF, (size_t)nq * n_chunks * TC_KP * sizeof(uint64_t), st));
+    uint32_t stamp = 0;
+    TCK(m->next_stamp((size_t)nq * n_chunks, dev_bytes, st, &stamp));
     TcScanParams p{};
     p.items = m->fitems.p; p.item_count = m->n_items.p + 4; p.pair_q = nullptr; p.pair_slot = nullptr;
     p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = rs.xnorm.p; p.ids = a.ids;
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
     p.P = n_chunks; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
+    p.row_stamp = m->row_stamp.p; p.stamp = stamp;
     p.work_counter = m->n_items.p + 5;
     TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
     uint32_t stages = std::min<uint32_t>(12u, 6u * KB);
@@ -2657,7 +2689,7 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
     if (tc_offload_merges()) tc_scan_kernel_t<true><<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(rs.tmap, p);
     else tc_scan_kernel_t<false><<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(rs.tmap, p);
     TCK(cudaGetLastError());
-    TCK(launch_merge_rows32(m->partial.p, nq, n_chunks, m->shortlist.p, st));
+    TCK(launch_merge_rows32(m->partial.p, nq, n_chunks, m->shortlist.p, st, m->row_stamp.p, stamp));
     TCK(rerank_prepare(m));
     rerank_kernel<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p,
                                                                          xmax_bits, nq, D, a.k,

@@ -724,7 +724,9 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
                         if (n == 0) continue;                                      // partial is pre-filled
                         mine = ((uint32_t)lane < n) ? sm.pend[j * P2_CAP + lane] : KEY_NONE;
                     }
-                    p.partial[(((size_t)sm.qidx[mb + j] * (2u * p.P) + rank * p.P + sm.qslot[mb + j]) * (p.S ? p.S : 1u) + it.sub) * TC_KP + lane] = mine;
+                    const size_t prow = ((size_t)sm.qidx[mb + j] * (2u * p.P) + rank * p.P + sm.qslot[mb + j]) * (p.S ? p.S : 1u) + it.sub;
+                    p.partial[prow * TC_KP + lane] = mine;
+                    if (lane == 0) p.row_stamp[prow] = p.stamp;
                 }
             }
             epi_bar_n(1);  // pools may be re-initialised for the next item

@@ -587,3 +587,38 @@ def test_coarse_selection_with_clumped_centroid_ids(nlist):
     o = O.hybrid_batch_search(ivf, None, None, q, k, nprobe, tiers=2)
     _assert_same(ids, dist, cnt, *o)
     assert eng.stats().last_fallback_queries < nq // 2
+
+
+@pytest.mark.parametrize("kernel", ["R", "P"])
+def test_hub_list_is_split_into_row_ranges(kernel, monkeypatch):
+    """A hub posting list (thousands of rows, probed by every query) is cut into row ranges with one work
+    item and one shortlist slot each.  Results — with tombstones and a filter bitmap on —
+    must equal the oracle's bit for bit, for kernel R and for the CTA-pair kernel."""
+    if kernel == "P":
+        monkeypatch.setenv("FVDB_TC_KERNEL", "P")
+    rng = np.random.default_rng(77)
+    d, nlist, nq, k, nprobe = 128, 12, 150, 10, 6
+    cents = rng.standard_normal((nlist, d)).astype(np.float32)
+    # list 0 is the hub: 7000 of the 10000 rows sit around its centroid; all queries come from there
+    owner = np.concatenate([np.zeros(7000, np.int64), rng.integers(1, nlist, 3000)])
+    rng.shuffle(owner)
+    x = (cents[owner] + np.float32(0.4) * rng.standard_normal((len(owner), d))).astype(np.float32)
+    q = (cents[0] + np.float32(0.5) * rng.standard_normal((nq, d))).astype(np.float32)
+    n = len(x)
+    eng = Engine(d, k_max=32)
+    _set_mode(eng, "tc")
+    eng.set_centroids(cents)
+    ids = np.arange(n, dtype=np.uint32)
+    eng.ivf_add(x, ids)
+    ivf = O.IVF(cents, x, ids)
+    assert max(ivf.list_len(l) for l in range(nlist)) > 4096       # long enough to be split
+    dele = np.arange(3, n, 41, dtype=np.uint32)
+    eng.set_deleted(dele, True)
+    fbits = O.make_bitmap(n, np.arange(0, n, 2, dtype=np.uint32))   # every other row passes the filter
+    got = eng.search(q, k, nprobe, tiers=L.TIER_HISTORICAL, filter_bits=fbits)
+    want = O.hybrid_batch_search(ivf, None, None, q, k, nprobe, tiers=2, deleted=O.make_bitmap(n, dele),
+                                 filter_bits=fbits)
+    _assert_same(*got, *want)
+    got = eng.search(q, k, nprobe, tiers=L.TIER_HISTORICAL)
+    want = O.hybrid_batch_search(ivf, None, None, q, k, nprobe, tiers=2, deleted=O.make_bitmap(n, dele))
+    _assert_same(*got, *want)
