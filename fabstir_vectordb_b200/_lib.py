@@ -92,6 +92,9 @@ SIGNATURES = {
     "fvdb_host_free": (None, [_vp]),
     "fvdb_search_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
                                      C.c_uint64, _vp, _vp, _vp, _vp]),
+    "fvdb_search_device_submit": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
+                                     C.c_uint64, _vp, _vp, _vp, _vp]),
+    "fvdb_search_device_finish": (C.c_int, [_vp, _vp]),
     "fvdb_coarse_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "fvdb_search_device_coarse": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
                                             C.c_uint64, _vp, _vp, _vp, _vp, _vp]),

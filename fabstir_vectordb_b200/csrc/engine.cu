@@ -146,6 +146,18 @@ struct fvdb_index {
     DevBuf<uint64_t> s_tmpbits;
     DevBuf<uint32_t> s_fb_idx;
     DevBuf<uint32_t> s_fb_idx_flat;
+    // batches enqueued by fvdb_search_device_submit and not yet checked by ..._finish
+    struct Pending {
+        const float* d_q; uint32_t nq, k, nprobe, tiers;
+        const uint64_t* d_filter; uint64_t filter_bits;
+        uint32_t* d_out_ids; float* d_out_dist; uint32_t* d_out_count;
+        bool used_tc, flat_tc, use_ivf, use_flat;
+        uint32_t n_bitmaps;   // tombstone / filter bitmaps read per row (for the algorithmic-bytes figure)
+        uint32_t* host;       // page-locked: [16] counter words, [2 nq] IVF fallback ids, [2 nq] flat fallback ids
+        size_t host_words;
+    };
+    std::vector<Pending> pending;
+    std::vector<std::pair<uint32_t*, size_t>> pending_pool;   // recycled page-locked blocks
     DevBuf<float> s_fb_q;
     DevBuf<uint64_t> s_fb_keys, s_fb_coarse;
     TcScratch tc;
@@ -751,7 +763,8 @@ bool is_pinned_host(const void* p) {
 int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,
                        uint32_t tiers, const uint64_t* d_filter, uint64_t filter_bits,
                        uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count,
-                       cudaStream_t st, const uint64_t* ext_coarse = nullptr, const HostOut* ho = nullptr) {
+                       cudaStream_t st, const uint64_t* ext_coarse = nullptr, const HostOut* ho = nullptr,
+                       bool defer = false) {
     if (k == 0) return h->fail(FVDB_ERR_INVALID_ARG, "k must be >= 1");
     if (k > h->k_max) return h->fail(FVDB_ERR_K_TOO_LARGE, "k exceeds k_max given at fvdb_create");
     h->stats.last_nq = nq;
@@ -881,6 +894,29 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
     CK(cudaEventRecord(h->ev_b, st));
     if (ho) CK(copy_out(ho, d_out_ids, d_out_dist, d_out_count, st));
 
+    if (defer) {
+        // stream-ordered variant: the counters and the fallback lists are copied to a page-locked
+        // record in stream order; fvdb_search_device_finish looks at them after ONE synchronisation
+        // for any number of batches (no GPU idle time between consecutive batches)
+        const size_t words = 16 + (size_t)4 * nq;
+        fvdb_index::Pending pb{d_q, nq, k, nprobe, tiers, d_filter, filter_bits, d_out_ids, d_out_dist, d_out_count,
+                               used_tc, flat_tc, use_ivf, use_flat, (tomb ? 1u : 0u) + (filt ? 1u : 0u), nullptr, 0};
+        for (size_t i = 0; i < h->pending_pool.size(); ++i)
+            if (h->pending_pool[i].second >= words) {
+                pb.host = h->pending_pool[i].first; pb.host_words = h->pending_pool[i].second;
+                h->pending_pool.erase(h->pending_pool.begin() + i);
+                break;
+            }
+        if (!pb.host) {
+            CK(cudaHostAlloc((void**)&pb.host, words * 4, cudaHostAllocDefault));
+            pb.host_words = words;
+        }
+        CK(cudaMemcpyAsync(pb.host, h->s_misc.p, 64, cudaMemcpyDeviceToHost, st));
+        if (used_tc) CK(cudaMemcpyAsync(pb.host + 16, h->s_fb_idx.p, (size_t)2 * nq * 4, cudaMemcpyDeviceToHost, st));
+        if (flat_tc) CK(cudaMemcpyAsync(pb.host + 16 + 2 * nq, h->s_fb_idx_flat.p, (size_t)2 * nq * 4, cudaMemcpyDeviceToHost, st));
+        h->pending.push_back(pb);
+        return FVDB_OK;
+    }
     // one synchronisation point per batch: NaN flag + counters
     uint32_t host_misc[16] = {0};
     CK(cudaMemcpyAsync(host_misc, h->s_misc.p, sizeof(host_misc), cudaMemcpyDeviceToHost, st));
@@ -1006,6 +1042,8 @@ void fvdb_destroy(fvdb_index* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     tc_release(h->tc);
     if (h->pin) cudaFreeHost(h->pin);
+    for (auto& pb : h->pending) cudaFreeHost(pb.host);
+    for (auto& pp : h->pending_pool) cudaFreeHost(pp.first);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
     if (h->ev_s0) cudaEventDestroy(h->ev_s0);
@@ -1391,6 +1429,83 @@ int fvdb_search_device(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return search_device_impl(h, d_q, nq, k, nprobe, tiers, d_filter_bits, filter_nbits, d_out_ids,
                               d_out_dist, d_out_count, st);
+}
+
+int fvdb_search_device_submit(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,
+                              uint32_t tiers, const uint64_t* d_filter_bits, uint64_t filter_nbits,
+                              uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count, void* stream) {
+    ENTER(h);
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (h->pending.size() >= 64) return h->fail(FVDB_ERR_INVALID_ARG, "64 batches are pending: call fvdb_search_device_finish");
+    return search_device_impl(h, d_q, nq, k, nprobe, tiers, d_filter_bits, filter_nbits, d_out_ids,
+                              d_out_dist, d_out_count, st, nullptr, nullptr, true);
+}
+
+int fvdb_search_device_finish(fvdb_index* h, void* stream) {
+    ENTER(h);
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (cudaStreamSynchronize(st) != cudaSuccess) { h->pending.clear(); return h->fail(FVDB_ERR_CUDA, "stream synchronisation failed"); }
+    int rc = FVDB_OK;
+    std::vector<fvdb_index::Pending> todo;
+    todo.swap(h->pending);
+    uint32_t fallbacks = 0;
+    for (const fvdb_index::Pending& pb : todo) {
+        if (rc == FVDB_OK && pb.host[0])
+            rc = h->fail(FVDB_ERR_NAN, "NaN in query (the reference panics on partial_cmp().unwrap())");
+        const uint32_t n_ivf = pb.used_tc ? std::min(pb.host[10], 2 * pb.nq) : 0;
+        const uint32_t n_flat = pb.flat_tc ? std::min(pb.host[11], 2 * pb.nq) : 0;
+        if (rc == FVDB_OK && (n_ivf || n_flat)) {
+            // proof failures: these queries are searched again on the exact path (both tiers as asked
+            // for) and their result rows replaced
+            std::vector<uint32_t> idx(pb.host + 16, pb.host + 16 + n_ivf);
+            idx.insert(idx.end(), pb.host + 16 + 2 * pb.nq, pb.host + 16 + 2 * pb.nq + n_flat);
+            std::sort(idx.begin(), idx.end());
+            idx.erase(std::unique(idx.begin(), idx.end()), idx.end());
+            const uint32_t m = (uint32_t)idx.size();
+            int r2 = [&]() -> int {
+                CK(h->s_fb_q.ensure((size_t)m * h->dim, 0, st, &h->dev_bytes));
+                CK(h->s_fb_idx.ensure(std::max<size_t>(m, 2 * pb.nq), 0, st, &h->dev_bytes));
+                CK(h->s_fb_keys.ensure((size_t)m * pb.k * 2 + m, 0, st, &h->dev_bytes));   // ids | dist | counts
+                CK(cudaMemcpyAsync(h->s_fb_idx.p, idx.data(), (size_t)m * 4, cudaMemcpyHostToDevice, st));
+                CK(launch_gather_rows(pb.d_q, pb.nq, nullptr, h->s_fb_idx.p, m, h->dim, h->s_fb_q.p, st));
+                uint32_t* t_ids = reinterpret_cast<uint32_t*>(h->s_fb_keys.p);
+                float* t_dist = reinterpret_cast<float*>(t_ids + (size_t)m * pb.k);
+                uint32_t* t_cnt = t_ids + (size_t)2 * m * pb.k;
+                // keep the fallback ids out of the recursion's scratch: a second buffer holds them
+                CK(h->s_fb_coarse.ensure(m, 0, st, &h->dev_bytes));
+                CK(cudaMemcpyAsync(h->s_fb_coarse.p, h->s_fb_idx.p, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
+                CK(cudaStreamSynchronize(st));   // idx (host vector) has been consumed
+                const uint32_t mode = h->scan_mode;
+                h->scan_mode = FVDB_SCAN_EXACT;
+                const int r3 = search_device_impl(h, h->s_fb_q.p, m, pb.k, pb.nprobe, pb.tiers, pb.d_filter, pb.filter_bits,
+                                                  t_ids, t_dist, t_cnt, st);
+                h->scan_mode = mode;
+                if (r3 != FVDB_OK) return r3;
+                CK(launch_scatter_result_rows(t_ids, t_dist, t_cnt, reinterpret_cast<const uint32_t*>(h->s_fb_coarse.p), m,
+                                              pb.k, pb.d_out_ids, pb.d_out_dist, pb.d_out_count, st));
+                CK(cudaStreamSynchronize(st));
+                return FVDB_OK;
+            }();
+            if (r2 != FVDB_OK) rc = r2;
+            fallbacks += m;
+        }
+    }
+    for (const fvdb_index::Pending& pb : todo) h->pending_pool.push_back({pb.host, pb.host_words});
+    if (!todo.empty()) {
+        const fvdb_index::Pending& lb = todo.back();   // the figures of the last batch, as the synchronous call reports them
+        uint64_t scanned = 0;
+        std::memcpy(&scanned, &lb.host[2], 8);
+        const uint64_t rows = scanned + (lb.use_flat ? h->flat_n : 0);
+        h->stats.last_nq = lb.nq;
+        h->stats.last_scanned_rows = rows;
+        h->stats.last_algorithmic_bytes = rows * h->dim * 4ull + (uint64_t)lb.nq * h->dim * 4ull + (uint64_t)lb.nq * lb.k * 8ull +
+                                          (lb.use_ivf ? (uint64_t)h->nlist * h->dim * 4ull : 0ull) + (uint64_t)lb.n_bitmaps * (rows / 8);
+        h->stats.last_fallback_queries = fallbacks;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_a, h->ev_b) == cudaSuccess) h->stats.last_device_ms = ms; else cudaGetLastError();
+        if (cudaEventElapsedTime(&ms, h->ev_s0, h->ev_s1) == cudaSuccess) h->stats.last_scan_ms = ms; else cudaGetLastError();
+    }
+    return rc;
 }
 
 int fvdb_coarse_device(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t nprobe, uint64_t* d_out_keys,

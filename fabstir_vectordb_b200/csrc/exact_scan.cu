@@ -750,6 +750,28 @@ cudaError_t launch_scatter_keys(const uint64_t* src, const uint32_t* idx, uint32
     return cudaGetLastError();
 }
 
+// Result rows of re-run queries back into the batch's result arrays (deferred proof failures of
+// fvdb_search_device_submit): row i of the sources goes to row idx[i] of the destinations.
+__global__ void scatter_result_rows_kernel(const uint32_t* __restrict__ ids, const float* __restrict__ dist,
+                                           const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ idx,
+                                           uint32_t n, uint32_t k, uint32_t* __restrict__ out_ids,
+                                           float* __restrict__ out_dist, uint32_t* __restrict__ out_cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * k) return;
+    const uint32_t r = i / k, c = i % k;
+    out_ids[(size_t)idx[r] * k + c] = ids[i];
+    out_dist[(size_t)idx[r] * k + c] = dist[i];
+    if (c == 0) out_cnt[idx[r]] = cnt[r];
+}
+
+cudaError_t launch_scatter_result_rows(const uint32_t* ids, const float* dist, const uint32_t* cnt,
+                                       const uint32_t* idx, uint32_t n, uint32_t k, uint32_t* out_ids,
+                                       float* out_dist, uint32_t* out_cnt, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    scatter_result_rows_kernel<<<(n * k + 255) / 256, 256, 0, stream>>>(ids, dist, cnt, idx, n, k, out_ids, out_dist, out_cnt);
+    return cudaGetLastError();
+}
+
 // NaN screen over a float matrix (the reference panics on NaN: src/ivf/core.rs:655,677).
 __global__ void nan_check_kernel(const float* __restrict__ x, size_t n, int* __restrict__ flag) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -57,6 +57,9 @@ cudaError_t launch_merge_parts(const uint32_t* ids, const float* dist, const uin
                                float* out_dist, uint32_t* out_count, cudaStream_t stream,
                                size_t stride_kv = 0, size_t stride_c = 0);
 // dst[idx[i]][0..k) = src[i][0..k)
+cudaError_t launch_scatter_result_rows(const uint32_t* ids, const float* dist, const uint32_t* cnt,
+                                       const uint32_t* idx, uint32_t n, uint32_t k, uint32_t* out_ids,
+                                       float* out_dist, uint32_t* out_cnt, cudaStream_t stream);
 cudaError_t launch_scatter_keys(const uint64_t* src, const uint32_t* idx, uint32_t n, uint32_t k,
                                 uint64_t* dst, cudaStream_t stream);
 cudaError_t launch_nan_check(const float* x, size_t n, int* flag, cudaStream_t stream);

@@ -290,6 +290,18 @@ class Engine:
                                               filter_nbits, d_out_ids, d_out_dist, d_out_count,
                                               _stream(stream)))
 
+    def search_device_submit(self, d_q: int, nq: int, k: int, nprobe: int, tiers: int, d_filter: int,
+                             filter_nbits: int, d_out_ids: int, d_out_dist: int, d_out_count: int,
+                             stream: int = 0):
+        """Stream-ordered search: enqueue and return; the results are valid after search_device_finish."""
+        self._ck(self._lib.fvdb_search_device_submit(self._h, d_q, nq, k, nprobe, tiers, d_filter or None,
+                                                     filter_nbits, d_out_ids, d_out_dist, d_out_count,
+                                                     _stream(stream)))
+
+    def search_device_finish(self, stream: int = 0):
+        """Wait for every submitted batch; raises NanInput if one of them held a NaN query."""
+        self._ck(self._lib.fvdb_search_device_finish(self._h, _stream(stream)))
+
     def coarse_device(self, d_q: int, nq: int, nprobe: int, d_out_keys: int, stream: int = 0):
         """Coarse ranking only: keys [nq x nprobe] u64 (device)."""
         self._ck(self._lib.fvdb_coarse_device(self._h, d_q, nq, nprobe, d_out_keys, _stream(stream)))

@@ -84,9 +84,9 @@ class ShardedIndex:
         """Assign rows to lists and keep those this rank owns."""
         return self.eng.ivf_add_device(x.data_ptr(), row_ids.data_ptr(), x.shape[0], self.world, self.rank)
 
-    def _buffers(self, nq: int, k: int, device):
+    def _buffers(self, nq: int, k: int, device, slot: int = 0):
         import torch
-        key = (nq, k)
+        key = (nq, k, slot)
         if key not in self._bufs:
             o_ids, o_dist, o_cnt, chunk = pack_layout(nq, k)
             # this rank's results are written straight into the three sections of its packed chunk
@@ -102,6 +102,23 @@ class ShardedIndex:
                 o_cnt=torch.empty((nq,), dtype=torch.int32, device=device),
             )
         return self._bufs[key]
+
+    def submit(self, q, k: int, nprobe: int, tiers: int = L.TIER_HISTORICAL, slot: int = 0):
+        """Single-GPU, stream-ordered: enqueue the batch (fvdb_search_device_submit) and return its result
+        tensors, which are valid after finish().  `slot` selects one of several result buffer sets, so
+        that batches in flight do not share one."""
+        import torch
+        assert self.world == 1, "the stream-ordered entry is the single-GPU path"
+        nq = q.shape[0]
+        b = self._buffers(nq, k, q.device, slot)
+        self.eng.search_device_submit(q.data_ptr(), nq, k, nprobe, tiers, 0, 0, b["ids"].data_ptr(),
+                                      b["dist"].data_ptr(), b["cnt"].data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream)
+        return b["ids"], b["dist"], b["cnt"]
+
+    def finish(self):
+        import torch
+        self.eng.search_device_finish(torch.cuda.current_stream().cuda_stream)
 
     def search(self, q, k: int, nprobe: int, tiers: int = L.TIER_HISTORICAL, filter_bits=None,
                filter_nbits: int = 0):

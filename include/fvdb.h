@@ -237,6 +237,20 @@ int fvdb_search_device(fvdb_index *h, const float *d_q, uint32_t nq, uint32_t k,
                        uint64_t filter_nbits, uint32_t *d_out_ids, float *d_out_dist,
                        uint32_t *d_out_count, void *stream);
 
+/* Stream-ordered pair for back-to-back batches (a serving loop that always has the next batch
+ * ready): _submit enqueues the whole batch on `stream` and returns WITHOUT waiting, so the GPU never
+ * idles between batches while the host turns a call around; the result arrays are valid in stream
+ * order, subject to _finish.  _finish waits for every submitted batch of the handle, reports
+ * FVDB_ERR_NAN if any of them held a NaN query, and re-runs on the exact path (replacing their result
+ * rows) the queries whose tensor-core proof failed.  Up to 64 batches may be pending; the query and
+ * result buffers of a batch must stay alive and untouched by the caller until _finish returns.
+ * (fvdb_search_device = _submit + _finish of one batch.) */
+int fvdb_search_device_submit(fvdb_index *h, const float *d_q, uint32_t nq, uint32_t k,
+                              uint32_t nprobe, uint32_t tiers, const uint64_t *d_filter_bits,
+                              uint64_t filter_nbits, uint32_t *d_out_ids, float *d_out_dist,
+                              uint32_t *d_out_count, void *stream);
+int fvdb_search_device_finish(fvdb_index *h, void *stream);
+
 /* The coarse step alone (src/ivf/core.rs:646-656) for nq device-resident queries:
  * d_out_keys [nq x nprobe] = (f32 bits of the exact centroid distance << 32) | list id, ascending,
  * ties to the lower list id (the reference's stable sort).  1 <= nprobe <= nlist.  Used by the

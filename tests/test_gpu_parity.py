@@ -622,3 +622,54 @@ def test_hub_list_is_split_into_row_ranges(kernel, monkeypatch):
     got = eng.search(q, k, nprobe, tiers=L.TIER_HISTORICAL)
     want = O.hybrid_batch_search(ivf, None, None, q, k, nprobe, tiers=2, deleted=O.make_bitmap(n, dele))
     _assert_same(*got, *want)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_stream_ordered_submit_finish(mode):
+    """fvdb_search_device_submit x N + one fvdb_search_device_finish == N synchronous calls: same bits as the
+    oracle, including queries whose tensor-core proof fails (near-duplicate neighbourhoods: repaired on the
+    exact path at finish time) and a NaN batch (reported by finish)."""
+    import torch
+    from fabstir_vectordb_b200 import NanInput
+    d, n, nlist, nq, k, nprobe = 128, 9000, 24, 80, 10, 6
+    rng = np.random.default_rng(5)
+    x = _data(n, d, 91)
+    # 120 near-copies of row 0 (1e-4 apart): the 32 best approximate distances of a query there are
+    # indistinguishable in TF32, so the proof must fail and the exact path must answer
+    x[1:121] = x[0] + np.float32(1e-4) * rng.standard_normal((120, d)).astype(np.float32)
+    cents = x[rng.choice(n, nlist, replace=False)].copy()
+    eng = Engine(d, k_max=32)
+    _set_mode(eng, mode)
+    eng.set_centroids(cents)
+    ids = np.arange(n, dtype=np.uint32)
+    eng.ivf_add(x, ids)
+    ivf = O.IVF(cents, x, ids)
+    qs = [_queries(nq, d, n, 100 + i) for i in range(3)]
+    qs[1][:7] = x[0] + np.float32(1e-4) * rng.standard_normal((7, d)).astype(np.float32)
+    dq = [torch.from_numpy(q).cuda() for q in qs]
+    outs = [(torch.empty((nq, k), dtype=torch.int32, device="cuda"), torch.empty((nq, k), dtype=torch.float32, device="cuda"),
+             torch.empty((nq,), dtype=torch.int32, device="cuda")) for _ in qs]
+    for q_, o_ in zip(dq, outs):
+        eng.search_device_submit(q_.data_ptr(), nq, k, nprobe, L.TIER_HISTORICAL, 0, 0,
+                                 o_[0].data_ptr(), o_[1].data_ptr(), o_[2].data_ptr())
+    eng.search_device_finish()
+    if mode == "tc":
+        assert eng.stats().last_fallback_queries >= 7
+    for q_, o_ in zip(qs, outs):
+        want = O.hybrid_batch_search(ivf, None, None, q_, k, nprobe, tiers=2)
+        _assert_same(o_[0].cpu().numpy().view(np.uint32), o_[1].cpu().numpy(), o_[2].cpu().numpy().view(np.uint32), *want)
+    # a NaN batch between two good ones: finish reports it, later calls work again
+    bad = dq[0].clone()
+    bad[3, 5] = float("nan")
+    eng.search_device_submit(dq[2].data_ptr(), nq, k, nprobe, L.TIER_HISTORICAL, 0, 0,
+                             outs[2][0].data_ptr(), outs[2][1].data_ptr(), outs[2][2].data_ptr())
+    eng.search_device_submit(bad.data_ptr(), nq, k, nprobe, L.TIER_HISTORICAL, 0, 0,
+                             outs[0][0].data_ptr(), outs[0][1].data_ptr(), outs[0][2].data_ptr())
+    with pytest.raises(NanInput):
+        eng.search_device_finish()
+    eng.search_device_submit(dq[0].data_ptr(), nq, k, nprobe, L.TIER_HISTORICAL, 0, 0,
+                             outs[0][0].data_ptr(), outs[0][1].data_ptr(), outs[0][2].data_ptr())
+    eng.search_device_finish()
+    want = O.hybrid_batch_search(ivf, None, None, qs[0], k, nprobe, tiers=2)
+    _assert_same(outs[0][0].cpu().numpy().view(np.uint32), outs[0][1].cpu().numpy(), outs[0][2].cpu().numpy().view(np.uint32), *want)
+    eng.close()
