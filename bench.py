@@ -421,10 +421,32 @@ def main():
         out = tuple(x.array for x in p_out)
         for w in range(3):
             eng.search(p_q[w % N_QUERY_SETS].array, K, NPROBE, tiers=L.TIER_HISTORICAL, out=out)
+        # stream-ordered: fvdb_search_submit per batch (its upload overlaps the previous batch's scan),
+        # one fvdb_search_finish per E2E_PIPE batches; every batch has its own result buffers
+        e2e_pipe = max(1, min(4, int(os.environ.get("FVDB_BENCH_E2E_PIPE", 4))))
+        p_more = [(PinnedArray((nq, K), np.uint32), PinnedArray((nq, K), np.float32), PinnedArray((nq,), np.uint32))
+                  for _ in range(e2e_pipe - 1)]   # (kept alive: the arrays are views of these buffers)
+        outs = [out] + [tuple(x.array for x in t_) for t_ in p_more]
+        if e2e_pipe > 1:   # warm-up of the stream-ordered path (its slots allocate on first use)
+            for w in range(8):
+                eng.search_submit(p_q[w % N_QUERY_SETS].array, K, NPROBE, L.TIER_HISTORICAL, outs[w % e2e_pipe])
+                if (w + 1) % e2e_pipe == 0:
+                    eng.search_finish()
+            eng.search_finish()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            if e2e_pipe > 1:
+                eng.search_submit(p_q[s % N_QUERY_SETS].array, K, NPROBE, L.TIER_HISTORICAL, outs[s % e2e_pipe])
+                if (s + 1) % e2e_pipe == 0 or s + 1 == args.steps:
+                    eng.search_finish()
+            else:
+                eng.search(p_q[s % N_QUERY_SETS].array, K, NPROBE, tiers=L.TIER_HISTORICAL, out=out)
+        e2e_dt = time.perf_counter() - t0
+        # the synchronous call, one batch at a time
         t0 = time.perf_counter()
         for s in range(args.steps):
             eng.search(p_q[s % N_QUERY_SETS].array, K, NPROBE, tiers=L.TIER_HISTORICAL, out=out)
-        e2e_dt = time.perf_counter() - t0
+        e2e_sync_qps = nq * args.steps / (time.perf_counter() - t0)
         # the same call with pageable numpy buffers (staged through the handle's pinned buffer)
         t0 = time.perf_counter()
         for s in range(args.steps):
@@ -449,6 +471,11 @@ def main():
     e2e_qps = nq * args.steps / e2e_dt
     if world > 1:
         e2e_pageable_qps = None
+        e2e_sync_qps = None
+        e2e_submission = "torch H2D copy + sharded search + D2H per batch"
+    else:
+        e2e_submission = (f"fvdb_search_submit per batch, fvdb_search_finish every {e2e_pipe}" if e2e_pipe > 1
+                          else "fvdb_search per batch")
     h2d = nq * DIM * 4
     d2h = nq * K * 8 + nq * 4
 
@@ -507,7 +534,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "host_buffers": "page-locked (fvdb_host_alloc)" if world == 1 else "page-locked (torch)",
-                "pageable_value": e2e_pageable_qps},
+                "pageable_value": e2e_pageable_qps, "synchronous_value": e2e_sync_qps,
+                "submission": e2e_submission},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -95,6 +95,8 @@ SIGNATURES = {
     "fvdb_search_device_submit": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
                                      C.c_uint64, _vp, _vp, _vp, _vp]),
     "fvdb_search_device_finish": (C.c_int, [_vp, _vp]),
+    "fvdb_search_submit": (C.c_int, [_vp, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, _f32p, _u32p]),
+    "fvdb_search_finish": (C.c_int, [_vp]),
     "fvdb_coarse_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "fvdb_search_device_coarse": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
                                             C.c_uint64, _vp, _vp, _vp, _vp, _vp]),

@@ -155,7 +155,21 @@ struct fvdb_index {
         uint32_t n_bitmaps;   // tombstone / filter bitmaps read per row (for the algorithmic-bytes figure)
         uint32_t* host;       // page-locked: [16] counter words, [2 nq] IVF fallback ids, [2 nq] flat fallback ids
         size_t host_words;
+        void *ho_ids, *ho_dist, *ho_cnt;   // fvdb_search_submit: the caller's page-locked result buffers (else NULL)
     };
+    // fvdb_search_submit: device-side query / result buffers of the batches in flight and the copy stream
+    // their uploads run on (so that batch i + 1 uploads while batch i is scanned)
+    struct HostSlot {
+        DevBuf<float> q;
+        DevBuf<uint32_t> ids, cnt;
+        DevBuf<float> dist;
+        cudaEvent_t uploaded = nullptr, done = nullptr;
+        bool used = false;
+    };
+    static constexpr int HOST_SLOTS = 4;
+    HostSlot host_slots[HOST_SLOTS];
+    uint32_t host_slot_next = 0;
+    cudaStream_t copy_stream = nullptr;
     std::vector<Pending> pending;
     std::vector<std::pair<uint32_t*, size_t>> pending_pool;   // recycled page-locked blocks
     DevBuf<float> s_fb_q;
@@ -900,7 +914,8 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         // for any number of batches (no GPU idle time between consecutive batches)
         const size_t words = 16 + (size_t)4 * nq;
         fvdb_index::Pending pb{d_q, nq, k, nprobe, tiers, d_filter, filter_bits, d_out_ids, d_out_dist, d_out_count,
-                               used_tc, flat_tc, use_ivf, use_flat, (tomb ? 1u : 0u) + (filt ? 1u : 0u), nullptr, 0};
+                               used_tc, flat_tc, use_ivf, use_flat, (tomb ? 1u : 0u) + (filt ? 1u : 0u), nullptr, 0,
+                               ho ? ho->ids : nullptr, ho ? ho->dist : nullptr, ho ? ho->cnt : nullptr};
         for (size_t i = 0; i < h->pending_pool.size(); ++i)
             if (h->pending_pool[i].second >= words) {
                 pb.host = h->pending_pool[i].first; pb.host_words = h->pending_pool[i].second;
@@ -1044,6 +1059,11 @@ void fvdb_destroy(fvdb_index* h) {
     if (h->pin) cudaFreeHost(h->pin);
     for (auto& pb : h->pending) cudaFreeHost(pb.host);
     for (auto& pp : h->pending_pool) cudaFreeHost(pp.first);
+    for (auto& sl : h->host_slots) {
+        if (sl.uploaded) cudaEventDestroy(sl.uploaded);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
     if (h->ev_s0) cudaEventDestroy(h->ev_s0);
@@ -1441,9 +1461,55 @@ int fvdb_search_device_submit(fvdb_index* h, const float* d_q, uint32_t nq, uint
                               d_out_dist, d_out_count, st, nullptr, nullptr, true);
 }
 
+static int finish_pending(fvdb_index* h, cudaStream_t st);
+
 int fvdb_search_device_finish(fvdb_index* h, void* stream) {
     ENTER(h);
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return finish_pending(h, stream ? (cudaStream_t)stream : h->stream);
+}
+
+// Page-locked host buffers, stream-ordered: the upload of this batch runs on a second stream while the
+// previous batch is still being scanned; the result copies follow the batch on the handle's stream.
+int fvdb_search_submit(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t nprobe, uint32_t tiers,
+                       uint32_t* out_ids, float* out_dist, uint32_t* out_count) {
+    ENTER(h);
+    if (!q || !out_ids || !out_dist || !out_count) return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_search_submit: null buffer");
+    if (!is_pinned_host(q) || !is_pinned_host(out_ids) || !is_pinned_host(out_dist) || !is_pinned_host(out_count))
+        return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_search_submit needs page-locked buffers (fvdb_host_alloc)");
+    if (h->pending.size() >= (size_t)fvdb_index::HOST_SLOTS)
+        return h->fail(FVDB_ERR_INVALID_ARG, "4 host-buffer batches are pending: call fvdb_search_finish");
+    if (nq == 0) return FVDB_OK;
+    cudaStream_t st = h->stream;
+    if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    fvdb_index::HostSlot& sl = h->host_slots[h->host_slot_next++ % fvdb_index::HOST_SLOTS];
+    if (!sl.uploaded) {
+        CK(cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    // growing a buffer frees the old one: no batch of this slot may still be running (pending < 4 slots,
+    // and every earlier batch of this slot was finished, so only the stream order has to be kept)
+    CK(sl.q.ensure((size_t)nq * h->dim, 0, st, &h->dev_bytes));
+    CK(sl.ids.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
+    CK(sl.dist.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
+    CK(sl.cnt.ensure(nq, 0, st, &h->dev_bytes));
+    if (sl.used) CK(cudaStreamWaitEvent(h->copy_stream, sl.done, 0));   // the slot's previous batch has read its queries
+    CK(cudaMemcpyAsync(sl.q.p, q, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(sl.uploaded, h->copy_stream));
+    CK(cudaStreamWaitEvent(st, sl.uploaded, 0));
+    const HostOut ho{out_ids, out_dist, out_count, (size_t)nq * k * 4, (size_t)nq * 4};
+    const int rc = search_device_impl(h, sl.q.p, nq, k, nprobe, tiers, nullptr, 0, sl.ids.p, sl.dist.p, sl.cnt.p, st,
+                                      nullptr, &ho, true);
+    CK(cudaEventRecord(sl.done, st));
+    sl.used = true;
+    return rc;
+}
+
+int fvdb_search_finish(fvdb_index* h) {
+    ENTER(h);
+    return finish_pending(h, h->stream);
+}
+
+static int finish_pending(fvdb_index* h, cudaStream_t st) {
     if (cudaStreamSynchronize(st) != cudaSuccess) { h->pending.clear(); return h->fail(FVDB_ERR_CUDA, "stream synchronisation failed"); }
     int rc = FVDB_OK;
     std::vector<fvdb_index::Pending> todo;
@@ -1483,6 +1549,10 @@ int fvdb_search_device_finish(fvdb_index* h, void* stream) {
                 if (r3 != FVDB_OK) return r3;
                 CK(launch_scatter_result_rows(t_ids, t_dist, t_cnt, reinterpret_cast<const uint32_t*>(h->s_fb_coarse.p), m,
                                               pb.k, pb.d_out_ids, pb.d_out_dist, pb.d_out_count, st));
+                if (pb.ho_ids) {
+                    const HostOut ho2{pb.ho_ids, pb.ho_dist, pb.ho_cnt, (size_t)pb.nq * pb.k * 4, (size_t)pb.nq * 4};
+                    CK(copy_out(&ho2, pb.d_out_ids, pb.d_out_dist, pb.d_out_count, st));
+                }
                 CK(cudaStreamSynchronize(st));
                 return FVDB_OK;
             }();

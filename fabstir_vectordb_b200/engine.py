@@ -282,6 +282,22 @@ class Engine:
                                        _p(ids, _u32p), _p(dist, _f32p), _p(cnt, _u32p)))
         return ids, dist, cnt
 
+    def search_submit(self, queries: np.ndarray, k: int, nprobe: int, tiers: int, out):
+        """Stream-ordered fvdb_search: `queries` and `out` = (ids, dist, count) must be views of PinnedArray
+        buffers; they belong to the engine until search_finish() returns."""
+        nq = queries.shape[0]
+        ids, dist, cnt = out
+        if queries.dtype != np.float32 or queries.ndim != 2 or queries.shape[1] != self.dim or not queries.flags.c_contiguous:
+            raise ValueError("queries must be a contiguous f32 [nq, dim] array")
+        if ids.shape != (nq, k) or dist.shape != (nq, k) or cnt.shape != (nq,) or ids.dtype != np.uint32 \
+                or dist.dtype != np.float32 or cnt.dtype != np.uint32:
+            raise ValueError("out must be (u32 [nq,k], f32 [nq,k], u32 [nq])")
+        self._ck(self._lib.fvdb_search_submit(self._h, _p(queries, _f32p), nq, k, nprobe, tiers,
+                                              _p(ids, _u32p), _p(dist, _f32p), _p(cnt, _u32p)))
+
+    def search_finish(self):
+        self._ck(self._lib.fvdb_search_finish(self._h))
+
     def search_device(self, d_q: int, nq: int, k: int, nprobe: int, tiers: int, d_filter: int,
                       filter_nbits: int, d_out_ids: int, d_out_dist: int, d_out_count: int,
                       stream: int = 0):

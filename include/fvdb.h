@@ -251,6 +251,14 @@ int fvdb_search_device_submit(fvdb_index *h, const float *d_q, uint32_t nq, uint
                               uint32_t *d_out_count, void *stream);
 int fvdb_search_device_finish(fvdb_index *h, void *stream);
 
+/* The same pair for HOST buffers, which must be page-locked (fvdb_host_alloc; else
+ * FVDB_ERR_INVALID_ARG): the upload of a batch runs on a second stream while the previous batch is
+ * still being scanned, the result copies follow the batch.  At most 4 batches may be pending; query
+ * and result buffers belong to the library until fvdb_search_finish returns.  No filter bitmap. */
+int fvdb_search_submit(fvdb_index *h, const float *q, uint32_t nq, uint32_t k, uint32_t nprobe,
+                       uint32_t tiers, uint32_t *out_ids, float *out_dist, uint32_t *out_count);
+int fvdb_search_finish(fvdb_index *h);
+
 /* The coarse step alone (src/ivf/core.rs:646-656) for nq device-resident queries:
  * d_out_keys [nq x nprobe] = (f32 bits of the exact centroid distance << 32) | list id, ascending,
  * ties to the lower list id (the reference's stable sort).  1 <= nprobe <= nlist.  Used by the

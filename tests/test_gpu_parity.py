@@ -673,3 +673,28 @@ def test_stream_ordered_submit_finish(mode):
     want = O.hybrid_batch_search(ivf, None, None, qs[0], k, nprobe, tiers=2)
     _assert_same(outs[0][0].cpu().numpy().view(np.uint32), outs[0][1].cpu().numpy(), outs[0][2].cpu().numpy().view(np.uint32), *want)
     eng.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_host_buffer_submit_finish(mode):
+    """fvdb_search_submit x N + fvdb_search_finish with page-locked buffers == N fvdb_search calls (the upload of
+    a batch overlaps the scan of the one before); pageable buffers are refused."""
+    from fabstir_vectordb_b200 import FvdbError, PinnedArray
+    d, n, nlist, nq, k, nprobe = 128, 8000, 20, 64, 10, 5
+    eng, ivf, x, cents, _, _ = _build(n, d, nlist, 61, mode)
+    qs = [_queries(nq, d, n, 200 + i) for i in range(6)]
+    pq = [PinnedArray((nq, d), np.float32) for _ in qs]
+    po = [(PinnedArray((nq, k), np.uint32), PinnedArray((nq, k), np.float32), PinnedArray((nq,), np.uint32)) for _ in qs]
+    for a, q_ in zip(pq, qs):
+        a.array[...] = q_
+    for rnd in range(2):          # two rounds: the slots and their device buffers are reused
+        for i in range(3 * rnd, 3 * rnd + 3):
+            eng.search_submit(pq[i].array, k, nprobe, L.TIER_HISTORICAL, tuple(b.array for b in po[i]))
+        eng.search_finish()
+    for i, q_ in enumerate(qs):
+        want = O.hybrid_batch_search(ivf, None, None, q_, k, nprobe, tiers=2)
+        _assert_same(po[i][0].array, po[i][1].array, po[i][2].array, *want)
+    with pytest.raises(FvdbError):
+        eng.search_submit(qs[0], k, nprobe, L.TIER_HISTORICAL, tuple(b.array for b in po[0]))   # pageable queries
+    eng.search_finish()           # nothing pending: a no-op
+    eng.close()
