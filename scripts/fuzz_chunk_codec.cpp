@@ -1,5 +1,5 @@
 // Mutation fuzzer for fvdb_chunk_decode (host code only).  Build and run from scripts/:
-//   g++ -std=c++17 -O1 -g -fsanitize=address,undefined -x c++ ../fabstir_vectordb_b200/csrc/chunk_codec.cu fuzz_chunk_codec.cpp -o /tmp/fuzz_chunk \&\& /tmp/fuzz_chunk
+//   g++ -std=c++17 -O1 -g -fsanitize=address,undefined -x c++ ../fabstir_vectordb_b200/csrc/chunk_codec.cu fuzz_chunk_codec.cpp -o /tmp/fuzz_chunk && /tmp/fuzz_chunk
 // 3 M mutated chunks (byte flips, truncations, insertions, CBOR control bytes): no sanitizer report, every
 // accepted input decodes identically in the sizing pass and the filling pass.
 #include <cstdio>
