@@ -198,3 +198,23 @@ def test_capacity_and_argument_errors():
     small = np.zeros(10, np.uint8)
     rc = lib.fvdb_chunk_encode(b"c", 0, 2, ids.ctypes.data, rows.ctypes.data, 3, 8, small.ctypes.data, small.size, C.byref(need))
     assert rc == L.ERR_INVALID_ARG and need.value == len(data)
+
+
+# ---- committed fixtures (tests/golden/vector_chunk_*.cbor, made by tests/golden/make_chunk_fixture.py) ----
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_committed_chunk_fixtures(name):
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    data = open(os.path.join(gold, f"vector_chunk_{name}.cbor"), "rb").read()
+    z = np.load(os.path.join(gold, "vector_chunk.npz"))
+    ids, rows = z[f"{name}_ids"], z[f"{name}_rows"]
+    start, end = (int(v) for v in z[f"{name}_meta"])
+    cid = bytes(z[f"{name}_chunk_id"]).decode()
+    ch = decode_vector_chunk(data)                      # native reader
+    assert (ch.chunk_id, ch.start_idx, ch.end_idx) == (cid, start, end)
+    assert np.array_equal(ch.ids, ids) and _same_bits(ch.rows, rows)
+    o = O.decode_chunk(data)                            # oracle reader
+    assert o[:3] == (cid, start, end) and np.array_equal(o[3], ids) and _same_bits(o[4], rows)
+    if name != "c":                                     # canonical spelling: both writers reproduce the bytes
+        assert encode_vector_chunk(cid, start, end, ids, rows) == data
+        assert O.encode_chunk(cid, start, end, ids, rows) == data
