@@ -23,7 +23,7 @@ SO = os.path.join(HERE, f"libfvdb_b200{_TAG}.so")
 STAMP = os.path.join(HERE, f".libfvdb_b200{_TAG}.stamp")
 
 SOURCES = ["engine.cu", "exact_scan.cu", "layout.cu", "kmeans.cu", "tc_scan.cu", "synth.cu", "chunk_codec.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "tc_scan.cuh", "tc_ptx.cuh", "tc_scan_pair.cuh"]
+HEADERS = ["common.cuh", "kernels.cuh", "tc_scan.cuh", "tc_ptx.cuh", "tc_scan_wide.cuh"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

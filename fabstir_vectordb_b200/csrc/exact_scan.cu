@@ -349,114 +349,129 @@ __device__ __forceinline__ uint64_t block_excl_scan_u64(uint64_t v, uint64_t* wa
     return r;
 }
 
-// One CTA: per-list pair offsets and the work-item table.  Lists that are the NEAREST list of
+// One CTA: per-list pair offsets and the work-item table(s).  Lists that are the NEAREST list of
 // at least one query come first in the item order (their scan tightens that query's threshold
 // for every other list); items of one list stay adjacent so a re-read hits L2.
+// Two tables when wide_min > 0: lists probed by at least wide_min queries go to `items_w` (query
+// groups of tile_q_w: the wide-tile scan kernel), the others to `items` (groups of tile_q).
 __global__ void __launch_bounds__(1024) probe_scan_kernel(const uint32_t* __restrict__ list_cnt,
                                   const uint32_t* __restrict__ list_off,
                                   const uint32_t* __restrict__ list_order, uint32_t nlist,
                                   uint32_t tile_q, uint32_t* __restrict__ pair_off,
                                   uint32_t* __restrict__ cursor, ScanItem* __restrict__ items,
                                   uint32_t* __restrict__ n_items, uint64_t* __restrict__ scanned_rows,
-                                  bool order_near, uint32_t rows_cap) {
+                                  bool order_near_in, uint32_t rows_cap, uint32_t wide_min, uint32_t tile_q_w,
+                                  ScanItem* __restrict__ items_w, uint32_t* __restrict__ n_items_w, bool wide_longest_first) {
     __shared__ uint64_t warp_tot[33];
     const int t = threadIdx.x;
     uint64_t my_rows = 0;
-    // offsets and items.  g = 0: the nearest-first group in list order; g = 1: the other
-    // lists, longest first when list_order is given — the dynamic tile scheduler then ends with
-    // the cheapest items, which keeps the tail of the scan short.  (Ordering the nearest group by
-    // length as well starts every CTA on the most popular lists with cold thresholds: measured
-    // 20 % more work.)
-    uint64_t carry = 0;
-    for (int g = 0; g < 2; ++g) {
-        for (uint32_t base = 0; base < nlist; base += 1024) {
-            const uint32_t l = (base + t < nlist) ? (((g || order_near) && list_order) ? list_order[base + t] : base + t) : nlist;
-            uint32_t c = 0, len = 0;
-            if (l < nlist) {
-                const uint32_t raw = list_cnt[l];
-                len = list_off[l + 1] - list_off[l];
-                c = len ? (raw & ~NEAREST_BIT) : 0u;
-                if (((raw & NEAREST_BIT) != 0) != (g == 0)) c = 0;   // not this group's list
-            }
-            const uint32_t ni = (c + tile_q - 1) / tile_q;
-            // a long list is cut into ns row ranges of at most rows_cap rows: ns items per query group,
-            // each with its own shortlist slot (ScanItem::sub), so that no single item is a long tail.
-            // Nearest-first group: only the FIRST range here, the others follow below.  Other lists
-            // (bounds already tight when they start): all ranges, adjacent.
-            const uint32_t ns = (rows_cap && len > rows_cap) ? (len + rows_cap - 1) / rows_cap : 1u;
-            const uint32_t ns_here = g ? ns : 1u;
-            const uint64_t v = ((uint64_t)(ni * ns_here) << 32) | c;
-            uint64_t tot;
-            const uint64_t ex = block_excl_scan_u64(v, warp_tot, &tot);
-            if (c > 0) {
-                const uint64_t off = carry + ex;
-                const uint32_t p_excl = (uint32_t)off, i_excl = (uint32_t)(off >> 32);
-                pair_off[l] = p_excl;
-                cursor[l] = p_excl;
-                for (uint32_t j = 0; j < ni; ++j) {
-                    for (uint32_t sb = 0; sb < ns_here; ++sb) {
-                        ScanItem it;
-                        it.row_begin = list_off[l] + (ns > 1 ? sb * rows_cap : 0u);
-                        it.row_end = (ns > 1) ? min(list_off[l + 1], it.row_begin + rows_cap) : list_off[l + 1];
-                        it.pair_begin = p_excl + j * tile_q;
-                        it.pair_count = min(tile_q, c - j * tile_q);
-                        it.slot = ni;  // query groups sharing this list (the TC scan keeps such lists in L2)
-                        it.identity = 0;
-                        it.sub = sb;
-                        items[i_excl + j * ns_here + sb] = it;
-                    }
-                }
-                my_rows += len;
-            }
-            carry += tot;
-        }
-        if (g == 0 && rows_cap) {
-            // the further row ranges of the nearest-first lists, range by range, behind every first
-            // range: by the time range s of a list starts, its range s - 1 has been scanned for a while
-            // and has published the queries' bounds (ranges that start together all start cold:
-            // measured 5 % more work).  The cheap far lists still come last.
-            for (uint32_t sb = 1; sb < 64; ++sb) {
-                uint32_t any = 0;
-                for (uint32_t base = 0; base < nlist; base += 1024) {
-                    const uint32_t l = (base + t < nlist) ? ((order_near && list_order) ? list_order[base + t] : base + t) : nlist;
-                    uint32_t c = 0, len = 0;
-                    if (l < nlist) {
-                        const uint32_t raw = list_cnt[l];
-                        len = list_off[l + 1] - list_off[l];
-                        c = (len && (raw & NEAREST_BIT)) ? (raw & ~NEAREST_BIT) : 0u;
-                    }
-                    const uint32_t ns = (len > rows_cap) ? (len + rows_cap - 1) / rows_cap : 1u;
-                    const uint32_t ni = (c && sb < ns) ? (c + tile_q - 1) / tile_q : 0u;
-                    uint64_t tot;
-                    const uint64_t ex = block_excl_scan_u64(ni, warp_tot, &tot);
-                    if (ni) {
-                        const uint32_t p_excl = pair_off[l];
-                        const uint32_t i0 = (uint32_t)(carry >> 32) + (uint32_t)ex;
-                        for (uint32_t j = 0; j < ni; ++j) {
+    uint64_t pair_carry = 0;   // pairs placed so far (both tables share the pair arrays)
+    for (int tbl = 0; tbl < (wide_min ? 2 : 1); ++tbl) {
+        // tbl 0 (when two tables): the wide table, so that its pairs come first
+        const bool wide = wide_min && tbl == 0;
+        const uint32_t tq = wide ? tile_q_w : tile_q;
+        ScanItem* out = wide ? items_w : items;
+        const bool order_near = order_near_in || (wide && wide_longest_first);
+        // offsets and items.  g = 0: the nearest-first group in list order; g = 1: the other
+        // lists, longest first when list_order is given — the dynamic tile scheduler then ends with
+        // the cheapest items, which keeps the tail of the scan short.  (Ordering the nearest group by
+        // length as well starts every CTA on the most popular lists with cold thresholds: measured
+        // 20 % more work.)
+        uint64_t carry = pair_carry;   // (items << 32) | pairs
+        auto mine = [&](uint32_t l, uint32_t& c, uint32_t& len, bool& nearest) {
+            c = 0; len = 0; nearest = false;
+            if (l >= nlist) return;
+            const uint32_t raw = list_cnt[l];
+            len = list_off[l + 1] - list_off[l];
+            c = len ? (raw & ~NEAREST_BIT) : 0u;
+            nearest = (raw & NEAREST_BIT) != 0;
+            if (wide_min && ((c >= wide_min) != wide)) c = 0;   // the other table's list
+        };
+        for (int g = 0; g < 2; ++g) {
+            for (uint32_t base = 0; base < nlist; base += 1024) {
+                const uint32_t l = (base + t < nlist) ? (((g || order_near) && list_order) ? list_order[base + t] : base + t) : nlist;
+                uint32_t c, len;
+                bool nearest;
+                mine(l, c, len, nearest);
+                if (nearest != (g == 0)) c = 0;   // not this group's list
+                const uint32_t ni = (c + tq - 1) / tq;
+                // a long list is cut into ns row ranges of at most rows_cap rows: ns items per query group,
+                // each with its own shortlist slot (ScanItem::sub), so that no single item is a long tail.
+                // Nearest-first group: only the FIRST range here, the others follow below.  Other lists
+                // (bounds already tight when they start): all ranges, adjacent.
+                const uint32_t ns = (rows_cap && len > rows_cap) ? (len + rows_cap - 1) / rows_cap : 1u;
+                const uint32_t ns_here = g ? ns : 1u;
+                const uint64_t v = ((uint64_t)(ni * ns_here) << 32) | c;
+                uint64_t tot;
+                const uint64_t ex = block_excl_scan_u64(v, warp_tot, &tot);
+                if (c > 0) {
+                    const uint64_t off = carry + ex;
+                    const uint32_t p_excl = (uint32_t)off, i_excl = (uint32_t)(off >> 32);
+                    pair_off[l] = p_excl;
+                    cursor[l] = p_excl;
+                    for (uint32_t j = 0; j < ni; ++j) {
+                        for (uint32_t sb = 0; sb < ns_here; ++sb) {
                             ScanItem it;
-                            it.row_begin = list_off[l] + sb * rows_cap;
-                            it.row_end = min(list_off[l + 1], it.row_begin + rows_cap);
-                            it.pair_begin = p_excl + j * tile_q;
-                            it.pair_count = min(tile_q, c - j * tile_q);
-                            it.slot = ni;
+                            it.row_begin = list_off[l] + (ns > 1 ? sb * rows_cap : 0u);
+                            it.row_end = (ns > 1) ? min(list_off[l + 1], it.row_begin + rows_cap) : list_off[l + 1];
+                            it.pair_begin = p_excl + j * tq;
+                            it.pair_count = min(tq, c - j * tq);
+                            it.slot = ni;  // query groups sharing this list (the TC scan keeps such lists in L2)
                             it.identity = 0;
                             it.sub = sb;
-                            items[i0 + j] = it;
+                            out[i_excl + j * ns_here + sb] = it;
                         }
                     }
-                    carry += tot << 32;
-                    any += (uint32_t)tot;
+                    my_rows += len;
                 }
-                if (any == 0) break;   // block-uniform: no list has this many ranges
+                carry += tot;
+            }
+            if (g == 0 && rows_cap) {
+                // the further row ranges of the nearest-first lists, range by range, behind every first
+                // range: by the time range s of a list starts, its range s - 1 has been scanned for a while
+                // and has published the queries' bounds (ranges that start together all start cold:
+                // measured 5 % more work).  The cheap far lists still come last.
+                for (uint32_t sb = 1; sb < 64; ++sb) {
+                    uint32_t any = 0;
+                    for (uint32_t base = 0; base < nlist; base += 1024) {
+                        const uint32_t l = (base + t < nlist) ? ((order_near && list_order) ? list_order[base + t] : base + t) : nlist;
+                        uint32_t c, len;
+                        bool nearest;
+                        mine(l, c, len, nearest);
+                        if (!nearest) c = 0;
+                        const uint32_t ns = (len > rows_cap) ? (len + rows_cap - 1) / rows_cap : 1u;
+                        const uint32_t ni = (c && sb < ns) ? (c + tq - 1) / tq : 0u;
+                        uint64_t tot;
+                        const uint64_t ex = block_excl_scan_u64(ni, warp_tot, &tot);
+                        if (ni) {
+                            const uint32_t p_excl = pair_off[l];
+                            const uint32_t i0 = (uint32_t)(carry >> 32) + (uint32_t)ex;
+                            for (uint32_t j = 0; j < ni; ++j) {
+                                ScanItem it;
+                                it.row_begin = list_off[l] + sb * rows_cap;
+                                it.row_end = min(list_off[l + 1], it.row_begin + rows_cap);
+                                it.pair_begin = p_excl + j * tq;
+                                it.pair_count = min(tq, c - j * tq);
+                                it.slot = ni;
+                                it.identity = 0;
+                                it.sub = sb;
+                                out[i0 + j] = it;
+                            }
+                        }
+                        carry += tot << 32;
+                        any += (uint32_t)tot;
+                    }
+                    if (any == 0) break;   // block-uniform: no list has this many ranges
+                }
             }
         }
+        if (t == 0) *(wide ? n_items_w : n_items) = (uint32_t)(carry >> 32);
+        pair_carry = carry & 0xFFFFFFFFull;
     }
-    const uint64_t carry_far = carry;
     uint64_t rows_total;
     block_excl_scan_u64(my_rows, warp_tot, &rows_total);
     if (t == 0) {
-        pair_off[nlist] = (uint32_t)carry_far;
-        *n_items = (uint32_t)(carry_far >> 32);
+        pair_off[nlist] = (uint32_t)pair_carry;
         if (scanned_rows) *scanned_rows = rows_total;
     }
 }
@@ -481,16 +496,20 @@ cudaError_t launch_probe_bucketing(const uint64_t* coarse_keys, uint32_t nq, uin
                                    uint32_t* list_cnt, uint32_t* pair_off, uint32_t* cursor,
                                    uint32_t* pair_q, uint32_t* pair_slot, ScanItem* items,
                                    uint32_t* n_items, uint64_t* scanned_rows, cudaStream_t stream,
-                                   const uint32_t* list_order, bool order_near, uint32_t rows_cap) {
+                                   const uint32_t* list_order, bool order_near, uint32_t rows_cap,
+                                   uint32_t wide_min, uint32_t tile_q_w, ScanItem* items_w, uint32_t* n_items_w,
+                                   bool wide_longest_first) {
     const uint32_t n_pairs = nq * nprobe;
     cudaError_t e = cudaMemsetAsync(list_cnt, 0, sizeof(uint32_t) * nlist, stream);
     if (e != cudaSuccess) return e;
     if (n_pairs == 0) {
+        if (wide_min) { e = cudaMemsetAsync(n_items_w, 0, sizeof(uint32_t), stream); if (e != cudaSuccess) return e; }
         return cudaMemsetAsync(n_items, 0, sizeof(uint32_t), stream);
     }
     probe_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, nprobe, list_cnt);
     probe_scan_kernel<<<1, 1024, 0, stream>>>(list_cnt, list_off, list_order, nlist, tile_q, pair_off, cursor,
-                                              items, n_items, scanned_rows, order_near, rows_cap);
+                                              items, n_items, scanned_rows, order_near, rows_cap, wide_min, tile_q_w,
+                                              items_w, n_items_w, wide_longest_first);
     probe_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(coarse_keys, n_pairs, nprobe,
                                                                    list_off, cursor, pair_q,
                                                                    pair_slot);

@@ -116,11 +116,6 @@ constexpr int R2_NBUF = 8;                       // accumulator buffers of R2_NQ
 constexpr int R2_NSLOT = FVDB_R2_NSLOT;          // |x|^2 strips in flight
 constexpr int R2_SLACK = FVDB_R2_SLACK;          // bytes reserved for aligning the dynamic shared memory to 1024 (0: trap if it is not)
 static_assert(R2_CAP <= 32 && R2_FLUSH < R2_CAP && R2_NSLOT > R2_NBUF + 2, "kernel R pools");
-// offloaded merges (tc_scan_kernel_t<true>): the pending pool is split into two halves that alternate by
-// tile, so the merge warps fold tile t while the epilogue warps compare tile t + 1
-constexpr int RO_CAP = R2_CAP / 2;               // pending candidates per query and half
-constexpr int RO_FLUSH = RO_CAP / 2;
-static_assert(2 * RO_CAP <= 32, "the final fold sorts both halves in one 32-lane network");
 constexpr int R2_THREADS = 320;
 constexpr uint32_t TC_SPLIT_MAX = 4;          // row ranges a long posting list is split into, at most
 constexpr uint32_t TC_SPLIT_MIN_ROWS = 2048;  // lists up to this length are never split
@@ -218,53 +213,12 @@ __device__ __forceinline__ void publish_bound(const TcScanParams& p, uint32_t qi
     }
 }
 
-// Stage the query tile of an item: warp lw stages queries lw, lw+4, ...; a lane moves float4 columns
-// lane, lane+32, ...; loads of four query rows are issued before any store (12 LDG.128 per lane in
-// flight).  Lane l of every loader warp holds the indices of queries l and l + 32 in qi0 / qi1.
-__device__ __forceinline__ void r2_load_queries(const R2Smem& sm, const TcScanParams& p, uint32_t qi0, uint32_t qi1,
-                                                uint32_t ncols, int lw, int lane, uint32_t KB, uint32_t D) {
-    const uint32_t f4_per_row = KB * 8;
-    for (uint32_t q0 = lw; q0 < ncols; q0 += 16) {
-        const float4* src[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const uint32_t q = q0 + 4 * g;
-            const uint32_t qa = __shfl_sync(0xffffffffu, qi0, q & 31), qb = __shfl_sync(0xffffffffu, qi1, q & 31);
-            const uint32_t qi = (q < 32) ? qa : qb;
-            src[g] = (q < ncols && qi != ID_NONE) ? reinterpret_cast<const float4*>(p.Q + (size_t)qi * D) : nullptr;
-        }
-        for (uint32_t c = lane; c < f4_per_row; c += 96) {
-            float4 v[3][4];
-#pragma unroll
-            for (int u = 0; u < 3; ++u)
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    v[u][g] = (src[g] && c + 32 * u < f4_per_row) ? __ldg(src[g] + c + 32 * u)
-                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const uint32_t cc = c + 32 * u;
-                if (cc >= f4_per_row) break;
-                const uint32_t kb = cc >> 3, ch = cc & 7;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const uint32_t q = q0 + 4 * g;
-                    if (q < ncols)
-                        *reinterpret_cast<float4*>(sm.q_tile + (size_t)kb * R2_QBLK_BYTES + q * 128 +
-                                                   ((ch ^ (q & 7)) << 4)) = v[u][g];
-                }
-            }
-        }
-    }
-}
-
 // stopwatch lap: the cycles since the previous lap of this role are charged to category i
 #define Q1_LAP(i) do { if (p.prof) { const long long n_ = clock64(); lap[i] += (unsigned long long)(n_ - tl); tl = n_; } } while (0)
 #define Q1_LAP_DUMP(role) do { if (p.prof && lane == 0) { for (int i_ = 0; i_ < 8; ++i_) p.prof[((size_t)blockIdx.x * 6 + (role)) * 8 + i_] = lap[i_]; } } while (0)
 
-template <bool OFF>   // OFF: the loader warps also fold the pending candidates (merges off the epilogue's path)
 __global__ void __launch_bounds__(R2_THREADS, 1)
-tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
+tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -284,16 +238,8 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
     const uint32_t bar_qready = bar_sempty + 8 * TC_SCHED;  // query tile + item metadata staged
     const uint32_t bar_qfree = bar_qready + 8;              // every MMA of the item has retired
     const uint32_t bar_mfree = bar_qfree + 8;               // epilogue is done with an item's metadata
-    const uint32_t bar_pfull = bar_mfree + 8;               // [2] OFF: every candidate of a round is in the pending half
-    const uint32_t bar_pfree = bar_pfull + 16;              // [2] OFF: the merge warps are done with the half
-    const uint32_t bar_idone = bar_pfree + 16;              // OFF: the item's shortlists are published
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(bar_pfull + 8 * i, 4);
-            mbar_init(bar_pfree + 8 * i, 4);
-        }
-        mbar_init(bar_idone, 4);
         for (int i = 0; i < 8; ++i) sm.redo[i] = 0;
         for (uint32_t s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
@@ -463,227 +409,6 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
         const int lw = warp - 6;
         const int lt = lw * 32 + lane;
         const uint32_t D = p.D;
-        if constexpr (OFF) {
-            // ===== loader + MERGE warps.  Job n = the n-th non-empty item of this CTA.  Load side: as in the
-            // classic variant.  Merge side: for every tile of the job, in rounds on the pending half
-            // (tile & 1): wait for the epilogue's `pfull`, fold the owned queries (j % 4 == lw) that hold
-            // more than RO_FLUSH pending, tighten / share their bounds, arrive on `pfree`.  A round that
-            // saw an overflow (redo mask) is followed by another round on the same half (the epilogue
-            // replays the rows it could not store).  Every wait of the load side services merge rounds.
-            const uint32_t jown = (uint32_t)lane * 4u + (uint32_t)lw;
-            uint32_t j_load = 0, j_done = 0;
-            uint32_t job_cnt0 = 0, job_cnt1 = 0, job_tiles0 = 0, job_tiles1 = 0, job_sub0 = 0, job_sub1 = 0;
-            uint32_t mt = 0, g_tile = 0, mround0 = 0, mround1 = 0, st_merge = 0;
-            bool job_open = false, own = false;
-            uint32_t qi_own = 0, thr_pending = F32_INF_BITS, peer_sent = F32_INF_BITS;
-            float qn_own = 0.f;
-
-            auto merge_owned = [&](unsigned need, uint32_t b) {
-                const uint64_t* pend = sm.pend + (size_t)b * R2_NQ * RO_CAP;
-                uint32_t* pcnt = sm.pcnt + b * R2_NQ;
-                st_merge += __popc(need);
-                if (__popc(need) == 1) {
-                    const int src = __ffs(need) - 1;
-                    const uint32_t q = (uint32_t)src * 4u + (uint32_t)lw;
-                    const uint32_t n = min(pcnt[q], (uint32_t)RO_CAP);
-                    uint64_t nw = ((uint32_t)lane < n) ? pend[q * RO_CAP + lane] : KEY_NONE;
-                    uint64_t lst = sm.sorted[q * TC_KP + lane];
-                    nw = warp_sort32(nw, lane);
-                    lst = warp_merge32(lst, nw, lane);
-                    sm.sorted[q * TC_KP + lane] = lst;
-                    const uint64_t last = shfl64(lst, 31);
-                    __syncwarp();
-                    if (lane == src) {
-                        pcnt[q] = 0;
-                        if (last != KEY_NONE) {
-                            sm.thrp[q] = fminf(sm.thrp[q], __uint_as_float((uint32_t)(last >> 32)) - qn_own);
-                            if (p.thr_g) publish_bound(p, qi_own, (uint32_t)(last >> 32), peer_sent);
-                        }
-                    }
-                    __syncwarp();
-                    return;
-                }
-                while (need) {
-                    uint32_t qs[4], nn[4];
-                    bool act[4];
-                    int src[4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        act[g] = need != 0;
-                        src[g] = act[g] ? (__ffs(need) - 1) : 0;
-                        if (act[g]) need &= need - 1;
-                        qs[g] = (uint32_t)src[g] * 4u + (uint32_t)lw;
-                        nn[g] = act[g] ? min(pcnt[qs[g]], (uint32_t)RO_CAP) : 0u;
-                    }
-                    uint64_t lst[4];
-                    r2_merge4(sm, qs, nn, act, lst, lane, pend, (uint32_t)RO_CAP);
-                    __syncwarp();
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (!act[g]) continue;
-                        sm.sorted[qs[g] * TC_KP + lane] = lst[g];
-                        const uint64_t last = shfl64(lst[g], 31);
-                        if (lane == src[g]) {
-                            pcnt[qs[g]] = 0;
-                            if (last != KEY_NONE) {
-                                sm.thrp[qs[g]] = fminf(sm.thrp[qs[g]], __uint_as_float((uint32_t)(last >> 32)) - qn_own);
-                                if (p.thr_g) publish_bound(p, qi_own, (uint32_t)(last >> 32), peer_sent);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-            };
-
-            // one merge round if the epilogue has posted one; false when there is nothing to do right now
-            auto service = [&]() -> bool {
-                if (j_done == j_load) return false;
-                const uint32_t b = g_tile & 1u;
-                const uint32_t mr = b ? mround1 : mround0;
-                if (!__all_sync(0xffffffffu, mbar_test(bar_pfull + 8 * b, mr & 1u) ? 1 : 0)) return false;
-                const uint32_t jb = j_done & 1u;
-                const uint32_t cnt = jb ? job_cnt1 : job_cnt0;
-                const uint32_t mb = jb * R2_NQ;
-                if (!job_open) {
-                    for (uint32_t j = (uint32_t)lw; j < (uint32_t)R2_NQ; j += 4) sm.sorted[j * TC_KP + lane] = KEY_NONE;
-                    own = lane < R2_NQ / 4 && jown < cnt;
-                    qi_own = own ? sm.qidx[mb + jown] : 0u;
-                    qn_own = own ? sm.qn[mb + jown] : 0.f;
-                    thr_pending = F32_INF_BITS;
-                    peer_sent = F32_INF_BITS;
-                    job_open = true;
-                    mt = 0;
-                    __syncwarp();
-                }
-                const uint32_t par = mr & 1u;
-                const uint32_t r0 = sm.redo[b * 4 + par * 2], r1 = sm.redo[b * 4 + par * 2 + 1];
-                __syncwarp();
-                if (lw == 0 && lane < 2) sm.redo[b * 4 + (par ^ 1u) * 2 + lane] = 0;   // the next round's mask
-                if (own) {
-                    // bound tightened meanwhile by CTAs scanning other lists of the same query
-                    sm.thrp[jown] = fminf(sm.thrp[jown], __uint_as_float(thr_pending) - qn_own);
-                    if (p.thr_g) thr_pending = *(volatile uint32_t*)(p.thr_g + qi_own);
-                }
-                const uint32_t pc = own ? sm.pcnt[b * R2_NQ + jown] : 0u;
-                merge_owned(__ballot_sync(0xffffffffu, pc > (uint32_t)RO_FLUSH), b);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_pfree + 8 * b);
-                if (b) ++mround1; else ++mround0;
-                if ((r0 | r1) == 0) {      // the tile is complete
-                    ++g_tile;
-                    ++mt;
-                    if (mt == (jb ? job_tiles1 : job_tiles0)) {
-                        // ---- job epilogue: fold what is pending in both halves, publish the shortlists.  A
-                        // query that never merged publishes its pending candidates UNSORTED (the shortlist
-                        // merge after the scan sorts such rows).
-                        for (uint32_t j = (uint32_t)lw; j < cnt; j += 4) {
-                            const uint32_t n0 = min(sm.pcnt[j], (uint32_t)RO_CAP), n1 = min(sm.pcnt[R2_NQ + j], (uint32_t)RO_CAP);
-                            const uint64_t lst = sm.sorted[j * TC_KP + lane];
-                            const bool has_sorted = __shfl_sync(0xffffffffu, lst != KEY_NONE ? 1 : 0, 0) != 0;
-                            if (n0 + n1 == 0 && !has_sorted) continue;      // partial is pre-filled
-                            uint64_t nw = KEY_NONE;
-                            if (lane < RO_CAP) { if ((uint32_t)lane < n0) nw = sm.pend[j * RO_CAP + lane]; }
-                            else if ((uint32_t)(lane - RO_CAP) < n1) nw = sm.pend[(size_t)(R2_NQ + j) * RO_CAP + (lane - RO_CAP)];
-                            uint64_t out = nw;
-                            if (has_sorted) {
-                                out = lst;
-                                if (n0 + n1) {
-                                    nw = warp_sort32(nw, lane);
-                                    out = warp_merge32(lst, nw, lane);
-                                    if (p.thr_g && lane == 31 && out != KEY_NONE) atomicMin(p.thr_g + sm.qidx[mb + j], (uint32_t)(out >> 32));
-                                }
-                            }
-                            const size_t prow = ((size_t)sm.qidx[mb + j] * p.P + sm.qslot[mb + j]) * (p.S ? p.S : 1u) + (jb ? job_sub1 : job_sub0);
-                            p.partial[prow * TC_KP + lane] = out;
-                            if (lane == 0) p.row_stamp[prow] = p.stamp;
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_idone);
-                        ++j_done;
-                        job_open = false;
-                    }
-                }
-                return true;
-            };
-            // wait on a barrier of the load side, folding pending candidates meanwhile
-            auto wait_serv = [&](uint32_t bar, uint32_t parity) {
-                long long t0 = 0;
-                bool timed = false;
-                while (!__all_sync(0xffffffffu, mbar_test(bar, parity) ? 1 : 0)) {
-                    if (service()) { timed = false; continue; }
-                    if (!timed) { t0 = clock64(); timed = true; }
-                    else if (clock64() - t0 > 4000000000ll) __trap();
-                }
-            };
-            auto drain_until = [&](uint32_t jobs_done) {
-                long long t0 = 0;
-                bool timed = false;
-                while (j_done < jobs_done) {
-                    if (service()) { timed = false; continue; }
-                    if (!timed) { t0 = clock64(); timed = true; }
-                    else if (clock64() - t0 > 4000000000ll) __trap();
-                }
-            };
-
-            uint32_t ss = 0, sphase = 0, nit = 0;
-            while (true) {
-                Q1_LAP(3);
-                wait_serv(bar_sfull + 8 * ss, sphase);
-                const uint32_t item = sm.sched[ss];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
-                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
-                Q1_LAP(0);
-                if (item == ITEM_END) break;
-                const ScanItem it = p.items[item];
-                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
-                const uint32_t cnt = it.pair_count;
-                const uint32_t ncols = (cnt + 15u) & ~15u;
-                uint32_t qi0 = ID_NONE, qi1 = ID_NONE, sl0 = 0, sl1 = 0;
-                if ((uint32_t)lane < cnt) {
-                    if (it.identity) { qi0 = it.pair_begin + lane; sl0 = it.slot; }
-                    else { qi0 = p.pair_q[it.pair_begin + lane]; sl0 = p.pair_slot[it.pair_begin + lane]; }
-                }
-                if ((uint32_t)lane + 32 < cnt) {
-                    if (it.identity) { qi1 = it.pair_begin + lane + 32; sl1 = it.slot; }
-                    else { qi1 = p.pair_q[it.pair_begin + lane + 32]; sl1 = p.pair_slot[it.pair_begin + lane + 32]; }
-                }
-                // metadata buffer and job slot (nit & 1) were last used by job nit - 2: the epilogue has
-                // released it (mfree) and this warp has published it
-                Q1_LAP(3);
-                if (nit >= 2) {
-                    drain_until(nit - 1);
-                    // ... and so have the other merge warps (they read the same metadata).  Job nit - 1 of
-                    // this warp done => the epilogue started item nit - 1 => it saw `idone` of job nit - 2;
-                    // otherwise wait for it here (nothing to service meanwhile: the epilogue posts no
-                    // round of job nit - 1 before that barrier completes, so the phase cannot be lapped)
-                    if (j_done == nit - 1) mbar_wait(bar_idone, nit & 1u);
-                    wait_serv(bar_mfree, nit & 1u);
-                }
-                Q1_LAP(1);
-                if (lw == 0) {
-                    const uint32_t mb = (nit & 1u) * R2_NQ;
-                    sm.qidx[mb + lane] = qi0; sm.qidx[mb + 32 + lane] = qi1;
-                    sm.qslot[mb + lane] = sl0; sm.qslot[mb + 32 + lane] = sl1;
-                    sm.qn[mb + lane] = (qi0 != ID_NONE) ? p.qnorm[qi0] : 0.f;
-                    sm.qn[mb + 32 + lane] = (qi1 != ID_NONE) ? p.qnorm[qi1] : 0.f;
-                }
-                {
-                    const uint32_t ntiles = (it.row_end - it.row_begin + R2_ROWS - 1) / R2_ROWS;
-                    if (nit & 1u) { job_cnt1 = cnt; job_tiles1 = ntiles; job_sub1 = it.sub; } else { job_cnt0 = cnt; job_tiles0 = ntiles; job_sub0 = it.sub; }
-                    j_load = nit + 1;
-                }
-                Q1_LAP(3);
-                if (nit >= 1) wait_serv(bar_qfree, (nit - 1) & 1u);
-                Q1_LAP(2);
-                r2_load_queries(sm, p, qi0, qi1, ncols, lw, lane, KB, D);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
-                mbar_arrive(bar_qready);
-                ++nit;
-            }
-            drain_until(j_load);
-            lap[7] = st_merge;
-        } else {
         uint32_t ss = 0, sphase = 0, nit = 0;
         while (true) {
             Q1_LAP(3);
@@ -766,7 +491,6 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
             ++nit;
             (void)lt;
         }
-        }
         if (warp == 6 && p.prof && lane == 0) {
             for (int i_ = 0; i_ < 4; ++i_) p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + i_] = lap[i_];
             p.prof[((size_t)blockIdx.x * 6 + 3) * 8 + 7] = lap[7];
@@ -782,136 +506,6 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
         uint32_t st_app = 0, st_ovf = 0, st_merge = 0, st_replay = 0, st_chunks = 0;
         // the query this lane owns in the merge phases (lanes 0..15): j = lane * 4 + ew
         const uint32_t jown = (uint32_t)lane * 4u + (uint32_t)ew;
-        if constexpr (OFF) {
-            // ===== compare-only epilogue: candidates go to the pending half (tile & 1); the merge warps
-            // fold it while this role compares the next tile.  Only an overflow (a query that met a
-            // full pending list) couples the two roles: wait for the fold, replay the rows concerned.
-            uint32_t round0 = 0, round1 = 0;     // rounds posted on each half (both roles count them alike)
-            while (true) {
-                Q1_LAP(6);
-                mbar_wait(bar_sfull + 8 * ss, sphase);
-                const uint32_t item = sm.sched[ss];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_sempty + 8 * ss);
-                if (++ss == TC_SCHED) { ss = 0; sphase ^= 1; }
-                Q1_LAP(0);
-                if (item == ITEM_END) break;
-                const ScanItem it = p.items[item];
-                if (it.pair_count == 0 || it.row_begin >= it.row_end) continue;
-                const uint32_t cnt = it.pair_count;
-                const uint32_t ncols = (cnt + 15u) & ~15u;
-                const uint32_t mb = (nit & 1u) * R2_NQ;
-                mbar_wait(bar_qready, nit & 1u);           // metadata of this item is staged
-                if (nit >= 1) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_mfree);
-                    mbar_wait(bar_idone, (nit - 1) & 1u);  // the previous item's pending pools are drained
-                }
-                Q1_LAP(1);
-                if (et < R2_NQ) {
-                    float thr = -__uint_as_float(F32_INF_BITS);  // padded columns never pass
-                    if ((uint32_t)et < cnt) {
-                        const uint32_t g = p.thr_g ? *(volatile uint32_t*)(p.thr_g + sm.qidx[mb + et]) : (uint32_t)0x7f800000u;
-                        thr = __uint_as_float(g) - sm.qn[mb + et];
-                    }
-                    sm.thrp[et] = thr;
-                    sm.pcnt[et] = 0;
-                    sm.pcnt[R2_NQ + et] = 0;
-                }
-                epi_bar_n(1);
-                Q1_LAP(6);
-                for (uint32_t rt = it.row_begin; rt < it.row_end; rt += R2_ROWS) {
-                    const uint32_t slot = tile % R2_NSLOT;
-                    Q1_LAP(4);
-                    mbar_wait(bar_nfull + 8 * slot, (tile / R2_NSLOT) & 1u);
-                    const float xn = sm.xn_ring[slot * R2_ROWS + trow];
-                    const uint32_t buf = tile & (R2_NBUF - 1);
-                    mbar_wait(bar_tfull + 8 * buf, (tile / R2_NBUF) & 1u);
-                    tc_fence_after();
-                    Q1_LAP(2);
-                    const uint32_t b = tile & 1u;
-                    uint32_t rnd = b ? round1 : round0;
-                    if (rnd) mbar_wait(bar_pfree + 8 * b, (rnd - 1) & 1u);   // the half is folded
-                    Q1_LAP(5);
-                    const uint32_t taddr = tmem_base + buf * R2_NQ + lane_taddr;
-                    const uint32_t pos = rt + (uint32_t)trow;
-                    uint64_t* pend = sm.pend + (size_t)b * R2_NQ * RO_CAP;
-                    uint32_t* pcnt = sm.pcnt + b * R2_NQ;
-                    uint64_t ovf = 0;  // queries whose pending list was full when this row passed
-
-                    auto append = [&](uint32_t q, float v) {
-                        const uint32_t s = atomicAdd(&pcnt[q], 1u);
-                        ++st_app;
-                        if (s < (uint32_t)RO_CAP)
-                            pend[q * RO_CAP + s] = ((uint64_t)__float_as_uint(fmaxf(v + sm.qn[mb + q], 0.0f)) << 32) | (uint64_t)pos;
-                        else {
-                            ovf |= 1ull << q;
-                            atomicOr(&sm.redo[b * 4 + (rnd & 1u) * 2 + (q >> 5)], 1u << (q & 31));
-                            ++st_ovf;
-                        }
-                    };
-
-                    for (uint32_t c0 = 0; c0 < ((p.debug & 1u) ? 0u : ncols); c0 += 16) {
-                        uint32_t acc[16];
-                        ++st_chunks;
-                        tmem_ld16(taddr + c0, acc);
-                        float thr[16];
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 t4 = *reinterpret_cast<const float4*>(sm.thrp + c0 + 4 * j4);
-                            thr[4 * j4 + 0] = t4.x; thr[4 * j4 + 1] = t4.y; thr[4 * j4 + 2] = t4.z; thr[4 * j4 + 3] = t4.w;
-                        }
-                        tmem_ld_wait();
-                        uint32_t pass = 0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float v = fmaf(-2.0f, __uint_as_float(acc[j]), xn);  // |x|^2 - 2 x.q
-                            pass |= (v < thr[j]) ? (1u << j) : 0u;
-                        }
-                        while (pass) {
-                            const uint32_t bb = (uint32_t)__ffs((int)pass) - 1u;
-                            pass &= pass - 1u;
-                            uint32_t a = acc[0];
-#pragma unroll
-                            for (int j = 1; j < 16; ++j) a = (bb == (uint32_t)j) ? acc[j] : a;
-                            append(c0 + bb, fmaf(-2.0f, __uint_as_float(a), xn));
-                        }
-                    }
-                    Q1_LAP(3);
-                    while (true) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_pfull + 8 * b);
-                        mbar_wait(bar_pfull + 8 * b, rnd & 1u);      // every candidate of the round is stored
-                        const uint32_t r0 = sm.redo[b * 4 + (rnd & 1u) * 2], r1 = sm.redo[b * 4 + (rnd & 1u) * 2 + 1];
-                        ++rnd;
-                        if ((r0 | r1) == 0) break;
-                        ++st_replay;
-                        mbar_wait(bar_pfree + 8 * b, (rnd - 1) & 1u);  // folded: thresholds tightened, lists emptied
-                        // replay: rows that met a full pending list are tested against the new thresholds
-                        uint64_t rm = ((uint64_t)r1 << 32) | r0;
-                        while (rm) {
-                            const uint32_t q = (uint32_t)__ffsll((long long)rm) - 1u;
-                            rm &= rm - 1;
-                            uint32_t a;
-                            tmem_ld1(taddr + q, a);
-                            tmem_ld_wait();
-                            if ((ovf >> q) & 1ull) {
-                                ovf &= ~(1ull << q);
-                                const float v = fmaf(-2.0f, __uint_as_float(a), xn);
-                                if (v < sm.thrp[q]) append(q, v);
-                            }
-                        }
-                    }
-                    if (b) round1 = rnd; else round0 = rnd;
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);  // accumulator may be overwritten
-                    ++tile;
-                    Q1_LAP(4);
-                }
-                ++nit;
-            }
-        } else {
         while (true) {
             Q1_LAP(6);
             mbar_wait(bar_sfull + 8 * ss, sphase);
@@ -1141,7 +735,6 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
             ++nit;
             Q1_LAP(5);
         }
-        }
         if (warp == 2) Q1_LAP_DUMP(2);
         if (p.prof && warp == 2) {
             const uint32_t a = __reduce_add_sync(0xffffffffu, st_app), o = __reduce_add_sync(0xffffffffu, st_ovf);
@@ -1168,65 +761,22 @@ tc_scan_kernel_t(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
 }
 
 
-#include "tc_scan_pair.cuh"
 
 // ================================================================================================
-// Kernel Q ("queries on lanes"): the query tile is the MMA A operand and lives in TENSOR MEMORY
-// (128 TMEM lanes = 128 queries, D <= 384 columns), database rows stream through shared memory
-// as the B operand (64 rows x 128 B per stage), accumulators double-buffered in the remaining
-// 128 TMEM columns.  One epilogue thread owns one query: the threshold test and the candidate
-// append are thread-private (no atomics, no votes, no CTA barriers); a query's 32-entry
-// shortlist is re-sorted by its warp only when 16+ new candidates are pending.  Shared memory
-// holds nothing but the row ring (up to 18 x 8 KB in flight) and the candidate pools.
+// Kernel Q ("queries on lanes"), dense form: the coarse step's distance matrix.  The query tile is
+// the MMA A operand and lives in TENSOR MEMORY (128 TMEM lanes = 128 queries, D <= 384 columns),
+// centroid rows stream through shared memory as the B operand (64 rows x 128 B per stage),
+// accumulators double-buffered in the remaining 128 TMEM columns.  One epilogue thread owns one
+// query and writes its approximate d2 to every centroid of the tile.  (The same orientation with
+// CTA pairs, thread-private candidate heaps and a split row stream is kernel W, tc_scan_wide.cuh.)
 // ================================================================================================
 constexpr int Q1_M = 128;                       // queries per work item
 constexpr int Q1_N = 64;                        // rows per tile
 constexpr int Q1_STAGE_BYTES = Q1_N * 128;      // 8 KB
-constexpr int Q1_POOL_LD = 65;                  // words per query: [0,32) sorted, [32,64) pending, +1 pad
 constexpr int Q1_TMEM_COLS = 512;
 constexpr int Q1_ACC_COL = 384;                 // accumulators at columns 384..511
 constexpr int Q1_NSLOT = 16;                    // ring of per-tile row-norm strips (see the producer)
 constexpr int Q1_XP_LD = 36;                    // floats per query row of the prologue transposition buffer
-
-struct QPool {
-    uint32_t* d;  // [Q1_M][Q1_POOL_LD] approx d2 bits
-    uint32_t* p;  // [Q1_M][Q1_POOL_LD] arena row
-};
-
-// Merge the pending entries of up to four queries (lanes `src[g]` of this warp, query rows
-// m[g]) into their sorted shortlists.  Returns the merged lists in `lst` (lane i = entry i).
-__device__ __forceinline__ void q1_merge4(const QPool& pool, const uint32_t (&m)[4], const uint32_t (&n_new)[4],
-                                          const bool (&act)[4], uint64_t (&lst)[4], int lane) {
-    uint64_t nw[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        lst[g] = KEY_NONE;
-        nw[g] = KEY_NONE;
-        if (act[g]) {
-            const uint32_t base = m[g] * Q1_POOL_LD;
-            const uint32_t dd = pool.d[base + lane];
-            if (dd != 0xFFFFFFFFu) lst[g] = ((uint64_t)dd << 32) | pool.p[base + lane];
-            if ((uint32_t)lane < n_new[g]) nw[g] = ((uint64_t)pool.d[base + 32 + lane] << 32) | pool.p[base + 32 + lane];
-        }
-    }
-    // sort the pending entries (4 networks in lockstep), then bitonic-merge with the lists
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
-            uint64_t o[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) o[g] = shfl_xor64(nw[g], j);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const uint64_t mn = nw[g] < o[g] ? nw[g] : o[g], mx = nw[g] < o[g] ? o[g] : nw[g];
-                nw[g] = keep_min ? mn : mx;
-            }
-        }
-    }
-    warp_merge32x4(lst, nw, lane);
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
@@ -1238,10 +788,8 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
     const uint32_t STAGES = p.stages;
     const uint32_t STAGE_BYTES = KBS * Q1_STAGE_BYTES;
     unsigned char* ring = smem;                                                     // STAGES x KBS x 8 KB
-    QPool pool;
-    pool.d = reinterpret_cast<uint32_t*>(ring + (size_t)STAGES * STAGE_BYTES);
-    pool.p = pool.d + Q1_M * Q1_POOL_LD;
-    float* xn_ring = reinterpret_cast<float*>(pool.p + Q1_M * Q1_POOL_LD);          // [Q1_NSLOT][64] tile row norms
+    float* xpose = reinterpret_cast<float*>(ring + (size_t)STAGES * STAGE_BYTES);      // [2][Q1_M][Q1_XP_LD] prologue transposition
+    float* xn_ring = xpose + 2 * Q1_M * Q1_XP_LD;                                    // [Q1_NSLOT][64] tile row norms
     uint64_t* bars = reinterpret_cast<uint64_t*>(xn_ring + Q1_NSLOT * Q1_N);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5 + 2 * TC_SCHED + Q1_NSLOT);
     uint32_t* sched_s = tmem_ptr_s + 1;
@@ -1430,14 +978,13 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
     } else {
         // ================= epilogue: one thread = one query =================
         const int quarter = warp & 3;                 // TMEM lane quarter of this warp
-        const uint32_t m = quarter * 32 + lane;       // TMEM lane == query row of the tile
         const uint32_t qslot_in_item = (uint32_t)lane * 4 + quarter;  // item query index held by this thread
         const uint32_t lane_taddr = (uint32_t)(quarter * 32) << 16;
         const uint32_t D = p.D;
         uint32_t buf = 0, ss = 0, sphase = 0, fph0 = 0, fph1 = 0, tcount = 0;
-        // prologue transposition buffers: this warp's (still empty) candidate pools
-        float* xp0 = reinterpret_cast<float*>(pool.d + quarter * 32 * Q1_POOL_LD);
-        float* xp1 = reinterpret_cast<float*>(pool.p + quarter * 32 * Q1_POOL_LD);
+        // prologue transposition buffers of this warp
+        float* xp0 = xpose + quarter * 32 * Q1_XP_LD;
+        float* xp1 = xpose + (Q1_M + quarter * 32) * Q1_XP_LD;
 
         while (true) {
             Q1_LAP(4);
@@ -1455,17 +1002,11 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
             // queries per load instruction), transposed through shared memory, and written by the
             // owning thread (TMEM lane = query) with one 32-column tcgen05.st per k-block.
             const bool have = qslot_in_item < it.pair_count;
-            uint32_t qi = ID_NONE, sl = 0;
-            float qn = 0.f, thrp = -__uint_as_float(F32_INF_BITS);
-            uint32_t thr_pending = F32_INF_BITS;
+            uint32_t qi = ID_NONE;
+            float qn = 0.f;
             if (have) {
-                if (it.identity) { qi = it.pair_begin + qslot_in_item; sl = it.slot; }
-                else { qi = p.pair_q[it.pair_begin + qslot_in_item]; sl = p.pair_slot[it.pair_begin + qslot_in_item]; }
+                qi = it.identity ? it.pair_begin + qslot_in_item : p.pair_q[it.pair_begin + qslot_in_item];
                 qn = p.qnorm[qi];
-                if (p.thr_g) {
-                    thr_pending = *(volatile uint32_t*)(p.thr_g + qi);
-                    thrp = __uint_as_float(thr_pending) - qn;
-                }
             }
             {
                 const float4* src[8];
@@ -1505,16 +1046,10 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_qready);
-            for (int i = 0; i < 32; ++i) pool.d[m * Q1_POOL_LD + i] = 0xFFFFFFFFu;  // empty shortlist
-            uint32_t cnt_new = 0;
             Q1_LAP(1);
 
             // ---- row tiles ----
             for (uint32_t rt = it.row_begin; rt < it.row_end; rt += Q1_N) {
-                // thresholds tightened meanwhile by CTAs scanning other lists of the same query:
-                // the value loaded during the previous tile is applied now (no exposed latency)
-                if (have) thrp = fminf(thrp, __uint_as_float(thr_pending) - qn);
-                if (have && p.thr_g) thr_pending = *(volatile uint32_t*)(p.thr_g + qi);
                 const uint32_t slot = tcount & (Q1_NSLOT - 1);
                 Q1_LAP(3);
                 mbar_wait(bar_nfull + 8 * slot, (tcount / Q1_NSLOT) & 1u);
@@ -1537,65 +1072,18 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                         xn[4 * j4 + 0] = t4.x; xn[4 * j4 + 1] = t4.y; xn[4 * j4 + 2] = t4.z; xn[4 * j4 + 3] = t4.w;
                     }
                     tmem_ld_wait();
-                    if (p.dense_out) {
-                        // coarse step: keep every approximate distance (rows = centroids)
-                        if (have) {
-                            float* dst = p.dense_out + (size_t)qi * p.dense_ld + (rt - it.row_begin + it.slot) + c0;
+                    // keep every approximate distance (rows = centroids)
+                    if (have) {
+                        float* dst = p.dense_out + (size_t)qi * p.dense_ld + (rt - it.row_begin + it.slot) + c0;
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                float4 o;
-                                o.x = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 0]), xn[4 * j4 + 0]) + qn;
-                                o.y = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 1]), xn[4 * j4 + 1]) + qn;
-                                o.z = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 2]), xn[4 * j4 + 2]) + qn;
-                                o.w = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 3]), xn[4 * j4 + 3]) + qn;
-                                *reinterpret_cast<float4*>(dst + 4 * j4) = o;
-                            }
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            float4 o;
+                            o.x = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 0]), xn[4 * j4 + 0]) + qn;
+                            o.y = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 1]), xn[4 * j4 + 1]) + qn;
+                            o.z = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 2]), xn[4 * j4 + 2]) + qn;
+                            o.w = fmaf(-2.0f, __uint_as_float(acc[4 * j4 + 3]), xn[4 * j4 + 3]) + qn;
+                            *reinterpret_cast<float4*>(dst + 4 * j4) = o;
                         }
-                        continue;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float v = fmaf(-2.0f, __uint_as_float(acc[j]), xn[j]);  // |x|^2 - 2 q.x
-                        if (v < thrp) {
-                            const uint32_t o = m * Q1_POOL_LD + 32 + cnt_new;
-                            pool.d[o] = __float_as_uint(fmaxf(v + qn, 0.0f));
-                            pool.p[o] = rt + c0 + j;
-                            ++cnt_new;
-                        }
-                    }
-                    // another 16 columns could overflow the 32 pending slots: refresh those queries
-                    unsigned need = __ballot_sync(0xffffffffu, cnt_new > 16);
-                    while (need) {
-                        uint32_t mm[4], nn[4];
-                        bool act[4];
-                        int src[4];
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            act[g] = need != 0;
-                            src[g] = act[g] ? (__ffs(need) - 1) : 0;
-                            if (act[g]) need &= need - 1;
-                            mm[g] = quarter * 32 + src[g];
-                            nn[g] = __shfl_sync(0xffffffffu, cnt_new, src[g]);
-                        }
-                        __syncwarp();
-                        uint64_t lst[4];
-                        q1_merge4(pool, mm, nn, act, lst, lane);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (!act[g]) continue;
-                            pool.d[mm[g] * Q1_POOL_LD + lane] = (uint32_t)(lst[g] >> 32);
-                            pool.p[mm[g] * Q1_POOL_LD + lane] = (uint32_t)lst[g];
-                            const uint64_t last = shfl64(lst[g], 31);
-                            if (lane == src[g]) {
-                                cnt_new = 0;
-                                if (last != KEY_NONE) {
-                                    thrp = __uint_as_float((uint32_t)(last >> 32)) - qn;
-                                    // any 32 rows below a value bound the global 32nd: share it at once
-                                    atomicMin(p.thr_g + qi, (uint32_t)(last >> 32));
-                                }
-                            }
-                        }
-                        __syncwarp();
                     }
                 }
                 tc_fence_before();
@@ -1603,35 +1091,6 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
                 buf ^= 1;
             }
-            // ---- item epilogue: final merge, publish the shortlists, tighten shared thresholds ----
-            Q1_LAP(3);
-            unsigned todo = __ballot_sync(0xffffffffu, have && p.dense_out == nullptr);
-            while (todo) {
-                uint32_t mm[4], nn[4], qis[4], sls[4];
-                bool act[4];
-                int src[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    act[g] = todo != 0;
-                    src[g] = act[g] ? (__ffs(todo) - 1) : 0;
-                    if (act[g]) todo &= todo - 1;
-                    mm[g] = quarter * 32 + src[g];
-                    nn[g] = __shfl_sync(0xffffffffu, cnt_new, src[g]);
-                    qis[g] = __shfl_sync(0xffffffffu, qi, src[g]);
-                    sls[g] = __shfl_sync(0xffffffffu, sl, src[g]);
-                }
-                __syncwarp();
-                uint64_t lst[4];
-                q1_merge4(pool, mm, nn, act, lst, lane);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (!act[g]) continue;
-                    p.partial[((size_t)qis[g] * p.P + sls[g]) * TC_KP + lane] = lst[g];
-                    if (lane == 0) p.row_stamp[(size_t)qis[g] * p.P + sls[g]] = p.stamp;
-                    if (lane == 31 && lst[g] != KEY_NONE) atomicMin(p.thr_g + qis[g], (uint32_t)(lst[g] >> 32));
-                }
-            }
-            __syncwarp();
             Q1_LAP(6);
         }
         if (warp == 2) Q1_LAP_DUMP(2);
@@ -1647,7 +1106,7 @@ tc_scan_q_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p)
 }
 
 size_t tc_scan_q_smem_bytes(uint32_t stages, uint32_t kbs) {
-    return (size_t)stages * kbs * Q1_STAGE_BYTES + (size_t)2 * Q1_M * Q1_POOL_LD * 4 + (size_t)Q1_NSLOT * Q1_N * 4 +
+    return (size_t)stages * kbs * Q1_STAGE_BYTES + (size_t)2 * Q1_M * Q1_XP_LD * 4 + (size_t)Q1_NSLOT * Q1_N * 4 +
            (size_t)(2 * stages + 5 + 2 * TC_SCHED + Q1_NSLOT) * 8 + 16 + (size_t)TC_SCHED * 4;
 }
 
@@ -1660,6 +1119,8 @@ uint32_t q1_pick_stages(uint32_t KB, uint32_t kbs) {
     return stages;
 }
 
+
+#include "tc_scan_wide.cuh"
 
 // ---- small support kernels ----------------------------------------------------------------------
 // optional riders of the query-norm pass: fill[r] = fill_value (the per-query bound reset) and the
@@ -1856,8 +1317,8 @@ __global__ void coarse_items_kernel(ScanItem* items, uint32_t nq, uint32_t nlist
 // identity work items of the flat-tier scan: (query group of TC_TILE_Q) x (row chunk); `slot` = chunk
 // index = the partial slot the item's shortlists are published to
 __global__ void flat_items_kernel(ScanItem* items, uint32_t nq, uint32_t n_rows, uint32_t chunk_rows,
-                                  uint32_t n_chunks, uint32_t* n_items) {
-    const uint32_t n_qg = (nq + TC_TILE_Q - 1) / TC_TILE_Q;
+                                  uint32_t n_chunks, uint32_t* n_items, uint32_t tile_q) {
+    const uint32_t n_qg = (nq + tile_q - 1) / tile_q;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *n_items = n_qg * n_chunks;
     if (i >= n_qg * n_chunks) return;
@@ -1866,8 +1327,8 @@ __global__ void flat_items_kernel(ScanItem* items, uint32_t nq, uint32_t n_rows,
     ScanItem it;
     it.row_begin = c * chunk_rows;
     it.row_end = min(n_rows, (c + 1) * chunk_rows);
-    it.pair_begin = g * TC_TILE_Q;
-    it.pair_count = min((uint32_t)TC_TILE_Q, nq - g * TC_TILE_Q);
+    it.pair_begin = g * tile_q;
+    it.pair_count = min(tile_q, nq - g * tile_q);
     it.slot = c;
     it.identity = n_qg > 1 ? 2 : 1;   // 2: the chunk is read by several query groups (keep it in L2)
     it.sub = 0;
@@ -2230,6 +1691,7 @@ struct TcScratchImpl {
     struct RowSet {            // cached per scanned row matrix: |x|^2, TMA descriptor (box 32 x 128)
         Buf<float> xnorm;
         CUtensorMap tmap;
+        CUtensorMap tmap_w;    // box 32 floats x 32 rows (kernel W)
         const float* rows = nullptr;
         uint64_t n = 0, version = ~0ull;
     } rs[2];                   // [0] recent tier, [1] centroid table (assignment)
@@ -2237,7 +1699,7 @@ struct TcScratchImpl {
     uint32_t list_order_n = 0;
     uint32_t max_list_len = 0;
     Buf<uint32_t> thr_g, list_cnt, pair_off, cursor, pair_q, pair_slot, n_items;
-    Buf<ScanItem> items;
+    Buf<ScanItem> items, items_w;   // work items of kernel R / kernel W
     Buf<uint64_t> partial, shortlist;
     Buf<uint32_t> row_stamp;   // one stamp per shortlist row of `partial`
     uint32_t stamp = 0;        // launch counter; a fresh or wrapped counter clears the stamps
@@ -2261,12 +1723,12 @@ struct TcScratchImpl {
     const float* tmap_cent_ptr = nullptr;
     uint32_t tmap_cent_n = 0;
     CUtensorMap tmap_arena;  // box 32 floats x 128 rows (kernel R)
-    CUtensorMap tmap_q;      // box 32 floats x 64 rows  (kernel Q)
+    CUtensorMap tmap_w;      // box 32 floats x 32 rows  (kernel W: each CTA of a pair streams half a tile)
+    bool smem_attr_set_w = false;
     bool smem_attr_set_q = false;
     const float* tmap_rows = nullptr;
     uint64_t tmap_n = 0;
     bool smem_attr_set = false;
-    bool smem_attr_set_pair = false;
     bool smem_attr_set_rerank = false;
 };
 
@@ -2284,18 +1746,12 @@ static cudaError_t rerank_prepare(TcScratchImpl* m) {
     return e;
 }
 
-// kernel R variant: FVDB_TC_MERGE=E keeps the merges in the epilogue warps (the classic variant)
-static bool tc_offload_merges() {
-    const char* e = getenv("FVDB_TC_MERGE");
-    return e && e[0] == 'O';
-}
-
 void tc_release(TcScratch& s) {
     if (!s.impl) return;
     TcScratchImpl* m = s.impl;
     m->xnorm.release(); m->qnorm.release(); m->misc.release(); m->thr_g.release(); m->list_cnt.release();
     m->pair_off.release(); m->cursor.release(); m->pair_q.release(); m->pair_slot.release(); m->n_items.release();
-    m->items.release(); m->partial.release(); m->shortlist.release(); m->row_stamp.release();
+    m->items.release(); m->items_w.release(); m->partial.release(); m->shortlist.release(); m->row_stamp.release();
     m->prof.release(); m->list_order.release(); m->rs[0].xnorm.release(); m->rs[1].xnorm.release(); m->fitems.release();
     m->cnorm.release(); m->dense.release(); m->coarse.release(); m->citems.release();
     delete m;
@@ -2311,6 +1767,69 @@ void tc_release(TcScratch& s) {
             return e__ == cudaErrorMemoryAllocation ? FVDB_ERR_OOM : FVDB_ERR_CUDA;    \
         }                                                                              \
     } while (0)
+
+// Which scan kernel(s): 'W' = kernel W for heavily probed lists and dense scans plus kernel R for the
+// sparsely probed lists (needs the query tile in tensor memory: D <= 384); 'R' (FVDB_TC_KERNEL=R, or
+// 384 < D <= 512) = kernel R alone
+static char tc_kernel_choice(uint32_t D, int sm_count) {
+    const char* kenv = getenv("FVDB_TC_KERNEL");
+    char c = (kenv && kenv[0] == 'R') ? 'R' : 'W';
+    if (c == 'W' && (D > 384 || sm_count < 2)) c = 'R';
+    return c;
+}
+
+static cudaError_t launch_wide(TcScratchImpl* m, const CUtensorMap& tmap, TcScanParams& p, uint32_t KB, int sm_count,
+                               size_t* dev_bytes, cudaStream_t st, cudaEvent_t ev0) {
+    const uint32_t kbs = wide_pick_kbs(KB);
+    uint32_t stages = wide_pick_stages(KB, kbs);
+    if (const char* e = getenv("FVDB_TC_STAGES")) { const uint32_t v = (uint32_t)atoi(e); if (v >= 2 && v < stages) stages = v; }
+    p.kbs = kbs;
+    p.stages = stages;
+    const size_t smem = tc_scan_wide_smem_bytes(stages, kbs) + 1024;
+    cudaError_t e;
+    if (!m->smem_attr_set_w) {
+        e = cudaFuncSetAttribute(tc_scan_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        m->smem_attr_set_w = true;
+    }
+    const uint32_t grid = (uint32_t)sm_count & ~1u;   // whole pairs; idle pairs exit at once
+    if (p.debug & 128u) {
+        e = m->prof.ensure((size_t)grid * 48, dev_bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(m->prof.p, 0, (size_t)grid * 48 * 8, st);
+        if (e != cudaSuccess) return e;
+        p.prof = m->prof.p;
+    }
+    if (ev0) { e = cudaEventRecord(ev0, st); if (e != cudaSuccess) return e; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(W_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, tc_scan_wide_kernel, tmap, p);
+    if (e != cudaSuccess) return e;
+    if (p.prof) return dump_prof(m->prof.p, grid, st);
+    return cudaSuccess;
+}
+
+static CUresult encode_rows_tmap(CUtensorMap* out, const float* rows, uint64_t n_rows, uint32_t D, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return CUDA_ERROR_NOT_SUPPORTED;
+    const cuuint64_t gdim[2] = {D, n_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)D * 4};
+    const cuuint32_t box[2] = {TC_KB_FLOATS, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(rows), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
 
 int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* dev_bytes, uint32_t* launches,
                   std::string* err) {
@@ -2341,18 +1860,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             if (err) *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
             return FVDB_ERR_CUDA;
         }
-        const cuuint32_t box_q[2] = {TC_KB_FLOATS, Q1_N};
-        const char* dbg_env = getenv("FVDB_TC_DEBUG");
-        cuuint64_t gdim_q[2] = {gdim[0], gdim[1]};
-        cuuint64_t gstride_q[1] = {gstride[0]};
-        if (dbg_env && (atoi(dbg_env) & 2)) {  // layout experiment: view the arena as [n_rows*KB][32]
-            gdim_q[0] = 32; gdim_q[1] = a.n_rows * KB; gstride_q[0] = 128;
-        }
-        r = enc(&m->tmap_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.rows), gdim_q, gstride_q, box_q, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            if (err) *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+        if (encode_rows_tmap(&m->tmap_w, a.rows, a.n_rows, D, W_NH) != CUDA_SUCCESS) {
+            if (err) *err = "cuTensorMapEncodeTiled (kernel W) failed";
             return FVDB_ERR_CUDA;
         }
         {
@@ -2378,30 +1887,39 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
 
     // ---- per-batch state ----
     const size_t n_pairs = (size_t)nq * np;
-    // kernel Q (queries in tensor memory) needs D <= 384 TMEM columns for the query tile;
-    // kernel R (rows on lanes, query tile in shared memory) covers 384 < D <= 512
-    const char* kenv = getenv("FVDB_TC_KERNEL");
-    const bool use_q = (D <= 384) && (kenv && kenv[0] == 'Q');
-    // kernel P (CTA pairs, 128-query items): needs an even grid and the pair's shared-memory budget
-    const bool use_pair = !use_q && (kenv && kenv[0] == 'P') && a.sm_count >= 2 &&
-                          tc_scan_pair_smem_bytes(KB, 2) + 1024 <= 232448;
-    const uint32_t tile_q = use_q ? (uint32_t)Q1_M : use_pair ? (uint32_t)P2_NQ : TC_TILE_Q;
+    // Two scan kernels share a batch.  Kernel W (wide query tiles on CTA pairs, queries in tensor
+    // memory: D <= 384) takes the lists probed by at least `wide_min` queries: a row enters one SM once
+    // per 256 queries, and with many live queries per warp its thread-per-query epilogue runs lane-
+    // parallel.  Kernel R (64-query items, query tile in shared memory, rows on the accumulator lanes,
+    // candidate handling shared by the 128 row threads) takes the sparsely probed lists, where its MMA
+    // cost (proportional to the queries of the item) and its cooperative epilogue are the cheaper ones.
+    const char kch = tc_kernel_choice(D, a.sm_count);
+    uint32_t wide_min = 0;                       // 0: kernel R only
+    if (kch == 'W') {
+        wide_min = TC_WIDE_MIN_QUERIES;
+        if (const char* e = getenv("FVDB_TC_WIDE_MIN")) wide_min = (uint32_t)std::max(1, atoi(e));
+    }
+    const bool use_wide = wide_min != 0;
+    const uint32_t tile_q = TC_TILE_Q;
     // Long posting lists are cut into row ranges (one work item and one shortlist slot each): a hub
     // list of 9 K rows probed by 64 queries is otherwise ONE item of 71 tiles — a third of the whole
     // scan on one SM, and the tail every other SM waits for.  At most TC_SPLIT_MAX ranges per list.
     uint32_t n_split = 1, rows_cap = 0;
-    if (!use_q) {
+    {
         uint32_t want = TC_SPLIT_MAX;
         if (const char* e = getenv("FVDB_TC_SPLIT")) want = std::min<uint32_t>(std::max(1, atoi(e)), 16u);
-        const uint32_t unit = use_pair ? 2u * R2_ROWS : (uint32_t)R2_ROWS;
+        const uint32_t unit = (uint32_t)R2_ROWS;   // a multiple of both kernels' tile heights
         if (want > 1 && m->max_list_len > TC_SPLIT_MIN_ROWS) {
             rows_cap = std::max<uint32_t>(TC_SPLIT_MIN_ROWS / 2, ((m->max_list_len + want - 1) / want + unit - 1) / unit * unit);
             n_split = (m->max_list_len + rows_cap - 1) / rows_cap;
             if (n_split <= 1) { n_split = 1; rows_cap = 0; }
         }
     }
-    const uint32_t prows = (use_pair ? 2u : 1u) * n_split;   // shortlist rows per (query, probe)
+    // shortlist rows per (query, probe): one per row range, times two when kernel W takes part (each
+    // half of its tiles publishes its own row; kernel R writes row `range` of the same block)
+    const uint32_t prows = (use_wide ? (uint32_t)W_SUBROWS : 1u) * n_split;
     const size_t max_items = ((size_t)a.nlist + (n_pairs + tile_q - 1) / tile_q) * n_split + 1;
+    const size_t max_items_w = use_wide ? ((size_t)a.nlist + (n_pairs + W_NQ - 1) / W_NQ) * n_split + 1 : 0;
     TCK(m->qnorm.ensure(nq, dev_bytes));
     TCK(m->thr_g.ensure(nq, dev_bytes));
     TCK(m->list_cnt.ensure(a.nlist + 1, dev_bytes));
@@ -2409,8 +1927,9 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     TCK(m->cursor.ensure(a.nlist + 1, dev_bytes));
     TCK(m->pair_q.ensure(n_pairs, dev_bytes));
     TCK(m->pair_slot.ensure(n_pairs, dev_bytes));
-    TCK(m->n_items.ensure(4, dev_bytes));
+    TCK(m->n_items.ensure(8, dev_bytes));   // [0] items R, [1] counter R, [2][3] coarse, [4][5] flat tier, [6] items W, [7] counter W
     TCK(m->items.ensure(max_items, dev_bytes));
+    if (use_wide) TCK(m->items_w.ensure(max_items_w, dev_bytes));
     TCK(m->partial.ensure(n_pairs * prows * TC_KP, dev_bytes));
     TCK(m->shortlist.ensure((size_t)nq * TC_KP, dev_bytes));
 
@@ -2499,7 +2018,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     TCK(launch_probe_bucketing(coarse_keys, nq, np, a.list_off, a.nlist, tile_q, m->list_cnt.p, m->pair_off.p,
                                m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st,
                                (m->list_order_n == a.nlist && !getenv("FVDB_TC_NO_ORDER")) ? m->list_order.p : nullptr,
-                               getenv("FVDB_TC_ORDER_NEAR") != nullptr, rows_cap));
+                               getenv("FVDB_TC_ORDER_NEAR") != nullptr, rows_cap, wide_min, (uint32_t)W_NQ,
+                               use_wide ? m->items_w.p : nullptr, m->n_items.p + 6, getenv("FVDB_TC_W_ORDER") != nullptr));
     (*launches) += 3;
     uint32_t stamp = 0;
     TCK(m->next_stamp(n_pairs * prows, dev_bytes, st, &stamp));
@@ -2509,7 +2029,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     p.items = m->items.p; p.item_count = m->n_items.p; p.pair_q = m->pair_q.p; p.pair_slot = m->pair_slot.p;
     p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = m->xnorm.p; p.ids = a.ids;
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
-    p.P = np; p.S = n_split; p.partial = m->partial.p; p.thr_g = a.thr_ext ? a.thr_ext : m->thr_g.p;
+    p.P = np; p.S = prows; p.partial = m->partial.p; p.thr_g = a.thr_ext ? a.thr_ext : m->thr_g.p;
     p.row_stamp = m->row_stamp.p; p.stamp = stamp;
     p.n_peer = a.thr_ext ? std::min(a.n_peers, TC_MAX_PEERS) : 0u;
     for (uint32_t r = 0; r < p.n_peer; ++r) p.thr_peer[r] = a.thr_peers[r];
@@ -2520,60 +2040,21 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         p.debug = dbg ? (uint32_t)atoi(dbg) : 0u;
     }
     TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
-    if (use_q) {
-        uint32_t kbs = 1;
-        for (uint32_t c : {4u, 3u, 2u}) if (KB % c == 0) { kbs = c; break; }
-        if (const char* e = getenv("FVDB_TC_KBS")) { const uint32_t v = (uint32_t)atoi(e); if (v && KB % v == 0) kbs = v; }
-        uint32_t stages = q1_pick_stages(KB, kbs);
-        p.stages = stages;
-        p.kbs = kbs;
-        const size_t smem = tc_scan_q_smem_bytes(stages, kbs) + 1024;
-        if (!m->smem_attr_set_q) {
-            TCK(cudaFuncSetAttribute(tc_scan_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-            m->smem_attr_set_q = true;
-        }
-        const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
-        if (p.debug & 128u) {
-            TCK(m->prof.ensure((size_t)grid * 48, dev_bytes));
-            TCK(cudaMemsetAsync(m->prof.p, 0, (size_t)grid * 48 * 8, st));
-            p.prof = m->prof.p;
-        }
-        if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
-        tc_scan_q_kernel<<<grid, TC_THREADS, smem, st>>>(m->tmap_q, p);
-        TCK(cudaGetLastError());
-        if (p.prof) TCK(dump_prof(m->prof.p, grid, st));
-    } else if (use_pair) {
-        uint32_t stages = std::min<uint32_t>(12u, 6u * KB);
-        while (stages > 2 && tc_scan_pair_smem_bytes(KB, stages) + 1024 > 232448) --stages;
-        if (const char* e = getenv("FVDB_TC_STAGES")) { const uint32_t v = (uint32_t)atoi(e); if (v >= 2 && v < stages) stages = v; }
-        p.stages = stages;
-        const size_t smem = tc_scan_pair_smem_bytes(KB, stages) + 1024;
-        if (!m->smem_attr_set_pair) {
-            TCK(cudaFuncSetAttribute(tc_scan_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-            m->smem_attr_set_pair = true;
-        }
-        const uint32_t grid = (uint32_t)a.sm_count & ~1u;   // whole pairs; idle pairs exit at once
-        if (p.debug & 128u) {
-            TCK(m->prof.ensure((size_t)grid * 48, dev_bytes));
-            TCK(cudaMemsetAsync(m->prof.p, 0, (size_t)grid * 48 * 8, st));
-            p.prof = m->prof.p;
-        }
-        if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(R2_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        TCK(cudaLaunchKernelEx(&cfg, tc_scan_pair_kernel, m->tmap_arena, p));
-        if (p.prof) TCK(dump_prof(m->prof.p, grid, st));
-    } else {
+    if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
+    auto run_wide = [&]() -> int {
+    if (use_wide) {
+        // the heavily probed lists first: most of them are some queries' nearest list, so their scan
+        // publishes tight bounds for everything that follows
+        TcScanParams pw = p;
+        pw.items = m->items_w.p; pw.item_count = m->n_items.p + 6; pw.work_counter = m->n_items.p + 7;
+        TCK(cudaMemsetAsync(pw.work_counter, 0, 4, st));
+        TCK(launch_wide(m, m->tmap_w, pw, KB, a.sm_count, dev_bytes, st, nullptr));
+        (*launches)++;
+    }
+    return FVDB_OK;
+    };
+    auto run_narrow = [&]() -> int {
+    {
         // deepest ring that fits; the norm-strip window (see the producer) caps it at 6 tiles
         uint32_t stages = std::min<uint32_t>(12u, (uint32_t)(R2_NSLOT - 2 - R2_NBUF) * KB);
         while (stages > 2 && tc_scan_smem_bytes(KB, stages) + R2_SLACK > 232448) --stages;
@@ -2582,8 +2063,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         const size_t smem = tc_scan_smem_bytes(KB, stages) + R2_SLACK;  // slack for the 1024-byte alignment
         if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
         if (!m->smem_attr_set) {
-            TCK(cudaFuncSetAttribute(tc_scan_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-            TCK(cudaFuncSetAttribute(tc_scan_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+            TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
             m->smem_attr_set = true;
         }
         const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
@@ -2592,11 +2072,21 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             TCK(cudaMemsetAsync(m->prof.p, 0, (size_t)grid * 48 * 8, st));
             p.prof = m->prof.p;
         }
-        if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
-        if (tc_offload_merges()) tc_scan_kernel_t<true><<<grid, R2_THREADS, smem, st>>>(m->tmap_arena, p);
-        else tc_scan_kernel_t<false><<<grid, R2_THREADS, smem, st>>>(m->tmap_arena, p);
+        tc_scan_kernel<<<grid, R2_THREADS, smem, st>>>(m->tmap_arena, p);
         TCK(cudaGetLastError());
         if (p.prof) TCK(dump_prof(m->prof.p, grid, st));
+    }
+    return FVDB_OK;
+    };
+    // Order: the sparsely probed lists first (kernel R), then the hub lists (kernel W).  Every query probes
+    // mostly sparse lists; after their scan its bound is already close to final, so the hub items — where a
+    // candidate is the expensive thing (one thread per query) — start warm.  FVDB_TC_ORDER=WR reverses it.
+    {
+        const char* oe = getenv("FVDB_TC_ORDER");
+        const bool wide_first = oe && oe[0] == 'W';
+        if (wide_first) { int r = run_wide(); if (r != FVDB_OK) return r; }
+        { int r = run_narrow(); if (r != FVDB_OK) return r; }
+        if (!wide_first) { int r = run_wide(); if (r != FVDB_OK) return r; }
     }
     if (a.ev_scan1) TCK(cudaEventRecord(a.ev_scan1, st));
     (*launches)++;
@@ -2639,57 +2129,76 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled (row set) failed"; return FVDB_ERR_CUDA; }
+        if (encode_rows_tmap(&rs.tmap_w, a.rows, a.n_rows, D, W_NH) != CUDA_SUCCESS) {
+            if (err) *err = "cuTensorMapEncodeTiled (row set, kernel W) failed";
+            return FVDB_ERR_CUDA;
+        }
         rs.rows = a.rows;
         rs.n = a.n_rows;
         rs.version = a.version;
         if (!a.state) s.flat_dirty = false;
     }
-    // ---- work items: every 64-query group against every row chunk ----
-    const uint32_t n_qg = (nq + TC_TILE_Q - 1) / TC_TILE_Q;
-    const uint32_t tiles = (uint32_t)((a.n_rows + TC_ROWS - 1) / TC_ROWS);
-    uint32_t n_chunks = std::max(1u, std::min(std::min(tiles, 128u), ((uint32_t)a.sm_count * 4 + n_qg - 1) / n_qg));
-    const uint32_t chunk_rows = ((tiles + n_chunks - 1) / n_chunks) * TC_ROWS;
+    // ---- work items: every query group (256 queries for kernel W, 64 for kernel R) against every row chunk ----
+    const bool use_wide = tc_kernel_choice(D, a.sm_count) == 'W';
+    const uint32_t tile_q = use_wide ? (uint32_t)W_NQ : TC_TILE_Q;
+    const uint32_t tile_rows = use_wide ? (uint32_t)W_N : (uint32_t)TC_ROWS;
+    const uint32_t n_qg = (nq + tile_q - 1) / tile_q;
+    const uint32_t tiles = (uint32_t)((a.n_rows + tile_rows - 1) / tile_rows);
+    // enough items to fill the machine a few times over (pairs for kernel W), never more than 128
+    // shortlist slots per query
+    const uint32_t workers = use_wide ? (uint32_t)a.sm_count / 2 : (uint32_t)a.sm_count;
+    uint32_t n_chunks = std::max(1u, std::min(std::min(tiles, 128u), (workers * 4 + n_qg - 1) / n_qg));
+    const uint32_t chunk_rows = ((tiles + n_chunks - 1) / n_chunks) * tile_rows;
     n_chunks = (uint32_t)((a.n_rows + chunk_rows - 1) / chunk_rows);
     const uint32_t n_items = n_qg * n_chunks;
     TCK(m->qnorm.ensure(nq, dev_bytes));
     TCK(m->thr_g.ensure(nq, dev_bytes));
     TCK(m->n_items.ensure(8, dev_bytes));
     TCK(m->fitems.ensure(n_items, dev_bytes));
-    TCK(m->partial.ensure((size_t)nq * n_chunks * TC_KP, dev_bytes));
+    const uint32_t frows = use_wide ? (uint32_t)W_SUBROWS : 1u;   // shortlist rows per (query, chunk)
+    TCK(m->partial.ensure((size_t)nq * n_chunks * frows * TC_KP, dev_bytes));
     TCK(m->shortlist.ensure((size_t)nq * TC_KP, dev_bytes));
     {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)nq * 32 + 255) / 256, (uint64_t)a.sm_count * 8);
-        row_norms_kernel<<<blocks, 256, 0, st>>>(a.Q, nq, D, m->qnorm.p, nullptr);
-        fill_u32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m->thr_g.p, nq, F32_INF_BITS);
+        // query norms; the same pass resets the per-query bounds
+        row_norms_kernel<<<blocks, 256, 0, st>>>(a.Q, nq, D, m->qnorm.p, nullptr, m->thr_g.p, F32_INF_BITS);
         flat_items_kernel<<<(n_items + 127) / 128, 128, 0, st>>>(m->fitems.p, nq, (uint32_t)a.n_rows, chunk_rows, n_chunks,
-                                                                m->n_items.p + 4);
+                                                                m->n_items.p + 4, tile_q);
         TCK(cudaGetLastError());
-        (*launches) += 3;
+        (*launches) += 2;
     }
     uint32_t stamp = 0;
-    TCK(m->next_stamp((size_t)nq * n_chunks, dev_bytes, st, &stamp));
+    TCK(m->next_stamp((size_t)nq * n_chunks * frows, dev_bytes, st, &stamp));
     TcScanParams p{};
     p.items = m->fitems.p; p.item_count = m->n_items.p + 4; p.pair_q = nullptr; p.pair_slot = nullptr;
     p.Q = a.Q; p.qnorm = m->qnorm.p; p.D = D; p.KB = KB; p.xnorm = rs.xnorm.p; p.ids = a.ids;
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
-    p.P = n_chunks; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
+    p.P = n_chunks; p.S = use_wide ? frows : 0u; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
     p.row_stamp = m->row_stamp.p; p.stamp = stamp;
     p.work_counter = m->n_items.p + 5;
-    TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
-    uint32_t stages = std::min<uint32_t>(12u, 6u * KB);
-    while (stages > 2 && tc_scan_smem_bytes(KB, stages) + 1024 > 232448) --stages;
-    p.stages = stages;
-    const size_t smem = tc_scan_smem_bytes(KB, stages) + 1024;
-    if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
-    if (!m->smem_attr_set) {
-        TCK(cudaFuncSetAttribute(tc_scan_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        TCK(cudaFuncSetAttribute(tc_scan_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        m->smem_attr_set = true;
+    {
+        const char* dbg = getenv("FVDB_TC_DEBUG");
+        p.debug = dbg ? (uint32_t)atoi(dbg) : 0u;
     }
-    if (tc_offload_merges()) tc_scan_kernel_t<true><<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(rs.tmap, p);
-    else tc_scan_kernel_t<false><<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(rs.tmap, p);
-    TCK(cudaGetLastError());
-    TCK(launch_merge_rows32(m->partial.p, nq, n_chunks, m->shortlist.p, st, m->row_stamp.p, stamp));
+    TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
+    if (a.ev_scan0 && !use_wide) TCK(cudaEventRecord(a.ev_scan0, st));
+    if (use_wide) {
+        TCK(launch_wide(m, rs.tmap_w, p, KB, a.sm_count, dev_bytes, st, a.ev_scan0));
+    } else {
+        uint32_t stages = std::min<uint32_t>(12u, 6u * KB);
+        while (stages > 2 && tc_scan_smem_bytes(KB, stages) + 1024 > 232448) --stages;
+        p.stages = stages;
+        const size_t smem = tc_scan_smem_bytes(KB, stages) + 1024;
+        if (smem > 232448) { if (err) *err = "TC scan does not fit shared memory for this dim"; return FVDB_ERR_INVALID_CONFIG; }
+        if (!m->smem_attr_set) {
+            TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+            m->smem_attr_set = true;
+        }
+        tc_scan_kernel<<<std::min<uint32_t>((uint32_t)a.sm_count, n_items), R2_THREADS, smem, st>>>(rs.tmap, p);
+        TCK(cudaGetLastError());
+    }
+    if (a.ev_scan1) TCK(cudaEventRecord(a.ev_scan1, st));
+    TCK(launch_merge_rows32(m->partial.p, nq, n_chunks * frows, m->shortlist.p, st, m->row_stamp.p, stamp));
     TCK(rerank_prepare(m));
     rerank_kernel<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p,
                                                                          xmax_bits, nq, D, a.k,

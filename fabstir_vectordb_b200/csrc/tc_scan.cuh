@@ -24,7 +24,8 @@ struct TcScratch {
 constexpr uint32_t TC_MAX_K = 16;        // largest k served by the 32-entry shortlist
 constexpr uint32_t TC_MAX_NPROBE = 256;  // partial lists merged in one pass
 constexpr uint32_t TC_MAX_NPROBE_COARSE = 96;  // tensor-core coarse step (else exact coarse)
-constexpr uint32_t TC_TILE_Q = 64;       // queries per work item of the TC scan
+constexpr uint32_t TC_TILE_Q = 64;       // queries per work item of kernel R
+constexpr uint32_t TC_WIDE_MIN_QUERIES = 129;  // lists probed by at least this many queries of a batch go to kernel W
 constexpr uint32_t TC_MAX_PEERS = 7;     // peer GPUs whose bound arrays one scan can push to
 
 struct TcSearchArgs {
@@ -85,6 +86,7 @@ struct TcFlatArgs {
     uint32_t state = 0;
     uint64_t version = 0;
     uint32_t rerank_r = 0;        // shortlist entries re-ranked exactly (0 = all 32)
+    cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;   // optional: recorded around the scan kernel
 };
 
 // dim % 32 == 0 (one 128-byte swizzle atom per k-block), dim <= 512 (query tile in smem)

@@ -589,13 +589,16 @@ def test_coarse_selection_with_clumped_centroid_ids(nlist):
     assert eng.stats().last_fallback_queries < nq // 2
 
 
-@pytest.mark.parametrize("kernel", ["R", "P"])
+@pytest.mark.parametrize("kernel", ["R", "W", "hybrid"])
 def test_hub_list_is_split_into_row_ranges(kernel, monkeypatch):
     """A hub posting list (thousands of rows, probed by every query) is cut into row ranges with one work
     item and one shortlist slot each.  Results — with tombstones and a filter bitmap on —
-    must equal the oracle's bit for bit, for kernel R and for the CTA-pair kernel."""
-    if kernel == "P":
-        monkeypatch.setenv("FVDB_TC_KERNEL", "P")
+    must equal the oracle's bit for bit: with kernel R alone, with kernel W alone (every list goes to the
+    wide-tile kernel) and with the product's split (the hub list to kernel W, the others to kernel R)."""
+    if kernel == "R":
+        monkeypatch.setenv("FVDB_TC_KERNEL", "R")
+    elif kernel == "W":
+        monkeypatch.setenv("FVDB_TC_WIDE_MIN", "1")
     rng = np.random.default_rng(77)
     d, nlist, nq, k, nprobe = 128, 12, 150, 10, 6
     cents = rng.standard_normal((nlist, d)).astype(np.float32)
