@@ -16,7 +16,7 @@ from .engine import (DimensionMismatch, DuplicateVector, Engine, FvdbError,  # n
 from .chunk import ChunkError, VectorChunk, decode_vector_chunk, encode_vector_chunk  # noqa: F401
 from .index import (AddClustersResult, BalanceResult, ClusterStats, HNSWConfig, HNSWIndex,  # noqa: F401
                     HybridConfig, HybridIndex, HybridSearchConfig, IVFConfig, IVFIndex, InvalidParameter,
-                    MetadataFilter, NotInitialized, OptimizationResult, RetrainResult, SearchConfig,
+                    NotInitialized, OptimizationResult, RetrainResult, SearchConfig,
                     SearchResult, TrainResult)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

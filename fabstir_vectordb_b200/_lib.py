@@ -37,6 +37,7 @@ OPT_SCAN_MODE = 1
 OPT_SHORTLIST = 2
 OPT_KMEANS_TC = 3
 OPT_COALESCE = 4
+OPT_PROOF_XMAX = 5
 
 
 class TrainResult(C.Structure):
@@ -88,6 +89,8 @@ SIGNATURES = {
     "fvdb_vacuum": (C.c_int, [_vp, _u64p]),
     "fvdb_search": (C.c_int, [_vp, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u64p,
                               C.c_uint64, _u32p, _f32p, _u32p]),
+    "fvdb_search_postfilter": (C.c_int, [_vp, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u64p,
+                                         C.c_uint64, _u32p, _f32p, _u32p]),
     "fvdb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "fvdb_host_free": (None, [_vp]),
     "fvdb_search_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
@@ -102,12 +105,15 @@ SIGNATURES = {
                                             C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     "fvdb_merge_topk_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32,
                                          _vp, _vp, _vp, _vp]),
+    "fvdb_ivf_max_sqnorm": (C.c_int, [_vp, _f32p]),
     "fvdb_bounds_export": (C.c_int, [_vp, C.c_uint32, _vp]),
     "fvdb_bounds_import": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32]),
     "fvdb_bounds_begin_batch": (C.c_int, [_vp, C.c_uint32, _vp]),
     "fvdb_merge_topk_packed_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]),
     "fvdb_ivf_add_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _u64p]),
     "fvdb_flat_add_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
+    "fvdb_ivf_add_device_owned": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, C.c_uint32, _u64p]),
+    "fvdb_assign_device": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp]),
     "fvdb_ivf_train_device": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp,
                                         C.c_uint64, C.POINTER(TrainResult)]),
     "fvdb_kmeans_accumulate_device": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),

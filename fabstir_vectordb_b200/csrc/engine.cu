@@ -65,16 +65,81 @@ struct DevBuf {
     void swap(DevBuf& o) { std::swap(p, o.p); std::swap(cap, o.cap); }
 };
 
-struct SplitMix {
-    uint64_t s;
-    explicit SplitMix(uint64_t seed) : s(seed) {}
-    uint64_t next() {
-        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-        return z ^ (z >> 31);
+// rand 0.8's StdRng as IVFIndex::new seeds it (`StdRng::seed_from_u64`, src/ivf/core.rs:176-179) and as
+// initialize_centroids draws from it (`gen_range(0..n)` :341, `gen::<f32>()` :359), restated from the
+// published algorithms: rand_core 0.6 seed_from_u64 = a PCG32 stream expanded into the 32-byte key;
+// StdRng = ChaCha with 12 rounds, 64-bit block counter from 0, stream 0, four blocks (64 words) per
+// refill, words consumed in order; next_u64 = two consecutive words, low first; u64 sample_single =
+// widening multiply with a rejection zone; Standard f32 = (next_u32 >> 8) * 2^-24.
+// rand is an un-vendored, un-pinned dependency of the reference (Cargo.toml:41): parity
+// with it is unpinned.  What IS tested: this generator == the oracle's independent restatement, and the
+// picks made with it == the oracle's fo_kmeanspp_init on the same seed.
+struct StdRng08 {
+    uint32_t key[8];
+    uint64_t counter = 0;
+    uint32_t buf[64];
+    uint32_t index = 64;   // next unread word; 64 = empty
+
+    explicit StdRng08(uint64_t seed) {
+        const uint64_t MUL = 6364136223846793005ull, INC = 11634580027462260723ull;
+        for (int i = 0; i < 8; ++i) {
+            seed = seed * MUL + INC;
+            const uint32_t xs = (uint32_t)(((seed >> 18) ^ seed) >> 27);
+            const uint32_t rot = (uint32_t)(seed >> 59);
+            key[i] = (xs >> rot) | (xs << ((32u - rot) & 31u));
+        }
     }
-    double u01() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    static uint32_t rotl(uint32_t v, int c) { return (v << c) | (v >> (32 - c)); }
+    static void quarter(uint32_t* x, int a, int b, int c, int d) {
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16);
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12);
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
+    }
+    void block(uint64_t ctr, uint32_t* out) const {
+        uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
+                           key[4], key[5], key[6], key[7], (uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+        uint32_t x[16];
+        std::memcpy(x, in, sizeof(x));
+        for (int r = 0; r < 6; ++r) {   // 12 rounds: six column + diagonal double rounds
+            quarter(x, 0, 4, 8, 12); quarter(x, 1, 5, 9, 13); quarter(x, 2, 6, 10, 14); quarter(x, 3, 7, 11, 15);
+            quarter(x, 0, 5, 10, 15); quarter(x, 1, 6, 11, 12); quarter(x, 2, 7, 8, 13); quarter(x, 3, 4, 9, 14);
+        }
+        for (int i = 0; i < 16; ++i) out[i] = x[i] + in[i];
+    }
+    void refill() {
+        for (int b = 0; b < 4; ++b) block(counter + (uint64_t)b, buf + 16 * b);
+        counter += 4;
+        index = 0;
+    }
+    uint32_t next_u32() {
+        if (index >= 64) refill();
+        return buf[index++];
+    }
+    uint64_t next_u64() {   // BlockRng::next_u64, including the word that straddles a refill
+        if (index < 63) {
+            const uint64_t lo = buf[index], hi = buf[index + 1];
+            index += 2;
+            return (hi << 32) | lo;
+        }
+        if (index >= 64) {
+            refill();
+            index = 2;
+            return ((uint64_t)buf[1] << 32) | buf[0];
+        }
+        const uint64_t lo = buf[63];
+        refill();
+        index = 1;
+        return ((uint64_t)buf[0] << 32) | lo;
+    }
+    uint64_t gen_range(uint64_t range) {   // gen_range(0..range), range > 0
+        const uint64_t zone = (range << __builtin_clzll(range)) - 1;
+        for (;;) {
+            const unsigned __int128 m = (unsigned __int128)next_u64() * range;
+            if ((uint64_t)m <= zone) return (uint64_t)(m >> 64);
+        }
+    }
+    float gen_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }
 };
 
 }  // namespace
@@ -103,6 +168,7 @@ struct fvdb_index {
     uint32_t scan_mode = FVDB_SCAN_EXACT;
     uint32_t shortlist = 0;
     uint32_t kmeans_tc = 0;
+    float proof_xmax_sq = 0.f;          // FVDB_OPT_PROOF_XMAX: max |x|^2 over ALL shards of a list-sharded index
     uint64_t centroids_version = 0;     // bumped whenever the centroid table changes
     uint64_t assign_fallback_rows = 0;  // rows re-assigned exactly after a failed tensor-core proof
     size_t dev_bytes = 0;
@@ -433,7 +499,8 @@ int assign_device(fvdb_index* h, const float* d_x, uint64_t n, uint32_t* d_assig
 }
 
 int ivf_add_device_impl(fvdb_index* h, const float* d_x, const uint32_t* d_ids, uint64_t n,
-                        uint32_t mod, uint32_t rem, uint64_t* kept_out, uint32_t* h_out_list) {
+                        uint32_t mod, uint32_t rem, uint64_t* kept_out, uint32_t* h_out_list,
+                        const uint32_t* d_owner = nullptr) {
     if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");
     if (kept_out) *kept_out = 0;
     if (n == 0) return FVDB_OK;
@@ -450,7 +517,8 @@ int ivf_add_device_impl(fvdb_index* h, const float* d_x, const uint32_t* d_ids, 
     }
     // list-sharded load: keep only rows whose list % mod == rem, compacted (grouped by list)
     CK(h->s_u32b.ensure(n, 0, st, &h->dev_bytes));
-    CK(launch_filter_keys_mod(h->s_u32a.p, n, mod, rem, h->nlist, h->s_u32b.p, st));
+    if (d_owner) CK(launch_filter_keys_owner(h->s_u32a.p, n, d_owner, rem, h->nlist, h->s_u32b.p, st));
+    else CK(launch_filter_keys_mod(h->s_u32a.p, n, mod, rem, h->nlist, h->s_u32b.p, st));
     CK(h->s_perm.ensure(n, 0, st, &h->dev_bytes));
     CK(h->s_group.ensure(stable_group_scratch_bytes(n, h->nlist), 0, st, &h->dev_bytes));
     CK(h->s_u32c.ensure(h->nlist + 2, 0, st, &h->dev_bytes));
@@ -538,56 +606,61 @@ int compute_error_device(fvdb_index* h, const float* d_data, uint64_t n, const u
     return FVDB_OK;
 }
 
-int train_device_impl(fvdb_index* h, const float* d_data, uint64_t n, uint32_t nlist,
-                      uint32_t max_iterations, const float* d_init, uint64_t seed,
-                      fvdb_train_result* out) {
+// The k-means proper.  Runs on h->centroids / h->nlist (the assignment kernels read them there); the
+// caller (train_device_impl) has moved the previous centroid table aside and puts it back if this fails.
+int train_body(fvdb_index* h, const float* d_data, uint64_t n, uint32_t nlist, uint32_t max_iterations,
+               const float* d_init, uint64_t seed, fvdb_train_result* out) {
     cudaStream_t st = h->stream;
     const uint32_t D = h->dim;
-    if (nlist == 0 || max_iterations == 0) return h->fail(FVDB_ERR_INVALID_CONFIG, "Invalid IVFConfig");
-    if (n == 0 || n < nlist)
-        return h->fail(FVDB_ERR_INSUFFICIENT_TRAINING, "Insufficient training data: got " +
-                       std::to_string(n) + ", need at least " + std::to_string(nlist));
-    if (n >= 0xFFFFFFF0ull) return h->fail(FVDB_ERR_INVALID_ARG, "training set exceeds u32 rows");
-    RET(check_nan_device(h, d_data, n * D, st));
     CK(h->centroids.ensure((size_t)nlist * D, 0, st, &h->dev_bytes));
     h->nlist = nlist;
     h->trained = false;
     h->tc.centroids_dirty = true; ++h->centroids_version;
     if (d_init) {
-        RET(check_nan_device(h, d_init, (size_t)nlist * D, st));
         CK(cudaMemcpyAsync(h->centroids.p, d_init, (size_t)nlist * D * 4, cudaMemcpyDeviceToDevice, st));
     } else {
-        // k-means++ (src/ivf/core.rs:336-371), running-min form, device-side picks
-        SplitMix rng(seed);
+        // k-means++ (src/ivf/core.rs:336-371) on the reference's own random stream (StdRng08 above).
+        // The distances are computed on the device in the reference's operation order (one launch per
+        // new centroid; the minimum over all chosen centroids :346-354 is kept as a running minimum,
+        // which is exact).  The pick itself is a SEQUENTIAL f32 prefix sum over the points (:357-367) —
+        // a parallel scan would move low bits and with them the picked index — so it runs on the host:
+        // one 4 n-byte read-back and two passes over n floats per centroid.
+        StdRng08 rng(seed);
+        DevBuf<uint32_t> zeros;                     // every point "assigned" to the newest centroid
+        CK(zeros.ensure(n, 0, st, nullptr, true));
+        CK(cudaMemsetAsync(zeros.p, 0, n * 4, st));
         CK(h->s_f32a.ensure(n, 0, st, &h->dev_bytes));
-        std::vector<float> inf(1, INFINITY);
-        // fill mind with +inf: 0x7f800000 pattern
-        CK(cudaMemsetAsync(h->s_f32a.p, 0, n * 4, st));
-        {
-            // memset cannot write 0x7f800000; use iota-free trick: copy from a host vector in chunks
-            std::vector<float> tmp(std::min<uint64_t>(n, 1 << 20), INFINITY);
-            for (uint64_t off = 0; off < n; off += tmp.size()) {
-                const uint64_t c = std::min<uint64_t>(tmp.size(), n - off);
-                CK(cudaMemcpyAsync(h->s_f32a.p + off, tmp.data(), c * 4, cudaMemcpyHostToDevice, st));
-                CK(cudaStreamSynchronize(st));
+        std::vector<float> mind(n, INFINITY), dist(n);
+        const uint64_t first = rng.gen_range(n);
+        CK(cudaMemcpyAsync(h->centroids.p, d_data + first * D, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+        uint32_t count = 1;
+        for (uint32_t i = 1; i < nlist; ++i) {
+            CK(launch_rowwise_dist(d_data, n, D, h->centroids.p + (size_t)(count - 1) * D, zeros.p, h->s_f32a.p, st));
+            RET(d2h(h, dist.data(), h->s_f32a.p, n * 4));
+            volatile float total = 0.0f;            // left folds in f32, as `.sum::<f32>()` / `+=`
+            for (uint64_t j = 0; j < n; ++j) {
+                const float m = mind[j] < dist[j] ? mind[j] : dist[j];
+                mind[j] = m;
+                total = total + m * m;
+            }
+            const float threshold = rng.gen_f32() * total;
+            volatile float cumulative = 0.0f;
+            for (uint64_t j = 0; j < n; ++j) {
+                cumulative = cumulative + mind[j] * mind[j];
+                if (cumulative >= threshold) {
+                    CK(cudaMemcpyAsync(h->centroids.p + (size_t)count * D, d_data + j * D, (size_t)D * 4,
+                                       cudaMemcpyDeviceToDevice, st));
+                    ++count;
+                    break;
+                }
             }
         }
-        const uint32_t nb = (uint32_t)((n + 1023) / 1024);
-        CK(h->s_f64.ensure(nb + 1, 0, st, &h->dev_bytes));
-        CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
-        uint32_t* d_pick = h->s_misc.p + 8;
-        const uint32_t first = (uint32_t)(rng.next() % n);
-        CK(cudaMemcpyAsync(d_pick, &first, 4, cudaMemcpyHostToDevice, st));
-        CK(launch_copy_row(d_data, d_pick, D, h->centroids.p, st));
-        for (uint32_t i = 1; i < nlist; ++i) {
-            uint32_t nblocks = 0;
-            CK(launch_kmeanspp_update(d_data, n, D, h->centroids.p + (size_t)(i - 1) * D, h->s_f32a.p,
-                                      h->s_f64.p, &nblocks, st));
-            const double u = (double)(float)((rng.next() >> 40) * (1.0 / 16777216.0));
-            CK(launch_kmeanspp_pick(h->s_f32a.p, n, h->s_f64.p, nblocks, u, d_pick, st));
-            CK(launch_copy_row(d_data, d_pick, D, h->centroids.p + (size_t)i * D, st));
-        }
         CK(cudaStreamSynchronize(st));
+        // f32 rounding can leave the cumulative sum below the threshold: the reference then ends up with
+        // fewer than n_clusters centroids and indexes out of range later — an error here
+        if (count < nlist)
+            return h->fail(FVDB_ERR_INVALID_CONFIG, "k-means++ produced " + std::to_string(count) + " of " +
+                           std::to_string(nlist) + " centroids (the cumulative f32 sum never reached the threshold)");
     }
 
     // Lloyd loop (src/ivf/core.rs:279-322)
@@ -632,8 +705,6 @@ int train_device_impl(fvdb_index* h, const float* d_data, uint64_t n, uint32_t n
     }
     float final_error = 0.f;
     RET(compute_error_device(h, d_data, n, assign.p, &final_error));
-    h->trained = true;
-    clear_lists(h);
     CK(h->list_off.ensure(nlist + 2, 0, st, &h->dev_bytes));
     CK(cudaMemsetAsync(h->list_off.p, 0, (nlist + 2) * 4, st));
     CK(cudaStreamSynchronize(st));
@@ -643,6 +714,40 @@ int train_device_impl(fvdb_index* h, const float* d_data, uint64_t n, uint32_t n
         out->initial_error = initial_error;
         out->final_error = final_error;
     }
+    return FVDB_OK;
+}
+
+// IVFIndex::train (src/ivf/core.rs:240-334).  Like the reference, every check comes before anything is
+// touched (:242-262), and a training run that fails half-way (CUDA error, out of memory) leaves the
+// index exactly as it was: the previous centroid table, nlist, trained flag and posting lists come back.
+int train_device_impl(fvdb_index* h, const float* d_data, uint64_t n, uint32_t nlist,
+                      uint32_t max_iterations, const float* d_init, uint64_t seed,
+                      fvdb_train_result* out) {
+    cudaStream_t st = h->stream;
+    const uint32_t D = h->dim;
+    if (nlist == 0 || max_iterations == 0) return h->fail(FVDB_ERR_INVALID_CONFIG, "Invalid IVFConfig");
+    if (n == 0 || n < nlist)
+        return h->fail(FVDB_ERR_INSUFFICIENT_TRAINING, "Insufficient training data: got " +
+                       std::to_string(n) + ", need at least " + std::to_string(nlist));
+    if (n >= 0xFFFFFFF0ull) return h->fail(FVDB_ERR_INVALID_ARG, "training set exceeds u32 rows");
+    RET(check_nan_device(h, d_data, n * D, st));
+    if (d_init) RET(check_nan_device(h, d_init, (size_t)nlist * D, st));
+    DevBuf<float> old_centroids;
+    old_centroids.swap(h->centroids);
+    const uint32_t old_nlist = h->nlist;
+    const bool old_trained = h->trained;
+    const int r = train_body(h, d_data, n, nlist, max_iterations, d_init, seed, out);
+    if (r != FVDB_OK) {
+        h->dev_bytes -= h->centroids.cap * sizeof(float);
+        h->centroids.swap(old_centroids);   // the failed run's table is freed with old_centroids
+        h->nlist = old_nlist;
+        h->trained = old_trained;
+        h->tc.centroids_dirty = true; ++h->centroids_version;
+        return r;
+    }
+    h->dev_bytes -= old_centroids.cap * sizeof(float);
+    h->trained = true;
+    clear_lists(h);   // src/ivf/core.rs:273-277
     return FVDB_OK;
 }
 
@@ -851,6 +956,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             ta.d_fallback_count = d_fb_count; ta.d_fallback_idx = h->s_fb_idx.p;
             ta.ev_scan0 = h->ev_s0; ta.ev_scan1 = h->ev_s1;
             ta.sm_count = h->sm_count;
+            ta.xmax_floor_sq = h->proof_xmax_sq;
             ta.d_nan = d_nan;
             if (!use_flat) {   // the only tier: the re-rank writes the result arrays itself
                 ta.fin_ids = d_out_ids; ta.fin_dist = d_out_dist; ta.fin_count = d_out_count;
@@ -1098,6 +1204,14 @@ int fvdb_set_option(fvdb_index* h, int option, uint64_t value) {
         case FVDB_OPT_COALESCE:
             h->coalesce = value ? 1u : 0u;
             return FVDB_OK;
+        case FVDB_OPT_PROOF_XMAX: {
+            const uint32_t b = (uint32_t)value;
+            float f;
+            std::memcpy(&f, &b, 4);
+            if (!(f >= 0.f)) return h->fail(FVDB_ERR_INVALID_ARG, "FVDB_OPT_PROOF_XMAX takes the f32 bits of a value >= 0");
+            h->proof_xmax_sq = f;
+            return FVDB_OK;
+        }
         default:
             return h->fail(FVDB_ERR_INVALID_ARG, "unknown option");
     }
@@ -1195,11 +1309,19 @@ int fvdb_ivf_retrain(fvdb_index* h, uint32_t nlist, uint32_t max_iterations, con
     h->track_ids = false;   // clear_lists() must not forget the ids: the same rows come back below
     int r = train_device_impl(h, rows.p, n, nlist, max_iterations, init_centroids ? d_init.p : nullptr, seed, out);
     h->track_ids = track;
-    if (r == FVDB_OK) r = ivf_add_device_impl(h, rows.p, ids.p, n, 1, 0, nullptr, nullptr);
+    if (r != FVDB_OK) {
+        // a failed training run restored the centroid table: the rows go back where they were and the
+        // index is what it was before the call
+        h->ivf_rows.swap(rows);
+        h->ivf_ids.swap(ids);
+        h->tc.arena_dirty = true;
+        return r;
+    }
+    r = ivf_add_device_impl(h, rows.p, ids.p, n, 1, 0, nullptr, nullptr);
     if (r == FVDB_OK) r = seal(h);
     if (r == FVDB_OK) h->dev_bytes -= rows.cap * sizeof(float) + ids.cap * sizeof(uint32_t);   // freed on return
     if (r != FVDB_OK) {
-        // leave the rows where they were; the index reports "not trained" until a train succeeds
+        // new centroids, rows still grouped by the old ones: keep the rows, report "not trained"
         h->ivf_rows.swap(rows);
         h->ivf_ids.swap(ids);
         h->ivf_n = n;
@@ -1268,6 +1390,24 @@ int fvdb_ivf_add_device(fvdb_index* h, const float* d_x, const uint32_t* d_row_i
     ENTER(h);
     h->track_ids = false;  // ids never visit the host on this path
     return ivf_add_device_impl(h, d_x, d_row_ids, n, list_filter_mod, list_filter_rem, kept, nullptr);
+}
+
+int fvdb_ivf_add_device_owned(fvdb_index* h, const float* d_x, const uint32_t* d_row_ids, uint64_t n,
+                              const uint32_t* d_owner, uint32_t my_rank, uint64_t* kept) {
+    ENTER(h);
+    if (!d_owner) return h->fail(FVDB_ERR_INVALID_ARG, "owner table is NULL");
+    h->track_ids = false;
+    return ivf_add_device_impl(h, d_x, d_row_ids, n, 2, my_rank, kept, nullptr, d_owner);
+}
+
+int fvdb_assign_device(fvdb_index* h, const float* d_x, uint64_t n, uint32_t* d_out_list, void* stream) {
+    ENTER(h);
+    if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");
+    if (n == 0) return FVDB_OK;
+    if (!d_x || !d_out_list) return h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    RET(check_nan_device(h, d_x, n * h->dim, st));
+    return assign_device(h, d_x, n, d_out_list, nullptr, nullptr, nullptr, st);
 }
 
 int fvdb_flat_add(fvdb_index* h, const float* x, const uint32_t* row_ids, uint64_t n) {
@@ -1428,12 +1568,20 @@ int fvdb_move_flat_to_ivf(fvdb_index* h, const uint32_t* row_ids, uint64_t n, ui
     CK(launch_gather_rows(h->flat_rows.p, fn, nullptr, h->s_perm.p, fn, D, nrows.p, st));
     CK(launch_gather_u32(h->flat_ids.p, fn, nullptr, h->s_perm.p, fn, nids.p, st));
     CK(cudaStreamSynchronize(st));
+    // append the moved rows to the IVF tier FIRST (assignment or allocation may fail); only then does
+    // the compacted array replace the flat tier — a failure leaves both tiers as they were
+    {
+        const int r = ivf_add_device_impl(h, nrows.p + stay * D, nids.p + stay, mv, 1, 0, nullptr, nullptr);
+        if (r != FVDB_OK) {
+            h->dev_bytes -= nrows.cap * 4 + nids.cap * 4;
+            return r;
+        }
+    }
     h->dev_bytes -= h->flat_rows.cap * 4 + h->flat_ids.cap * 4;
     h->flat_rows.swap(nrows);
     h->flat_ids.swap(nids);
     h->flat_n = stay;
     h->tc.flat_dirty = true;
-    RET(ivf_add_device_impl(h, h->flat_rows.p + stay * D, h->flat_ids.p + stay, mv, 1, 0, nullptr, nullptr));
     if (h->track_ids)
         for (uint64_t i = 0; i < n; ++i)
             if (row_ids[i] < h->id_state.size() && (h->id_state[row_ids[i]] & 3) == 1)
@@ -1785,6 +1933,43 @@ int fvdb_search(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t
     return r.rc;
 }
 
+// HybridIndex::search_with_filter (src/hybrid/core.rs:513-549): search(3k), keep what matches, truncate(k).
+// The oversampled search and the compaction both run on the device; `keep_bits` is the host's
+// evaluation of the filter (one bit per row id; rows without metadata are 0, :536-541).
+int fvdb_search_postfilter(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t nprobe, uint32_t tiers,
+                           const uint64_t* keep_bits, uint64_t keep_nbits, uint32_t* out_ids, float* out_dist,
+                           uint32_t* out_count) {
+    ENTER(h);
+    if (k == 0) return h->fail(FVDB_ERR_INVALID_ARG, "k must be >= 1");
+    if ((uint64_t)k * 3 > h->k_max)
+        return h->fail(FVDB_ERR_K_TOO_LARGE, "the 3x post-filter searches 3k candidates: 3k exceeds k_max given at fvdb_create");
+    if (nq == 0) return FVDB_OK;
+    if (!q || !out_ids || !out_dist || !out_count || !keep_bits) return h->fail(FVDB_ERR_INVALID_ARG, "NULL buffer");
+    cudaStream_t st = h->stream;
+    const uint32_t D = h->dim, k3 = 3 * k;
+    const size_t words = std::max<uint64_t>((keep_nbits + 63) / 64, 1);
+    CK(h->s_q.ensure((size_t)nq * D, 0, st, &h->dev_bytes));
+    CK(h->s_filter.ensure(words, 0, st, &h->dev_bytes));
+    CK(h->s_out_ids.ensure((size_t)nq * (k3 + k), 0, st, &h->dev_bytes));
+    CK(h->s_out_dist.ensure((size_t)nq * (k3 + k), 0, st, &h->dev_bytes));
+    CK(h->s_out_cnt.ensure((size_t)2 * nq, 0, st, &h->dev_bytes));
+    RET(h2d(h, h->s_q.p, q, (size_t)nq * D * 4));
+    if (keep_nbits) RET(h2d(h, h->s_filter.p, keep_bits, (keep_nbits + 63) / 64 * 8));
+    uint32_t* c_ids = h->s_out_ids.p;
+    float* c_dist = h->s_out_dist.p;
+    uint32_t* c_cnt = h->s_out_cnt.p;
+    uint32_t* f_ids = c_ids + (size_t)nq * k3;
+    float* f_dist = c_dist + (size_t)nq * k3;
+    uint32_t* f_cnt = c_cnt + nq;
+    RET(search_device_impl(h, h->s_q.p, nq, k3, nprobe, tiers, nullptr, 0, c_ids, c_dist, c_cnt, st));
+    CK(launch_postfilter_rows(c_ids, c_dist, c_cnt, nq, k3, k, h->s_filter.p, keep_nbits, f_ids, f_dist, f_cnt, st));
+    h->stats.last_launches += 1;
+    RET(d2h(h, out_ids, f_ids, (size_t)nq * k * 4));
+    RET(d2h(h, out_dist, f_dist, (size_t)nq * k * 4));
+    RET(d2h(h, out_count, f_cnt, (size_t)nq * 4));
+    return FVDB_OK;
+}
+
 int fvdb_host_alloc(size_t bytes, void** out) {
     if (!out) return FVDB_ERR_INVALID_ARG;
     *out = nullptr;
@@ -1799,6 +1984,25 @@ int fvdb_host_alloc(size_t bytes, void** out) {
 
 void fvdb_host_free(void* p) {
     if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
+}
+
+int fvdb_ivf_max_sqnorm(fvdb_index* h, float* out) {
+    ENTER(h);
+    if (!out) return h->fail(FVDB_ERR_INVALID_ARG, "out is NULL");
+    *out = 0.f;
+    RET(seal(h));
+    if (h->ivf_n == 0) return FVDB_OK;
+    cudaStream_t st = h->stream;
+    CK(h->s_f32a.ensure(h->ivf_n, 0, st, &h->dev_bytes));
+    CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
+    uint32_t* d_max = h->s_misc.p + 13;
+    CK(cudaMemsetAsync(d_max, 0, 4, st));
+    CK(launch_max_sqnorm(h->ivf_rows.p, h->ivf_n, h->dim, h->s_f32a.p, d_max, st));
+    uint32_t bits = 0;
+    CK(cudaMemcpyAsync(&bits, d_max, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::memcpy(out, &bits, 4);
+    return FVDB_OK;
 }
 
 int fvdb_bounds_export(fvdb_index* h, uint32_t nq_cap, void* handle_out) {
@@ -1821,6 +2025,11 @@ int fvdb_bounds_export(fvdb_index* h, uint32_t nq_cap, void* handle_out) {
 
 int fvdb_bounds_import(fvdb_index* h, const void* handles, uint32_t n_ranks, uint32_t my_rank) {
     ENTER(h);
+    if (n_ranks == 0) {   // close every imported array (before a peer re-exports a larger one)
+        for (uint32_t* pb : h->peer_bounds) cudaIpcCloseMemHandle(pb);
+        h->peer_bounds.clear();
+        return FVDB_OK;
+    }
     if (!h->bounds) return h->fail(FVDB_ERR_INVALID_ARG, "call fvdb_bounds_export first");
     if (!handles || my_rank >= n_ranks || n_ranks - 1 > TC_MAX_PEERS)
         return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_bounds_import: 2..8 ranks, my_rank < n_ranks");

@@ -791,6 +791,43 @@ cudaError_t launch_scatter_result_rows(const uint32_t* ids, const float* dist, c
     return cudaGetLastError();
 }
 
+// The reference's 3x POST-filter (HybridIndex::search_with_filter, src/hybrid/core.rs:529-546) on the
+// device: of a query's k3 = 3k candidates (already ascending) keep, in order, those whose row id has
+// its bit set in `keep` (bit = "metadata present and filter.matches", evaluated once per row by the
+// host), and truncate to k.  One thread per query: k3 <= 3 * k_max entries, a sequential compaction.
+__global__ void postfilter_rows_kernel(const uint32_t* __restrict__ ids, const float* __restrict__ dist,
+                                       const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t k3, uint32_t k,
+                                       const uint64_t* __restrict__ keep, uint64_t keep_bits,
+                                       uint32_t* __restrict__ out_ids, float* __restrict__ out_dist,
+                                       uint32_t* __restrict__ out_cnt) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint32_t n = min(cnt[q], k3);
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < n && r < k; ++i) {
+        const uint32_t id = ids[(size_t)q * k3 + i];
+        if (bit_test(keep, keep_bits, id)) {
+            out_ids[(size_t)q * k + r] = id;
+            out_dist[(size_t)q * k + r] = dist[(size_t)q * k3 + i];
+            ++r;
+        }
+    }
+    out_cnt[q] = r;
+    for (; r < k; ++r) {
+        out_ids[(size_t)q * k + r] = ID_NONE;
+        out_dist[(size_t)q * k + r] = __uint_as_float(0x7f800000u);
+    }
+}
+
+cudaError_t launch_postfilter_rows(const uint32_t* ids, const float* dist, const uint32_t* cnt, uint32_t nq,
+                                   uint32_t k3, uint32_t k, const uint64_t* keep, uint64_t keep_bits,
+                                   uint32_t* out_ids, float* out_dist, uint32_t* out_cnt, cudaStream_t stream) {
+    if (nq == 0) return cudaSuccess;
+    postfilter_rows_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(ids, dist, cnt, nq, k3, k, keep, keep_bits, out_ids,
+                                                                out_dist, out_cnt);
+    return cudaGetLastError();
+}
+
 // NaN screen over a float matrix (the reference panics on NaN: src/ivf/core.rs:655,677).
 __global__ void nan_check_kernel(const float* __restrict__ x, size_t n, int* __restrict__ flag) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -64,6 +64,10 @@ cudaError_t launch_merge_parts(const uint32_t* ids, const float* dist, const uin
 cudaError_t launch_scatter_result_rows(const uint32_t* ids, const float* dist, const uint32_t* cnt,
                                        const uint32_t* idx, uint32_t n, uint32_t k, uint32_t* out_ids,
                                        float* out_dist, uint32_t* out_cnt, cudaStream_t stream);
+// 3x post-filter of src/hybrid/core.rs:529-546: keep the candidates whose id bit is set, truncate to k
+cudaError_t launch_postfilter_rows(const uint32_t* ids, const float* dist, const uint32_t* cnt, uint32_t nq,
+                                   uint32_t k3, uint32_t k, const uint64_t* keep, uint64_t keep_bits,
+                                   uint32_t* out_ids, float* out_dist, uint32_t* out_cnt, cudaStream_t stream);
 cudaError_t launch_scatter_keys(const uint64_t* src, const uint32_t* idx, uint32_t n, uint32_t k,
                                 uint64_t* dst, cudaStream_t stream);
 cudaError_t launch_nan_check(const float* x, size_t n, int* flag, cudaStream_t stream);
@@ -90,6 +94,9 @@ cudaError_t launch_set_bits(uint64_t* bits, uint64_t nbits, const uint32_t* ids,
 // keys_out[i] = (keys[i] % mod == rem) ? keys[i] : drop
 cudaError_t launch_filter_keys_mod(const uint32_t* keys, uint64_t n, uint32_t mod, uint32_t rem,
                                    uint32_t drop, uint32_t* keys_out, cudaStream_t stream);
+// keys_out[i] = (owner[keys[i]] == rank) ? keys[i] : drop   (owner: device table over the `drop` lists)
+cudaError_t launch_filter_keys_owner(const uint32_t* keys, uint64_t n, const uint32_t* owner, uint32_t rank,
+                                     uint32_t drop, uint32_t* keys_out, cudaStream_t stream);
 cudaError_t launch_iota_u32(uint32_t* p, uint64_t n, uint32_t start, cudaStream_t stream);
 cudaError_t launch_extract_assign(const uint64_t* keys, uint64_t n, uint32_t* assign, float* dist,
                                   const uint32_t* prev_assign, uint32_t* changed, cudaStream_t stream);
@@ -110,13 +117,6 @@ cudaError_t launch_accumulate_sums(const float* data, uint64_t n, uint32_t D, co
                                    cudaStream_t stream);
 cudaError_t launch_apply_means(const float* sums, const uint32_t* counts, uint32_t nlist, uint32_t D,
                                float* centroids, cudaStream_t stream);
-// k-means++ round (src/ivf/core.rs:346-367): mind[j] = min(mind[j], L2(x_j, c_new)); block sums
-// of mind^2 (f64) -> pick first j with cumulative >= u * total.
-cudaError_t launch_kmeanspp_update(const float* data, uint64_t n, uint32_t D, const float* c_new,
-                                   float* mind, double* block_sums, uint32_t* n_blocks_out,
-                                   cudaStream_t stream);
-cudaError_t launch_kmeanspp_pick(const float* mind, uint64_t n, const double* block_sums,
-                                 uint32_t n_blocks, double u01, uint32_t* picked, cudaStream_t stream);
 cudaError_t launch_copy_row(const float* data, const uint32_t* idx, uint32_t D, float* dst,
                             cudaStream_t stream);
 

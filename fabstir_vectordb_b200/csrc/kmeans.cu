@@ -105,67 +105,6 @@ __global__ void apply_means_kernel(const float* __restrict__ sums, const uint32_
     if (cnt > 0) centroids[i] = __fdiv_rn(sums[i], (float)cnt);
 }
 
-constexpr uint32_t PP_POINTS_PER_BLOCK = 1024;
-
-// k-means++ round: distance of every point to the newest centroid, running minimum, and the
-// block's sum of mind^2 (f64).  Not order-faithful by design: the seeded stream is unpinned.
-__global__ void __launch_bounds__(256) kmeanspp_update_kernel(const float* __restrict__ data, uint64_t n,
-                                                              uint32_t D, const float* __restrict__ c_new,
-                                                              float* __restrict__ mind,
-                                                              double* __restrict__ block_sums) {
-    __shared__ double wsum[8];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint64_t b = (uint64_t)blockIdx.x * PP_POINTS_PER_BLOCK;
-    const uint64_t e = min(n, b + PP_POINTS_PER_BLOCK);
-    double acc = 0.0;
-    for (uint64_t i = b + w; i < e; i += 8) {
-        const float* x = data + (size_t)i * D;
-        float s = 0.f;
-        for (uint32_t d = lane; d < D; d += 32) {
-            const float t = __ldg(x + d) - __ldg(c_new + d);
-            s += t * t;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float dist = sqrtf(s);
-        float m = mind[i];
-        m = fminf(m, dist);
-        if (lane == 0) mind[i] = m;
-        acc += (double)m * (double)m;
-    }
-    if (lane == 0) wsum[w] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int j = 0; j < 8; ++j) t += wsum[j];
-        block_sums[blockIdx.x] = t;
-    }
-}
-
-// first j with cumulative(mind^2) >= u * total  (src/ivf/core.rs:357-367)
-__global__ void kmeanspp_pick_kernel(const float* __restrict__ mind, uint64_t n,
-                                     const double* __restrict__ block_sums, uint32_t n_blocks,
-                                     double u01, uint32_t* __restrict__ picked) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double total = 0.0;
-    for (uint32_t b = 0; b < n_blocks; ++b) total += block_sums[b];
-    const double threshold = u01 * total;
-    double cum = 0.0;
-    uint32_t blk = n_blocks - 1;
-    for (uint32_t b = 0; b < n_blocks; ++b) {
-        if (cum + block_sums[b] >= threshold) { blk = b; break; }
-        cum += block_sums[b];
-    }
-    const uint64_t s = (uint64_t)blk * PP_POINTS_PER_BLOCK;
-    const uint64_t e = min(n, s + PP_POINTS_PER_BLOCK);
-    uint64_t pick = e - 1;
-    for (uint64_t j = s; j < e; ++j) {
-        cum += (double)mind[j] * (double)mind[j];
-        if (cum >= threshold) { pick = j; break; }
-    }
-    *picked = (uint32_t)pick;
-}
-
 __global__ void copy_row_kernel(const float* __restrict__ data, const uint32_t* __restrict__ idx,
                                 uint32_t D, float* __restrict__ dst) {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,22 +146,6 @@ cudaError_t launch_apply_means(const float* sums, const uint32_t* counts, uint32
     const uint64_t n = (uint64_t)nlist * D;
     if (n == 0) return cudaSuccess;
     apply_means_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, stream>>>(sums, counts, nlist, D, centroids);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_kmeanspp_update(const float* data, uint64_t n, uint32_t D, const float* c_new,
-                                   float* mind, double* block_sums, uint32_t* n_blocks_out,
-                                   cudaStream_t stream) {
-    const uint32_t blocks = (uint32_t)((n + PP_POINTS_PER_BLOCK - 1) / PP_POINTS_PER_BLOCK);
-    *n_blocks_out = blocks;
-    if (blocks == 0) return cudaSuccess;
-    kmeanspp_update_kernel<<<blocks, 256, 0, stream>>>(data, n, D, c_new, mind, block_sums);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_kmeanspp_pick(const float* mind, uint64_t n, const double* block_sums,
-                                 uint32_t n_blocks, double u01, uint32_t* picked, cudaStream_t stream) {
-    kmeanspp_pick_kernel<<<1, 32, 0, stream>>>(mind, n, block_sums, n_blocks, u01, picked);
     return cudaGetLastError();
 }
 

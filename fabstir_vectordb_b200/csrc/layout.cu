@@ -180,6 +180,18 @@ __global__ void filter_keys_mod_kernel(const uint32_t* __restrict__ keys, uint64
     }
 }
 
+// list -> GPU placement table (size-balanced list sharding): keep a row when its list's owner is `rank`
+__global__ void filter_keys_owner_kernel(const uint32_t* __restrict__ keys, uint64_t n,
+                                         const uint32_t* __restrict__ owner, uint32_t rank, uint32_t drop,
+                                         uint32_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const uint32_t k = keys[i];
+        out[i] = (k < drop && __ldg(owner + k) == rank) ? k : drop;
+    }
+}
+
 __global__ void iota_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t start) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -266,6 +278,13 @@ cudaError_t launch_filter_keys_mod(const uint32_t* keys, uint64_t n, uint32_t mo
                                    uint32_t drop, uint32_t* keys_out, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     filter_keys_mod_kernel<<<grid_for(n), 256, 0, stream>>>(keys, n, mod, rem, drop, keys_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_filter_keys_owner(const uint32_t* keys, uint64_t n, const uint32_t* owner, uint32_t rank,
+                                     uint32_t drop, uint32_t* keys_out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    filter_keys_owner_kernel<<<grid_for(n), 256, 0, stream>>>(keys, n, owner, rank, drop, keys_out);
     return cudaGetLastError();
 }
 

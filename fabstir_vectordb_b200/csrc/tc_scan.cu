@@ -1236,7 +1236,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
                                                      const float* __restrict__ rows, const uint32_t* __restrict__ ids,
                                                      const float* __restrict__ Q, const float* __restrict__ qnorm,
                                                      const uint32_t* __restrict__ xmax_bits, uint32_t nq, uint32_t D,
-                                                     uint32_t k, uint32_t R, uint64_t* __restrict__ out_keys,
+                                                     uint32_t k, uint32_t R, float xmax_floor_sq, uint64_t* __restrict__ out_keys,
                                                      uint32_t* __restrict__ fb_count, uint32_t* __restrict__ fb_idx,
                                                      uint32_t* __restrict__ fin_ids = nullptr, float* __restrict__ fin_dist = nullptr,
                                                      uint32_t* __restrict__ fin_count = nullptr) {
@@ -1273,7 +1273,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
     const uint64_t kth = shfl64(ekey, (int)k - 1);
     if (lane == 0 && a_last_key != KEY_NONE) {
         const float a_last = __uint_as_float((uint32_t)(a_last_key >> 32));
-        const float xmax = sqrtf(__uint_as_float(*xmax_bits));
+        // xmax_floor_sq: list-sharded search with shared bounds — a row of THIS shard may have been
+        // dropped by a bound a peer published, so every shard has to use the same (largest) norm term
+        const float xmax = sqrtf(fmaxf(__uint_as_float(*xmax_bits), xmax_floor_sq));
         const float eps = 1.05f * 0.00390625f * sqrtf(qnorm[q]) * xmax + 3.1e-5f * a_last + 1e-30f;
         bool ok = false;
         if (kth != KEY_NONE) {
@@ -1668,6 +1670,14 @@ static cudaError_t dump_prof(const unsigned long long* d_prof, uint32_t grid, cu
         fprintf(stderr, "\n");
     }
     return cudaSuccess;
+}
+
+cudaError_t launch_max_sqnorm(const float* x, uint64_t n, uint32_t D, float* scratch_norms, uint32_t* max_bits,
+                              cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)148 * 16);
+    row_norms_kernel<<<blocks, 256, 0, stream>>>(x, n, D, scratch_norms, max_bits);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t stream) {
@@ -2095,7 +2105,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     TCK(launch_merge_rows32(m->partial.p, nq, np * prows, m->shortlist.p, st, m->row_stamp.p, stamp));
     TCK(rerank_prepare(m));
     rerank_kernel<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k, (uint32_t)TC_KP,
-                                               a.out_keys, a.d_fallback_count, a.d_fallback_idx, a.fin_ids, a.fin_dist, a.fin_count);
+                                               a.xmax_floor_sq, a.out_keys, a.d_fallback_count, a.d_fallback_idx, a.fin_ids, a.fin_dist, a.fin_count);
     TCK(cudaGetLastError());
     (*launches) += 2;
     return FVDB_OK;
@@ -2202,7 +2212,7 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
     TCK(rerank_prepare(m));
     rerank_kernel<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p,
                                                                          xmax_bits, nq, D, a.k,
-                                                                         a.rerank_r ? a.rerank_r : (uint32_t)TC_KP, a.out_keys,
+                                                                         a.rerank_r ? a.rerank_r : (uint32_t)TC_KP, 0.0f, a.out_keys,
                                                                          a.d_fallback_count, a.d_fallback_idx);
     TCK(cudaGetLastError());
     (*launches) += 3;

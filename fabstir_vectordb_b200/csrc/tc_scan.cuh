@@ -58,6 +58,7 @@ struct TcSearchArgs {
     uint32_t* thr_ext = nullptr;
     uint32_t* thr_peers[TC_MAX_PEERS] = {};
     uint32_t n_peers = 0;
+    float xmax_floor_sq = 0.f;        // lower bound of the max |x|^2 term of the proof (max over all shards)
     // optional fusions with the caller's steps (both save a launch per batch):
     int* d_nan = nullptr;             // set to 1 when Q holds a NaN (the query-norm pass sees every element)
     uint32_t* fin_ids = nullptr;      // when given, the re-rank also writes the caller-facing result
@@ -103,5 +104,8 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
                    std::string* err);
 void tc_release(TcScratch& s);
 cudaError_t launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t stream);
+// norms[i] = |x_i|^2 (scratch, n floats), *max_bits = max over rows as f32 bits (caller zeroes it)
+cudaError_t launch_max_sqnorm(const float* x, uint64_t n, uint32_t D, float* scratch_norms, uint32_t* max_bits,
+                              cudaStream_t stream);
 
 }  // namespace fvdb

@@ -310,7 +310,9 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
             if (leader) {
                 uint32_t stage = 0, phase = 0, ss = 0, sphase = 0, tile = 0, nit = 0;
                 const uint32_t ring_base = smem_u32(ring);
-                const uint32_t idesc = umma_idesc_tf32(2 * W_M, W_N);
+                // timing experiments (FVDB_TC_DEBUG): bit 5 = N = 32 per instruction, bit 4 = a quarter of the instructions
+                const uint32_t idesc = umma_idesc_tf32(2 * W_M, (p.debug & 32u) ? W_N / 2 : W_N);
+                const uint32_t k4_n = (p.debug & 16u) ? 1u : 4u;
                 while (true) {
                     Q1_LAP(4);
                     const uint32_t item = next_item(ss, sphase);
@@ -343,7 +345,7 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
                                         const uint32_t a0 = tmem_base + (st * KBS + j) * 32;
 #pragma unroll
                                         for (uint32_t k4 = 0; k4 < 4; ++k4)   // A: 8 tf32 = 8 TMEM columns per step
-                                            umma_tf32_ts_pair(d_tmem, a0 + k4 * 8, b0 + 2 * k4, idesc, (st | j | k4) != 0 ? 1u : 0u);
+                                            if (k4 < k4_n) umma_tf32_ts_pair(d_tmem, a0 + k4 * 8, b0 + 2 * k4, idesc, (st | j | k4) != 0 ? 1u : 0u);
                                     }
                                 }
                                 umma_commit_pair(bar_empty + 8 * stage);    // frees the stage in both CTAs

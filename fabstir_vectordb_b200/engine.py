@@ -282,6 +282,26 @@ class Engine:
                                        _p(ids, _u32p), _p(dist, _f32p), _p(cnt, _u32p)))
         return ids, dist, cnt
 
+    def search_postfilter(self, queries, k: int, nprobe: int, keep_bits, tiers: int = L.TIER_BOTH):
+        """The reference's 3x post-filter (fvdb_search_postfilter): search(3k), keep rows whose bit is set in
+        `keep_bits` (u64 words over row ids), truncate to k."""
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        if q.shape[1] != self.dim:
+            raise DimensionMismatch(self.dim, q.shape[1])
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint32)
+        dist = np.empty((nq, k), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        kb = np.ascontiguousarray(keep_bits, dtype=np.uint64)
+        nbits = kb.size * 64
+        if kb.size == 0:
+            kb = np.zeros(1, dtype=np.uint64)
+        self._ck(self._lib.fvdb_search_postfilter(self._h, _p(q, _f32p), nq, k, nprobe, tiers, _p(kb, _u64p), nbits,
+                                                  _p(ids, _u32p), _p(dist, _f32p), _p(cnt, _u32p)))
+        return ids, dist, cnt
+
     def search_submit(self, queries: np.ndarray, k: int, nprobe: int, tiers: int, out):
         """Stream-ordered fvdb_search: `queries` and `out` = (ids, dist, count) must be views of PinnedArray
         buffers; they belong to the engine until search_finish() returns."""
@@ -335,6 +355,14 @@ class Engine:
                                                   d_out_ids, d_out_dist, d_out_count,
                                                   _stream(stream)))
 
+    def ivf_max_sqnorm(self) -> float:
+        v = C.c_float()
+        self._ck(self._lib.fvdb_ivf_max_sqnorm(self._h, C.byref(v)))
+        return float(v.value)
+
+    def bounds_close_peers(self):
+        self._ck(self._lib.fvdb_bounds_import(self._h, None, 0, 0))
+
     def bounds_export(self, nq_cap: int) -> bytes:
         buf = C.create_string_buffer(64)
         self._ck(self._lib.fvdb_bounds_export(self._h, nq_cap, buf))
@@ -356,6 +384,14 @@ class Engine:
         kept = C.c_uint64()
         self._ck(self._lib.fvdb_ivf_add_device(self._h, d_x, d_ids, n, mod, rem, C.byref(kept)))
         return kept.value
+
+    def ivf_add_device_owned(self, d_x: int, d_ids: int, n: int, d_owner: int, my_rank: int) -> int:
+        kept = C.c_uint64()
+        self._ck(self._lib.fvdb_ivf_add_device_owned(self._h, d_x, d_ids, n, d_owner, my_rank, C.byref(kept)))
+        return kept.value
+
+    def assign_device(self, d_x: int, n: int, d_out: int, stream: int = 0):
+        self._ck(self._lib.fvdb_assign_device(self._h, d_x, n, d_out, _stream(stream)))
 
     def flat_add_device(self, d_x: int, d_ids: int, n: int):
         self._ck(self._lib.fvdb_flat_add_device(self._h, d_x, d_ids, n))

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib as L
 from .engine import (DimensionMismatch, DuplicateVector, Engine, FvdbError,
-                     InconsistentDimensions, InsufficientTrainingData, InvalidConfig, NotTrained,
+                     InconsistentDimensions, InsufficientTrainingData, InvalidConfig, NanInput, NotTrained,
                      VectorNotFound)
 
 
@@ -131,6 +131,17 @@ class _IdMap:
         for _ in range(n):
             vid = self.to_id.pop()
             del self.to_row[vid]
+
+    def release(self, vid: Hashable):
+        """A vacuumed vector: its VectorId may be inserted again (the reference removes the entry
+        physically, src/ivf/operations.rs:625-645).  The row-id slot stays (row ids are dense and
+        never reused), pointing at nothing."""
+        row = self.to_row.pop(vid, None)
+        if row is not None:
+            self.to_id[row] = None
+
+    def live(self) -> int:
+        return len(self.to_row)
 
 
 def _as_matrix(vectors: Sequence[Sequence[float]], dim: Optional[int]) -> np.ndarray:
@@ -383,9 +394,12 @@ class IVFIndex:
         return vid in self._deleted
 
     def vacuum(self) -> int:
+        """src/ivf/operations.rs:625-645: the entries are removed physically, so a vacuumed
+        VectorId can be inserted again."""
         removed = self._eng.vacuum() if self._eng else 0
         for v in self._deleted:
             self._lists.pop(v, None)
+            self._ids.release(v)
         self._deleted = set()
         return removed
 
@@ -431,7 +445,7 @@ class HNSWIndex:
         self._dimension: Optional[int] = None
 
     def node_count(self) -> int:
-        return len(self._ids.to_id)
+        return self._ids.live()
 
     def dimension(self) -> Optional[int]:
         return self._dimension
@@ -455,7 +469,11 @@ class HNSWIndex:
         except DuplicateVector:
             self._ids.rollback(len(rows))
             raise
-        self._eng.flat_add(x, np.asarray(rows, dtype=np.uint32))
+        try:
+            self._eng.flat_add(x, np.asarray(rows, dtype=np.uint32))
+        except FvdbError:
+            self._ids.rollback(len(rows))
+            raise
 
     def search(self, query, k: int, ef: int = 50) -> List[SearchResult]:
         """src/hnsw/core.rs:398-467.  Empty index -> [] (:404-407)."""
@@ -480,117 +498,21 @@ class HNSWIndex:
 
     def vacuum(self) -> int:
         removed = self._eng.vacuum() if self._eng else 0
+        for v in self._deleted:
+            self._ids.release(v)
         self._deleted = set()
         return removed
 
 
-# ---- metadata filter (host side: producer of the bitmap) -------------------------------------
+# ---- metadata filter ------------------------------------------------------------------------
+# The reference evaluates a MetadataFilter (src/core/metadata_filter.rs) against JSON metadata on the
+# host; that evaluator is outside the hot path.  Here a filter is any callable
+# `metadata -> bool` (or an object with a `.matches(metadata)` method): the mirror evaluates it once per
+# row and hands the engine a bitmap.
 
-class FilterError(ValueError):
-    pass
-
-
-class MetadataFilter:
-    """MetadataFilter, src/core/metadata_filter.rs:32-357: Mongo-style Equals / In / Range /
-    And / Or with dotted paths (get_field :359-373) and array-contains equality (:272-281)."""
-
-    def __init__(self, kind, **kw):
-        self.kind = kind
-        self.__dict__.update(kw)
-
-    @staticmethod
-    def from_json(value) -> "MetadataFilter":
-        if not isinstance(value, dict):
-            raise FilterError("Filter must be a JSON object")
-        if "$and" in value:
-            v = value["$and"]
-            if not isinstance(v, list):
-                raise FilterError("$and must be an array")
-            return MetadataFilter("and", filters=[MetadataFilter.from_json(f) for f in v])
-        if "$or" in value:
-            v = value["$or"]
-            if not isinstance(v, list):
-                raise FilterError("$or must be an array")
-            return MetadataFilter("or", filters=[MetadataFilter.from_json(f) for f in v])
-        for key in value:
-            if key.startswith("$"):
-                raise FilterError(f"Unsupported operator: {key}")
-        if len(value) == 1:
-            (f, fv), = value.items()
-            return MetadataFilter._field(f, fv)
-        return MetadataFilter("and", filters=[MetadataFilter._field(f, fv) for f, fv in value.items()])
-
-    @staticmethod
-    def _num(v):
-        return float(v) if isinstance(v, (int, float)) and not isinstance(v, bool) else None
-
-    @staticmethod
-    def _field(fld, value) -> "MetadataFilter":
-        if isinstance(value, dict):
-            if "$in" in value:
-                if not isinstance(value["$in"], list):
-                    raise FilterError("$in value must be an array")
-                return MetadataFilter("in", field=fld, values=value["$in"])
-            gte, gt = MetadataFilter._num(value.get("$gte")), MetadataFilter._num(value.get("$gt"))
-            lte, lt = MetadataFilter._num(value.get("$lte")), MetadataFilter._num(value.get("$lt"))
-            if gte is not None and gt is not None:
-                raise FilterError("Cannot use both $gte and $gt in the same range filter")
-            if lte is not None and lt is not None:
-                raise FilterError("Cannot use both $lte and $lt in the same range filter")
-            mn, mn_inc = (gte, True) if gte is not None else ((gt, False) if gt is not None else (None, True))
-            mx, mx_inc = (lte, True) if lte is not None else ((lt, False) if lt is not None else (None, True))
-            if mn is not None or mx is not None:
-                return MetadataFilter("range", field=fld, min=mn, max=mx, min_inclusive=mn_inc,
-                                      max_inclusive=mx_inc)
-            for key in value:
-                if key.startswith("$") and key not in ("$in", "$gte", "$gt", "$lte", "$lt"):
-                    raise FilterError(f"Unsupported operator: {key}")
-            if not value:
-                raise FilterError(f"Empty object for field '{fld}' - must specify a value or operator")
-        return MetadataFilter("equals", field=fld, value=value)
-
-    @staticmethod
-    def _get(metadata, path):
-        cur = metadata
-        for part in path.split("."):
-            if not isinstance(cur, dict) or part not in cur:
-                return None, False
-            cur = cur[part]
-        return cur, True
-
-    @staticmethod
-    def _json_eq(a, b) -> bool:
-        # serde_json Value equality: bool is not a number; 1 == 1.0 is false in serde_json for
-        # differing representations only when one is a float with a fractional part
-        if isinstance(a, bool) or isinstance(b, bool):
-            return isinstance(a, bool) and isinstance(b, bool) and a == b
-        return a == b
-
-    def matches(self, metadata) -> bool:
-        k = self.kind
-        if k == "equals":
-            fv, ok = self._get(metadata, self.field)
-            if not ok:
-                return False
-            if isinstance(fv, list):
-                return any(self._json_eq(x, self.value) for x in fv)
-            return self._json_eq(fv, self.value)
-        if k == "in":
-            fv, ok = self._get(metadata, self.field)
-            return ok and any(self._json_eq(fv, v) for v in self.values)
-        if k == "range":
-            fv, ok = self._get(metadata, self.field)
-            num = self._num(fv) if ok else None
-            if num is None:
-                return False
-            mn_ok = True if self.min is None else (num >= self.min if self.min_inclusive else num > self.min)
-            mx_ok = True if self.max is None else (num <= self.max if self.max_inclusive else num < self.max)
-            return mn_ok and mx_ok
-        if k == "and":
-            return all(f.matches(metadata) for f in self.filters)
-        if k == "or":
-            return any(f.matches(metadata) for f in self.filters)
-        raise FilterError(f"unknown filter kind {k}")
+def _matches(flt, metadata) -> bool:
+    m = getattr(flt, "matches", None)
+    return bool(m(metadata) if m is not None else flt(metadata))
 
 
 @dataclass
@@ -696,19 +618,40 @@ class HybridIndex:
         self._ensure_engine(x.shape[1])
         if x.shape[1] != self._dimension:
             raise DimensionMismatch(self._dimension, x.shape[1])
-        for v in ids:
-            if v in self.timestamps:
+        ids = list(ids)
+        seen = set()
+        for v in ids:   # duplicates against the index AND inside the batch, before any id is registered
+            if v in self._ids.to_row or v in seen:
                 raise DuplicateVector(f"Vector with ID {v!r} already exists")
+            seen.add(v)
+        if np.isnan(x).any():   # the engine would reject the batch half-way (flat rows in, IVF rows not)
+            raise NanInput("NaN in input (the reference panics on partial_cmp().unwrap())")
         now = time.time()
-        rows = [self._ids.add(v) for v in ids]
-        rows = np.asarray(rows, dtype=np.uint32)
+        rows = np.asarray([self._ids.add(v) for v in ids], dtype=np.uint32)
         ts = np.asarray(timestamps, dtype=np.float64)
         age = np.maximum(now - ts, 0.0)
         recent = np.ones(len(rows), dtype=bool) if not self.ivf_trained else (age < self.config.recent_threshold)
-        if recent.any():
-            self._eng.flat_add(x[recent], rows[recent])
-        if (~recent).any():
-            self._eng.ivf_add(x[~recent], rows[~recent])
+        flat_done = False
+        try:
+            if recent.any():
+                self._eng.flat_add(x[recent], rows[recent])
+                flat_done = True
+            if (~recent).any():
+                self._eng.ivf_add(x[~recent], rows[~recent])
+        except FvdbError:
+            # nothing of a failed batch may stay behind: forget the ids, and take the rows the first
+            # call already placed out of the device again
+            if flat_done:
+                self._eng.set_deleted(rows[recent], True)
+                self._eng.vacuum()
+                if self._deleted:   # vacuum dropped earlier soft-deleted rows as well
+                    for v in self._deleted:
+                        self._tier.pop(v, None)
+                        self.timestamps.pop(v, None)
+                        self._ids.release(v)
+                    self._deleted = set()
+            self._ids.rollback(len(rows))
+            raise
         for v, t, r in zip(ids, ts, recent):
             self.timestamps[v] = float(t)
             self._tier[v] = 1 if r else 2
@@ -746,6 +689,8 @@ class HybridIndex:
         removed = self._eng.vacuum() if self._eng else 0
         for v in self._deleted:
             self._tier.pop(v, None)
+            self.timestamps.pop(v, None)
+            self._ids.release(v)
         self._deleted = set()
         return removed
 
@@ -800,30 +745,40 @@ class HybridIndex:
             return ids, dist, cnt
         return _results(self._ids, ids, dist, cnt)
 
-    def filter_bitmap(self, flt: MetadataFilter, metadata_map: Dict[str, Any]) -> np.ndarray:
-        """Evaluate the filter once per row on the host -> 1 bit per row id."""
+    def filter_bitmap(self, flt, metadata_map: Dict[str, Any]) -> np.ndarray:
+        """Evaluate the filter once per row on the host -> 1 bit per row id.  A row
+        missing from `metadata_map` gets bit 0, as the reference drops it (src/hybrid/core.rs:536-541)."""
         n = len(self._ids.to_id)
         words = np.zeros((n + 63) // 64 or 1, dtype=np.uint64)
         for vid, row in self._ids.to_row.items():
             md = metadata_map.get(str(vid))
-            if md is not None and flt.matches(md):
+            if md is not None and _matches(flt, md):
                 words[row >> 6] |= np.uint64(1) << np.uint64(row & 63)
         return words
 
-    def search_with_filter(self, query, k: int, flt: Optional[MetadataFilter],
-                           metadata_map: Dict[str, Any]) -> List[SearchResult]:
-        """src/hybrid/core.rs:513-549 — the reference's 3x oversample POST-filter."""
+    def search_with_filter(self, query, k: int, flt, metadata_map: Dict[str, Any]) -> List[SearchResult]:
+        """src/hybrid/core.rs:513-549 — the reference's 3x oversample POST-filter, as one device call
+        (fvdb_search_postfilter: search(3k), keep the rows whose bit is set, truncate(k)).  `flt` is any
+        callable metadata -> bool (or an object with .matches)."""
         if flt is None:
             return self.search(query, k)
-        cands = self.search(query, k * 3)
-        out = []
-        for r in cands:
-            md = metadata_map.get(str(r.vector_id))
-            if md is not None and flt.matches(md):
-                out.append(r)
-        return out[:k]
+        if not self.initialized or self._eng is None or k == 0:
+            return []
+        if 3 * k > self._k_max:
+            raise InvalidParameter(f"search_with_filter searches 3k candidates: k={k} needs k_max >= {3 * k} "
+                                   f"(this index was created with k_max={self._k_max})")
+        if self.config.auto_migrate:
+            self.migrate_old_vectors()
+        q = np.asarray(query, dtype=np.float32).reshape(1, -1)
+        if q.shape[1] != self._dimension:
+            return []
+        cfg = HybridSearchConfig(k=k)
+        tiers = L.TIER_RECENT | (L.TIER_HISTORICAL if self.ivf_trained else 0)
+        bits = self.filter_bitmap(flt, metadata_map)
+        ids, dist, cnt = self._eng.search_postfilter(q, k, cfg.ivf_n_probe, bits, tiers)
+        return _results(self._ids, ids, dist, cnt)[0]
 
-    def search_with_prefilter(self, query, k: int, flt: MetadataFilter, metadata_map) -> List[SearchResult]:
+    def search_with_prefilter(self, query, k: int, flt, metadata_map) -> List[SearchResult]:
         """In-kernel bitmap PRE-filter (semantics of bindings/wasm/src/index.rs:164-186): never
         returns fewer than k when >= k matching rows are reachable."""
         bits = self.filter_bitmap(flt, metadata_map)

@@ -74,6 +74,14 @@ class ShardedIndex:
         """Exchange the inter-process handles of the per-query bound arrays (once per capacity)."""
         import torch
         import torch.distributed as dist
+        # no rank may free its exported array while a peer still has it mapped
+        self.eng.bounds_close_peers()
+        dist.barrier(group=self.group)
+        # rows of this shard can be dropped by a bound a peer published: the tensor-core proof of every
+        # shard uses the largest row norm of ALL shards (FVDB_OPT_PROOF_XMAX)
+        xm = torch.tensor([self.eng.ivf_max_sqnorm()], dtype=torch.float32, device=device)
+        dist.all_reduce(xm, op=dist.ReduceOp.MAX, group=self.group)
+        self.eng.set_option(L.OPT_PROOF_XMAX, int(np.float32(xm.item()).view(np.uint32)))
         mine = torch.frombuffer(bytearray(self.eng.bounds_export(nq)), dtype=torch.uint8).to(device)
         allh = torch.empty((self.world * 64,), dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(allh, mine, group=self.group)

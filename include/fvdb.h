@@ -84,7 +84,11 @@ typedef enum fvdb_option {
     FVDB_OPT_SCAN_MODE = 1,   /* FVDB_SCAN_EXACT | FVDB_SCAN_TC (default TC when dim%32==0) */
     FVDB_OPT_SHORTLIST = 2,   /* shortlist length k' of the TC mode (default max(32, ..)) */
     FVDB_OPT_KMEANS_TC = 3,   /* 1: k-means assignment on tensor cores with exact verify */
-    FVDB_OPT_COALESCE = 4     /* 1 (default): concurrent fvdb_search calls are coalesced into one device batch */
+    FVDB_OPT_COALESCE = 4,    /* 1 (default): concurrent fvdb_search calls are coalesced into one device batch */
+    FVDB_OPT_PROOF_XMAX = 5   /* list-sharded multi-GPU search with shared bounds: f32 bits of the largest
+                                 |x|^2 over ALL shards (fvdb_ivf_max_sqnorm, max-reduced by the driver).  A
+                                 row of this shard may be dropped by a bound a peer published, so the
+                                 tensor-core proof must not use a smaller norm term than the peer's. */
 } fvdb_option;
 
 /* TrainResult, src/ivf/core.rs:103-109. */
@@ -119,7 +123,7 @@ typedef struct fvdb_stats {
 
 /* IVFIndex::new / HNSWIndex::new / HybridIndex::new (src/ivf/core.rs:171, src/hnsw/core.rs,
  * src/hybrid/core.rs).  device: CUDA ordinal.  k_max: largest k any search will ask for
- * (<= 1024).  Fails with FVDB_ERR_NO_DEVICE when no CUDA device is usable. */
+ * (1..512; FVDB_ERR_INVALID_CONFIG otherwise).  Fails with FVDB_ERR_NO_DEVICE when no CUDA device is usable. */
 int fvdb_create(int device, uint32_t dim, int metric, uint32_t k_max, fvdb_index **out);
 void fvdb_destroy(fvdb_index *h);
 const char *fvdb_last_error(const fvdb_index *h); /* h may be NULL: last create error */
@@ -182,7 +186,8 @@ int fvdb_vacuum(fvdb_index *h, uint64_t *removed);
  *   recent-tier rows first on ties, truncated to k, no de-duplication across tiers.
  * One call = IVFIndex::batch_search (src/ivf/operations.rs:132-145) done as one batch.
  *   q            [nq x dim] host, row-major
- *   nprobe       lists probed per query (clamped to nlist, like truncate(n_probe) :656)
+ *   nprobe       lists probed per query (clamped to nlist, like truncate(n_probe) :656; more than 512
+ *                after clamping is FVDB_ERR_INVALID_ARG)
  *   tiers        FVDB_TIER_* bits; FVDB_TIER_HISTORICAL is ignored until trained
  *                (src/hybrid/core.rs:465)
  *   filter_bits  NULL, or a bitmap over row ids (bit id set = row passes): the in-kernel
@@ -201,6 +206,17 @@ int fvdb_vacuum(fvdb_index *h, uint64_t *removed);
 int fvdb_search(fvdb_index *h, const float *q, uint32_t nq, uint32_t k, uint32_t nprobe,
                 uint32_t tiers, const uint64_t *filter_bits, uint64_t filter_nbits,
                 uint32_t *out_ids, float *out_dist, uint32_t *out_count);
+
+/* HybridIndex::search_with_filter (src/hybrid/core.rs:513-549), the reference's 3x oversampling
+ * POST-filter, for a batch: search(3k) over the selected tiers exactly as fvdb_search does, keep — in
+ * order — the candidates whose row id has its bit set in keep_bits, truncate to k (:529-546).
+ * keep_bits is the host's evaluation of `metadata_map.get(id)` + `filter.matches` once per row (a row
+ * without metadata has bit 0, :536-541; ids >= keep_nbits fail).  Like the reference it may return
+ * fewer than k results although >= k matching rows exist (the in-kernel pre-filter of fvdb_search
+ * does not).  Needs 3k <= k_max (FVDB_ERR_K_TOO_LARGE otherwise).  Tombstoned rows never appear. */
+int fvdb_search_postfilter(fvdb_index *h, const float *q, uint32_t nq, uint32_t k, uint32_t nprobe,
+                           uint32_t tiers, const uint64_t *keep_bits, uint64_t keep_nbits,
+                           uint32_t *out_ids, float *out_dist, uint32_t *out_count);
 
 /* IVFIndex::retrain (src/ivf/operations.rs:148-193; add_clusters :195-219 and optimize_clusters
  * :221-260 are the same operation with nlist + n / the same nlist): k-means over every row the
@@ -282,12 +298,16 @@ int fvdb_search_device_coarse(fvdb_index *h, const float *d_q, uint32_t nq, uint
  *   fvdb_bounds_export      allocates this handle's [2][nq_cap] bound array and writes its
  *                           FVDB_BOUNDS_HANDLE_BYTES-byte inter-process handle (all-gather these);
  *   fvdb_bounds_import      opens the arrays of the other ranks (handles of ALL ranks, rank-major);
+ *                           n_ranks == 0 closes them again — every rank does that, then a barrier, BEFORE
+ *                           any rank re-exports (fvdb_bounds_export frees the previous array);
  *   fvdb_bounds_begin_batch flips the batch parity and resets this rank's half to +inf on `stream`.
  * Protocol (every rank, every batch): begin_batch -> fvdb_coarse_device on a slice -> all-gather of
  * the coarse keys -> fvdb_search_device_coarse.  The all-gather orders every rank's reset before
  * any peer's scan of that batch, and the parity keeps a rank that is one batch ahead out of the
  * array a slower peer still reads.  Results are independent of the sharing (bounds only ever drop
  * rows that cannot be among a query's 32 nearest); without these calls each rank uses a private array. */
+/* Largest squared row norm of the IVF tier (0 when empty): input of FVDB_OPT_PROOF_XMAX. */
+int fvdb_ivf_max_sqnorm(fvdb_index *h, float *out);
 #define FVDB_BOUNDS_HANDLE_BYTES 64
 int fvdb_bounds_export(fvdb_index *h, uint32_t nq_cap, void *handle_out);
 int fvdb_bounds_import(fvdb_index *h, const void *handles, uint32_t n_ranks, uint32_t my_rank);
@@ -317,6 +337,15 @@ int fvdb_merge_topk_device(fvdb_index *h, const uint32_t *d_ids, const float *d_
 int fvdb_ivf_add_device(fvdb_index *h, const float *d_x, const uint32_t *d_row_ids, uint64_t n,
                         uint32_t list_filter_mod, uint32_t list_filter_rem, uint64_t *kept);
 int fvdb_flat_add_device(fvdb_index *h, const float *d_x, const uint32_t *d_row_ids, uint64_t n);
+/* fvdb_ivf_add_device with a list -> GPU placement TABLE instead of the l % mod rule: a row is kept when
+ * d_owner[its list] == my_rank (d_owner: [nlist] u32, device).  The multi-GPU driver fills the table by
+ * greedy size-balanced bin packing of the lists, so that every GPU streams the same number
+ * of rows per batch. */
+int fvdb_ivf_add_device_owned(fvdb_index *h, const float *d_x, const uint32_t *d_row_ids, uint64_t n,
+                              const uint32_t *d_owner, uint32_t my_rank, uint64_t *kept);
+/* fvdb_assign (find_nearest_centroid for a batch, src/ivf/core.rs:373-386) with device buffers: the list
+ * histogram the placement above is computed from, without moving rows. */
+int fvdb_assign_device(fvdb_index *h, const float *d_x, uint64_t n, uint32_t *d_out_list, void *stream);
 int fvdb_ivf_train_device(fvdb_index *h, const float *d_data, uint64_t n, uint32_t nlist,
                           uint32_t max_iterations, const float *d_init_centroids, uint64_t seed,
                           fvdb_train_result *out);

@@ -90,7 +90,9 @@ def test_ivf_search_parity(mode, n, d, nlist, nprobe, k, nq):
     o = O.hybrid_batch_search(ivf, None, None, q, k, nprobe, tiers=2)
     _assert_same(ids, dist, cnt, *o)
     if mode == "tc":
-        assert eng.stats().last_fallback_queries <= nq
+        # the tensor-core path must carry these well-separated shapes itself: a proof that failed for more
+        # than a stray query would mean "tc" parity is really the exact fallback's
+        assert eng.stats().last_fallback_queries <= nq // 16
 
 
 @pytest.mark.parametrize("d", [2, 3, 7, 30, 100])
@@ -324,23 +326,33 @@ def test_kmeans_lloyd_parity_shared_init(n, d, nlist, iters):
     assert eng.stats().ivf_rows == 0  # training leaves the lists empty
 
 
-def test_kmeanspp_seeded_training_quality():
-    # seeded k-means++ is parity-unpinned (rand 0.8 stream is an un-vendored dependency): check
-    # that the device k-means++ behaves like the oracle's — its final error falls inside the
-    # spread the oracle's own seeded runs produce on the same data
-    n, d, nlist = 6000, 32, 12
+@pytest.mark.parametrize("n,d,nlist,seed", [(6000, 32, 12, 42), (20000, 384, 64, 7), (500, 8, 40, 123456789012345)])
+def test_kmeanspp_seeded_training_equals_the_oracle(n, d, nlist, seed):
+    """IVFIndex::train with a seed (src/ivf/core.rs:176-179, 240-371): the device draws from the
+    reference's own generator (rand 0.8 StdRng = ChaCha12, restated in engine.cu) and makes the
+    sequential f32 prefix pick of :357-367, so on the same seed the k-means++ centroids — and with them
+    the whole training run — equal the oracle's fo_kmeanspp_init + Lloyd loop bit for bit.  (Both are
+    restatements of rand's published algorithm: parity with the crate itself stays unpinned)"""
     x = _data(n, d, 71, n_comp=nlist, sigma=0.2)
-    errs = []
-    for seed in range(8):
-        init, _ = O.kmeanspp_init(x, nlist, seed)
-        errs.append(O.train_lloyd(x, init, 10)[2]["final_error"])
-    for seed in (42, 43):
-        eng = Engine(d)
-        res = eng.train(x, nlist, 10, seed=seed)
-        assert res["final_error"] <= 1.25 * max(errs)
-        assert res["final_error"] >= 0.99 * min(errs)
-        assert res["final_error"] < res["initial_error"]
-        assert eng.get_centroids().shape == (nlist, d)
+    init, picked = O.kmeanspp_init(x, nlist, seed)
+    assert len(picked) == nlist
+    # max_iterations = 1: centroids after one Lloyd step from the k-means++ start
+    eng = Engine(d)
+    eng.set_option(L.OPT_SCAN_MODE, L.SCAN_EXACT)
+    res = eng.train(x, nlist, 1, seed=seed)
+    o_c, _, o_r = O.train_lloyd(x, init, 1)
+    assert np.array_equal(eng.get_centroids().view(np.uint32), o_c.view(np.uint32))
+    assert np.float32(res["initial_error"]).view(np.uint32) == np.float32(o_r["initial_error"]).view(np.uint32)
+    # the full run
+    iters = 10
+    res = eng.train(x, nlist, iters, seed=seed)
+    o_c, _, o_r = O.train_lloyd(x, init, iters)
+    assert res["iterations"] == o_r["iterations"] and res["converged"] == o_r["converged"]
+    assert np.array_equal(eng.get_centroids().view(np.uint32), o_c.view(np.uint32))
+    assert np.float32(res["final_error"]).view(np.uint32) == np.float32(o_r["final_error"]).view(np.uint32)
+    # another seed, another start
+    eng.train(x, nlist, 1, seed=seed + 1)
+    assert not np.array_equal(eng.get_centroids().view(np.uint32), O.train_lloyd(x, init, 1)[0].view(np.uint32))
 
 
 @pytest.mark.parametrize("mode", MODES)
