@@ -38,6 +38,7 @@ OPT_SHORTLIST = 2
 OPT_KMEANS_TC = 3
 OPT_COALESCE = 4
 OPT_PROOF_XMAX = 5
+OPT_PIPELINE = 6
 
 
 class TrainResult(C.Structure):

@@ -222,6 +222,8 @@ struct fvdb_index {
         uint32_t* host;       // page-locked: [16] counter words, [2 nq] IVF fallback ids, [2 nq] flat fallback ids
         size_t host_words;
         void *ho_ids, *ho_dist, *ho_cnt;   // fvdb_search_submit: the caller's page-locked result buffers (else NULL)
+        int slot;             // pipeline slot the batch ran in (-1: the handle's own stream and scratch)
+        cudaStream_t user_stream;
     };
     // fvdb_search_submit: device-side query / result buffers of the batches in flight and the copy stream
     // their uploads run on (so that batch i + 1 uploads while batch i is scanned)
@@ -241,6 +243,26 @@ struct fvdb_index {
     DevBuf<float> s_fb_q;
     DevBuf<uint64_t> s_fb_keys, s_fb_coarse;
     TcScratch tc;
+    // Software pipeline of the stream-ordered entries (fvdb_search_device_submit / fvdb_search_submit):
+    // consecutive batches alternate between two SLOTS, each with its own stream and its own copy of the
+    // per-batch scratch (tensor-core tables, coarse keys, counters).  The scans of consecutive batches are
+    // serialised by an event (each one fills the machine), but batch i + 1's query norms, coarse step and
+    // bucketing and batch i's shortlist merge and re-rank no longer queue behind one another: they run in
+    // the scans' ramps and tails and next to kernel R's CTAs wherever registers and shared memory allow.
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
+        cudaEvent_t ev_in = nullptr, ev_scan_end = nullptr, ev_done = nullptr;
+        DevBuf<uint32_t> s_misc, s_fb_idx;
+        DevBuf<uint64_t> s_coarse, s_ivf_keys;
+        TcScratch tc;
+        bool busy = false;
+    };
+    static constexpr int N_SLOTS = 2;
+    Slot slots[N_SLOTS];
+    uint32_t slot_next = 0;
+    cudaEvent_t prev_scan_end = nullptr;   // recorded behind the most recently enqueued slot scan
+    uint32_t pipeline = 1;                 // FVDB_OPT_PIPELINE
     // submission queue of fvdb_search: concurrent host-buffer calls are coalesced into one batch
     std::mutex qmu;
     std::deque<SearchReq*> queue;
@@ -278,6 +300,20 @@ struct fvdb_index {
         return e;
     }
 };
+
+static inline void mark_arena_dirty(fvdb_index* h) {
+    h->tc.arena_dirty = true;
+    for (auto& sl : h->slots) sl.tc.arena_dirty = true;
+}
+static inline void mark_centroids_dirty(fvdb_index* h) {
+    h->tc.centroids_dirty = true;
+    for (auto& sl : h->slots) sl.tc.centroids_dirty = true;
+}
+// Every batch still running in a pipeline slot has to finish before anything it reads may move.
+static inline void quiesce_slots(fvdb_index* h) {
+    for (auto& sl : h->slots)
+        if (sl.busy && sl.stream) { cudaStreamSynchronize(sl.stream); sl.busy = false; }
+}
 
 #define CK(call)                                                      \
     do {                                                              \
@@ -379,6 +415,7 @@ int scan_all_exact(fvdb_index* h, const float* X, const uint32_t* ids, uint64_t 
 // Regroup sealed + pending IVF rows so every list is one contiguous row range.
 int seal(fvdb_index* h) {
     if (h->pend_n == 0) return FVDB_OK;
+    quiesce_slots(h);   // the arena is about to be replaced
     cudaStream_t st = h->stream;
     const uint64_t total = h->ivf_n + h->pend_n;
     if (total >= 0xFFFFFFF0ull) return h->fail(FVDB_ERR_INVALID_ARG, "IVF tier exceeds u32 rows");
@@ -414,7 +451,7 @@ int seal(fvdb_index* h) {
     h->pend_list.release();
     h->ivf_n = kept;
     h->pend_n = 0;
-    h->tc.arena_dirty = true;
+    mark_arena_dirty(h);
     return FVDB_OK;
 }
 
@@ -582,7 +619,7 @@ void clear_lists(fvdb_index* h) {
         for (auto& s : h->id_state) if ((s & 3) == 2) { if (s & 0x80) h->deleted_count--; s = 0; }
     h->ivf_n = 0;
     h->pend_n = 0;
-    h->tc.arena_dirty = true;
+    mark_arena_dirty(h);
 }
 
 float host_mean_sq(const std::vector<float>& dist) {
@@ -615,7 +652,7 @@ int train_body(fvdb_index* h, const float* d_data, uint64_t n, uint32_t nlist, u
     CK(h->centroids.ensure((size_t)nlist * D, 0, st, &h->dev_bytes));
     h->nlist = nlist;
     h->trained = false;
-    h->tc.centroids_dirty = true; ++h->centroids_version;
+    mark_centroids_dirty(h); ++h->centroids_version;
     if (d_init) {
         CK(cudaMemcpyAsync(h->centroids.p, d_init, (size_t)nlist * D * 4, cudaMemcpyDeviceToDevice, st));
     } else {
@@ -687,7 +724,7 @@ int train_body(fvdb_index* h, const float* d_data, uint64_t n, uint32_t nlist, u
         CK(launch_stable_group(assign.p, n, nlist, h->s_u32c.p, h->s_perm.p, h->s_group.p, st));
         CK(launch_centroid_update(d_data, D, h->s_u32c.p, h->s_perm.p, nlist, h->centroids.p, st));
         CK(cudaStreamSynchronize(st));
-        h->tc.centroids_dirty = true; ++h->centroids_version;
+        mark_centroids_dirty(h); ++h->centroids_version;
         if (iterations >= max_iterations) break;
         float current_error = 0.f;
         RET(compute_error_device(h, d_data, n, assign.p, &current_error));
@@ -742,7 +779,7 @@ int train_device_impl(fvdb_index* h, const float* d_data, uint64_t n, uint32_t n
         h->centroids.swap(old_centroids);   // the failed run's table is freed with old_centroids
         h->nlist = old_nlist;
         h->trained = old_trained;
-        h->tc.centroids_dirty = true; ++h->centroids_version;
+        mark_centroids_dirty(h); ++h->centroids_version;
         return r;
     }
     h->dev_bytes -= old_centroids.cap * sizeof(float);
@@ -883,7 +920,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
                        uint32_t tiers, const uint64_t* d_filter, uint64_t filter_bits,
                        uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count,
                        cudaStream_t st, const uint64_t* ext_coarse = nullptr, const HostOut* ho = nullptr,
-                       bool defer = false) {
+                       bool defer = false, bool want_pipe = false, cudaEvent_t wait_first = nullptr) {
     if (k == 0) return h->fail(FVDB_ERR_INVALID_ARG, "k must be >= 1");
     if (k > h->k_max) return h->fail(FVDB_ERR_K_TOO_LARGE, "k exceeds k_max given at fvdb_create");
     h->stats.last_nq = nq;
@@ -900,18 +937,53 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
     const bool use_flat = (tiers & FVDB_TIER_RECENT) && h->flat_n > 0;
     const uint64_t* tomb = h->deleted_count ? h->tomb.p : nullptr;
     const uint64_t* filt = d_filter;
-
-    CK(cudaEventRecord(h->ev_a, st));
-    CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
-    // s_misc words: [0] nan flag, [2..3] scanned rows (u64), [4] kmeans changed, [6] item count,
-    // [8] kmeans++ pick, [10] TC fallback count
-    int* d_nan = reinterpret_cast<int*>(h->s_misc.p);
-    uint64_t* d_scanned = reinterpret_cast<uint64_t*>(h->s_misc.p + 2);
-    uint32_t* d_fb_count = h->s_misc.p + 10;
-    CK(cudaMemsetAsync(h->s_misc.p, 0, 64, st));
     // the tensor-core IVF path looks at every query element anyway (query norms): it raises the flag
     const bool tc_ivf = use_ivf && (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D) && k <= TC_MAX_K &&
                         std::min(nprobe, h->nlist) <= TC_MAX_NPROBE;
+
+    // Pipeline slot (stream-ordered entries, IVF tier alone on the tensor-core path): this batch runs on
+    // the slot's stream with the slot's scratch; `st` (the caller's stream) is only what its inputs are
+    // ordered after.  Everything else runs on `st` with the handle's own scratch, after the slots drained.
+    const cudaStream_t user_st = st;
+    int slot = -1;
+    const bool tc_coarse_ok = D <= 384 && std::min(nprobe, h->nlist) <= TC_MAX_NPROBE_COARSE && !getenv("FVDB_EXACT_COARSE");
+    if (defer && want_pipe && h->pipeline && tc_ivf && tc_coarse_ok && !use_flat && !ext_coarse) {
+        slot = (int)(h->slot_next++ % fvdb_index::N_SLOTS);
+        fvdb_index::Slot& sl = h->slots[slot];
+        if (!sl.stream) {
+            CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreate(&sl.ev_a)); CK(cudaEventCreate(&sl.ev_b));
+            CK(cudaEventCreate(&sl.ev_s0)); CK(cudaEventCreate(&sl.ev_s1));
+            CK(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.ev_scan_end, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(sl.ev_in, user_st));
+        CK(cudaStreamWaitEvent(sl.stream, sl.ev_in, 0));
+        if (wait_first) CK(cudaStreamWaitEvent(sl.stream, wait_first, 0));
+        st = sl.stream;
+        sl.busy = true;
+    } else {
+        quiesce_slots(h);
+        if (wait_first) CK(cudaStreamWaitEvent(st, wait_first, 0));
+    }
+    fvdb_index::Slot* const sl = slot >= 0 ? &h->slots[slot] : nullptr;
+    DevBuf<uint32_t>& b_misc = sl ? sl->s_misc : h->s_misc;
+    DevBuf<uint32_t>& b_fb_idx = sl ? sl->s_fb_idx : h->s_fb_idx;
+    DevBuf<uint64_t>& b_coarse = sl ? sl->s_coarse : h->s_coarse;
+    DevBuf<uint64_t>& b_ivf_keys = sl ? sl->s_ivf_keys : h->s_ivf_keys;
+    TcScratch& b_tc = sl ? sl->tc : h->tc;
+    const cudaEvent_t e_a = sl ? sl->ev_a : h->ev_a, e_b = sl ? sl->ev_b : h->ev_b;
+    const cudaEvent_t e_s0 = sl ? sl->ev_s0 : h->ev_s0, e_s1 = sl ? sl->ev_s1 : h->ev_s1;
+
+    CK(cudaEventRecord(e_a, st));
+    CK(b_misc.ensure(64, 0, st, &h->dev_bytes));
+    // s_misc words: [0] nan flag, [2..3] scanned rows (u64), [4] kmeans changed, [6] item count,
+    // [8] kmeans++ pick, [10] TC fallback count
+    int* d_nan = reinterpret_cast<int*>(b_misc.p);
+    uint64_t* d_scanned = reinterpret_cast<uint64_t*>(b_misc.p + 2);
+    uint32_t* d_fb_count = b_misc.p + 10;
+    CK(cudaMemsetAsync(b_misc.p, 0, 64, st));
     if (!tc_ivf) {
         CK(launch_nan_check(d_q, (size_t)nq * D, d_nan, st));
         h->stats.last_launches += 1;
@@ -925,8 +997,8 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
     if (use_ivf) {
         np = std::min(nprobe, h->nlist);
         if (np > 512) return h->fail(FVDB_ERR_INVALID_ARG, "nprobe > 512 is not supported");
-        CK(h->s_ivf_keys.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
-        ivf_keys = h->s_ivf_keys.p;
+        CK(b_ivf_keys.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
+        ivf_keys = b_ivf_keys.p;
         used_tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D) && k <= TC_MAX_K && np <= TC_MAX_NPROBE;
         // coarse step: all centroid distances, nearest np lists (src/ivf/core.rs:646-656); exact
         // CUDA-core scan, or (TC mode, D <= 384, np <= 128) tensor-core distances + exact verify
@@ -935,14 +1007,14 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
                                !getenv("FVDB_EXACT_COARSE");
         const uint64_t* coarse_in = ext_coarse;
         if (!ext_coarse) {
-            CK(h->s_coarse.ensure((size_t)nq * np, 0, st, &h->dev_bytes));
-            coarse_in = h->s_coarse.p;
+            CK(b_coarse.ensure((size_t)nq * np, 0, st, &h->dev_bytes));
+            coarse_in = b_coarse.p;
             if (!tc_coarse)
                 RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_q, nq, np, nullptr, 0, nullptr, 0,
-                                   h->s_coarse.p, st));
+                                   b_coarse.p, st));
         }
         if (used_tc) {
-            CK(h->s_fb_idx.ensure((size_t)2 * nq, 0, st, &h->dev_bytes));
+            CK(b_fb_idx.ensure((size_t)2 * nq, 0, st, &h->dev_bytes));
             TcSearchArgs ta{};
             ta.rows = h->ivf_rows.p; ta.ids = h->ivf_ids.p; ta.n_rows = h->ivf_n;
             ta.list_off = h->list_off.p; ta.nlist = h->nlist;
@@ -953,8 +1025,8 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             ta.tomb = tomb; ta.tomb_bits = h->tomb_bits; ta.filt = filt; ta.filt_bits = filter_bits;
             ta.out_keys = ivf_keys;
             ta.d_scanned_rows = d_scanned;
-            ta.d_fallback_count = d_fb_count; ta.d_fallback_idx = h->s_fb_idx.p;
-            ta.ev_scan0 = h->ev_s0; ta.ev_scan1 = h->ev_s1;
+            ta.d_fallback_count = d_fb_count; ta.d_fallback_idx = b_fb_idx.p;
+            ta.ev_scan0 = e_s0; ta.ev_scan1 = e_s1;
             ta.sm_count = h->sm_count;
             ta.xmax_floor_sq = h->proof_xmax_sq;
             ta.d_nan = d_nan;
@@ -970,7 +1042,13 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             }
             h->bounds_armed_nq = 0;
             uint32_t launches = 0;
-            int r = tc_ivf_search(h->tc, ta, st, &h->dev_bytes, &launches, &h->err);
+            if (sl) {
+                // one scan at a time: this one waits for the scan of the batch enqueued before it
+                ta.wait_before_scan = h->prev_scan_end;
+                ta.record_after_scan = sl->ev_scan_end;
+            }
+            int r = tc_ivf_search(b_tc, ta, st, &h->dev_bytes, &launches, &h->err);
+            if (sl && r == FVDB_OK) h->prev_scan_end = sl->ev_scan_end;
             if (r != FVDB_OK) return r;
             h->stats.last_launches += launches;
             scan_timed = true;
@@ -981,7 +1059,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         }
     }
     bool flat_tc = false;
-    uint32_t* d_fb_count_flat = h->s_misc.p + 11;
+    uint32_t* d_fb_count_flat = b_misc.p + 11;
     if (use_flat) {
         CK(h->s_flat_keys.ensure((size_t)nq * k, 0, st, &h->dev_bytes));
         flat_keys = h->s_flat_keys.p;
@@ -1011,7 +1089,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
         h->stats.last_launches += 1;
     }
-    CK(cudaEventRecord(h->ev_b, st));
+    CK(cudaEventRecord(e_b, st));
     if (ho) CK(copy_out(ho, d_out_ids, d_out_dist, d_out_count, st));
 
     if (defer) {
@@ -1021,7 +1099,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         const size_t words = 16 + (size_t)4 * nq;
         fvdb_index::Pending pb{d_q, nq, k, nprobe, tiers, d_filter, filter_bits, d_out_ids, d_out_dist, d_out_count,
                                used_tc, flat_tc, use_ivf, use_flat, (tomb ? 1u : 0u) + (filt ? 1u : 0u), nullptr, 0,
-                               ho ? ho->ids : nullptr, ho ? ho->dist : nullptr, ho ? ho->cnt : nullptr};
+                               ho ? ho->ids : nullptr, ho ? ho->dist : nullptr, ho ? ho->cnt : nullptr, slot, user_st};
         for (size_t i = 0; i < h->pending_pool.size(); ++i)
             if (h->pending_pool[i].second >= words) {
                 pb.host = h->pending_pool[i].first; pb.host_words = h->pending_pool[i].second;
@@ -1032,9 +1110,10 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             CK(cudaHostAlloc((void**)&pb.host, words * 4, cudaHostAllocDefault));
             pb.host_words = words;
         }
-        CK(cudaMemcpyAsync(pb.host, h->s_misc.p, 64, cudaMemcpyDeviceToHost, st));
-        if (used_tc) CK(cudaMemcpyAsync(pb.host + 16, h->s_fb_idx.p, (size_t)2 * nq * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pb.host, b_misc.p, 64, cudaMemcpyDeviceToHost, st));
+        if (used_tc) CK(cudaMemcpyAsync(pb.host + 16, b_fb_idx.p, (size_t)2 * nq * 4, cudaMemcpyDeviceToHost, st));
         if (flat_tc) CK(cudaMemcpyAsync(pb.host + 16 + 2 * nq, h->s_fb_idx_flat.p, (size_t)2 * nq * 4, cudaMemcpyDeviceToHost, st));
+        if (sl) CK(cudaEventRecord(sl->ev_done, st));
         h->pending.push_back(pb);
         return FVDB_OK;
     }
@@ -1161,6 +1240,13 @@ void fvdb_destroy(fvdb_index* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& sl : h->slots) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        tc_release(sl.tc);
+        for (cudaEvent_t e : {sl.ev_a, sl.ev_b, sl.ev_s0, sl.ev_s1, sl.ev_in, sl.ev_scan_end, sl.ev_done})
+            if (e) cudaEventDestroy(e);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     tc_release(h->tc);
     if (h->pin) cudaFreeHost(h->pin);
     for (auto& pb : h->pending) cudaFreeHost(pb.host);
@@ -1180,11 +1266,16 @@ void fvdb_destroy(fvdb_index* h) {
     delete h;
 }
 
-#define ENTER(h)                                            \
+#define ENTER_PIPE(h)                                       \
     if (!(h)) return FVDB_ERR_INVALID_ARG;                  \
     std::lock_guard<std::mutex> guard__((h)->mu);           \
     (h)->err.clear();                                       \
     if (cudaSetDevice((h)->device) != cudaSuccess) return (h)->fail(FVDB_ERR_CUDA, "cudaSetDevice failed")
+// every entry but the stream-ordered submits first lets the batches in the pipeline slots finish: nothing
+// they read (arena, centroids, bitmaps) may move under them
+#define ENTER(h)                                            \
+    ENTER_PIPE(h);                                          \
+    quiesce_slots(h)
 
 int fvdb_set_option(fvdb_index* h, int option, uint64_t value) {
     ENTER(h);
@@ -1203,6 +1294,9 @@ int fvdb_set_option(fvdb_index* h, int option, uint64_t value) {
             return FVDB_OK;
         case FVDB_OPT_COALESCE:
             h->coalesce = value ? 1u : 0u;
+            return FVDB_OK;
+        case FVDB_OPT_PIPELINE:
+            h->pipeline = value ? 1u : 0u;
             return FVDB_OK;
         case FVDB_OPT_PROOF_XMAX: {
             const uint32_t b = (uint32_t)value;
@@ -1241,7 +1335,7 @@ int fvdb_ivf_set_centroids(fvdb_index* h, const float* centroids, uint32_t nlist
     RET(h2d(h, h->centroids.p, centroids, (size_t)nlist * h->dim * 4));
     h->nlist = nlist;
     h->trained = true;
-    h->tc.centroids_dirty = true; ++h->centroids_version;
+    mark_centroids_dirty(h); ++h->centroids_version;
     clear_lists(h);
     CK(h->list_off.ensure(nlist + 2, 0, h->stream, &h->dev_bytes));
     CK(cudaMemsetAsync(h->list_off.p, 0, (nlist + 2) * 4, h->stream));
@@ -1314,7 +1408,7 @@ int fvdb_ivf_retrain(fvdb_index* h, uint32_t nlist, uint32_t max_iterations, con
         // index is what it was before the call
         h->ivf_rows.swap(rows);
         h->ivf_ids.swap(ids);
-        h->tc.arena_dirty = true;
+        mark_arena_dirty(h);
         return r;
     }
     r = ivf_add_device_impl(h, rows.p, ids.p, n, 1, 0, nullptr, nullptr);
@@ -1327,7 +1421,7 @@ int fvdb_ivf_retrain(fvdb_index* h, uint32_t nlist, uint32_t max_iterations, con
         h->ivf_n = n;
         h->pend_n = 0;
         h->trained = false;
-        h->tc.arena_dirty = true;
+        mark_arena_dirty(h);
     }
     return r;
 }
@@ -1497,7 +1591,7 @@ int fvdb_vacuum(fvdb_index* h, uint64_t* removed) {
         h->ivf_list.swap(nl);
         gone += n - kept;
         h->ivf_n = kept;
-        h->tc.arena_dirty = true;
+        mark_arena_dirty(h);
     }
     if (h->flat_n) {
         const uint64_t n = h->flat_n;
@@ -1602,11 +1696,11 @@ int fvdb_search_device(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
 int fvdb_search_device_submit(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,
                               uint32_t tiers, const uint64_t* d_filter_bits, uint64_t filter_nbits,
                               uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count, void* stream) {
-    ENTER(h);
+    ENTER_PIPE(h);
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     if (h->pending.size() >= 64) return h->fail(FVDB_ERR_INVALID_ARG, "64 batches are pending: call fvdb_search_device_finish");
     return search_device_impl(h, d_q, nq, k, nprobe, tiers, d_filter_bits, filter_nbits, d_out_ids,
-                              d_out_dist, d_out_count, st, nullptr, nullptr, true);
+                              d_out_dist, d_out_count, st, nullptr, nullptr, true, true);
 }
 
 static int finish_pending(fvdb_index* h, cudaStream_t st);
@@ -1620,7 +1714,7 @@ int fvdb_search_device_finish(fvdb_index* h, void* stream) {
 // previous batch is still being scanned; the result copies follow the batch on the handle's stream.
 int fvdb_search_submit(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, uint32_t nprobe, uint32_t tiers,
                        uint32_t* out_ids, float* out_dist, uint32_t* out_count) {
-    ENTER(h);
+    ENTER_PIPE(h);
     if (!q || !out_ids || !out_dist || !out_count) return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_search_submit: null buffer");
     if (!is_pinned_host(q) || !is_pinned_host(out_ids) || !is_pinned_host(out_dist) || !is_pinned_host(out_count))
         return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_search_submit needs page-locked buffers (fvdb_host_alloc)");
@@ -1643,12 +1737,15 @@ int fvdb_search_submit(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, u
     if (sl.used) CK(cudaStreamWaitEvent(h->copy_stream, sl.done, 0));   // the slot's previous batch has read its queries
     CK(cudaMemcpyAsync(sl.q.p, q, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, h->copy_stream));
     CK(cudaEventRecord(sl.uploaded, h->copy_stream));
-    CK(cudaStreamWaitEvent(st, sl.uploaded, 0));
     const HostOut ho{out_ids, out_dist, out_count, (size_t)nq * k * 4, (size_t)nq * 4};
+    // the batch (in a pipeline slot when it qualifies) starts once its queries are on the device
     const int rc = search_device_impl(h, sl.q.p, nq, k, nprobe, tiers, nullptr, 0, sl.ids.p, sl.dist.p, sl.cnt.p, st,
-                                      nullptr, &ho, true);
-    CK(cudaEventRecord(sl.done, st));
-    sl.used = true;
+                                      nullptr, &ho, true, true, sl.uploaded);
+    if (rc == FVDB_OK && !h->pending.empty()) {
+        const int ps = h->pending.back().slot;
+        CK(cudaEventRecord(sl.done, ps >= 0 ? h->slots[ps].stream : st));
+        sl.used = true;
+    }
     return rc;
 }
 
@@ -1658,7 +1755,13 @@ int fvdb_search_finish(fvdb_index* h) {
 }
 
 static int finish_pending(fvdb_index* h, cudaStream_t st) {
-    if (cudaStreamSynchronize(st) != cudaSuccess) { h->pending.clear(); return h->fail(FVDB_ERR_CUDA, "stream synchronisation failed"); }
+    // results are valid "in stream order" on the caller's stream: it waits for the slots' batches
+    for (const fvdb_index::Pending& pb : h->pending)
+        if (pb.slot >= 0) cudaStreamWaitEvent(st, h->slots[pb.slot].ev_done, 0);
+    bool bad = false;
+    for (auto& sl : h->slots)
+        if (sl.busy && sl.stream) { bad |= cudaStreamSynchronize(sl.stream) != cudaSuccess; sl.busy = false; }
+    if (bad || cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); h->pending.clear(); return h->fail(FVDB_ERR_CUDA, "stream synchronisation failed"); }
     int rc = FVDB_OK;
     std::vector<fvdb_index::Pending> todo;
     todo.swap(h->pending);
@@ -1720,8 +1823,9 @@ static int finish_pending(fvdb_index* h, cudaStream_t st) {
                                           (lb.use_ivf ? (uint64_t)h->nlist * h->dim * 4ull : 0ull) + (uint64_t)lb.n_bitmaps * (rows / 8);
         h->stats.last_fallback_queries = fallbacks;
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->ev_a, h->ev_b) == cudaSuccess) h->stats.last_device_ms = ms; else cudaGetLastError();
-        if (cudaEventElapsedTime(&ms, h->ev_s0, h->ev_s1) == cudaSuccess) h->stats.last_scan_ms = ms; else cudaGetLastError();
+        const fvdb_index::Slot* ls = lb.slot >= 0 ? &h->slots[lb.slot] : nullptr;
+        if (cudaEventElapsedTime(&ms, ls ? ls->ev_a : h->ev_a, ls ? ls->ev_b : h->ev_b) == cudaSuccess) h->stats.last_device_ms = ms; else cudaGetLastError();
+        if (cudaEventElapsedTime(&ms, ls ? ls->ev_s0 : h->ev_s0, ls ? ls->ev_s1 : h->ev_s1) == cudaSuccess) h->stats.last_scan_ms = ms; else cudaGetLastError();
     }
     return rc;
 }
@@ -2096,7 +2200,7 @@ int fvdb_kmeans_apply_device(fvdb_index* h, const float* d_sums, const uint32_t*
     if (!h->nlist || !h->centroids.p) return h->fail(FVDB_ERR_NOT_TRAINED, "centroids not set");
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     CK(launch_apply_means(d_sums, d_counts, h->nlist, h->dim, h->centroids.p, st));
-    h->tc.centroids_dirty = true; ++h->centroids_version;
+    mark_centroids_dirty(h); ++h->centroids_version;
     return FVDB_OK;
 }
 

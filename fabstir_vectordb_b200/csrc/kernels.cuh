@@ -42,7 +42,9 @@ cudaError_t launch_probe_bucketing(const uint64_t* coarse_keys, uint32_t nq, uin
                                    // optional second table: lists probed by >= wide_min queries become items
                                    // of tile_q_w queries in items_w (the wide-tile scan kernel's share)
                                    uint32_t wide_min = 0, uint32_t tile_q_w = 0, ScanItem* items_w = nullptr,
-                                   uint32_t* n_items_w = nullptr, bool wide_longest_first = false);
+                                   uint32_t* n_items_w = nullptr, bool wide_longest_first = false,
+                                   // optional (with list_order): the non-empty lists, ascending — only those are walked
+                                   const uint32_t* live_ids = nullptr, uint32_t n_live = 0);
 // one warp per (query, probed list): sparse batches (few queries per list)
 cudaError_t launch_exact_pair_scan(const uint64_t* coarse_keys, uint32_t nq, uint32_t nprobe, const uint32_t* list_off,
                                    const float* X, const uint32_t* ids, const float* Q, uint32_t D, uint32_t P,

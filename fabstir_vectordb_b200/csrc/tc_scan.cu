@@ -1698,6 +1698,8 @@ struct TcScratchImpl {
     Buf<uint32_t> misc;  // [0] = max |x|^2 bits
     Buf<unsigned long long> prof;
     Buf<uint32_t> list_order;  // lists by descending length (tile-scheduler order)
+    Buf<uint32_t> live_ids;    // the non-empty lists, ascending (the bucketing pass walks only these)
+    uint32_t n_live = 0;
     struct RowSet {            // cached per scanned row matrix: |x|^2, TMA descriptor (box 32 x 128)
         Buf<float> xnorm;
         CUtensorMap tmap;
@@ -1762,7 +1764,7 @@ void tc_release(TcScratch& s) {
     m->xnorm.release(); m->qnorm.release(); m->misc.release(); m->thr_g.release(); m->list_cnt.release();
     m->pair_off.release(); m->cursor.release(); m->pair_q.release(); m->pair_slot.release(); m->n_items.release();
     m->items.release(); m->items_w.release(); m->partial.release(); m->shortlist.release(); m->row_stamp.release();
-    m->prof.release(); m->list_order.release(); m->rs[0].xnorm.release(); m->rs[1].xnorm.release(); m->fitems.release();
+    m->prof.release(); m->list_order.release(); m->live_ids.release(); m->rs[0].xnorm.release(); m->rs[1].xnorm.release(); m->fitems.release();
     m->cnorm.release(); m->dense.release(); m->coarse.release(); m->citems.release();
     delete m;
     s.impl = nullptr;
@@ -1887,6 +1889,12 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             });
             TCK(m->list_order.ensure(a.nlist, dev_bytes));
             TCK(cudaMemcpyAsync(m->list_order.p, order.data(), (size_t)a.nlist * 4, cudaMemcpyHostToDevice, st));
+            // the non-empty lists in id order (a shard of a list-sharded index owns 1 / world of them)
+            std::vector<uint32_t> live;
+            for (uint32_t l = 0; l < a.nlist; ++l) if (off[l + 1] > off[l]) live.push_back(l);
+            m->n_live = (uint32_t)live.size();
+            TCK(m->live_ids.ensure(std::max<size_t>(live.size(), 1), dev_bytes));
+            if (!live.empty()) TCK(cudaMemcpyAsync(m->live_ids.p, live.data(), live.size() * 4, cudaMemcpyHostToDevice, st));
             TCK(cudaStreamSynchronize(st));
             m->list_order_n = a.nlist;
         }
@@ -2029,7 +2037,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
                                m->cursor.p, m->pair_q.p, m->pair_slot.p, m->items.p, m->n_items.p, a.d_scanned_rows, st,
                                (m->list_order_n == a.nlist && !getenv("FVDB_TC_NO_ORDER")) ? m->list_order.p : nullptr,
                                getenv("FVDB_TC_ORDER_NEAR") != nullptr, rows_cap, wide_min, (uint32_t)W_NQ,
-                               use_wide ? m->items_w.p : nullptr, m->n_items.p + 6, getenv("FVDB_TC_W_ORDER") != nullptr));
+                               use_wide ? m->items_w.p : nullptr, m->n_items.p + 6, getenv("FVDB_TC_W_ORDER") != nullptr,
+                               (m->list_order_n == a.nlist && !getenv("FVDB_TC_NO_ORDER")) ? m->live_ids.p : nullptr, m->n_live));
     (*launches) += 3;
     uint32_t stamp = 0;
     TCK(m->next_stamp(n_pairs * prows, dev_bytes, st, &stamp));
@@ -2050,6 +2059,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         p.debug = dbg ? (uint32_t)atoi(dbg) : 0u;
     }
     TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
+    if (a.wait_before_scan) TCK(cudaStreamWaitEvent(st, a.wait_before_scan, 0));
     if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
     auto run_wide = [&]() -> int {
     if (use_wide) {
@@ -2099,6 +2109,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         if (!wide_first) { int r = run_wide(); if (r != FVDB_OK) return r; }
     }
     if (a.ev_scan1) TCK(cudaEventRecord(a.ev_scan1, st));
+    if (a.record_after_scan) TCK(cudaEventRecord(a.record_after_scan, st));
     (*launches)++;
 
     // ---- merge the per-(query, probe) shortlists, exact re-rank, proof ----

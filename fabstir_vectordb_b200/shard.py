@@ -22,6 +22,35 @@ def owner_of_list(list_id: int, world: int) -> int:
     return list_id % world
 
 
+def place_lists(sizes, world: int) -> np.ndarray:
+    """Size-balanced list -> rank placement: greedy bin packing, longest list first, each to
+    the rank that holds the fewest rows so far (ties: the lower rank; equal sizes: the lower list id first),
+    so that every GPU streams the same number of rows per batch.  Deterministic: every rank computes the
+    same table from the same histogram.  Returns owner[nlist] (u32).  `l % world` (owner_of_list) is the
+    fallback when no histogram is known."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    owner = np.zeros(sizes.shape[0], dtype=np.uint32)
+    load = [0] * world
+    for l in np.lexsort((np.arange(sizes.shape[0]), -sizes)):
+        r = min(range(world), key=lambda i: (load[i], i))
+        owner[l] = r
+        load[r] += int(sizes[l])
+    return owner
+
+
+def kmeans_allreduce_step(sums, counts, sqerr, changed, group=None):
+    """The exchange step of sharded k-means: every rank holds the per-cluster f32 sums
+    [nlist x dim], counts [nlist], the squared-error sum and the "some assignment changed" flag of ITS
+    points; one all-reduce (sum) of each makes them global, in place.  torch tensors on any device (NCCL on
+    GPUs, gloo in the CPU tests).  Returns (total squared error, changed points, total points)."""
+    import torch.distributed as dist
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(sqerr, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(changed, op=dist.ReduceOp.SUM, group=group)
+    return float(sqerr.item()), int(changed.item()), int(counts.sum().item())
+
+
 def gather_layout(nq: int, k: int, world: int) -> Tuple[Tuple[int, ...], Tuple[int, ...]]:
     """Shapes of the all-gathered buffers consumed by fvdb_merge_topk_device:
     ids/dist [world][nq][k], count [world][nq]."""
@@ -69,6 +98,8 @@ class ShardedIndex:
         self.share_bounds = os.environ.get("FVDB_SHARE_BOUNDS", "1") != "0"
         self._bounds_cap = 0
         self._bufs = {}
+        self.owner = None
+        self.owner_host = None
 
     def _setup_bound_sharing(self, nq: int, device):
         """Exchange the inter-process handles of the per-query bound arrays (once per capacity)."""
@@ -88,9 +119,74 @@ class ShardedIndex:
         self.eng.bounds_import(bytes(allh.cpu().numpy().tobytes()), self.world, self.rank)
         self._bounds_cap = nq
 
+    def set_placement(self, owner):
+        """Install a list -> rank table (place_lists) in place of the l % world rule; `owner` is a host
+        array [nlist].  Rows loaded afterwards are kept when owner[list] == rank."""
+        import torch
+        self.owner_host = np.ascontiguousarray(owner, dtype=np.uint32)
+        self.owner = torch.from_numpy(self.owner_host.view(np.int32)).to(torch.device("cuda", torch.cuda.current_device()))
+
+    def list_histogram_device(self, x, hist):
+        """hist[l] += number of rows of x (CUDA tensor [n x dim]) whose nearest centroid is l: the input of
+        place_lists, computed without moving rows (fvdb_assign_device)."""
+        import torch
+        a = torch.empty((x.shape[0],), dtype=torch.int32, device=x.device)
+        self.eng.assign_device(x.data_ptr(), x.shape[0], a.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        hist += torch.bincount(a.long(), minlength=hist.shape[0])
+
     def add_rows_device(self, x, row_ids) -> int:
         """Assign rows to lists and keep those this rank owns."""
+        if getattr(self, "owner", None) is not None:
+            return self.eng.ivf_add_device_owned(x.data_ptr(), row_ids.data_ptr(), x.shape[0], self.owner.data_ptr(),
+                                                 self.rank)
         return self.eng.ivf_add_device(x.data_ptr(), row_ids.data_ptr(), x.shape[0], self.world, self.rank)
+
+    def train(self, points, nlist: int, max_iterations: int, init_centroids):
+        """IVFIndex::train (src/ivf/core.rs:240-334) with the points sharded over the ranks (SURVEY §8e):
+        `points` is THIS rank's slice (CUDA tensor [n_r x dim]), `init_centroids` [nlist x dim] (host array,
+        the same on every rank).  Per iteration every rank assigns its points against the replicated
+        centroid table and accumulates per-cluster sums and counts (fvdb_kmeans_accumulate_device), one
+        all-reduce makes them global (kmeans_allreduce_step), every rank installs the same means
+        (fvdb_kmeans_apply_device; an empty cluster keeps its centroid, :410-415).  Stop rule of :303-321 on
+        the mean squared distance measured at assignment time.  The sums are unordered f32 atomics, so the
+        centroids agree with the single-GPU (order-faithful) ones to rounding, not bit for bit.
+        Returns dict(iterations, converged, initial_error, final_error); like the reference, training
+        leaves every posting list empty."""
+        import torch
+        dev = points.device
+        dim = points.shape[1]
+        n_r = points.shape[0]
+        stream = torch.cuda.current_stream().cuda_stream
+        self.eng.set_centroids(np.ascontiguousarray(init_centroids, dtype=np.float32))
+        sums = torch.zeros((nlist, dim), dtype=torch.float32, device=dev)
+        counts = torch.zeros((nlist,), dtype=torch.int32, device=dev)
+        sqerr = torch.zeros((1,), dtype=torch.float64, device=dev)
+        changed = torch.zeros((1,), dtype=torch.int32, device=dev)
+        assign = torch.zeros((max(n_r, 1),), dtype=torch.int32, device=dev)    # vec![ClusterId(0); n]
+        prev_err, initial, err = float("inf"), None, 0.0
+        converged, iterations = False, 0
+        for it in range(max_iterations):
+            iterations = it + 1
+            sums.zero_(); counts.zero_(); sqerr.zero_(); changed.zero_()
+            if n_r:
+                self.eng.kmeans_accumulate_device(points.data_ptr(), n_r, sums.data_ptr(), counts.data_ptr(),
+                                                  sqerr.data_ptr(), assign.data_ptr(), changed.data_ptr(), stream)
+            if self.world > 1:
+                tot, n_changed, n_total = kmeans_allreduce_step(sums, counts, sqerr, changed, self.group)
+            else:
+                tot, n_changed, n_total = float(sqerr.item()), int(changed.item()), int(counts.sum().item())
+            err = tot / max(1, n_total)
+            if initial is None:
+                initial = err
+            self.eng.kmeans_apply_device(sums.data_ptr(), counts.data_ptr(), stream)
+            if iterations >= max_iterations:
+                break
+            if n_changed == 0 or (prev_err != float("inf") and abs(prev_err - err) / prev_err < 1e-4):
+                converged = True
+                break
+            prev_err = err
+        torch.cuda.synchronize()
+        return dict(iterations=iterations, converged=converged, initial_error=initial, final_error=err)
 
     def _buffers(self, nq: int, k: int, device, slot: int = 0):
         import torch

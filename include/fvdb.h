@@ -85,6 +85,9 @@ typedef enum fvdb_option {
     FVDB_OPT_SHORTLIST = 2,   /* shortlist length k' of the TC mode (default max(32, ..)) */
     FVDB_OPT_KMEANS_TC = 3,   /* 1: k-means assignment on tensor cores with exact verify */
     FVDB_OPT_COALESCE = 4,    /* 1 (default): concurrent fvdb_search calls are coalesced into one device batch */
+    FVDB_OPT_PIPELINE = 6,    /* 1 (default): batches of the stream-ordered entries alternate between two
+                                 internal streams with their own scratch, so that a batch's coarse step and
+                                 bucketing overlap the previous batch's scan tail, merge and re-rank */
     FVDB_OPT_PROOF_XMAX = 5   /* list-sharded multi-GPU search with shared bounds: f32 bits of the largest
                                  |x|^2 over ALL shards (fvdb_ivf_max_sqnorm, max-reduced by the driver).  A
                                  row of this shard may be dropped by a bound a peer published, so the
@@ -254,9 +257,11 @@ int fvdb_search_device(fvdb_index *h, const float *d_q, uint32_t nq, uint32_t k,
                        uint32_t *d_out_count, void *stream);
 
 /* Stream-ordered pair for back-to-back batches (a serving loop that always has the next batch
- * ready): _submit enqueues the whole batch on `stream` and returns WITHOUT waiting, so the GPU never
- * idles between batches while the host turns a call around; the result arrays are valid in stream
- * order, subject to _finish.  _finish waits for every submitted batch of the handle, reports
+ * ready): _submit enqueues the whole batch behind whatever `stream` holds and returns WITHOUT waiting, so
+ * the GPU never idles between batches while the host turns a call around.  Consecutive batches run in two
+ * internal pipeline slots (FVDB_OPT_PIPELINE): their scans are serialised, the smaller steps around the
+ * scans overlap.  The result arrays are valid — also for work enqueued on `stream` afterwards — once
+ * _finish has returned.  _finish waits for every submitted batch of the handle, reports
  * FVDB_ERR_NAN if any of them held a NaN query, and re-runs on the exact path (replacing their result
  * rows) the queries whose tensor-core proof failed.  Up to 64 batches may be pending; the query and
  * result buffers of a batch must stay alive and untouched by the caller until _finish returns.

@@ -84,3 +84,70 @@ def test_owner_rule_partitions_lists():
         owners = [owner_of_list(l, world) for l in range(64)]
         assert set(owners) == set(range(world))
         assert all(o == l % world for l, o in enumerate(owners))
+
+
+def test_place_lists_balances_rows():
+    """Greedy size-balanced placement: every list gets exactly one owner, the heaviest and the
+    lightest rank differ by at most the largest list, and the table is a pure function of the histogram."""
+    from fabstir_vectordb_b200.shard import place_lists
+    rng = np.random.default_rng(5)
+    sizes = (rng.pareto(1.5, 4096) * 300).astype(np.int64) + 1          # a few hub lists, many small ones
+    for world in (1, 2, 4, 8):
+        owner = place_lists(sizes, world)
+        assert owner.shape == sizes.shape and owner.max() == world - 1
+        load = np.bincount(owner, weights=sizes, minlength=world)
+        assert load.sum() == sizes.sum()
+        assert load.max() - load.min() <= sizes.max()
+        if world > 1:
+            mod_load = np.bincount(np.arange(sizes.size) % world, weights=sizes, minlength=world)
+            assert load.max() <= mod_load.max()                               # never worse than l % world
+        assert np.array_equal(owner, place_lists(sizes.copy(), world))
+    # ties go to the lower rank, equal sizes are placed in list order
+    assert place_lists([5, 5, 5, 5], 2).tolist() == [0, 1, 0, 1]
+
+
+def _kmeans_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fabstir_vectordb_b200.shard import kmeans_allreduce_step
+        x, _, cents = _case()
+        per = (N + world - 1) // world
+        mine = x[rank * per:(rank + 1) * per]
+        # this rank's share of one Lloyd iteration: assignment (oracle standing in for the per-GPU engine),
+        # per-cluster sums / counts / squared error of ITS points
+        a = O.assign(mine, cents)
+        sums = np.zeros((NLIST, D), dtype=np.float32)
+        np.add.at(sums, a, mine)
+        counts = np.bincount(a, minlength=NLIST).astype(np.int32)
+        d = O.l2_many(mine[0], cents[a[:1]])  # (shape check of the helper)
+        assert d.shape == (1,)
+        sq = float(sum(O.l2(mine[i], cents[a[i]]) ** 2 for i in range(mine.shape[0])))
+        t_sums, t_counts = torch.from_numpy(sums), torch.from_numpy(counts)
+        t_sq, t_ch = torch.tensor([sq], dtype=torch.float64), torch.tensor([1 if rank == 0 else 0], dtype=torch.int32)
+        tot, changed, total = kmeans_allreduce_step(t_sums, t_counts, t_sq, t_ch)
+        means = cents.copy()
+        nz = t_counts.numpy() > 0
+        means[nz] = t_sums.numpy()[nz] / t_counts.numpy()[nz, None].astype(np.float32)
+        np.savez(os.path.join(out_dir, f"km{rank}.npz"), means=means, counts=t_counts.numpy(), tot=tot,
+                 changed=changed, total=total)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_kmeans_exchange_step_world2(tmp_path):
+    """Points sharded over two ranks, one all-reduce of sums / counts / error (kmeans_allreduce_step): both
+    ranks end up with the same means, equal to the unsharded update_centroids (src/ivf/core.rs:388-417) up
+    to the f32 summation order, with exact counts and the unsharded error."""
+    world = 2
+    mp.spawn(_kmeans_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    x, _, cents = _case()
+    a = O.assign(x, cents)
+    want = O.update_centroids(x, a, cents)
+    r0, r1 = np.load(tmp_path / "km0.npz"), np.load(tmp_path / "km1.npz")
+    assert np.array_equal(r0["means"].view(np.uint32), r1["means"].view(np.uint32))
+    assert r0["counts"].tolist() == np.bincount(a, minlength=NLIST).tolist()
+    assert int(r0["total"]) == N and int(r0["changed"]) == 1
+    np.testing.assert_allclose(r0["means"], want, rtol=2e-5, atol=2e-6)
+    assert abs(float(r0["tot"]) / N - O.compute_error(x, cents, a)) < 1e-4
