@@ -32,6 +32,16 @@ ROWS_PER_GPU = int(os.environ.get("FVDB_BENCH_ROWS", 1_000_000))
 NLIST_PER_GPU = int(os.environ.get("FVDB_BENCH_NLIST", 1024))
 NQ_PER_GPU = int(os.environ.get("FVDB_BENCH_NQ", 1024))
 NPROBE = int(os.environ.get("FVDB_BENCH_NPROBE", 32))
+# weak scaling multiplies the number of lists by the world size; a fixed nprobe then probes a shrinking
+# share of the index and recall@10 sinks towards the 0.95 floor (0.9555 at 8 GPUs with 32 of 8192 lists).
+# nprobe per world size keeps recall@10 >= 0.97 (measured; FVDB_BENCH_NPROBE overrides).
+NPROBE_BY_WORLD = {1: 32, 2: 32, 4: 32, 8: 48}
+
+
+def nprobe_for(world):
+    if "FVDB_BENCH_NPROBE" in os.environ:
+        return NPROBE
+    return NPROBE_BY_WORLD.get(world, 48 if world > 4 else 32)
 K = 10
 SIGMA = float(os.environ.get("FVDB_BENCH_SIGMA", 1.0))
 SEED = 1234
@@ -106,21 +116,39 @@ def measured_peak_hbm():
 
 
 def workload_name(world):
-    return (f"IVF search {ROWS_PER_GPU * world}x{DIM} nlist={NLIST_PER_GPU * world} nprobe={NPROBE} "
+    return (f"IVF search {ROWS_PER_GPU * world}x{DIM} nlist={NLIST_PER_GPU * world} nprobe={nprobe_for(world)} "
             f"nq={NQ_PER_GPU * world}/batch k={K}")
 
 
 # ---------------------------------------------------------------------------------------------
 # index construction (shared by both arms so they search the identical index)
 # ---------------------------------------------------------------------------------------------
-def build_index(torch, eng, rank, world, log):
-    """Generate the synthetic database on the device, train centroids, load this rank's lists.
-    Returns (centroids tensor [nlist x D], n_total, nlist, n_comp)."""
+def train_sample_rows(n_total, n_train):
+    """Database rows of the training sample: blocks of 64 consecutive rows every 64*stride rows."""
+    stride = max(1, n_total // n_train)
+    i = np.arange(n_train, dtype=np.uint64)
+    return (i // np.uint64(64)) * np.uint64(64 * stride) + (i % np.uint64(64))
+
+
+def init_rows_of_sample(nlist, n_train):
+    """Which rows of the training sample seed k-means: one per list, each from a different mixture component."""
+    blk = np.arange(nlist, dtype=np.int64)
+    per = n_train // nlist
+    if os.environ.get("FVDB_BENCH_CLUMPED_INIT") or per != 64:
+        return blk * per
+    return blk * 64 + (blk // max(1, nlist // 16)) % 64
+
+
+def build_index(torch, eng, rank, world, log, sh=None, scale=None):
+    """Generate the synthetic database on the device, train centroids, load this rank's lists
+    (size-balanced placement when a ShardedIndex is given).  `scale` = how many times the
+    single-GPU workload (default: the world size).  Returns (n_total, nlist, n_comp)."""
     from fabstir_vectordb_b200 import _lib as L
     lib = L.load()
     dev = torch.device("cuda", torch.cuda.current_device())
-    n_total = ROWS_PER_GPU * world
-    nlist = NLIST_PER_GPU * world
+    scale = world if scale is None else scale
+    n_total = ROWS_PER_GPU * scale
+    nlist = NLIST_PER_GPU * scale
     n_comp = n_comp_for(nlist)
     stream = torch.cuda.current_stream().cuda_stream
     t0 = time.time()
@@ -138,12 +166,7 @@ def build_index(torch, eng, rank, world, log):
     # the first row of every 64-row block picks rows 64*stride*j, whose components (row mod n_comp)
     # collapse onto n_comp/64 values: 16 seeds per component, a clumped k-means — FVDB_BENCH_CLUMPED_INIT=1
     # reproduces that earlier set-up.)
-    blk = torch.arange(nlist, device=dev)
-    per = n_train // nlist
-    if os.environ.get("FVDB_BENCH_CLUMPED_INIT") or per != 64:
-        init = train[blk * per].contiguous()
-    else:
-        init = train[blk * 64 + (blk // max(1, nlist // 16)) % 64].contiguous()
+    init = train[torch.from_numpy(init_rows_of_sample(nlist, n_train)).to(dev)].contiguous()
     res = eng.train_device(train.data_ptr(), n_train, nlist, TRAIN_ITERS, init.data_ptr(), SEED)
     torch.cuda.synchronize()
     t1 = time.time()
@@ -151,6 +174,17 @@ def build_index(torch, eng, rank, world, log):
     del train
     buf = torch.empty((CH, DIM), dtype=torch.float32, device=dev)
     ids = torch.empty((CH,), dtype=torch.int32, device=dev)
+    if sh is not None and world > 1 and os.environ.get("FVDB_SHARD_PLACEMENT", "balanced") == "balanced":
+        # pass 1: list histogram of the whole database (every rank computes the same one), then greedy
+        # size-balanced placement of the lists (l % world leaves the shards 12 % apart at 8 GPUs)
+        from fabstir_vectordb_b200.shard import place_lists
+        hist = torch.zeros((nlist,), dtype=torch.int64, device=dev)
+        for r0 in range(0, n_total, CH):
+            n = min(CH, n_total - r0)
+            assert lib.fvdb_synth_rows_device(buf.data_ptr(), r0, n, DIM, n_comp, SIGMA, SEED, stream) == 0
+            sh.list_histogram_device(buf[:n], hist)
+        torch.cuda.synchronize()
+        sh.set_placement(place_lists(hist.cpu().numpy(), world))
     kept = 0
     for r0 in range(0, n_total, CH):
         n = min(CH, n_total - r0)
@@ -158,7 +192,10 @@ def build_index(torch, eng, rank, world, log):
         assert rc == 0
         ids[:n] = torch.arange(r0, r0 + n, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
-        kept += eng.ivf_add_device(buf.data_ptr(), ids.data_ptr(), n, world, rank)
+        if sh is not None:
+            kept += sh.add_rows_device(buf[:n], ids[:n])
+        else:
+            kept += eng.ivf_add_device(buf.data_ptr(), ids.data_ptr(), n, world, rank)
     log(f"rank {rank}: loaded {kept} of {n_total} rows in {time.time() - t1:.1f}s")
     return n_total, nlist, n_comp
 
@@ -244,34 +281,77 @@ def cpu_search_qps(ivf, q_host, k, nprobe, threads=0):
     return q_host.shape[0] / dt, dt, (ids, dist, cnt)
 
 
+def host_index(n_total, nlist, n_comp, log):
+    """The bench index built WITHOUT the product library: numpy twin of the data generator (bit-identical
+    to the device generator), the oracle's Lloyd loop from the same seeds (bit-identical to the engine's,
+    tests/test_gpu_parity.py), the oracle's own assignment."""
+    import oracle as O
+    from concurrent.futures import ThreadPoolExecutor
+    from fabstir_vectordb_b200 import synth
+    t0 = time.time()
+    x = np.empty((n_total, DIM), dtype=np.float32)
+    CH = 1 << 15
+
+    def fill(r0):
+        n = min(CH, n_total - r0)
+        x[r0:r0 + n] = synth.rows(r0, n, DIM, n_comp, SIGMA, SEED)
+
+    with ThreadPoolExecutor(max_workers=max(1, (os.cpu_count() or 2) - 1)) as ex:
+        list(ex.map(fill, range(0, n_total, CH)))
+    n_train = min(n_total, TRAIN_ROWS_PER_LIST * nlist)
+    tr_rows = train_sample_rows(n_total, n_train).astype(np.int64)
+    train = x[tr_rows]
+    init = train[init_rows_of_sample(nlist, n_train)].copy()
+    cents, _, res = O.train_lloyd(train, init, TRAIN_ITERS)
+    log(f"host index: generated {n_total} rows, trained nlist={nlist}: {res} in {time.time() - t0:.1f}s")
+    ivf = O.IVF(cents, x, np.arange(n_total, dtype=np.uint32))
+    log(f"host index: assigned and grouped in {time.time() - t0:.1f}s total")
+    return ivf, x
+
+
+def host_queries(nq, n_total, n_comp, set_idx):
+    from fabstir_vectordb_b200 import synth
+    return synth.queries(set_idx * nq, nq, DIM, n_total, n_comp, SIGMA, SEED, synth.default_qnoise(DIM, SIGMA), SEED_Q)
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU search path (oracle port, all host threads) on the
-    same index / metric / config.  Rank 0 only; a step = a bounded sample of one batch."""
+    """--impl reference: the reference's CPU search path (oracle port, all host threads) on the same
+    index / metric / config as the product arm.  Rank 0 only; a step = a bounded sample of one batch.
+    One GPU's workload: the index is built on the host (no product library is loaded).  N > 1: the same
+    N-times larger workload as the product arm; its 1M x N rows cannot be assigned on the host inside a
+    bench run (N^2 x 1e9 distances), so there — and only there — the engine generates and assigns them;
+    the timed region is pure host code either way."""
     if rank != 0:
         return
-    import torch
     import oracle as O
-    from fabstir_vectordb_b200 import Engine, _lib as L
-    lib = L.load()
-    torch.cuda.set_device(0)
     log = lambda m: print(f"[reference] {m}", file=sys.stderr, flush=True)
-    # the index is built exactly as in the product arm (same generator, same centroids, same
-    # assignment) so both arms search identical data; only index construction touches the GPU,
-    # the timed path below is pure host code.
-    eng = Engine(DIM, k_max=16)
-    eng.set_option(L.OPT_SCAN_MODE, L.SCAN_EXACT)
-    n_total, nlist, n_comp = build_index(torch, eng, 0, 1, log)
-    ivf, _ = host_index_from_device(torch, lib, eng, n_total, n_comp)
+    nprobe = nprobe_for(world)
+    nq = NQ_PER_GPU * world
     sample = CPU_SAMPLE_QUERIES
-    qsets = [make_queries(torch, lib, NQ_PER_GPU, n_total, n_comp, s).cpu().numpy()[:sample]
-             for s in range(N_QUERY_SETS)]
-    eng.close()
+    if world == 1:
+        n_total, nlist = ROWS_PER_GPU, NLIST_PER_GPU
+        n_comp = n_comp_for(nlist)
+        ivf, _ = host_index(n_total, nlist, n_comp, log)
+        qsets = [host_queries(sample, n_total, n_comp, s * (nq // sample)) for s in range(N_QUERY_SETS)]
+        built = "host (numpy generator + oracle k-means / assignment)"
+    else:
+        import torch
+        from fabstir_vectordb_b200 import Engine, _lib as L
+        lib = L.load()
+        torch.cuda.set_device(0)
+        eng = Engine(DIM, k_max=16)
+        eng.set_option(L.OPT_SCAN_MODE, L.SCAN_EXACT)
+        n_total, nlist, n_comp = build_index(torch, eng, 0, 1, log, scale=world)
+        ivf, _ = host_index_from_device(torch, lib, eng, n_total, n_comp)
+        qsets = [make_queries(torch, lib, nq, n_total, n_comp, s).cpu().numpy()[:sample] for s in range(N_QUERY_SETS)]
+        eng.close()
+        built = "device generator + engine assignment (host build infeasible at this size); timed region is host-only"
     threads = O.num_threads()
     for w in range(args.warmup):
-        cpu_search_qps(ivf, qsets[w % N_QUERY_SETS][:16], K, NPROBE)
+        cpu_search_qps(ivf, qsets[w % N_QUERY_SETS][:16], K, nprobe)
     t0 = time.perf_counter()
     for s in range(args.steps):
-        cpu_search_qps(ivf, qsets[s % N_QUERY_SETS], K, NPROBE)
+        cpu_search_qps(ivf, qsets[s % N_QUERY_SETS], K, nprobe)
     dt = time.perf_counter() - t0
     qps = args.steps * sample / dt
     line = {
@@ -279,10 +359,10 @@ def run_reference(args, rank, world):
         "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(1), "note": "oracle C port of the Rust reference "
-                   "(rustc/cargo absent), tight mode, OpenMP over queries"},
+        "config": {"workload": workload_name(world), "note": "oracle C port of the Rust reference "
+                   "(rustc/cargo absent), tight mode, OpenMP over queries", "index_built_by": built},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} of {NQ_PER_GPU} queries per step, full 1M-row index"},
+                         "sample": f"{sample} of {nq} queries per step, full {n_total}-row index"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -328,9 +408,10 @@ def main():
     elif args.mode == "tc":
         eng.set_option(L.OPT_SCAN_MODE, L.SCAN_TC)
         eng.set_option(L.OPT_KMEANS_TC, 1)
-    n_total, nlist, n_comp = build_index(torch, eng, rank, world, log)
     sh = ShardedIndex(eng, rank, world)
+    n_total, nlist, n_comp = build_index(torch, eng, rank, world, log, sh=sh)
     nq = NQ_PER_GPU * world
+    NPROBE = nprobe_for(world)
     qsets = [make_queries(torch, lib, nq, n_total, n_comp, s) for s in range(N_QUERY_SETS)]
 
     def step(i):
@@ -361,8 +442,8 @@ def main():
     # (N > 1: a FIXED count — every step is a collective, so all ranks must run the same number)
     t_w = time.perf_counter()
     w = 0
-    n_fixed = max(args.warmup, 300) if world > 1 else 0
-    pipe = max(1, int(os.environ.get("FVDB_BENCH_PIPE", 4))) if world == 1 else 1
+    pipe = max(1, int(os.environ.get("FVDB_BENCH_PIPE", 8)))
+    n_fixed = (max(args.warmup, 300) + pipe - 1) // pipe * pipe if world > 1 else 0
     while (w < n_fixed) if world > 1 else (w < args.warmup or (time.perf_counter() - t_w < 0.6 and w < 5000)):
         if pipe > 1:   # warm up the path that is timed: stream-ordered submits (both pipeline slots), one finish per group
             sh.submit(qsets[w % N_QUERY_SETS], K, NPROBE, tiers=L.TIER_HISTORICAL, slot=w % pipe)
@@ -397,7 +478,7 @@ def main():
         st = eng.stats()
         scan_ms.append(st.last_scan_ms)
         n_in_group = ((s % pipe) + 1) if pipe > 1 else 1
-        launches += (st.last_launches + (1 if world > 1 else 0)) * n_in_group
+        launches += (st.last_launches + (4 if world > 1 else 0)) * n_in_group   # N > 1: + coarse slice (3) + merge
         alg_bytes = st.last_algorithmic_bytes
         scan_rows = st.last_scanned_rows
     ev1.record()
@@ -460,16 +541,33 @@ def main():
             eng.search(h_q[s % N_QUERY_SETS], K, NPROBE, tiers=L.TIER_HISTORICAL)
         e2e_pageable_qps = nq * args.steps / (time.perf_counter() - t0)
     else:
-        pinned = [torch.from_numpy(a).pin_memory() for a in h_q]
+        # every rank uploads ONLY its slice of the batch (nq / world queries over its own PCIe link), the
+        # slices are all-gathered over NVLink; results go to page-locked host memory with asynchronous
+        # copies (every step's results are read back; one synchronisation at the end)
+        per = nq // world
+        pinned = [torch.from_numpy(np.ascontiguousarray(a[rank * per:(rank + 1) * per])).pin_memory() for a in h_q]
+        dq_slice = torch.empty((per, DIM), dtype=torch.float32, device="cuda")
         dq = torch.empty_like(qsets[0])
-        out_h = None
+        out_h = (torch.empty((nq, K), dtype=torch.int32).pin_memory(), torch.empty((nq, K), dtype=torch.float32).pin_memory(),
+                 torch.empty((nq,), dtype=torch.int32).pin_memory())
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
+        dqs = [torch.empty_like(qsets[0]) for _ in range(pipe)]
+        prev = None
         for s in range(args.steps):
-            dq.copy_(pinned[s % N_QUERY_SETS], non_blocking=True)
-            ids_, dist_, cnt_ = sh.search(dq, K, NPROBE, tiers=L.TIER_HISTORICAL)
-            out_h = (ids_.cpu(), dist_.cpu(), cnt_.cpu())
+            dq_slice.copy_(pinned[s % N_QUERY_SETS], non_blocking=True)
+            dist.all_gather_into_tensor(dqs[s % pipe].view(-1), dq_slice.view(-1))
+            cur = sh.submit(dqs[s % pipe], K, NPROBE, tiers=L.TIER_HISTORICAL, slot=s % pipe)
+            if prev is not None:   # the batch before this one has been exchanged and merged (stream order)
+                for dst, src in zip(out_h, prev):
+                    dst.copy_(src, non_blocking=True)
+            prev = cur
+            if (s + 1) % pipe == 0 or s + 1 == args.steps:
+                sh.finish()
+                for dst, src in zip(out_h, prev):
+                    dst.copy_(src, non_blocking=True)
+                prev = None
         torch.cuda.synchronize()
         e2e_dt = time.perf_counter() - t0
         t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
@@ -479,12 +577,13 @@ def main():
     if world > 1:
         e2e_pageable_qps = None
         e2e_sync_qps = None
-        e2e_submission = "torch H2D copy + sharded search + D2H per batch"
+        e2e_submission = ("per rank: H2D of its nq/world query slice + NVLink all-gather + pipelined sharded search "
+                          f"(submit per batch, finish every {pipe}) + async D2H of the results")
     else:
         e2e_submission = (f"fvdb_search_submit per batch, fvdb_search_finish every {e2e_pipe}" if e2e_pipe > 1
                           else "fvdb_search per batch")
-    h2d = nq * DIM * 4
-    d2h = nq * K * 8 + nq * 4
+    h2d = nq * DIM * 4            # whole job: every query crosses PCIe once (N > 1: nq / world per rank)
+    d2h = (nq * K * 8 + nq * 4) * world   # every rank reads the merged results back
 
     # ---- roofline of the dominant kernel (posting-list scan) -----------------------------------
     peak, peak_src = measured_peak_hbm()
@@ -506,6 +605,23 @@ def main():
     # ---- CPU baseline beside it (rank 0, N == 1) -------------------------------------------------
     cpu = None
     parity = None
+    if world > 1 and not args.no_cpu_baseline and os.environ.get("FVDB_BENCH_PARITY", "1") != "0":
+        # oracle parity of the SHARDED search: rank 0 builds the unsharded host index (the other ranks only
+        # take part in the collective search of the sample) and compares 64 queries bit for bit
+        sample = min(64, nq)
+        cq_dev = qsets[0][:sample].contiguous()
+        g = sh.search(cq_dev, K, NPROBE, tiers=L.TIER_HISTORICAL)
+        torch.cuda.synchronize()
+        if rank == 0:
+            import oracle as O
+            ivf, _ = host_index_from_device(torch, lib, eng, n_total, n_comp)
+            _, _, cres = cpu_search_qps(ivf, h_q[0][:sample], K, NPROBE)
+            g_ids = g[0].cpu().numpy().view(np.uint32)
+            g_dist = g[1].cpu().numpy()
+            same_ids = int((g_ids == cres[0]).all(axis=1).sum())
+            same_bits = int((g_dist.view(np.uint32) == cres[1].view(np.uint32)).all(axis=1).sum())
+            parity = {"queries": sample, "identical_id_lists": same_ids, "identical_distance_bits": same_bits}
+            log(f"sharded search vs unsharded oracle: {parity}")
     if world == 1 and not args.no_cpu_baseline:
         import oracle as O
         ivf, _ = host_index_from_device(torch, lib, eng, n_total, n_comp)
@@ -536,7 +652,8 @@ def main():
                    "nlist": nlist, "nprobe": NPROBE, "nq_per_batch": nq, "k": K, "sigma": SIGMA,
                    "mixture_components": n_comp, "scan_mode": args.mode,
                    "cache": "index (1.5 GB/GPU) >> 126 MB L2; 4 rotating query sets",
-                   "sharding": f"list l on rank l % {world}; all-gather top-k + merge" if world > 1 else "single GPU"},
+                   "sharding": (f"lists placed on {world} ranks by greedy size-balanced bin packing; coarse step sharded by "
+                                f"query + all-gather of the keys; all-gather of the per-rank top-k + merge") if world > 1 else "single GPU"},
         "recall_at_10": recall, "recall_queries": RECALL_QUERIES, "fallback_queries": int(fallback_q),
         "clocks": clocks,
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

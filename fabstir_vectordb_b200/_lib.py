@@ -104,6 +104,10 @@ SIGNATURES = {
     "fvdb_coarse_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "fvdb_search_device_coarse": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
                                             C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
+    "fvdb_coarse_device_submit": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "fvdb_search_device_coarse_submit": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp,
+                                                   C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
+    "fvdb_search_device_wait": (C.c_int, [_vp, C.c_uint32, _vp]),
     "fvdb_merge_topk_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32,
                                          _vp, _vp, _vp, _vp]),
     "fvdb_ivf_max_sqnorm": (C.c_int, [_vp, _f32p]),

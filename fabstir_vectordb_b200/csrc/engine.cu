@@ -239,6 +239,7 @@ struct fvdb_index {
     uint32_t host_slot_next = 0;
     cudaStream_t copy_stream = nullptr;
     std::vector<Pending> pending;
+    std::vector<std::pair<uint32_t*, size_t>> pending_coarse;   // records of fvdb_coarse_device_submit
     std::vector<std::pair<uint32_t*, size_t>> pending_pool;   // recycled page-locked blocks
     DevBuf<float> s_fb_q;
     DevBuf<uint64_t> s_fb_keys, s_fb_coarse;
@@ -853,7 +854,7 @@ int ivf_scan_exact(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uin
 // list id), ascending, ties to the lower list id.  Tensor cores + exact verify when possible;
 // queries whose proof fails are re-ranked by the exact kernel.
 int coarse_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t np, uint64_t* d_out_keys,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool defer = false) {
     const uint32_t D = h->dim;
     if (nq == 0) return FVDB_OK;
     CK(h->s_misc.ensure(64, 0, st, &h->dev_bytes));
@@ -875,6 +876,25 @@ int coarse_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t np
         if (r != FVDB_OK) return r;
     } else {
         RET(scan_all_exact(h, h->centroids.p, nullptr, h->nlist, d_q, nq, np, nullptr, 0, nullptr, 0, d_out_keys, st));
+    }
+    if (defer) {
+        // stream-ordered: the NaN flag and the number of queries whose tensor-core proof failed go to a
+        // page-locked record that fvdb_search_device_finish looks at (it reports them; the caller re-runs
+        // the batch through the synchronous entry, which repairs them)
+        uint32_t* rec = nullptr;
+        for (size_t i = 0; i < h->pending_pool.size(); ++i)
+            if (h->pending_pool[i].second >= 16) {
+                rec = h->pending_pool[i].first;
+                h->pending_coarse.push_back(h->pending_pool[i]);
+                h->pending_pool.erase(h->pending_pool.begin() + i);
+                break;
+            }
+        if (!rec) {
+            CK(cudaHostAlloc((void**)&rec, 16 * 4, cudaHostAllocDefault));
+            h->pending_coarse.push_back({rec, 16});
+        }
+        CK(cudaMemcpyAsync(rec, h->s_misc.p, 64, cudaMemcpyDeviceToHost, st));
+        return FVDB_OK;
     }
     uint32_t host_misc[16] = {0};
     CK(cudaMemcpyAsync(host_misc, h->s_misc.p, sizeof(host_misc), cudaMemcpyDeviceToHost, st));
@@ -947,7 +967,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
     const cudaStream_t user_st = st;
     int slot = -1;
     const bool tc_coarse_ok = D <= 384 && std::min(nprobe, h->nlist) <= TC_MAX_NPROBE_COARSE && !getenv("FVDB_EXACT_COARSE");
-    if (defer && want_pipe && h->pipeline && tc_ivf && tc_coarse_ok && !use_flat && !ext_coarse) {
+    if (defer && want_pipe && h->pipeline && tc_ivf && (tc_coarse_ok || ext_coarse) && !use_flat) {
         slot = (int)(h->slot_next++ % fvdb_index::N_SLOTS);
         fvdb_index::Slot& sl = h->slots[slot];
         if (!sl.stream) {
@@ -1044,7 +1064,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             uint32_t launches = 0;
             if (sl) {
                 // one scan at a time: this one waits for the scan of the batch enqueued before it
-                ta.wait_before_scan = h->prev_scan_end;
+                ta.wait_before_scan = getenv("FVDB_PIPE_NOSERIAL") ? nullptr : h->prev_scan_end;
                 ta.record_after_scan = sl->ev_scan_end;
             }
             int r = tc_ivf_search(b_tc, ta, st, &h->dev_bytes, &launches, &h->err);
@@ -1251,6 +1271,7 @@ void fvdb_destroy(fvdb_index* h) {
     if (h->pin) cudaFreeHost(h->pin);
     for (auto& pb : h->pending) cudaFreeHost(pb.host);
     for (auto& pp : h->pending_pool) cudaFreeHost(pp.first);
+    for (auto& pp : h->pending_coarse) cudaFreeHost(pp.first);
     for (auto& sl : h->host_slots) {
         if (sl.uploaded) cudaEventDestroy(sl.uploaded);
         if (sl.done) cudaEventDestroy(sl.done);
@@ -1812,6 +1833,14 @@ static int finish_pending(fvdb_index* h, cudaStream_t st) {
         }
     }
     for (const fvdb_index::Pending& pb : todo) h->pending_pool.push_back({pb.host, pb.host_words});
+    for (auto& rec : h->pending_coarse) {
+        if (rc == FVDB_OK && rec.first[0])
+            rc = h->fail(FVDB_ERR_NAN, "NaN in query (the reference panics on partial_cmp().unwrap())");
+        fallbacks += rec.first[10];   // unrepaired: the caller re-runs the batch through the synchronous entries
+        h->pending_pool.push_back(rec);
+    }
+    h->pending_coarse.clear();
+    if (todo.empty()) h->stats.last_fallback_queries = fallbacks;
     if (!todo.empty()) {
         const fvdb_index::Pending& lb = todo.back();   // the figures of the last batch, as the synchronous call reports them
         uint64_t scanned = 0;
@@ -1838,6 +1867,39 @@ int fvdb_coarse_device(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t np
         return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_coarse_device needs 1 <= nprobe <= min(nlist, 512)");
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return coarse_device_impl(h, d_q, nq, nprobe, d_out_keys, st);
+}
+
+int fvdb_coarse_device_submit(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t nprobe, uint64_t* d_out_keys,
+                              void* stream) {
+    ENTER_PIPE(h);
+    if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");
+    if (nprobe == 0 || nprobe > h->nlist || nprobe > 512)
+        return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_coarse_device needs 1 <= nprobe <= min(nlist, 512)");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return coarse_device_impl(h, d_q, nq, nprobe, d_out_keys, st, true);
+}
+
+int fvdb_search_device_coarse_submit(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,
+                                     uint32_t tiers, const uint64_t* d_filter_bits, uint64_t filter_nbits,
+                                     const uint64_t* d_coarse_keys, uint32_t* d_out_ids, float* d_out_dist,
+                                     uint32_t* d_out_count, void* stream) {
+    ENTER_PIPE(h);
+    if (d_coarse_keys && nprobe > h->nlist)
+        return h->fail(FVDB_ERR_INVALID_ARG, "coarse keys are [nq x nprobe]: nprobe must not exceed nlist");
+    if (h->pending.size() >= 64) return h->fail(FVDB_ERR_INVALID_ARG, "64 batches are pending: call fvdb_search_device_finish");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return search_device_impl(h, d_q, nq, k, nprobe, tiers, d_filter_bits, filter_nbits, d_out_ids,
+                              d_out_dist, d_out_count, st, d_coarse_keys, nullptr, true, true);
+}
+
+// Device-side join: `stream` waits for the batch submitted `age` submits ago (0 = the latest).
+int fvdb_search_device_wait(fvdb_index* h, uint32_t age, void* stream) {
+    ENTER_PIPE(h);
+    if (age >= h->pending.size()) return FVDB_OK;
+    const fvdb_index::Pending& pb = h->pending[h->pending.size() - 1 - age];
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (pb.slot >= 0) CK(cudaStreamWaitEvent(st, h->slots[pb.slot].ev_done, 0));
+    return FVDB_OK;
 }
 
 int fvdb_search_device_coarse(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k, uint32_t nprobe,

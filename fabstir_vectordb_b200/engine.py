@@ -349,6 +349,19 @@ class Engine:
                                                      filter_nbits, d_coarse_keys or None, d_out_ids,
                                                      d_out_dist, d_out_count, _stream(stream)))
 
+    def coarse_device_submit(self, d_q: int, nq: int, nprobe: int, d_out_keys: int, stream: int = 0):
+        self._ck(self._lib.fvdb_coarse_device_submit(self._h, d_q, nq, nprobe, d_out_keys, _stream(stream)))
+
+    def search_device_coarse_submit(self, d_q: int, nq: int, k: int, nprobe: int, tiers: int, d_filter: int,
+                                    filter_nbits: int, d_coarse_keys: int, d_out_ids: int, d_out_dist: int,
+                                    d_out_count: int, stream: int = 0):
+        self._ck(self._lib.fvdb_search_device_coarse_submit(self._h, d_q, nq, k, nprobe, tiers, d_filter or None,
+                                                            filter_nbits, d_coarse_keys or None, d_out_ids,
+                                                            d_out_dist, d_out_count, _stream(stream)))
+
+    def search_device_wait(self, age: int = 0, stream: int = 0):
+        self._ck(self._lib.fvdb_search_device_wait(self._h, age, _stream(stream)))
+
     def merge_topk_device(self, d_ids: int, d_dist: int, d_count: int, parts: int, nq: int, k: int,
                           d_out_ids: int, d_out_dist: int, d_out_count: int, stream: int = 0):
         self._ck(self._lib.fvdb_merge_topk_device(self._h, d_ids, d_dist, d_count, parts, nq, k,

@@ -100,6 +100,9 @@ class ShardedIndex:
         self._bufs = {}
         self.owner = None
         self.owner_host = None
+        self._inflight = None      # pipelined sharded search: the batch whose results are not exchanged yet
+        self._group = []           # ... and every batch submitted since the last finish()
+        self._nlist = None
 
     def _setup_bound_sharing(self, nq: int, device):
         """Exchange the inter-process handles of the per-query bound arrays (once per capacity)."""
@@ -208,30 +211,95 @@ class ShardedIndex:
         return self._bufs[key]
 
     def submit(self, q, k: int, nprobe: int, tiers: int = L.TIER_HISTORICAL, slot: int = 0):
-        """Single-GPU, stream-ordered: enqueue the batch (fvdb_search_device_submit) and return its result
-        tensors, which are valid after finish().  `slot` selects one of several result buffer sets, so
-        that batches in flight do not share one."""
+        """Stream-ordered search: enqueue the batch and return its result tensors, which are valid after
+        finish().  `slot` selects one of several buffer sets, so that batches in flight do not share one;
+        `q` must stay alive and untouched until finish().
+
+        One GPU: fvdb_search_device_submit.  Several GPUs: a two-deep software pipeline over the same four
+        steps as search() — while the engine scans batch i in one of its pipeline slots, batch i + 1's
+        coarse slice and the all-gather of its keys are already running on the caller's stream, and batch
+        i's result exchange (one all-gather of the packed chunks + merge) is enqueued only after batch
+        i + 1's scan has been handed to the engine (fvdb_search_device_wait joins it on the device).  No
+        host synchronisation per batch.  The NVLink bound arrays stay safe: a rank's reset for batch i + 2
+        is ordered behind its all-gather of batch i's results, which needs every peer's finished scan of i."""
         import torch
-        assert self.world == 1, "the stream-ordered entry is the single-GPU path"
+        import torch.distributed as dist
         nq = q.shape[0]
         b = self._buffers(nq, k, q.device, slot)
-        self.eng.search_device_submit(q.data_ptr(), nq, k, nprobe, tiers, 0, 0, b["ids"].data_ptr(),
-                                      b["dist"].data_ptr(), b["cnt"].data_ptr(),
-                                      torch.cuda.current_stream().cuda_stream)
-        return b["ids"], b["dist"], b["cnt"]
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.world == 1:
+            self.eng.search_device_submit(q.data_ptr(), nq, k, nprobe, tiers, 0, 0, b["ids"].data_ptr(),
+                                          b["dist"].data_ptr(), b["cnt"].data_ptr(), stream)
+            return b["ids"], b["dist"], b["cnt"]
+        assert (tiers & L.TIER_HISTORICAL) and nprobe > 0 and self.shard_coarse, "pipelined sharded search: IVF tier"
+        np_ = min(nprobe, self.eng.stats().nlist) if self._nlist is None else min(nprobe, self._nlist)
+        if self._nlist is None:
+            self._nlist = self.eng.stats().nlist
+        if self.share_bounds and self.world <= 8:
+            if nq > self._bounds_cap:
+                self._setup_bound_sharing(nq, q.device)
+            self.eng.bounds_begin_batch(nq, stream)
+        per = (nq + self.world - 1) // self.world
+        key = ("coarse", nq, np_, slot)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.empty((per, np_), dtype=torch.int64, device=q.device),
+                               torch.empty((self.world * per, np_), dtype=torch.int64, device=q.device))
+        mine, allk = self._bufs[key]
+        lo = min(nq, self.rank * per)
+        n_mine = max(0, min(nq, lo + per) - lo)
+        if n_mine < per:
+            mine.fill_(-1)
+        if n_mine:
+            self.eng.coarse_device_submit(q[lo:lo + n_mine].data_ptr(), n_mine, np_, mine.data_ptr(), stream)
+        dist.all_gather_into_tensor(allk, mine, group=self.group)
+        self.eng.search_device_coarse_submit(q.data_ptr(), nq, k, np_, tiers, 0, 0, allk.data_ptr(),
+                                             b["ids"].data_ptr(), b["dist"].data_ptr(), b["cnt"].data_ptr(), stream)
+        if self._inflight is not None:
+            self._exchange(self._inflight, age=1)
+        self._inflight = (b, nq, k)
+        self._group.append((q, k, nprobe, tiers, slot))
+        return b["o_ids"], b["o_dist"], b["o_cnt"]
+
+    def _exchange(self, rec, age: int):
+        """Result exchange of a submitted batch: join its scan on the device, ONE all-gather, merge."""
+        import torch
+        import torch.distributed as dist
+        b, nq, k = rec
+        stream = torch.cuda.current_stream().cuda_stream
+        self.eng.search_device_wait(age, stream)
+        dist.all_gather_into_tensor(b["g_pack"].view(-1), b["pack"], group=self.group)
+        self.eng.merge_topk_packed_device(b["g_pack"].data_ptr(), self.world, nq, k, b["o_ids"].data_ptr(),
+                                          b["o_dist"].data_ptr(), b["o_cnt"].data_ptr(), stream)
 
     def finish(self):
+        """Wait for every submitted batch.  Raises NanInput if one held a NaN query.  Several GPUs: if the
+        tensor-core proof failed for some query on ANY rank (rare), every rank re-runs the group through the
+        synchronous path, which repairs such queries before results are exchanged."""
         import torch
-        self.eng.search_device_finish(torch.cuda.current_stream().cuda_stream)
+        import torch.distributed as dist
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.world > 1 and self._inflight is not None:
+            self._exchange(self._inflight, age=0)
+            self._inflight = None
+        self.eng.search_device_finish(stream)
+        if self.world > 1:
+            group, self._group = self._group, []
+            fb = torch.tensor([self.eng.stats().last_fallback_queries], dtype=torch.int32,
+                              device=torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(fb, op=dist.ReduceOp.MAX, group=self.group)
+            if int(fb.item()) > 0:
+                for q, k, nprobe, tiers, slot in group:
+                    self.search(q, k, nprobe, tiers=tiers, slot=slot)
+                torch.cuda.synchronize()
 
     def search(self, q, k: int, nprobe: int, tiers: int = L.TIER_HISTORICAL, filter_bits=None,
-               filter_nbits: int = 0):
+               filter_nbits: int = 0, slot: int = 0):
         """q: [nq x dim] CUDA tensor, identical on every rank.  Returns (ids, dist, cnt) CUDA
         tensors holding the GLOBAL top-k on every rank."""
         import torch
         import torch.distributed as dist
         nq = q.shape[0]
-        b = self._buffers(nq, k, q.device)
+        b = self._buffers(nq, k, q.device, slot)
         stream = torch.cuda.current_stream().cuda_stream
         f_ptr = filter_bits.data_ptr() if filter_bits is not None else 0
         if self.world == 1:

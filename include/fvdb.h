@@ -295,6 +295,25 @@ int fvdb_search_device_coarse(fvdb_index *h, const float *d_q, uint32_t nq, uint
                               uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count,
                               void *stream);
 
+/* Stream-ordered twins of the two calls above for a pipelined multi-GPU driver (no host synchronisation
+ * per batch): _coarse_device_submit enqueues the coarse step of a query slice; _search_device_coarse_submit
+ * enqueues a batch whose coarse ranking is handed in — in one of the handle's pipeline slots, behind
+ * whatever `stream` holds (e.g. the all-gather of the coarse keys); fvdb_search_device_wait makes `stream`
+ * wait, on the device, for the batch submitted `age` submits ago (0 = the latest), so that a collective
+ * on `stream` can consume its results while the NEXT batch is already scanning.  fvdb_search_device_finish
+ * ends a group as usual: NaN -> FVDB_ERR_NAN; queries whose tensor-core proof failed are repaired locally
+ * (scan) or merely counted (coarse step) and reported in fvdb_stats.last_fallback_queries — a sharded
+ * driver then re-runs the group through the synchronous entries, because results it has already
+ * exchanged were built from the unrepaired ones. */
+int fvdb_coarse_device_submit(fvdb_index *h, const float *d_q, uint32_t nq, uint32_t nprobe,
+                              uint64_t *d_out_keys, void *stream);
+int fvdb_search_device_coarse_submit(fvdb_index *h, const float *d_q, uint32_t nq, uint32_t k,
+                                     uint32_t nprobe, uint32_t tiers, const uint64_t *d_filter_bits,
+                                     uint64_t filter_nbits, const uint64_t *d_coarse_keys,
+                                     uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count,
+                                     void *stream);
+int fvdb_search_device_wait(fvdb_index *h, uint32_t age, void *stream);
+
 /* Multi-GPU bound sharing over NVLink peer memory (one process per GPU, lists sharded by
  * l % world as above).  During the posting-list scan every query carries a running upper bound of
  * its 32nd-nearest approximate distance; rows above it are dropped in the epilogue.  A shard that

@@ -23,11 +23,11 @@ if world > 1:
 lib = L.load()
 eng = Engine(bench.DIM, k_max=16, device=local)
 log = lambda m: None
-n_total, nlist, n_comp = bench.build_index(torch, eng, rank, world, log)
 sh = ShardedIndex(eng, rank, world)
+n_total, nlist, n_comp = bench.build_index(torch, eng, rank, world, log, sh=sh)
 nq = bench.NQ_PER_GPU * world
 qsets = [bench.make_queries(torch, lib, nq, n_total, n_comp, s) for s in range(4)]
-K, NP = bench.K, bench.NPROBE
+K, NP = bench.K, bench.nprobe_for(world)
 for i in range(6):
     sh.search(qsets[i % 4], K, NP)
 torch.cuda.synchronize()
