@@ -35,13 +35,13 @@ NPROBE = int(os.environ.get("FVDB_BENCH_NPROBE", 32))
 # weak scaling multiplies the number of lists by the world size; a fixed nprobe then probes a shrinking
 # share of the index and recall@10 sinks towards the 0.95 floor (0.9555 at 8 GPUs with 32 of 8192 lists).
 # nprobe per world size keeps recall@10 >= 0.97 (measured; FVDB_BENCH_NPROBE overrides).
-NPROBE_BY_WORLD = {1: 32, 2: 32, 4: 32, 8: 48}
+NPROBE_BY_WORLD = {1: 32, 2: 32, 4: 32, 8: 64}
 
 
 def nprobe_for(world):
     if "FVDB_BENCH_NPROBE" in os.environ:
         return NPROBE
-    return NPROBE_BY_WORLD.get(world, 48 if world > 4 else 32)
+    return NPROBE_BY_WORLD.get(world, 64 if world > 4 else 32)
 K = 10
 SIGMA = float(os.environ.get("FVDB_BENCH_SIGMA", 1.0))
 SEED = 1234

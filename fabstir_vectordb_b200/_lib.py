@@ -28,6 +28,9 @@ ERR_INVALID_ARG = -12
 ERR_K_TOO_LARGE = -13
 ERR_OOM = -14
 
+METRIC_L2 = 0
+METRIC_COS = 1
+METRIC_DOT = 2
 TIER_RECENT = 1
 TIER_HISTORICAL = 2
 TIER_BOTH = 3

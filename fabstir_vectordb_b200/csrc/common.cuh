@@ -26,6 +26,39 @@ __host__ __device__ __forceinline__ uint64_t make_key(float dist, uint32_t id) {
 __host__ __device__ __forceinline__ uint32_t key_id(uint64_t k) { return (uint32_t)k; }
 __device__ __forceinline__ float key_dist(uint64_t k) { return __uint_as_float((uint32_t)(k >> 32)); }
 
+// Metrics other than L2 rank by a SIMILARITY, best = largest (dot_product_scalar / cosine_similarity_scalar,
+// src/core/vector_ops.rs:35-49, ranked by top_k_indices :12-23: descending, ties in index order).  Their
+// candidates use the same u64 keys, ascending = best first: the upper word is an order-preserving image of
+// -similarity (the usual sign-flip of the f32 bits), so every selection, merge and tie rule of the L2 path
+// applies unchanged; -0.0 is folded onto +0.0 first (the reference compares them equal).
+constexpr int METRIC_L2 = 0, METRIC_COS = 1, METRIC_DOT = 2;
+__host__ __device__ __forceinline__ uint32_t sim_to_key32(float s) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(-(s + 0.0f));
+#else
+    union { float f; uint32_t u; } c;
+    c.f = -(s + 0.0f);
+    uint32_t b = c.u;
+#endif
+    if (b == 0x80000000u) b = 0u;   // -(+0) = -0: fold onto +0
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key32_to_sim(uint32_t k) {
+    const uint32_t b = k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu);
+    // 0 - x, not -x: the image of a zero similarity decodes to +0.0, as the scalar kernels return it
+#ifdef __CUDA_ARCH__
+    return 0.0f - __uint_as_float(b);
+#else
+    union { float f; uint32_t u; } c;
+    c.u = b;
+    return 0.0f - c.f;
+#endif
+}
+// the value a caller sees for a key: the true L2 distance, or the similarity
+__device__ __forceinline__ float key_value(uint64_t k, int metric) {
+    return metric == METRIC_L2 ? __uint_as_float((uint32_t)(k >> 32)) : key32_to_sim((uint32_t)(k >> 32));
+}
+
 // bitmap over row ids (u64 words).  nbits bounds the bitmap; ids beyond it read as 0.
 __device__ __forceinline__ bool bit_test(const uint64_t* __restrict__ bits, uint64_t nbits,
                                          uint32_t id) {

@@ -382,7 +382,8 @@ uint32_t pick_nsplit(fvdb_index* h, uint32_t nq, uint64_t rows) {
 // Scan every query against rows [0,rows) of X; result keys[nq][k] sorted (exact arithmetic).
 int scan_all_exact(fvdb_index* h, const float* X, const uint32_t* ids, uint64_t rows, const float* Q,
                    uint32_t nq, uint32_t k, const uint64_t* tomb, uint64_t tomb_bits,
-                   const uint64_t* filt, uint64_t filt_bits, uint64_t* out_keys, cudaStream_t st) {
+                   const uint64_t* filt, uint64_t filt_bits, uint64_t* out_keys, cudaStream_t st,
+                   int metric = FVDB_METRIC_L2) {
     if (rows >= 0xFFFFFFFFull) return h->fail(FVDB_ERR_INVALID_ARG, "row count exceeds u32");
     const uint32_t nsplit = pick_nsplit(h, nq, rows);
     uint32_t n_items = 0;
@@ -404,6 +405,7 @@ int scan_all_exact(fvdb_index* h, const float* X, const uint32_t* ids, uint64_t 
     a.P = nsplit; a.k = k;
     a.tomb = tomb; a.tomb_bits = tomb_bits; a.filt = filt; a.filt_bits = filt_bits;
     a.partial = partial;
+    a.metric = metric;
     CK(launch_exact_scan(a, n_items, st));
     h->stats.last_launches += 3;
     if (nsplit > 1) {
@@ -953,6 +955,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
     if (nq == 0) return FVDB_OK;
     RET(seal(h));
     const uint32_t D = h->dim;
+    // the IVF tier exists for L2 only (fvdb_ivf_* reject a similarity handle), so use_ivf implies L2
     const bool use_ivf = (tiers & FVDB_TIER_HISTORICAL) && h->trained && h->ivf_n > 0 && nprobe > 0;
     const bool use_flat = (tiers & FVDB_TIER_RECENT) && h->flat_n > 0;
     const uint64_t* tomb = h->deleted_count ? h->tomb.p : nullptr;
@@ -1086,7 +1089,8 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         // recent tier: exhaustive scan instead of the HNSW walk (src/hnsw/core.rs:398-467); on the
         // tensor cores when the batch is large enough to amortise the item set-up
         flat_tc = (h->scan_mode == FVDB_SCAN_TC) && tc_supported(D) && k <= TC_MAX_K &&
-                  (uint64_t)h->flat_n * nq >= (4ull << 20) && !getenv("FVDB_FLAT_EXACT");
+                  (uint64_t)h->flat_n * nq >= (4ull << 20) && !getenv("FVDB_FLAT_EXACT") &&
+                  (h->metric == FVDB_METRIC_L2 || D <= 384);
         if (flat_tc) {
             CK(h->s_fb_idx_flat.ensure((size_t)2 * nq, 0, st, &h->dev_bytes));
             TcFlatArgs fa{};
@@ -1096,17 +1100,18 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             fa.out_keys = flat_keys;
             fa.d_fallback_count = d_fb_count_flat; fa.d_fallback_idx = h->s_fb_idx_flat.p;
             fa.sm_count = h->sm_count;
+            fa.metric = h->metric;
             uint32_t launches = 0;
             int r = tc_flat_search(h->tc, fa, st, &h->dev_bytes, &launches, &h->err);
             if (r != FVDB_OK) return r;
             h->stats.last_launches += launches;
         } else {
             RET(scan_all_exact(h, h->flat_rows.p, h->flat_ids.p, h->flat_n, d_q, nq, k, tomb, h->tomb_bits,
-                               filt, filter_bits, flat_keys, st));
+                               filt, filter_bits, flat_keys, st, h->metric));
         }
     }
     if (!fused_finalize) {
-        CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
+        CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st, h->metric));
         h->stats.last_launches += 1;
     }
     CK(cudaEventRecord(e_b, st));
@@ -1160,9 +1165,9 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         CK(h->s_fb_keys.ensure((size_t)n_fb_flat * k, 0, st, &h->dev_bytes));
         CK(launch_gather_rows(d_q, nq, nullptr, h->s_fb_idx_flat.p, n_fb_flat, D, h->s_fb_q.p, st));
         RET(scan_all_exact(h, h->flat_rows.p, h->flat_ids.p, h->flat_n, h->s_fb_q.p, n_fb_flat, k, tomb, h->tomb_bits,
-                           filt, filter_bits, h->s_fb_keys.p, st));
+                           filt, filter_bits, h->s_fb_keys.p, st, h->metric));
         CK(launch_scatter_keys(h->s_fb_keys.p, h->s_fb_idx_flat.p, n_fb_flat, k, flat_keys, st));
-        CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
+        CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st, h->metric));
         if (ho) CK(copy_out(ho, d_out_ids, d_out_dist, d_out_count, st));
         CK(cudaStreamSynchronize(st));
         h->stats.last_launches += 3;
@@ -1181,7 +1186,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
         RET(ivf_scan_exact(h, h->s_fb_q.p, n_fb, k, np, h->s_fb_coarse.p, tomb, filt, filter_bits,
                            h->s_fb_keys.p, nullptr, false, st));
         CK(launch_scatter_keys(h->s_fb_keys.p, h->s_fb_idx.p, n_fb, k, ivf_keys, st));
-        CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st));
+        CK(launch_finalize(flat_keys, ivf_keys, nq, k, d_out_ids, d_out_dist, d_out_count, st, h->metric));
         if (ho) CK(copy_out(ho, d_out_ids, d_out_dist, d_out_count, st));
         CK(cudaStreamSynchronize(st));
         h->stats.last_launches += 3;
@@ -1221,7 +1226,8 @@ int fvdb_create(int device, uint32_t dim, int metric, uint32_t k_max, fvdb_index
     if (!out) return fail(FVDB_ERR_INVALID_ARG, "out is NULL");
     *out = nullptr;
     if (dim == 0) return fail(FVDB_ERR_INVALID_CONFIG, "dim must be > 0");
-    if (metric != FVDB_METRIC_L2) return fail(FVDB_ERR_INVALID_CONFIG, "only FVDB_METRIC_L2 is implemented");
+    if (metric != FVDB_METRIC_L2 && metric != FVDB_METRIC_COS && metric != FVDB_METRIC_DOT)
+        return fail(FVDB_ERR_INVALID_CONFIG, "metric must be FVDB_METRIC_L2, FVDB_METRIC_COS or FVDB_METRIC_DOT");
     if (k_max == 0 || k_max > 512) return fail(FVDB_ERR_INVALID_CONFIG, "k_max must be in 1..512");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -1349,6 +1355,9 @@ int fvdb_get_stats(fvdb_index* h, fvdb_stats* out) {
 
 int fvdb_ivf_set_centroids(fvdb_index* h, const float* centroids, uint32_t nlist) {
     ENTER(h);
+    if (h->metric != FVDB_METRIC_L2)
+        return h->fail(FVDB_ERR_INVALID_CONFIG, "the IVF tier is L2 only, like the reference's IVFIndex (src/ivf/core.rs:373-386, 646-678): "
+                       "a cosine / dot handle serves the flat tier (batch_cosine_similarity + top_k_indices, src/core/vector_ops.rs:8-23)");
     if (!centroids || nlist == 0) return h->fail(FVDB_ERR_INVALID_CONFIG, "centroids empty");
     for (size_t i = 0; i < (size_t)nlist * h->dim; ++i)
         if (std::isnan(centroids[i])) return h->fail(FVDB_ERR_NAN, "NaN in centroids");
@@ -1376,6 +1385,9 @@ int fvdb_ivf_train_device(fvdb_index* h, const float* d_data, uint64_t n, uint32
                           uint32_t max_iterations, const float* d_init_centroids, uint64_t seed,
                           fvdb_train_result* out) {
     ENTER(h);
+    if (h->metric != FVDB_METRIC_L2)
+        return h->fail(FVDB_ERR_INVALID_CONFIG, "the IVF tier is L2 only, like the reference's IVFIndex (src/ivf/core.rs:373-386, 646-678): "
+                       "a cosine / dot handle serves the flat tier (batch_cosine_similarity + top_k_indices, src/core/vector_ops.rs:8-23)");
     return train_device_impl(h, d_data, n, nlist, max_iterations, d_init_centroids, seed, out);
 }
 
@@ -1383,6 +1395,9 @@ int fvdb_ivf_train(fvdb_index* h, const float* data, uint64_t n, uint32_t nlist,
                    uint32_t max_iterations, const float* init_centroids, uint64_t seed,
                    fvdb_train_result* out) {
     ENTER(h);
+    if (h->metric != FVDB_METRIC_L2)
+        return h->fail(FVDB_ERR_INVALID_CONFIG, "the IVF tier is L2 only, like the reference's IVFIndex (src/ivf/core.rs:373-386, 646-678): "
+                       "a cosine / dot handle serves the flat tier (batch_cosine_similarity + top_k_indices, src/core/vector_ops.rs:8-23)");
     if (nlist == 0 || max_iterations == 0) return h->fail(FVDB_ERR_INVALID_CONFIG, "Invalid IVFConfig");
     if (n == 0 || n < nlist)
         return h->fail(FVDB_ERR_INSUFFICIENT_TRAINING, "Insufficient training data: got " +

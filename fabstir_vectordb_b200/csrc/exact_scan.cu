@@ -51,7 +51,11 @@ __device__ __forceinline__ void warp_insert(uint64_t* list, int k, uint64_t cand
     __syncwarp();
 }
 
-template <bool VEC>
+// METRIC: how a pair is scored, always in the reference's operation order (strictly sequential f32, no FMA):
+//   L2   sqrt(sum (q - x)^2)                      euclidean_distance_scalar  src/core/vector_ops.rs:51-57
+//   DOT  sum q * x                                dot_product_scalar         :35-37
+//   COS  dot / (sqrt(dot(q,q)) * sqrt(dot(x,x))), 0 if either norm is 0      cosine_similarity_scalar :39-49
+template <bool VEC, int METRIC>
 __global__ void __launch_bounds__(NT) exact_scan_kernel(ExactScanArgs a) {
     const uint32_t n_items = a.item_count ? *a.item_count : a.n_items;
     if (blockIdx.x >= n_items) return;
@@ -104,6 +108,7 @@ __global__ void __launch_bounds__(NT) exact_scan_kernel(ExactScanArgs a) {
         }
 
         float acc[4][4];
+        float qq_acc[4] = {0.f, 0.f, 0.f, 0.f}, xx_acc[4] = {0.f, 0.f, 0.f, 0.f};   // COS: dot(q,q), dot(x,x)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -171,10 +176,21 @@ __global__ void __launch_bounds__(NT) exact_scan_kernel(ExactScanArgs a) {
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        // reference order: (a - b), squared, added — never fused
-                        const float df = __fsub_rn(qq[i], xx[j]);
-                        acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(df, df));
+                        if (METRIC == METRIC_L2) {
+                            // reference order: (a - b), squared, added — never fused
+                            const float df = __fsub_rn(qq[i], xx[j]);
+                            acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(df, df));
+                        } else {
+                            acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(qq[i], xx[j]));   // x * y, summed
+                        }
                     }
+                if (METRIC == METRIC_COS) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        qq_acc[i] = __fadd_rn(qq_acc[i], __fmul_rn(qq[i], qq[i]));
+                        xx_acc[i] = __fadd_rn(xx_acc[i], __fmul_rn(xx[i], xx[i]));
+                    }
+                }
             }
             __syncthreads();
         }
@@ -183,12 +199,19 @@ __global__ void __launch_bounds__(NT) exact_scan_kernel(ExactScanArgs a) {
         float* dist_s = Xs;  // [TQ][XS_LD]
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float4 o;
-            o.x = __fsqrt_rn(acc[i][0]);
-            o.y = __fsqrt_rn(acc[i][1]);
-            o.z = __fsqrt_rn(acc[i][2]);
-            o.w = __fsqrt_rn(acc[i][3]);
-            *reinterpret_cast<float4*>(&dist_s[(tq * 4 + i) * XS_LD + tr * 4]) = o;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (METRIC == METRIC_L2) {
+                    o[j] = __fsqrt_rn(acc[i][j]);
+                } else if (METRIC == METRIC_DOT) {
+                    o[j] = acc[i][j];
+                } else {
+                    const float na = __fsqrt_rn(qq_acc[i]), nb = __fsqrt_rn(xx_acc[j]);
+                    o[j] = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(acc[i][j], __fmul_rn(na, nb));
+                }
+            }
+            *reinterpret_cast<float4*>(&dist_s[(tq * 4 + i) * XS_LD + tr * 4]) = make_float4(o[0], o[1], o[2], o[3]);
         }
         __syncthreads();
 
@@ -203,7 +226,11 @@ __global__ void __launch_bounds__(NT) exact_scan_kernel(ExactScanArgs a) {
             for (int c = 0; c < TR / 32; ++c) {
                 const int r = lane + 32 * c;
                 const uint32_t id = rowid_s[r];
-                uint64_t key = (id == ID_NONE) ? KEY_NONE : make_key(dist_s[q * XS_LD + r], id);
+                uint64_t key = KEY_NONE;
+                if (id != ID_NONE) {
+                    const float v = dist_s[q * XS_LD + r];
+                    key = METRIC == METRIC_L2 ? make_key(v, id) : (((uint64_t)sim_to_key32(v) << 32) | id);
+                }
                 unsigned m = __ballot_sync(0xffffffffu, key < thr);
                 while (m) {
                     const int src = __ffs(m) - 1;
@@ -239,18 +266,17 @@ cudaError_t launch_exact_scan(const ExactScanArgs& a, uint32_t grid, cudaStream_
     const size_t smem = exact_scan_smem_bytes(a.k);
     const bool vec = (a.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.X) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(a.Q) & 15) == 0);
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, NT, smem, stream>>>(a);
+        return cudaSuccess;
+    };
     cudaError_t e;
-    if (vec) {
-        e = cudaFuncSetAttribute(exact_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem);
-        if (e != cudaSuccess) return e;
-        exact_scan_kernel<true><<<grid, NT, smem, stream>>>(a);
-    } else {
-        e = cudaFuncSetAttribute(exact_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem);
-        if (e != cudaSuccess) return e;
-        exact_scan_kernel<false><<<grid, NT, smem, stream>>>(a);
-    }
+    if (a.metric == METRIC_COS) e = vec ? go(exact_scan_kernel<true, METRIC_COS>) : go(exact_scan_kernel<false, METRIC_COS>);
+    else if (a.metric == METRIC_DOT) e = vec ? go(exact_scan_kernel<true, METRIC_DOT>) : go(exact_scan_kernel<false, METRIC_DOT>);
+    else e = vec ? go(exact_scan_kernel<true, METRIC_L2>) : go(exact_scan_kernel<false, METRIC_L2>);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
@@ -679,7 +705,7 @@ cudaError_t launch_merge_partials(const uint64_t* in, uint32_t nq, uint32_t P, u
 // into ids / distances / count.  Either input may be null.
 __global__ void finalize_kernel(const uint64_t* __restrict__ recent, const uint64_t* __restrict__ ivf,
                                 uint32_t nq, uint32_t k, uint32_t* __restrict__ out_ids,
-                                float* __restrict__ out_dist, uint32_t* __restrict__ out_count) {
+                                float* __restrict__ out_dist, uint32_t* __restrict__ out_count, int metric) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const uint64_t* a = recent ? recent + (size_t)q * k : nullptr;
@@ -694,22 +720,22 @@ __global__ void finalize_kernel(const uint64_t* __restrict__ recent, const uint6
         if (kb == KEY_NONE || (ka != KEY_NONE && (uint32_t)(ka >> 32) <= (uint32_t)(kb >> 32))) { pick = ka; ++ia; }
         else { pick = kb; ++ib; }
         out_ids[(size_t)q * k + o] = key_id(pick);
-        out_dist[(size_t)q * k + o] = key_dist(pick);
+        out_dist[(size_t)q * k + o] = key_value(pick, metric);
         ++o;
     }
     out_count[q] = o;
     for (; o < k; ++o) {
         out_ids[(size_t)q * k + o] = ID_NONE;
-        out_dist[(size_t)q * k + o] = __uint_as_float(0x7f800000u);
+        out_dist[(size_t)q * k + o] = __uint_as_float(metric == METRIC_L2 ? 0x7f800000u : 0xff800000u);   // worst value
     }
 }
 
 cudaError_t launch_finalize(const uint64_t* recent, const uint64_t* ivf, uint32_t nq, uint32_t k,
                             uint32_t* out_ids, float* out_dist, uint32_t* out_count,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, int metric) {
     if (nq == 0) return cudaSuccess;
     finalize_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(recent, ivf, nq, k, out_ids, out_dist,
-                                                         out_count);
+                                                         out_count, metric);
     return cudaGetLastError();
 }
 

@@ -23,6 +23,7 @@ struct ExactScanArgs {
     const uint64_t* filt;      // filter bitmap over ids (bit set = passes) or nullptr
     uint64_t filt_bits;
     uint64_t* partial;         // [nq][P][k] sorted keys
+    int metric = 0;            // METRIC_L2 | METRIC_COS | METRIC_DOT (common.cuh): how a (query, row) pair is scored
 };
 
 size_t exact_scan_smem_bytes(uint32_t k);
@@ -57,7 +58,7 @@ cudaError_t launch_merge_rows32(const uint64_t* in, uint32_t nq, uint32_t P, uin
                                 cudaStream_t stream, const uint32_t* row_stamp, uint32_t stamp);
 cudaError_t launch_finalize(const uint64_t* recent, const uint64_t* ivf, uint32_t nq, uint32_t k,
                             uint32_t* out_ids, float* out_dist, uint32_t* out_count,
-                            cudaStream_t stream);
+                            cudaStream_t stream, int metric = 0);
 cudaError_t launch_merge_parts(const uint32_t* ids, const float* dist, const uint32_t* cnt,
                                uint32_t parts, uint32_t nq, uint32_t k, uint32_t* out_ids,
                                float* out_dist, uint32_t* out_count, cudaStream_t stream,

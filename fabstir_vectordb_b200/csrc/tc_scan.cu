@@ -67,6 +67,8 @@ struct TcScanParams {
     uint32_t dense_ld;
     uint32_t debug;          // timing experiments. bit 0: skip the epilogue math; 3: no MMAs; 4: a quarter of the MMAs; 5: N = 16
     unsigned long long* prof; // debug bit 7: [grid][3 roles][8] cycle counters (stopwatch laps per role)
+    int metric;               // kernel W only: METRIC_L2 | METRIC_COS | METRIC_DOT (kernel R and Q are L2)
+    const uint32_t* xmax_bits; // kernel W, METRIC_DOT: max |x|^2 of the row set (f32 bits, device)
 };
 constexpr int TC_SCHED = 4;          // depth of the in-CTA work-item ring
 constexpr uint32_t ITEM_END = 0xFFFFFFFFu;
@@ -1171,9 +1173,12 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t v
 constexpr int GATHER_STAGES_ROWS = 6;      // re-rank: rows come from HBM
 constexpr int GATHER_STAGES_CENT = 4;      // coarse step: centroids come from L2
 __host__ __device__ constexpr int gather_warp_bytes(int stages) { return stages * 32 * 128; }
-template <int GATHER_STAGES>
+// METRIC_DOT / METRIC_COS: the same walk with dot_product_scalar's arithmetic (x * y summed, sequential, no
+// FMA, src/core/vector_ops.rs:35-37); for the cosine the row's own dot(x, x) is accumulated alongside and
+// cosine_similarity_scalar's quotient is formed at the end from the caller's dot(q, q) (:39-49).
+template <int GATHER_STAGES, int METRIC = METRIC_L2>
 __device__ __forceinline__ float exact_l2_lane_gather(const float* __restrict__ q_s, const float* __restrict__ row,
-                                                      uint32_t KB, uint32_t warp_stage_base, int lane) {
+                                                      uint32_t KB, uint32_t warp_stage_base, int lane, float qq = 0.0f) {
     // instruction j of a stage: this lane fetches chunk (lane & 7) of the row owned by lane 4 j + lane / 8
     const char* src[8];
     uint32_t dst[8];
@@ -1199,7 +1204,7 @@ __device__ __forceinline__ float exact_l2_lane_gather(const float* __restrict__ 
     const float4* q4 = reinterpret_cast<const float4*>(q_s);
     const uint32_t mine = warp_stage_base + (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)lane & 7u;
-    float acc = 0.0f;
+    float acc = 0.0f, xx = 0.0f;
     for (uint32_t kb = 0; kb < KB; ++kb) {
         issue(kb + GATHER_STAGES - 1);
         asm volatile("cp.async.wait_group %0;" ::"n"(GATHER_STAGES - 1) : "memory");
@@ -1212,18 +1217,30 @@ __device__ __forceinline__ float exact_l2_lane_gather(const float* __restrict__ 
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                              : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                              : "r"(st + ((j ^ sw) << 4)));
-                const float4 qq = q4[kb * 8 + j];
-                float t;
-                t = __fsub_rn(qq.x, x.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
-                t = __fsub_rn(qq.y, x.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
-                t = __fsub_rn(qq.z, x.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
-                t = __fsub_rn(qq.w, x.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                const float4 qv = q4[kb * 8 + j];
+                if (METRIC == METRIC_L2) {
+                    float t;
+                    t = __fsub_rn(qv.x, x.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                    t = __fsub_rn(qv.y, x.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                    t = __fsub_rn(qv.z, x.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                    t = __fsub_rn(qv.w, x.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                } else {
+                    acc = __fadd_rn(acc, __fmul_rn(qv.x, x.x)); acc = __fadd_rn(acc, __fmul_rn(qv.y, x.y));
+                    acc = __fadd_rn(acc, __fmul_rn(qv.z, x.z)); acc = __fadd_rn(acc, __fmul_rn(qv.w, x.w));
+                    if (METRIC == METRIC_COS) {
+                        xx = __fadd_rn(xx, __fmul_rn(x.x, x.x)); xx = __fadd_rn(xx, __fmul_rn(x.y, x.y));
+                        xx = __fadd_rn(xx, __fmul_rn(x.z, x.z)); xx = __fadd_rn(xx, __fmul_rn(x.w, x.w));
+                    }
+                }
             }
         }
         __syncwarp();   // the stage may be overwritten by the next iteration's copies
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    return __fsqrt_rn(acc);
+    if (METRIC == METRIC_L2) return __fsqrt_rn(acc);
+    if (METRIC == METRIC_DOT) return acc;
+    const float na = __fsqrt_rn(qq), nb = __fsqrt_rn(xx);
+    return (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(acc, __fmul_rn(na, nb));
 }
 
 // Exact re-rank + proof.  One warp per query, lane = shortlist entry.  Distances are recomputed
@@ -1232,6 +1249,11 @@ __device__ __forceinline__ float exact_l2_lane_gather(const float* __restrict__ 
 // approx d2 >= a_last (the largest approx d2 kept), hence exact d2 >= a_last - eps, where eps
 // bounds |approx - exact| for TF32 operands (2^-10 relative each) — if that is above the exact
 // k-th d2 the shortlist provably contains the exact top-k.
+// METRIC_COS / METRIC_DOT (flat tier of a similarity handle): the shortlist keys are the non-negative images
+// kernel W builds (1 - cosine, B - dot); the candidates are re-scored with the scalar kernels' arithmetic,
+// keyed by sim_to_key32 (descending similarity, ties to the lower id), and the proof compares in the
+// approximate key's units: dot products of TF32 operands are off by at most ~2^-9 |q| |x|.
+template <int METRIC = METRIC_L2>
 __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict__ shortlist,  // [nq][KP]
                                                      const float* __restrict__ rows, const uint32_t* __restrict__ ids,
                                                      const float* __restrict__ Q, const float* __restrict__ qnorm,
@@ -1253,17 +1275,22 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
     const uint64_t akey = shortlist[(size_t)q * TC_KP + lane];
     const bool have = akey != KEY_NONE && (uint32_t)lane < R;
     const uint32_t pos = have ? (uint32_t)akey : 0u;
-    const float dist = exact_l2_lane_gather<GATHER_STAGES_ROWS>(q_s, have ? rows + (size_t)pos * D : nullptr, D / 32,
-                                                                smem_u32(rr_sm) + (uint32_t)w * GWB, lane);
+    float qq = 0.0f;
+    if (METRIC == METRIC_COS)      // dot(q, q) in the scalar kernel's order (every lane the same chain)
+        for (uint32_t d = 0; d < D; ++d) qq = __fadd_rn(qq, __fmul_rn(q_s[d], q_s[d]));
+    const float dist = exact_l2_lane_gather<GATHER_STAGES_ROWS, METRIC>(q_s, have ? rows + (size_t)pos * D : nullptr, D / 32,
+                                                                        smem_u32(rr_sm) + (uint32_t)w * GWB, lane, qq);
     uint64_t ekey = KEY_NONE;
-    if (have) ekey = make_key(dist, ids ? ids[pos] : pos);
+    if (have) ekey = METRIC == METRIC_L2 ? make_key(dist, ids ? ids[pos] : pos)
+                                         : (((uint64_t)sim_to_key32(dist) << 32) | (ids ? ids[pos] : pos));
     ekey = warp_sort32(ekey, lane);
     if ((uint32_t)lane < k) out_keys[(size_t)q * k + lane] = ekey;
     if (fin_ids) {
         // the caller-facing arrays as finalize_kernel writes them when this tier is the only one
         if ((uint32_t)lane < k) {
             fin_ids[(size_t)q * k + lane] = ekey != KEY_NONE ? key_id(ekey) : ID_NONE;
-            fin_dist[(size_t)q * k + lane] = ekey != KEY_NONE ? key_dist(ekey) : __uint_as_float(0x7f800000u);
+            fin_dist[(size_t)q * k + lane] = ekey != KEY_NONE ? key_value(ekey, METRIC)
+                                                              : __uint_as_float(METRIC == METRIC_L2 ? 0x7f800000u : 0xff800000u);
         }
         const uint32_t found = __popc(__ballot_sync(0xffffffffu, ekey != KEY_NONE && (uint32_t)lane < k));
         if (lane == 0) fin_count[q] = found;
@@ -1279,10 +1306,22 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
         const float eps = 1.05f * 0.00390625f * sqrtf(qnorm[q]) * xmax + 3.1e-5f * a_last + 1e-30f;
         bool ok = false;
         if (kth != KEY_NONE) {
-            const float dk = key_dist(kth);
-            ok = (a_last - eps) > dk * dk * 1.000001f;
+            if (METRIC == METRIC_L2) {
+                const float dk = key_dist(kth);
+                ok = (a_last - eps) > dk * dk * 1.000001f;
+            } else {
+                // the exact k-th similarity in the approximate key's units (see kernel W)
+                const float sk = key32_to_sim((uint32_t)(kth >> 32));
+                const float qn = sqrtf(qnorm[q]);
+                const float scale = METRIC == METRIC_COS ? 1.0f : qn * xmax;
+                const float ek = METRIC == METRIC_COS ? 1.0f - sk : 1.02f * qn * xmax - sk;
+                const float eps_s = (1.05f * 0.001953125f + 1.0e-4f) * scale + 1e-30f;
+                ok = (a_last - eps_s) > ek && (METRIC != METRIC_COS || qn > 0.0f);
+            }
         }
         if (!ok) fb_idx[atomicAdd(fb_count, 1u)] = q;
+    } else if (METRIC == METRIC_COS && lane == 0 && qnorm[q] == 0.0f) {
+        fb_idx[atomicAdd(fb_count, 1u)] = q;   // a zero query passes nothing in the scan: the exact path scores it
     }
 }
 
@@ -1736,7 +1775,7 @@ struct TcScratchImpl {
     uint32_t tmap_cent_n = 0;
     CUtensorMap tmap_arena;  // box 32 floats x 128 rows (kernel R)
     CUtensorMap tmap_w;      // box 32 floats x 32 rows  (kernel W: each CTA of a pair streams half a tile)
-    bool smem_attr_set_w = false;
+    uint32_t smem_attr_set_w = 0;   // bit per metric instantiation of kernel W
     bool smem_attr_set_q = false;
     const float* tmap_rows = nullptr;
     uint64_t tmap_n = 0;
@@ -1752,7 +1791,9 @@ static size_t coarse_select_smem_bytes(uint32_t D, uint32_t KC) {
 }
 static cudaError_t rerank_prepare(TcScratchImpl* m) {
     if (m->smem_attr_set_rerank) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rerank_smem_bytes(512));
+    cudaError_t e = cudaFuncSetAttribute(rerank_kernel<METRIC_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rerank_smem_bytes(512));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rerank_kernel<METRIC_COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rerank_smem_bytes(512));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rerank_kernel<METRIC_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rerank_smem_bytes(512));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(coarse_select_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_select_smem_bytes(512, 128));
     if (e == cudaSuccess) m->smem_attr_set_rerank = true;
     return e;
@@ -1799,10 +1840,12 @@ static cudaError_t launch_wide(TcScratchImpl* m, const CUtensorMap& tmap, TcScan
     p.stages = stages;
     const size_t smem = tc_scan_wide_smem_bytes(stages, kbs) + 1024;
     cudaError_t e;
-    if (!m->smem_attr_set_w) {
-        e = cudaFuncSetAttribute(tc_scan_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    auto kern = p.metric == METRIC_COS ? tc_scan_wide_kernel<METRIC_COS>
+              : p.metric == METRIC_DOT ? tc_scan_wide_kernel<METRIC_DOT> : tc_scan_wide_kernel<METRIC_L2>;
+    if (!(m->smem_attr_set_w & (1u << p.metric))) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
-        m->smem_attr_set_w = true;
+        m->smem_attr_set_w |= 1u << p.metric;
     }
     const uint32_t grid = (uint32_t)sm_count & ~1u;   // whole pairs; idle pairs exit at once
     if (p.debug & 128u) {
@@ -1825,7 +1868,7 @@ static cudaError_t launch_wide(TcScratchImpl* m, const CUtensorMap& tmap, TcScan
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, tc_scan_wide_kernel, tmap, p);
+    e = cudaLaunchKernelEx(&cfg, kern, tmap, p);
     if (e != cudaSuccess) return e;
     if (p.prof) return dump_prof(m->prof.p, grid, st);
     return cudaSuccess;
@@ -2115,7 +2158,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     // ---- merge the per-(query, probe) shortlists, exact re-rank, proof ----
     TCK(launch_merge_rows32(m->partial.p, nq, np * prows, m->shortlist.p, st, m->row_stamp.p, stamp));
     TCK(rerank_prepare(m));
-    rerank_kernel<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k, (uint32_t)TC_KP,
+    rerank_kernel<METRIC_L2><<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, m->misc.p, nq, D, a.k, (uint32_t)TC_KP,
                                                a.xmax_floor_sq, a.out_keys, a.d_fallback_count, a.d_fallback_idx, a.fin_ids, a.fin_dist, a.fin_count);
     TCK(cudaGetLastError());
     (*launches) += 2;
@@ -2161,6 +2204,7 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
     }
     // ---- work items: every query group (256 queries for kernel W, 64 for kernel R) against every row chunk ----
     const bool use_wide = tc_kernel_choice(D, a.sm_count) == 'W';
+    if (a.metric != METRIC_L2 && !use_wide) { if (err) *err = "cosine / dot scans need kernel W (dim <= 384)"; return FVDB_ERR_INVALID_CONFIG; }
     const uint32_t tile_q = use_wide ? (uint32_t)W_NQ : TC_TILE_Q;
     const uint32_t tile_rows = use_wide ? (uint32_t)W_N : (uint32_t)TC_ROWS;
     const uint32_t n_qg = (nq + tile_q - 1) / tile_q;
@@ -2196,6 +2240,7 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
     p.tomb = a.tomb; p.tomb_bits = a.tomb_bits; p.filt = a.filt; p.filt_bits = a.filt_bits;
     p.P = n_chunks; p.S = use_wide ? frows : 0u; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
     p.row_stamp = m->row_stamp.p; p.stamp = stamp;
+    p.metric = a.metric; p.xmax_bits = xmax_bits;
     p.work_counter = m->n_items.p + 5;
     {
         const char* dbg = getenv("FVDB_TC_DEBUG");
@@ -2221,10 +2266,11 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
     if (a.ev_scan1) TCK(cudaEventRecord(a.ev_scan1, st));
     TCK(launch_merge_rows32(m->partial.p, nq, n_chunks * frows, m->shortlist.p, st, m->row_stamp.p, stamp));
     TCK(rerank_prepare(m));
-    rerank_kernel<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p,
-                                                                         xmax_bits, nq, D, a.k,
-                                                                         a.rerank_r ? a.rerank_r : (uint32_t)TC_KP, 0.0f, a.out_keys,
-                                                                         a.d_fallback_count, a.d_fallback_idx);
+    auto rr = a.metric == METRIC_COS ? rerank_kernel<METRIC_COS> : a.metric == METRIC_DOT ? rerank_kernel<METRIC_DOT>
+                                                                                            : rerank_kernel<METRIC_L2>;
+    rr<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, xmax_bits, nq, D, a.k,
+                                                        a.rerank_r ? a.rerank_r : (uint32_t)TC_KP, 0.0f, a.out_keys,
+                                                        a.d_fallback_count, a.d_fallback_idx, nullptr, nullptr, nullptr);
     TCK(cudaGetLastError());
     (*launches) += 3;
     return FVDB_OK;

@@ -89,6 +89,7 @@ struct TcFlatArgs {
     uint32_t state = 0;
     uint64_t version = 0;
     uint32_t rerank_r = 0;        // shortlist entries re-ranked exactly (0 = all 32)
+    int metric = 0;               // METRIC_L2 | METRIC_COS | METRIC_DOT (common.cuh)
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;   // optional: recorded around the scan kernel
 };
 

@@ -144,6 +144,14 @@ __device__ __noinline__ uint32_t wide_fold(uint32_t hb, uint32_t pb, uint32_t pc
     return root;
 }
 
+// METRIC (flat-tier scans of a similarity handle, include/fvdb.h fvdb_metric): the accumulator is q.x either
+// way; what changes is the per-row strip and the map from accumulator to the non-negative, smaller-is-better
+// approximate key the heaps, bounds and the shortlist merge work on:
+//   L2   strip |x|^2,       v = strip - 2 acc,   key = v + |q|^2                  (approximate d^2)
+//   COS  strip -1 / |x|,    v = strip * acc,     key = v / |q| + 1                (1 - cosine; a zero row scores 0)
+//   DOT  strip -1,          v = strip * acc,     key = v + B, B = 1.02 |q| max|x| (B - dot >= 0)
+// Masked rows carry +inf (L2) / NaN (COS, DOT) in the strip and never pass `v < threshold`.
+template <int METRIC>
 __global__ void __launch_bounds__(W_THREADS, 1)
 tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -396,6 +404,15 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
                             }
                         }
                     }
+                    if (METRIC != METRIC_L2) {
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) {
+                            const float xn = xnv[h];
+                            if (xn == __uint_as_float(F32_INF_BITS)) xnv[h] = __uint_as_float(0x7fc00000u);   // masked: NaN
+                            else if (METRIC == METRIC_DOT) xnv[h] = -1.0f;
+                            else xnv[h] = xn > 0.0f ? -rsqrtf(xn) : 0.0f;
+                        }
+                    }
 #pragma unroll
                     for (int t4 = 0; t4 < 4; ++t4) {
                         if (rt + t4 * W_N >= it.row_end) break;
@@ -516,14 +533,23 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
             // ---- item prologue: this thread's query, its threshold from the shared bound ----
             const bool have = jq < it.pair_count;
             uint32_t qi = 0, sl = 0;
-            float qn = 0.f, thrp = -__uint_as_float(F32_INF_BITS);   // lanes without a query never pass
+            // key = v * qa + qn (see the table above the kernel); a bound in key units maps back to v units
+            // as (bound - qn) * qia.  L2: qa = qia = 1 and qn = |q|^2, so both maps are the plain +- |q|^2.
+            float qn = 0.f, qa = 1.0f, qia = 1.0f, thrp = -__uint_as_float(F32_INF_BITS);   // lanes without a query never pass
             uint32_t thr_pending = F32_INF_BITS, root_pub = F32_INF_BITS, peer_sent = F32_INF_BITS;
             if (have) {
                 if (it.identity) { qi = it.pair_begin + jq; sl = it.slot; }
                 else { qi = p.pair_q[it.pair_begin + jq]; sl = p.pair_slot[it.pair_begin + jq]; }
                 qn = p.qnorm[qi];
+                if (METRIC == METRIC_COS) {
+                    qa = qn > 0.0f ? rsqrtf(qn) : 0.0f;     // a zero query scores 0 everywhere: nothing passes, and
+                    qia = qn > 0.0f ? sqrtf(qn) : 0.0f;     // the re-rank hands it to the exact path
+                    qn = 1.0f;
+                } else if (METRIC == METRIC_DOT) {
+                    qn = 1.02f * sqrtf(qn) * sqrtf(__uint_as_float(*p.xmax_bits));
+                }
                 if (p.thr_g) thr_pending = *(volatile uint32_t*)(p.thr_g + qi);
-                thrp = __uint_as_float(thr_pending) - qn;
+                thrp = (__uint_as_float(thr_pending) - qn) * qia;
             }
             uint32_t hcnt = 0;   // entries in this thread's candidate list (filling, then a max-heap on the approx d2 bits)
             uint32_t pcnt = 0;   // candidates parked since the last fold (heap phase)
@@ -533,7 +559,7 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
             uint32_t root = 0xFFFFFFFFu;   // the heap's root once the list is full (hcnt == 32)
             auto fold = [&]() {
                 root = wide_fold(hb, pb, pcnt, root);
-                thrp = fminf(thrp, __uint_as_float(root) - qn);
+                thrp = fminf(thrp, (__uint_as_float(root) - qn) * qia);
                 pcnt = 0;
             };
             Q1_LAP(0);
@@ -542,7 +568,7 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
             for (uint32_t rt = it.row_begin; rt < it.row_end; rt += W_N) {
                 // bound tightened meanwhile by the other half's warp and by CTAs scanning other lists of
                 // the same query (loaded behind the release of an earlier accumulator: no exposed latency)
-                if (have) thrp = fminf(thrp, __uint_as_float(thr_pending) - qn);
+                if (have) thrp = fminf(thrp, (__uint_as_float(thr_pending) - qn) * qia);
                 if (p.debug & 2u) thrp = -__uint_as_float(F32_INF_BITS);   // timing experiment: nothing ever passes
                 const uint32_t slot = tcount % W_NSLOT;
                 Q1_LAP(0);
@@ -582,7 +608,8 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
                         uint32_t pass = 0;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            v[j] = fmaf(-2.0f, __uint_as_float(g ? acc1[j] : acc0[j]), v[j]);   // |x|^2 - 2 q.x
+                            if (METRIC == METRIC_L2) v[j] = fmaf(-2.0f, __uint_as_float(g ? acc1[j] : acc0[j]), v[j]);   // |x|^2 - 2 q.x
+                            else v[j] = __uint_as_float(g ? acc1[j] : acc0[j]) * v[j];                                    // -(q.x) [/ |x|]
                             pass |= (v[j] < thrp) ? (1u << j) : 0u;
                         }
                         Q1_LAP(3);
@@ -596,7 +623,7 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
                                         ++hcnt;
                                         ++st_app;
                                         sts_v2(hb + 8 * hcnt, pos0 + 16u * (uint32_t)g + (uint32_t)j,
-                                               __float_as_uint(fmaxf(v[j] + qn, 0.0f)));
+                                               __float_as_uint(fmaxf(fmaf(v[j], qa, qn), 0.0f)));
                                         pass &= ~(1u << j);
                                     }
                                 }
@@ -606,7 +633,7 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
                                     const uint32_t r = wide_heapify(hb, filled);
                                     if (filled) {
                                         root = r;
-                                        thrp = fminf(thrp, __uint_as_float(root) - qn);
+                                        thrp = fminf(thrp, (__uint_as_float(root) - qn) * qia);
                                     }
                                     Q1_LAP(5);
                                 }
@@ -623,7 +650,7 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
                                     for (int j = 1; j < 16; ++j) vb = (b == (uint32_t)j) ? v[j] : vb;
                                     if (vb < thrp) {         // (the threshold may have moved since the compare pass)
                                         ++st_app;
-                                        sts_v2(pb + 8 * pcnt, pos0 + 16u * (uint32_t)g + b, __float_as_uint(fmaxf(vb + qn, 0.0f)));
+                                        sts_v2(pb + 8 * pcnt, pos0 + 16u * (uint32_t)g + b, __float_as_uint(fmaxf(fmaf(vb, qa, qn), 0.0f)));
                                         ++pcnt;
                                     }
                                 }

@@ -122,13 +122,14 @@ def _stream(stream: int):
 
 
 class Engine:
-    def __init__(self, dim: int, k_max: int = 128, device: int = 0):
+    def __init__(self, dim: int, k_max: int = 128, device: int = 0, metric: int = L.METRIC_L2):
         self._lib = L.load()
         self._h = C.c_void_p()
         self.dim = int(dim)
         self.k_max = int(k_max)
         self.device = int(device)
-        rc = self._lib.fvdb_create(device, dim, 0, k_max, C.byref(self._h))
+        self.metric = int(metric)
+        rc = self._lib.fvdb_create(device, dim, self.metric, k_max, C.byref(self._h))
         if rc != 0:
             msg = self._lib.fvdb_last_error(None)
             self._h = None

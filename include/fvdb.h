@@ -65,8 +65,18 @@ typedef enum fvdb_status {
     FVDB_ERR_OOM = -14
 } fvdb_status;
 
+/* How a (query, row) pair is scored.  The reference's indexes (IVFIndex, HNSWIndex, HybridIndex) are L2
+ * only; cosine and dot product exist as scalar kernels ranked exhaustively (batch_cosine_similarity +
+ * top_k_indices, src/core/vector_ops.rs:8-23).  A COS / DOT handle therefore serves the FLAT tier
+ * (fvdb_flat_add + fvdb_search with FVDB_TIER_RECENT): every row is scored, the k LARGEST similarities
+ * are returned best first, ties to the lower row id (top_k_indices is a stable descending sort), and
+ * out_dist holds the similarity itself, bit-identical to the scalar kernels (sequential f32, no FMA;
+ * cosine = dot / (sqrt(dot(a,a)) * sqrt(dot(b,b))), 0 when either norm is 0).  Tombstones and the filter
+ * bitmap apply as for L2.  The fvdb_ivf_* entries return FVDB_ERR_INVALID_CONFIG on such a handle. */
 typedef enum fvdb_metric {
-    FVDB_METRIC_L2 = 0 /* euclidean_distance_scalar, src/core/vector_ops.rs:51-57 */
+    FVDB_METRIC_L2 = 0,  /* euclidean_distance_scalar, src/core/vector_ops.rs:51-57 */
+    FVDB_METRIC_COS = 1, /* cosine_similarity_scalar :39-49, Embedding::cosine_similarity src/core/types.rs:79-103 */
+    FVDB_METRIC_DOT = 2  /* dot_product_scalar :35-37 */
 } fvdb_metric;
 
 /* Tier selection bits for fvdb_search: HybridSearchConfig.search_recent /

@@ -87,6 +87,9 @@ def _declare(L):
                                    C.c_uint64, _u32p, _f32p]
     L.fo_hybrid_search_postfilter.restype = C.c_size_t
     L.fo_hybrid_search_postfilter.argtypes = L.fo_hybrid_search.argtypes
+    L.fo_flat_search_metric.restype = C.c_size_t
+    L.fo_flat_search_metric.argtypes = [_f32p, _u32p, C.c_size_t, C.c_size_t, _f32p, C.c_size_t, C.c_int, _u64p,
+                                        C.c_uint64, _u64p, C.c_uint64, _u32p, _f32p]
     L.fo_hybrid_batch_search.restype = None
     L.fo_hybrid_batch_search.argtypes = [C.c_void_p, _f32p, _u32p, C.c_size_t, C.c_size_t, _f32p,
                                          C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint, _u64p,
@@ -326,6 +329,29 @@ def hybrid_search_postfilter(ivf, flat_rows, flat_ids, q, k, nprobe, match_bits,
     m = lib().fo_hybrid_search_postfilter(h, pfr, pfi, fn, d, pq, k, nprobe, tiers, pd, nd, pm, nm,
                                           oi.ctypes.data_as(_u32p), od.ctypes.data_as(_f32p))
     return oi[:m].copy(), od[:m].copy()
+
+
+COSINE, DOT = 1, 2
+
+
+def flat_search_metric(rows, ids, queries, k, metric, deleted=None, filter_bits=None):
+    """batch_cosine_similarity / dot scoring of every row + top_k_indices (src/core/vector_ops.rs:8-23) per
+    query: (ids [nq,k], scores [nq,k], counts [nq]), best (largest) first, ties in input order."""
+    x, px = _f32(rows)
+    i, pi = _u32(ids)
+    q, _ = _f32(queries)
+    q = q.reshape(-1, x.shape[1])
+    nq = q.shape[0]
+    oi = np.full((nq, max(k, 1)), 0xFFFFFFFF, dtype=np.uint32)
+    osc = np.full((nq, max(k, 1)), -np.inf, dtype=np.float32)
+    oc = np.zeros(nq, dtype=np.uint32)
+    _d, pd, nd = _bits(deleted)
+    _f, pf, nf = _bits(filter_bits)
+    for j in range(nq):
+        qj = np.ascontiguousarray(q[j])
+        oc[j] = lib().fo_flat_search_metric(px, pi, x.shape[0], x.shape[1], qj.ctypes.data_as(_f32p), k, metric, pd, nd,
+                                            pf, nf, oi[j].ctypes.data_as(_u32p), osc[j].ctypes.data_as(_f32p))
+    return oi, osc, oc
 
 
 def recall(found, found_cnt, truth, truth_cnt, k) -> float:

@@ -427,6 +427,40 @@ FO_EXPORT size_t fo_ivf_search_faithful(const fo_ivf *ix, const float *q, size_t
     return r;
 }
 
+/* Exhaustive scoring with a similarity metric, the only way the reference uses its cosine / dot kernels:
+ * batch_cosine_similarity (src/core/vector_ops.rs:8-10) over every vector, then top_k_indices (:12-23) —
+ * a STABLE sort by descending score, first k (ties keep the order of the input).  metric: 1 = cosine
+ * (cosine_similarity_scalar :39-49, the query is `a`), 2 = dot product (:35-37).  Deleted / filtered-out
+ * rows are skipped as in the L2 searches.  Returns the number of results. */
+typedef struct { float score; uint32_t id; size_t order; } fo_scored;
+static int cmp_scored_desc(const void *pa, const void *pb) {
+    const fo_scored *a = (const fo_scored *)pa, *b = (const fo_scored *)pb;
+    if (a->score > b->score) return -1;     /* b.partial_cmp(a): larger score first */
+    if (a->score < b->score) return 1;
+    return a->order < b->order ? -1 : (a->order > b->order ? 1 : 0);   /* stable */
+}
+FO_EXPORT size_t fo_flat_search_metric(const float *rows, const uint32_t *ids, size_t n, size_t d,
+                                       const float *q, size_t k, int metric, const uint64_t *deleted,
+                                       uint64_t deleted_nbits, const uint64_t *filter,
+                                       uint64_t filter_nbits, uint32_t *out_ids, float *out_score) {
+    fo_scored *sc = (fo_scored *)malloc((n ? n : 1) * sizeof(fo_scored));
+    size_t m = 0;
+    for (size_t r = 0; r < n; ++r) {
+        uint32_t id = ids ? ids[r] : (uint32_t)r;
+        if (bit_get(deleted, deleted_nbits, id)) continue;
+        if (filter && !bit_get(filter, filter_nbits, id)) continue;
+        sc[m].score = metric == 1 ? fo_cosine(q, rows + r * d, d) : fo_dot(q, rows + r * d, d);
+        sc[m].id = id;
+        sc[m].order = m;
+        ++m;
+    }
+    qsort(sc, m, sizeof(fo_scored), cmp_scored_desc);
+    size_t out = m < k ? m : k;
+    for (size_t i = 0; i < out; ++i) { out_ids[i] = sc[i].id; out_score[i] = sc[i].score; }
+    free(sc);
+    return out;
+}
+
 /* Exact scan of a flat tier: the ground truth for recall, and the replacement semantics of
  * the recent tier (HNSWIndex::search, src/hnsw/core.rs:398-467, returns an approximate
  * subset of this; deleted nodes dropped :452-459). */

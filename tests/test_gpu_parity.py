@@ -713,3 +713,47 @@ def test_host_buffer_submit_finish(mode):
         eng.search_submit(qs[0], k, nprobe, L.TIER_HISTORICAL, tuple(b.array for b in po[0]))   # pageable queries
     eng.search_finish()           # nothing pending: a no-op
     eng.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("metric", ["cos", "dot"])
+@pytest.mark.parametrize("d,n,nq", [(384, 12000, 300), (64, 9000, 70), (30, 2000, 9)])
+def test_cosine_and_dot_metrics(mode, metric, d, n, nq):
+    """FVDB_METRIC_COS / FVDB_METRIC_DOT (src/core/vector_ops.rs:35-49, ranked as top_k_indices does :12-23):
+    a similarity handle scores the flat tier exhaustively; ids and similarity BITS equal the oracle's
+    batch scoring + stable descending sort, in the exact mode and through kernel W + exact re-rank."""
+    if mode == "tc" and d % 32:
+        pytest.skip("tc needs dim % 32 == 0")
+    m = L.METRIC_COS if metric == "cos" else L.METRIC_DOT
+    om = O.COSINE if metric == "cos" else O.DOT
+    rng = np.random.default_rng(d + n)
+    x = _data(n, d, 41, n_comp=24, sigma=0.7) * rng.uniform(0.2, 3.0, size=(n, 1)).astype(np.float32)   # unequal norms
+    x[17] = 0.0                                                                                          # a zero row scores 0
+    x[n - 5] = x[11]                                                                                     # an exact tie: lower id first
+    q = _queries(nq, d, n, 41, n_comp=24, sigma=0.7) * rng.uniform(0.5, 2.0, size=(nq, 1)).astype(np.float32)
+    q[3] = 0.0                                                                                           # a zero query: every cosine is 0
+    ids = np.arange(n, dtype=np.uint32)
+    eng = Engine(d, k_max=16, metric=m)
+    _set_mode(eng, mode)
+    eng.flat_add(x, ids)
+    dele = np.arange(5, n, 61, dtype=np.uint32)
+    eng.set_deleted(dele, True)
+    got = eng.search(q, 10, 0, tiers=L.TIER_RECENT)
+    want = O.flat_search_metric(x, ids, q, 10, om, deleted=O.make_bitmap(n, dele))
+    assert got[2].tolist() == want[2].tolist()
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+    if mode == "tc" and d == 384:
+        assert eng.stats().last_fallback_queries <= max(2, nq // 16)   # kernel W carries it (the zero query falls back)
+    # with a filter bitmap; fewer than k live rows
+    fb = O.make_bitmap(n, np.arange(0, n, 7))
+    got = eng.search(q[:20], 10, 0, tiers=L.TIER_RECENT, filter_bits=fb)
+    want = O.flat_search_metric(x, ids, q[:20], 10, om, deleted=O.make_bitmap(n, dele), filter_bits=fb)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+    few = O.make_bitmap(n, [1, 2, 3])
+    got = eng.search(q[:4], 10, 0, tiers=L.TIER_RECENT, filter_bits=few)
+    assert got[2].tolist() == [3] * 4
+    # the IVF tier is L2 only, as in the reference
+    from fabstir_vectordb_b200 import InvalidConfig
+    with pytest.raises(InvalidConfig):
+        eng.set_centroids(x[:8])

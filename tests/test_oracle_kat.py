@@ -234,3 +234,31 @@ def test_retrain_restatement_properties():
     assert 1 <= res["iterations"] <= 7
     # the training data is exactly the stored vectors, reordered
     assert np.array_equal(new_ivf.rows, x[order])
+
+
+def test_flat_search_metric_is_batch_cosine_plus_top_k_indices():
+    """The metric search of the oracle = batch_cosine_similarity (tests/core/vector_ops.rs:8-27: 1.0, 0.0,
+    ~0.707) followed by top_k_indices (:29-35: a stable descending sort); zero vectors score 0
+    (src/core/vector_ops.rs:44-46); ties keep the input order."""
+    q = np.array([[1.0, 0.0, 0.0]], dtype=np.float32)
+    rows = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.707, 0.707, 0.0], [0.0, 0.0, 0.0], [2.0, 0.0, 0.0]],
+                    dtype=np.float32)
+    ids = np.arange(5, dtype=np.uint32)
+    i, s, c = O.flat_search_metric(rows, ids, q, 5, O.COSINE)
+    assert c.tolist() == [5]
+    assert i[0].tolist() == [0, 4, 2, 1, 3]            # 1.0, 1.0 (tie: input order), 0.707, 0.0, 0.0 (tie)
+    assert abs(s[0, 0] - 1.0) < 1e-6 and abs(s[0, 2] - 0.707) < 0.01 and s[0, 3] == 0.0 and s[0, 4] == 0.0
+    # scores are the scalar kernels' own values, the order is top_k_indices' over them
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((200, 16)).astype(np.float32)
+    qq = rng.standard_normal((3, 16)).astype(np.float32)
+    for metric, fn in ((O.COSINE, O.cosine), (O.DOT, O.dot)):
+        i, s, c = O.flat_search_metric(x, np.arange(200, dtype=np.uint32), qq, 7, metric)
+        for j in range(3):
+            scores = np.array([fn(qq[j], x[r]) for r in range(200)], dtype=np.float32)
+            assert i[j].tolist() == O.top_k_indices(scores, 7)
+            assert s[j].view(np.uint32).tolist() == scores[i[j]].view(np.uint32).tolist()
+    # deleted rows and the filter bitmap are skipped before scoring
+    dele = O.make_bitmap(200, [int(i[0, 0])])
+    i2, _, _ = O.flat_search_metric(x, np.arange(200, dtype=np.uint32), qq[:1], 7, O.DOT, deleted=dele)
+    assert int(i[0, 0]) not in i2[0].tolist()
