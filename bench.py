@@ -369,8 +369,165 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------
+def measured_peak_tf32():
+    """TF32 dense peak: not in MEASURED_PEAKS.json — half the measured bf16 throughput (SURVEY §8d says so)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            d = json.load(fh)
+        return 0.5 * float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "0.5 x measured bf16 sustained (MEASURED_PEAKS.json)"
+    except Exception:
+        return 0.5 * 2250.0, "0.5 x nominal bf16 (B200_PROFILING.md)"
+
+
+def run_cfg3(args):
+    """BASELINE.json configs[2]: IVF k-means training on 1M x 384, nlist = 4096, 20 iterations, shared initial
+    centroids, one GPU.  A secondary line: the assignment (2 N k D flops per iteration, TF32 tensor cores +
+    exact verification) is the dominant step; `achieved` divides its flops by the WHOLE iteration time
+    (assignment + order-faithful centroid update + the f32 error fold), so it understates the kernel."""
+    import torch
+    import oracle as O
+    from fabstir_vectordb_b200 import Engine, _lib as L
+    torch.cuda.set_device(0)
+    lib = L.load()
+    n, nlist, iters = int(os.environ.get("FVDB_KM_ROWS", 1_000_000)), int(os.environ.get("FVDB_KM_NLIST", 4096)), 20
+    n_comp = n_comp_for(nlist)
+    data = torch.empty((n, DIM), dtype=torch.float32, device="cuda")
+    assert lib.fvdb_synth_rows_device(data.data_ptr(), 0, n, DIM, n_comp, SIGMA, SEED, torch.cuda.current_stream().cuda_stream) == 0
+    init = data[torch.arange(nlist, device="cuda") * (n // nlist)].contiguous()
+    eng = Engine(DIM, k_max=16)
+    eng.train_device(data.data_ptr(), n, nlist, 1, init.data_ptr(), SEED)   # warm-up: allocations, descriptors
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    res = eng.train_device(data.data_ptr(), n, nlist, iters, init.data_ptr(), SEED)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    cents = eng.get_centroids()
+    rows = np.linspace(0, n - 1, 2048).astype(np.int64)
+    xs = data[torch.from_numpy(rows).cuda()].cpu().numpy()
+    same = int((eng.assign(xs) == O.assign(xs, cents)).sum())
+    t1 = time.perf_counter()
+    O.assign(xs, cents)
+    cpu_rows_s = len(rows) / (time.perf_counter() - t1)
+    flops = 2.0 * n * nlist * DIM * res["iterations"]
+    peak, src = measured_peak_tf32()
+    line = {"metric": "k-means seconds per Lloyd iteration, 1M x 384, nlist=4096", "value": dt / res["iterations"], "unit": "s/iteration",
+            "n_gpus": 1, "steps": res["iterations"], "warmup": 1, "ms_per_step": dt / res["iterations"] * 1e3,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 assignment, exact verify)",
+            "data": "synthetic", "config": {"workload": f"k-means {n}x{DIM} nlist={nlist} max_iter={iters} shared init"},
+            "train_result": res, "seconds_total": dt, "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": flops / dt / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / dt / 1e12 / peak, "traffic": None, "kernel": "nearest-centroid assignment (kernel W, identity items)",
+                         "peak_source": src, "note": "assignment flops / whole iteration time"},
+            "cpu_baseline": {"value": n / cpu_rows_s, "unit": "s/iteration (assignment only, extrapolated from 2048 rows)",
+                             "cores": O.num_threads(), "kind": "port", "sample": "2048 of 1M rows against the final centroids"},
+            "parity_vs_oracle": {"rows": int(len(rows)), "identical_assignments": same}}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def run_cfg4(args):
+    """BASELINE.json configs[3]: 1M x 384 filtered search, hybrid tiers: 300K rows in the recent (flat) tier,
+    700K in the IVF tier, filter bitmap with 10 % selectivity, 1 % tombstones, 1024-query batches."""
+    import torch
+    import oracle as O
+    from fabstir_vectordb_b200 import Engine, _lib as L, synth
+    torch.cuda.set_device(0)
+    lib = L.load()
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    n_total, n_recent, nlist, nq, k, nprobe = 1_000_000, 300_000, 1024, 1024, K, 32
+    n_ivf = n_total - n_recent
+    n_comp = n_comp_for(nlist)
+    eng = Engine(DIM, k_max=16)
+    n_train = TRAIN_ROWS_PER_LIST * nlist
+    train = torch.empty((n_train, DIM), dtype=torch.float32, device=dev)
+    assert lib.fvdb_synth_rows_strided_device(train.data_ptr(), 0, n_train, DIM, n_comp, SIGMA, SEED, 64,
+                                              max(1, n_total // n_train), stream) == 0
+    init = train[torch.from_numpy(init_rows_of_sample(nlist, n_train)).to(dev)].contiguous()
+    eng.train_device(train.data_ptr(), n_train, nlist, TRAIN_ITERS, init.data_ptr(), SEED)
+    CH = 1 << 18
+    x_host = np.empty((n_total, DIM), dtype=np.float32)
+    buf = torch.empty((CH, DIM), dtype=torch.float32, device=dev)
+    for r0 in range(0, n_total, CH):
+        n = min(CH, n_total - r0)
+        assert lib.fvdb_synth_rows_device(buf.data_ptr(), r0, n, DIM, n_comp, SIGMA, SEED, stream) == 0
+        ids = torch.arange(r0, r0 + n, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        a = max(0, min(n, n_ivf - r0))
+        if a > 0:
+            eng.ivf_add_device(buf.data_ptr(), ids.data_ptr(), a)
+        if a < n:
+            eng.flat_add_device(buf[a:].data_ptr(), ids[a:].data_ptr(), n - a)
+        x_host[r0:r0 + n] = buf[:n].cpu().numpy()
+    fbits = synth.filter_bitmap((n_total + 63) // 64 * 64, 10, 99)
+    dele = np.arange(7, n_total, 100, dtype=np.uint32)
+    eng.set_deleted(dele, True)
+    qs = [make_queries(torch, lib, nq, n_total, n_comp, s) for s in range(N_QUERY_SETS)]
+    d_f = torch.from_numpy(fbits.view(np.int64)).to(dev)
+    o_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    o_dst = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+
+    def step(i):
+        eng.search_device(qs[i % N_QUERY_SETS].data_ptr(), nq, k, nprobe, L.TIER_BOTH, d_f.data_ptr(), fbits.size * 64,
+                          o_ids.data_ptr(), o_dst.data_ptr(), o_cnt.data_ptr(), stream)
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    st = eng.stats()
+    step(0)
+    torch.cuda.synchronize()
+    ns = 32
+    cents = eng.get_centroids()
+    ivf = O.IVF(cents, x_host[:n_ivf], np.arange(n_ivf, dtype=np.uint32), assign_=eng.assign(x_host[:n_ivf]))
+    q0 = qs[0][:ns].cpu().numpy()
+    t0 = time.perf_counter()
+    want = O.hybrid_batch_search(ivf, x_host[n_ivf:], np.arange(n_ivf, n_total, dtype=np.uint32), q0, k, nprobe, tiers=3,
+                                 deleted=O.make_bitmap(n_total, dele), filter_bits=fbits)
+    cpu_qps = ns / (time.perf_counter() - t0)
+    g_ids = o_ids[:ns].cpu().numpy().view(np.uint32)
+    g_dst = o_dst[:ns].cpu().numpy()
+    peak, src = measured_peak_hbm()
+    alg = int(st.last_algorithmic_bytes)
+    line = {"metric": "QPS, 1M x 384 filtered hybrid search (10 % bitmap, 1 % tombstones)", "value": nq / (ms * 1e-3), "unit": "queries/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "300K recent (flat) + 700K IVF rows, nlist=1024 nprobe=32 nq=1024/batch k=10, filter bitmap "
+                                   "10 % pass, 1 % tombstones", "cache": "index 1.5 GB >> L2; 4 rotating query sets"},
+            "fallback_queries": int(st.last_fallback_queries), "gpu_launches": int(st.last_launches) * args.steps, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "kernel": "whole batch (IVF scan + flat-tier scan): rows are streamed, then masked",
+                         "algorithmic_bytes_per_launch": alg, "peak_source": src,
+                         "note": "the flat tier scores 1024 x 300K pairs: that scan is tensor-bound, not HBM-bound"},
+            "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": O.num_threads(), "kind": "port",
+                             "sample": f"{ns} of {nq} queries of one batch"},
+            "parity_vs_oracle": {"queries": ns, "identical_id_lists": int((g_ids == want[0]).all(axis=1).sum()),
+                                 "identical_distance_bits": int((g_dst.view(np.uint32) == want[1].view(np.uint32)).all(axis=1).sum())}}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2 (default): the headline line, BASELINE.json configs[1].  cfg3 / cfg4: secondary lines for "
+                         "configs[2] (k-means) and configs[3] (filtered hybrid), one GPU.  cfg5: configs[4], 100M x 384 "
+                         "over 8 GPUs (12.5M rows, 2048 lists, 1250 queries per GPU; run under torchrun with --gpus 8)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
@@ -384,9 +541,22 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
 
+    if args.config == "cfg5":
+        # BASELINE.json configs[4]: 100M x 384 sharded by list over 8 GPUs, nlist 16384, nprobe 64, 10 K-query batches
+        global ROWS_PER_GPU, NLIST_PER_GPU, NQ_PER_GPU, NPROBE
+        # nprobe: SURVEY §8d suggests 64 and lets the builder retune for recall >= 0.95: 64 of 16384 lists gives
+        # recall@10 = 0.934 on this data, 96 holds the floor (FVDB_BENCH_CFG5_NPROBE overrides)
+        np5 = int(os.environ.get("FVDB_BENCH_CFG5_NPROBE", 96))
+        ROWS_PER_GPU, NLIST_PER_GPU, NQ_PER_GPU, NPROBE = 12_500_000, 2048, 1250, np5
+        os.environ["FVDB_BENCH_NPROBE"] = str(np5)
+        os.environ.setdefault("FVDB_BENCH_PARITY", "0")   # the unsharded host index would be 154 GB: recall vs exact instead
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.config == "cfg3":
+        return run_cfg3(args) if rank == 0 else None
+    if args.config == "cfg4":
+        return run_cfg4(args) if rank == 0 else None
 
     import torch
     import torch.distributed as dist

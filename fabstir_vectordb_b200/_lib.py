@@ -42,6 +42,7 @@ OPT_KMEANS_TC = 3
 OPT_COALESCE = 4
 OPT_PROOF_XMAX = 5
 OPT_PIPELINE = 6
+OPT_SCAN_SMS = 7
 
 
 class TrainResult(C.Structure):

@@ -168,6 +168,7 @@ struct fvdb_index {
     uint32_t scan_mode = FVDB_SCAN_EXACT;
     uint32_t shortlist = 0;
     uint32_t kmeans_tc = 0;
+    uint32_t scan_sms = 0;              // FVDB_OPT_SCAN_SMS
     float proof_xmax_sq = 0.f;          // FVDB_OPT_PROOF_XMAX: max |x|^2 over ALL shards of a list-sharded index
     uint64_t centroids_version = 0;     // bumped whenever the centroid table changes
     uint64_t assign_fallback_rows = 0;  // rows re-assigned exactly after a failed tensor-core proof
@@ -1052,6 +1053,7 @@ int search_device_impl(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t k,
             ta.ev_scan0 = e_s0; ta.ev_scan1 = e_s1;
             ta.sm_count = h->sm_count;
             ta.xmax_floor_sq = h->proof_xmax_sq;
+            ta.scan_sms = sl ? h->scan_sms : 0;   // only pipelined batches have neighbours to leave room for
             ta.d_nan = d_nan;
             if (!use_flat) {   // the only tier: the re-rank writes the result arrays itself
                 ta.fin_ids = d_out_ids; ta.fin_dist = d_out_dist; ta.fin_count = d_out_count;
@@ -1252,6 +1254,7 @@ int fvdb_create(int device, uint32_t dim, int metric, uint32_t k_max, fvdb_index
     h->k_max = k_max;
     h->sm_count = prop.multiProcessorCount;
     h->scan_mode = tc_supported(dim) ? FVDB_SCAN_TC : FVDB_SCAN_EXACT;
+    if (const char* e = getenv("FVDB_SCAN_SMS")) h->scan_sms = (uint32_t)std::max(0, atoi(e));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev_a) != cudaSuccess || cudaEventCreate(&h->ev_b) != cudaSuccess ||
         cudaEventCreate(&h->ev_s0) != cudaSuccess || cudaEventCreate(&h->ev_s1) != cudaSuccess) {
@@ -1321,6 +1324,9 @@ int fvdb_set_option(fvdb_index* h, int option, uint64_t value) {
             return FVDB_OK;
         case FVDB_OPT_COALESCE:
             h->coalesce = value ? 1u : 0u;
+            return FVDB_OK;
+        case FVDB_OPT_SCAN_SMS:
+            h->scan_sms = (uint32_t)value;
             return FVDB_OK;
         case FVDB_OPT_PIPELINE:
             h->pipeline = value ? 1u : 0u;

@@ -67,6 +67,7 @@ struct TcScanParams {
     uint32_t dense_ld;
     uint32_t debug;          // timing experiments. bit 0: skip the epilogue math; 3: no MMAs; 4: a quarter of the MMAs; 5: N = 16
     unsigned long long* prof; // debug bit 7: [grid][3 roles][8] cycle counters (stopwatch laps per role)
+    uint32_t scan_sms;        // host side: CTAs of the IVF scan kernels (0 = one per SM)
     int metric;               // kernel W only: METRIC_L2 | METRIC_COS | METRIC_DOT (kernel R and Q are L2)
     const uint32_t* xmax_bits; // kernel W, METRIC_DOT: max |x|^2 of the row set (f32 bits, device)
 };
@@ -1781,6 +1782,11 @@ struct TcScratchImpl {
     uint64_t tmap_n = 0;
     bool smem_attr_set = false;
     bool smem_attr_set_rerank = false;
+    // experiment (FVDB_TC_FORK=1): kernel W of an IVF batch on a side stream, forked behind the bucketing and joined
+    // before the shortlist merge: its CTA pairs start wherever kernel R's CTAs have left an SM pair, instead of
+    // behind kernel R's slowest CTA
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 bool tc_supported(uint32_t D) { return D % 32 == 0 && D >= 32 && D <= 512; }
@@ -1807,6 +1813,9 @@ void tc_release(TcScratch& s) {
     m->items.release(); m->items_w.release(); m->partial.release(); m->shortlist.release(); m->row_stamp.release();
     m->prof.release(); m->list_order.release(); m->live_ids.release(); m->rs[0].xnorm.release(); m->rs[1].xnorm.release(); m->fitems.release();
     m->cnorm.release(); m->dense.release(); m->coarse.release(); m->citems.release();
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->side) cudaStreamDestroy(m->side);
     delete m;
     s.impl = nullptr;
 }
@@ -1847,7 +1856,8 @@ static cudaError_t launch_wide(TcScratchImpl* m, const CUtensorMap& tmap, TcScan
         if (e != cudaSuccess) return e;
         m->smem_attr_set_w |= 1u << p.metric;
     }
-    const uint32_t grid = (uint32_t)sm_count & ~1u;   // whole pairs; idle pairs exit at once
+    uint32_t grid = (uint32_t)sm_count & ~1u;   // whole pairs; idle pairs exit at once
+    if (p.scan_sms && p.scan_sms < grid) grid = p.scan_sms & ~1u;
     if (p.debug & 128u) {
         e = m->prof.ensure((size_t)grid * 48, dev_bytes);
         if (e != cudaSuccess) return e;
@@ -2101,17 +2111,35 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
         const char* dbg = getenv("FVDB_TC_DEBUG");
         p.debug = dbg ? (uint32_t)atoi(dbg) : 0u;
     }
+    const bool wide_first_env = [] { const char* oe = getenv("FVDB_TC_ORDER"); return oe && oe[0] == 'W'; }();
+    // opt-in experiment (FVDB_TC_FORK=1): measured 0.4045 -> 0.391 ms for the two scan kernels, but 0.468 -> 0.476 ms
+    // per pipelined batch — the gaps kernel W now fills were where the neighbouring batches' small kernels ran
+    const bool fork_wide = use_wide && !wide_first_env && !(p.debug & 128u) && getenv("FVDB_TC_FORK") != nullptr;
+    if (fork_wide && !m->side) {
+        TCK(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+        TCK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+        TCK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    }
+    p.scan_sms = a.scan_sms;
     TCK(cudaMemsetAsync(p.work_counter, 0, 4, st));
+    if (use_wide) TCK(cudaMemsetAsync(m->n_items.p + 7, 0, 4, st));   // kernel W's work counter
     if (a.wait_before_scan) TCK(cudaStreamWaitEvent(st, a.wait_before_scan, 0));
     if (a.ev_scan0) TCK(cudaEventRecord(a.ev_scan0, st));
+    if (fork_wide) TCK(cudaEventRecord(m->ev_fork, st));
     auto run_wide = [&]() -> int {
     if (use_wide) {
-        // the heavily probed lists first: most of them are some queries' nearest list, so their scan
-        // publishes tight bounds for everything that follows
         TcScanParams pw = p;
         pw.items = m->items_w.p; pw.item_count = m->n_items.p + 6; pw.work_counter = m->n_items.p + 7;
-        TCK(cudaMemsetAsync(pw.work_counter, 0, 4, st));
-        TCK(launch_wide(m, m->tmap_w, pw, KB, a.sm_count, dev_bytes, st, nullptr));
+        if (fork_wide) {
+            // `st` holds kernel R by now (launched just before): kernel W goes to the side stream, ordered
+            // behind everything R itself was ordered behind
+            TCK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+            TCK(launch_wide(m, m->tmap_w, pw, KB, a.sm_count, dev_bytes, m->side, nullptr));
+            TCK(cudaEventRecord(m->ev_join, m->side));
+            TCK(cudaStreamWaitEvent(st, m->ev_join, 0));
+        } else {
+            TCK(launch_wide(m, m->tmap_w, pw, KB, a.sm_count, dev_bytes, st, nullptr));
+        }
         (*launches)++;
     }
     return FVDB_OK;
@@ -2129,7 +2157,8 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
             TCK(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
             m->smem_attr_set = true;
         }
-        const uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
+        uint32_t grid = (uint32_t)std::min<size_t>((size_t)a.sm_count, max_items);
+        if (p.scan_sms && p.scan_sms < grid) grid = p.scan_sms;
         if (p.debug & 128u) {
             TCK(m->prof.ensure((size_t)grid * 48, dev_bytes));
             TCK(cudaMemsetAsync(m->prof.p, 0, (size_t)grid * 48 * 8, st));
@@ -2145,8 +2174,7 @@ int tc_ivf_search(TcScratch& s, const TcSearchArgs& a, cudaStream_t st, size_t* 
     // mostly sparse lists; after their scan its bound is already close to final, so the hub items — where a
     // candidate is the expensive thing (one thread per query) — start warm.  FVDB_TC_ORDER=WR reverses it.
     {
-        const char* oe = getenv("FVDB_TC_ORDER");
-        const bool wide_first = oe && oe[0] == 'W';
+        const bool wide_first = wide_first_env;
         if (wide_first) { int r = run_wide(); if (r != FVDB_OK) return r; }
         { int r = run_narrow(); if (r != FVDB_OK) return r; }
         if (!wide_first) { int r = run_wide(); if (r != FVDB_OK) return r; }

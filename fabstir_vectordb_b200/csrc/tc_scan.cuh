@@ -60,6 +60,7 @@ struct TcSearchArgs {
     uint32_t n_peers = 0;
     cudaEvent_t wait_before_scan = nullptr;    // pipeline slots: the scan kernels start behind this event ...
     cudaEvent_t record_after_scan = nullptr;   // ... and this one is recorded behind them
+    uint32_t scan_sms = 0;            // CTAs of the scan kernels (0 = one per SM); see FVDB_OPT_SCAN_SMS
     float xmax_floor_sq = 0.f;        // lower bound of the max |x|^2 term of the proof (max over all shards)
     // optional fusions with the caller's steps (both save a launch per batch):
     int* d_nan = nullptr;             // set to 1 when Q holds a NaN (the query-norm pass sees every element)

@@ -14,7 +14,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _lib as L
-from .engine import Engine
+from .engine import Engine, NanInput
 
 
 def owner_of_list(list_id: int, world: int) -> int:
@@ -103,6 +103,8 @@ class ShardedIndex:
         self._inflight = None      # pipelined sharded search: the batch whose results are not exchanged yet
         self._group = []           # ... and every batch submitted since the last finish()
         self._nlist = None
+        self._deferred_error = None
+        self.coarse_async = os.environ.get("FVDB_SHARD_COARSE_ASYNC", "0") == "1"
 
     def _setup_bound_sharing(self, nq: int, device):
         """Exchange the inter-process handles of the per-query bound arrays (once per capacity)."""
@@ -250,7 +252,19 @@ class ShardedIndex:
         if n_mine < per:
             mine.fill_(-1)
         if n_mine:
-            self.eng.coarse_device_submit(q[lo:lo + n_mine].data_ptr(), n_mine, np_, mine.data_ptr(), stream)
+            # The coarse step of the slice.  Default: the synchronous entry — it repairs on the spot the few
+            # queries whose tensor-core proof fails (dense centroid tables: nlist 16384), and its host
+            # synchronisation only waits for THIS stream, while the previous batch keeps scanning in its slot.
+            # FVDB_SHARD_COARSE_ASYNC=1: the stream-ordered entry (a proof failure then makes finish() re-run
+            # the whole group).
+            try:
+                if self.coarse_async:
+                    self.eng.coarse_device_submit(q[lo:lo + n_mine].data_ptr(), n_mine, np_, mine.data_ptr(), stream)
+                else:
+                    self.eng.coarse_device(q[lo:lo + n_mine].data_ptr(), n_mine, np_, mine.data_ptr(), stream)
+            except NanInput as e:      # every rank has to reach the collectives: raise at finish()
+                mine.fill_(-1)
+                self._deferred_error = e
         dist.all_gather_into_tensor(allk, mine, group=self.group)
         self.eng.search_device_coarse_submit(q.data_ptr(), nq, k, np_, tiers, 0, 0, allk.data_ptr(),
                                              b["ids"].data_ptr(), b["dist"].data_ptr(), b["cnt"].data_ptr(), stream)
@@ -281,7 +295,13 @@ class ShardedIndex:
         if self.world > 1 and self._inflight is not None:
             self._exchange(self._inflight, age=0)
             self._inflight = None
-        self.eng.search_device_finish(stream)
+        try:
+            self.eng.search_device_finish(stream)
+        finally:
+            err, self._deferred_error = self._deferred_error, None
+        if err is not None:
+            self._group = []
+            raise err
         if self.world > 1:
             group, self._group = self._group, []
             fb = torch.tensor([self.eng.stats().last_fallback_queries], dtype=torch.int32,

@@ -98,6 +98,10 @@ typedef enum fvdb_option {
     FVDB_OPT_PIPELINE = 6,    /* 1 (default): batches of the stream-ordered entries alternate between two
                                  internal streams with their own scratch, so that a batch's coarse step and
                                  bucketing overlap the previous batch's scan tail, merge and re-rank */
+    FVDB_OPT_SCAN_SMS = 7,    /* pipelined batches: the posting-list scan kernels run on this many SMs (0 = all),
+                                 the rest stay free for the neighbouring batches' coarse step, bucketing, merge,
+                                 re-rank and — multi-GPU — the NCCL kernels, which otherwise only run in the
+                                 scans' gaps (the scan kernels are persistent and fill every SM) */
     FVDB_OPT_PROOF_XMAX = 5   /* list-sharded multi-GPU search with shared bounds: f32 bits of the largest
                                  |x|^2 over ALL shards (fvdb_ivf_max_sqnorm, max-reduced by the driver).  A
                                  row of this shard may be dropped by a bound a peer published, so the

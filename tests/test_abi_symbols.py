@@ -55,3 +55,33 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "fvdb_oracle" not in text, f
+
+
+def _build_c_driver(tmp_path, built_lib):
+    import subprocess
+    exe = tmp_path / "abi_driver"
+    libdir = os.path.dirname(built_lib)
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-O1", "-ffp-contract=off", "-Wall", "-Wextra", "-Werror", "-I",
+                           os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_driver.c"),
+                           "-L", libdir, "-lfvdb_b200", f"-Wl,-rpath,{libdir}", "-lm", "-o", str(exe)])
+    return exe
+
+
+@pytest.mark.skipif(HAS_GPU, reason="only meaningful on a box without a GPU")
+def test_c_driver_links_and_sees_no_device(tmp_path, built_lib):
+    """A plain C99 program (tests/c/abi_driver.c) builds against include/fvdb.h alone, links the library and —
+    without a GPU — is told FVDB_ERR_NO_DEVICE: there is no CPU path behind the ABI."""
+    import subprocess
+    exe = _build_c_driver(tmp_path, built_lib)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.startswith("no-device"), (out.stdout, out.stderr)
+
+
+@pytest.mark.gpu
+def test_c_driver_end_to_end(tmp_path, built_lib):
+    """The same program on a GPU: inserts, tombstone, hybrid search, 3x post-filter, a cosine handle — every
+    result bit-identical to the scalar loops in the C file (which restate src/core/vector_ops.rs:39-57)."""
+    import subprocess
+    exe = _build_c_driver(tmp_path, built_lib)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "abi-driver ok" in out.stdout, (out.stdout, out.stderr)
