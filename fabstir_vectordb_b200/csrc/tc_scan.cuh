@@ -23,7 +23,7 @@ struct TcScratch {
 
 constexpr uint32_t TC_MAX_K = 16;        // largest k served by the 32-entry shortlist
 constexpr uint32_t TC_MAX_NPROBE = 256;  // partial lists merged in one pass
-constexpr uint32_t TC_MAX_NPROBE_COARSE = 96;  // tensor-core coarse step (else exact coarse)
+constexpr uint32_t TC_MAX_NPROBE_COARSE = 112;  // tensor-core coarse step (else exact coarse)
 constexpr uint32_t TC_TILE_Q = 64;       // queries per work item of kernel R
 constexpr uint32_t TC_WIDE_MIN_QUERIES = 129;  // lists probed by at least this many queries of a batch go to kernel W
 constexpr uint32_t TC_MAX_PEERS = 7;     // peer GPUs whose bound arrays one scan can push to
