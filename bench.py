@@ -32,21 +32,22 @@ ROWS_PER_GPU = int(os.environ.get("FVDB_BENCH_ROWS", 1_000_000))
 NLIST_PER_GPU = int(os.environ.get("FVDB_BENCH_NLIST", 1024))
 NQ_PER_GPU = int(os.environ.get("FVDB_BENCH_NQ", 1024))
 NPROBE = int(os.environ.get("FVDB_BENCH_NPROBE", 32))
-# weak scaling multiplies the number of lists by the world size; a fixed nprobe then probes a shrinking
-# share of the index and recall@10 sinks towards the 0.95 floor (0.9555 at 8 GPUs with 32 of 8192 lists).
-# nprobe per world size keeps recall@10 >= 0.97 (measured; FVDB_BENCH_NPROBE overrides).
-NPROBE_BY_WORLD = {1: 32, 2: 32, 4: 32, 8: 64}
+# weak scaling multiplies the number of lists by the world size while nprobe stays 32: recall@10 sinks from 0.999
+# (1 GPU) to 0.976 (8 GPUs, 32 of 8192 lists) with 20 training iterations — it was 0.9555 with the 8 iterations of
+# round 1, close to the metric's 0.95 floor; probing more lists instead (48: 0.963, 64: 0.970 on the 8-iteration
+# index) costs the per-GPU work the scaling run is meant to hold constant.  FVDB_BENCH_NPROBE overrides.
+NPROBE_BY_WORLD = {1: 32, 2: 32, 4: 32, 8: 32}
 
 
 def nprobe_for(world):
     if "FVDB_BENCH_NPROBE" in os.environ:
         return NPROBE
-    return NPROBE_BY_WORLD.get(world, 64 if world > 4 else 32)
+    return NPROBE_BY_WORLD.get(world, 32)
 K = 10
 SIGMA = float(os.environ.get("FVDB_BENCH_SIGMA", 1.0))
 SEED = 1234
 SEED_Q = 5678
-TRAIN_ITERS = int(os.environ.get("FVDB_BENCH_TRAIN_ITERS", 8))
+TRAIN_ITERS = int(os.environ.get("FVDB_BENCH_TRAIN_ITERS", 20))   # cfg-3-style training (20 iterations)
 TRAIN_ROWS_PER_LIST = 64
 N_QUERY_SETS = 4
 RECALL_QUERIES = 256
@@ -113,6 +114,16 @@ def measured_peak_hbm():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def scan_source_digest():
+    """sha256 over the sources of the scan kernels (what profiles/scan_traffic.json is stamped with)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("tc_scan.cu", "tc_scan_wide.cuh", "tc_ptx.cuh", "tc_scan.cuh"):
+        with open(os.path.join(ROOT, "fabstir_vectordb_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
 
 
 def workload_name(world):
@@ -760,16 +771,25 @@ def main():
     scan_bytes = scan_rows * DIM * 4 + scan_rows * 4  # rows + row norms/ids touched once
     mean_scan_ms = float(np.mean(scan_ms)) if scan_ms else 0.0
     achieved = scan_bytes / (mean_scan_ms * 1e-3) / 1e9 if mean_scan_ms > 0 else 0.0
-    traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, one ncu --set full capture
+    # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernels (R + W) from one ncu --set full capture of
+    # this very command (profiles/scan_traffic.json, written by scripts/summarize_ncu.py --traffic).  The file is
+    # stamped with a digest of the kernel sources: a capture of other code is not reported.
+    traffic, traffic_note = None, None
+    try:
         with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as fh:
-            traffic = float(json.load(fh)["dram_bytes_per_launch"]) if world == 1 else None
+            tj = json.load(fh)
+        if world != 1:
+            traffic_note = "captured on the single-GPU workload only"
+        elif tj.get("source_digest") != scan_source_digest():
+            traffic_note = "profiles/scan_traffic.json was captured from different kernel sources: not reported"
+        else:
+            traffic = float(tj["dram_bytes_per_launch"])
     except Exception:
-        traffic = None
+        traffic_note = "no capture on file"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic,
                 "kernel": "ivf posting-list scan", "kernel_ms": mean_scan_ms,
-                "algorithmic_bytes_per_launch": scan_bytes, "peak_source": peak_src,
+                "traffic_note": traffic_note, "algorithmic_bytes_per_launch": scan_bytes, "peak_source": peak_src,
                 "share_of_step": mean_scan_ms / (elapsed_ms / args.steps) if elapsed_ms else None}
 
     # ---- CPU baseline beside it (rank 0, N == 1) -------------------------------------------------

@@ -1,5 +1,7 @@
 """Summarise an ncu report (--set full) into a small text file for profiles/.
-usage: python scripts/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/out.txt"""
+usage: python scripts/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/out.txt [--traffic]
+--traffic: also write profiles/scan_traffic.json = DRAM bytes (read + write) of one kernel R launch + one kernel W
+launch (one batch's scan), stamped with the digest of the kernel sources (bench.py refuses a stale stamp)."""
 import csv
 import subprocess
 import sys
@@ -33,3 +35,21 @@ with open(out, "w") as fh:
                 except ValueError:
                     pass
 print(open(out).read())
+
+if "--traffic" in sys.argv:
+    import json, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    for r in rows[2:]:
+        d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
+        name = "W" if "tc_scan_wide" in d.get("Kernel Name", "") else ("R" if "tc_scan_kernel" in d.get("Kernel Name", "") else None)
+        if name is None or name in per:
+            continue
+        per[name] = sum(float(d[k].replace(",", "")) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    out_j = {"dram_bytes_per_launch": sum(per.values()), "per_kernel": per, "source_digest": bench.scan_source_digest(),
+             "from": os.path.basename(rep), "note": "one kernel R launch + one kernel W launch = the scan of one 1024-query batch"}
+    with open(os.path.join(os.path.dirname(os.path.abspath(out)), "scan_traffic.json"), "w") as fh:
+        json.dump(out_j, fh, indent=1)
+    print(out_j)
