@@ -757,3 +757,42 @@ def test_cosine_and_dot_metrics(mode, metric, d, n, nq):
     from fabstir_vectordb_b200 import InvalidConfig
     with pytest.raises(InvalidConfig):
         eng.set_centroids(x[:8])
+
+
+def test_near_duplicate_neighbourhood_falls_back_and_still_matches():
+    """The adversarial case for the tensor-core proof: 60 rows within 1e-4 of one another sit exactly where the
+    k-th neighbour is, so the 32-entry approximate shortlist cannot be proven to contain the exact top-k (the TF32
+    bound is wider than their gaps).  Such queries MUST take the exact fallback — and the result must still be
+    the oracle's, bit for bit, with ties in id order."""
+    d, n, nlist = 384, 6000, 8
+    rng = np.random.default_rng(7)
+    x = _data(n, d, 91, n_comp=8, sigma=0.6)
+    base = x[100].copy()
+    for j in range(60):                       # a shell of near-duplicates around one row (some exact copies)
+        x[200 + j] = base if j % 3 == 0 else base + (1e-4 * rng.standard_normal(d)).astype(np.float32)
+    cents = x[rng.choice(n, nlist, replace=False)].copy()
+    ids = np.arange(n, dtype=np.uint32)
+    eng = Engine(d, k_max=64)
+    _set_mode(eng, "tc")
+    eng.set_centroids(cents)
+    eng.ivf_add(x, ids)
+    ivf = O.IVF(cents, x, ids)
+    q = np.stack([base + (0.05 * rng.standard_normal(d)).astype(np.float32) for _ in range(24)] +
+                 [x[i] + np.float32(0.01) for i in range(1000, 1040)])
+    got = eng.search(q, 10, nlist, tiers=L.TIER_HISTORICAL)
+    fb = eng.stats().last_fallback_queries
+    _assert_same(*got, *O.hybrid_batch_search(ivf, None, None, q, 10, nlist, tiers=2))
+    assert fb >= 12, f"the queries inside the duplicate shell must fail the proof (fell back: {fb})"
+    assert fb < len(q), "the ordinary queries must not"
+    # the same batch through the stream-ordered entry: repaired at finish time
+    import torch
+    dq = torch.from_numpy(q).cuda()
+    o = (torch.empty((len(q), 10), dtype=torch.int32, device="cuda"), torch.empty((len(q), 10), dtype=torch.float32, device="cuda"),
+         torch.empty((len(q),), dtype=torch.int32, device="cuda"))
+    s = torch.cuda.current_stream().cuda_stream
+    eng.search_device_submit(dq.data_ptr(), len(q), 10, nlist, L.TIER_HISTORICAL, 0, 0, o[0].data_ptr(), o[1].data_ptr(),
+                             o[2].data_ptr(), s)
+    eng.search_device_finish(s)
+    want = O.hybrid_batch_search(ivf, None, None, q, 10, nlist, tiers=2)
+    assert np.array_equal(o[0].cpu().numpy().view(np.uint32), want[0])
+    assert np.array_equal(o[1].cpu().numpy().view(np.uint32), want[1].view(np.uint32))
