@@ -514,6 +514,7 @@ int assign_device(fvdb_index* h, const float* d_x, uint64_t n, uint32_t* d_assig
             fa.d_fallback_count = d_fb; fa.d_fallback_idx = h->s_fb_idx_flat.p;
             fa.sm_count = h->sm_count;
             fa.state = 1; fa.version = h->centroids_version; fa.rerank_r = 4;
+            fa.argmin_only = d_dist == nullptr;
             uint32_t launches = 0;
             int r = tc_flat_search(h->tc, fa, st, &h->dev_bytes, &launches, &h->err);
             if (r != FVDB_OK) return r;
@@ -626,14 +627,15 @@ void clear_lists(fvdb_index* h) {
     mark_arena_dirty(h);
 }
 
-float host_mean_sq(const std::vector<float>& dist) {
-    // compute_error, src/ivf/core.rs:419-429: f32 left fold of dist*dist, then / n
-    volatile float total = 0.0f;
-    for (size_t i = 0; i < dist.size(); ++i) {
-        volatile float sq = dist[i] * dist[i];
+// compute_error, src/ivf/core.rs:419-429: f32 left fold of dist*dist, then / n.  (The library is built with
+// -ffp-contract=off and without fast-math: the compiler neither fuses nor re-associates this loop.)
+float host_mean_sq(const float* dist, size_t n) {
+    float total = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        const float sq = dist[i] * dist[i];
         total = total + sq;
     }
-    return total / (float)dist.size();
+    return total / (float)n;
 }
 
 int compute_error_device(fvdb_index* h, const float* d_data, uint64_t n, const uint32_t* d_assign,
@@ -641,9 +643,11 @@ int compute_error_device(fvdb_index* h, const float* d_data, uint64_t n, const u
     cudaStream_t st = h->stream;
     CK(h->s_f32a.ensure(n, 0, st, &h->dev_bytes));
     CK(launch_rowwise_dist(d_data, n, h->dim, h->centroids.p, d_assign, h->s_f32a.p, st));
-    std::vector<float> dist(n);
-    RET(d2h(h, dist.data(), h->s_f32a.p, n * 4));
-    *out = host_mean_sq(dist);
+    // the per-row distances come back into the handle's page-locked buffer and are folded where they land
+    CK(h->ensure_pin(n * sizeof(float)));
+    CK(cudaMemcpyAsync(h->pin, h->s_f32a.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *out = host_mean_sq(static_cast<const float*>(h->pin), n);
     return FVDB_OK;
 }
 

@@ -68,6 +68,7 @@ struct TcScanParams {
     uint32_t debug;          // timing experiments. bit 0: skip the epilogue math; 3: no MMAs; 4: a quarter of the MMAs; 5: N = 16
     unsigned long long* prof; // debug bit 7: [grid][3 roles][8] cycle counters (stopwatch laps per role)
     uint32_t scan_sms;        // host side: CTAs of the IVF scan kernels (0 = one per SM)
+    uint32_t small_list;      // host side: kernel W keeps 8 candidates per thread in registers (assignment: k = 1)
     int metric;               // kernel W only: METRIC_L2 | METRIC_COS | METRIC_DOT (kernel R and Q are L2)
     const uint32_t* xmax_bits; // kernel W, METRIC_DOT: max |x|^2 of the row set (f32 bits, device)
 };
@@ -1262,7 +1263,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
                                                      uint32_t k, uint32_t R, float xmax_floor_sq, uint64_t* __restrict__ out_keys,
                                                      uint32_t* __restrict__ fb_count, uint32_t* __restrict__ fb_idx,
                                                      uint32_t* __restrict__ fin_ids = nullptr, float* __restrict__ fin_dist = nullptr,
-                                                     uint32_t* __restrict__ fin_count = nullptr) {
+                                                     uint32_t* __restrict__ fin_count = nullptr, uint32_t skip_separated = 0) {
     // R = shortlist entries that are re-ranked (TC_KP for search; a handful for nearest-centroid
     // assignment, where entry R — the best approximate value NOT re-ranked — is the proof bound)
     constexpr int GWB = gather_warp_bytes(GATHER_STAGES_ROWS);
@@ -1270,10 +1271,28 @@ __global__ void __launch_bounds__(128) rerank_kernel(const uint64_t* __restrict_
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * 4 + w;
     if (q >= nq) return;
+    const uint64_t akey = shortlist[(size_t)q * TC_KP + lane];
+    if (skip_separated && METRIC == METRIC_L2) {
+        // nearest-centroid assignment where only the ARGMIN is wanted (k = 1, no distance): when the two best
+        // approximate values are further apart than twice the TF32 bound, the best one is the exact argmin — no
+        // row is fetched.  (Exact ties, e.g. duplicate centroids, are never separated: they take the exact path
+        // and its lowest-id rule.)  The distance word of the key is then the approximate one.
+        const uint64_t k0 = shfl64(akey, 0), k1 = shfl64(akey, 1);
+        if (k0 != KEY_NONE) {
+            const float a0 = __uint_as_float((uint32_t)(k0 >> 32));
+            const float a1 = k1 != KEY_NONE ? __uint_as_float((uint32_t)(k1 >> 32)) : __uint_as_float(0x7f800000u);
+            const float xmax = sqrtf(fmaxf(__uint_as_float(*xmax_bits), xmax_floor_sq));
+            const float eps = 1.05f * 0.00390625f * sqrtf(qnorm[q]) * xmax + 3.1e-5f * a1 + 1e-30f;
+            if (a1 - a0 > 2.02f * eps) {
+                const uint32_t pos0 = (uint32_t)k0;
+                if (lane == 0) out_keys[(size_t)q * k] = make_key(sqrtf(a0), ids ? ids[pos0] : pos0);
+                return;
+            }
+        }
+    }
     float* q_s = reinterpret_cast<float*>(rr_sm + 4 * GWB) + (size_t)w * D;
     for (uint32_t d = lane; d < D; d += 32) q_s[d] = __ldg(Q + (size_t)q * D + d);
     __syncwarp();
-    const uint64_t akey = shortlist[(size_t)q * TC_KP + lane];
     const bool have = akey != KEY_NONE && (uint32_t)lane < R;
     const uint32_t pos = have ? (uint32_t)akey : 0u;
     float qq = 0.0f;
@@ -1849,12 +1868,15 @@ static cudaError_t launch_wide(TcScratchImpl* m, const CUtensorMap& tmap, TcScan
     p.stages = stages;
     const size_t smem = tc_scan_wide_smem_bytes(stages, kbs) + 1024;
     cudaError_t e;
-    auto kern = p.metric == METRIC_COS ? tc_scan_wide_kernel<METRIC_COS>
+    const bool small = p.small_list != 0 && p.metric == METRIC_L2;
+    auto kern = small ? tc_scan_wide_kernel<METRIC_L2, true>
+              : p.metric == METRIC_COS ? tc_scan_wide_kernel<METRIC_COS>
               : p.metric == METRIC_DOT ? tc_scan_wide_kernel<METRIC_DOT> : tc_scan_wide_kernel<METRIC_L2>;
-    if (!(m->smem_attr_set_w & (1u << p.metric))) {
+    const uint32_t kbit = small ? 8u : (1u << p.metric);
+    if (!(m->smem_attr_set_w & kbit)) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
-        m->smem_attr_set_w |= 1u << p.metric;
+        m->smem_attr_set_w |= kbit;
     }
     uint32_t grid = (uint32_t)sm_count & ~1u;   // whole pairs; idle pairs exit at once
     if (p.scan_sms && p.scan_sms < grid) grid = p.scan_sms & ~1u;
@@ -2269,6 +2291,7 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
     p.P = n_chunks; p.S = use_wide ? frows : 0u; p.partial = m->partial.p; p.thr_g = m->thr_g.p;
     p.row_stamp = m->row_stamp.p; p.stamp = stamp;
     p.metric = a.metric; p.xmax_bits = xmax_bits;
+    p.small_list = (a.k == 1 && a.rerank_r && a.rerank_r + 1 <= (uint32_t)W_SMALL_N && !getenv("FVDB_ASSIGN_HEAP")) ? 1u : 0u;
     p.work_counter = m->n_items.p + 5;
     {
         const char* dbg = getenv("FVDB_TC_DEBUG");
@@ -2298,7 +2321,8 @@ int tc_flat_search(TcScratch& s, const TcFlatArgs& a, cudaStream_t st, size_t* d
                                                                                             : rerank_kernel<METRIC_L2>;
     rr<<<(nq + 3) / 4, 128, rerank_smem_bytes(D), st>>>(m->shortlist.p, a.rows, a.ids, a.Q, m->qnorm.p, xmax_bits, nq, D, a.k,
                                                         a.rerank_r ? a.rerank_r : (uint32_t)TC_KP, 0.0f, a.out_keys,
-                                                        a.d_fallback_count, a.d_fallback_idx, nullptr, nullptr, nullptr);
+                                                        a.d_fallback_count, a.d_fallback_idx, nullptr, nullptr, nullptr,
+                                                        (a.argmin_only && a.k == 1 && !getenv("FVDB_ASSIGN_RERANK_ALL")) ? 1u : 0u);
     TCK(cudaGetLastError());
     (*launches) += 3;
     return FVDB_OK;

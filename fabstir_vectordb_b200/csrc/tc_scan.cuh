@@ -91,6 +91,7 @@ struct TcFlatArgs {
     uint64_t version = 0;
     uint32_t rerank_r = 0;        // shortlist entries re-ranked exactly (0 = all 32)
     int metric = 0;               // METRIC_L2 | METRIC_COS | METRIC_DOT (common.cuh)
+    bool argmin_only = false;     // k = 1 and the caller wants ids only: provably separated queries skip the exact re-rank
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;   // optional: recorded around the scan kernel
 };
 

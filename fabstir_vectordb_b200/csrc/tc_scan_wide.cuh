@@ -151,7 +151,13 @@ __device__ __noinline__ uint32_t wide_fold(uint32_t hb, uint32_t pb, uint32_t pc
 //   COS  strip -1 / |x|,    v = strip * acc,     key = v / |q| + 1                (1 - cosine; a zero row scores 0)
 //   DOT  strip -1,          v = strip * acc,     key = v + B, B = 1.02 |q| max|x| (B - dot >= 0)
 // Masked rows carry +inf (L2) / NaN (COS, DOT) in the strip and never pass `v < threshold`.
-template <int METRIC>
+// SMALL (nearest-centroid assignment: k = 1, four candidates re-ranked, the fifth is the proof bound): a thread keeps
+// its 8 best candidates in REGISTERS, sorted, instead of the 32-entry heap in shared memory — a running top-8 of
+// the 2048 centroids a thread sees takes ~45 insertions of eight min / max pairs instead of ~165 heap updates, and
+// its bound tightens four times faster.  At the end of the item the list is spilled into the heap's slots and
+// published through the common path (rows of 32 keys, 8 of them valid).
+constexpr int W_SMALL_N = 8;
+template <int METRIC, bool SMALL = false>
 __global__ void __launch_bounds__(W_THREADS, 1)
 tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -551,6 +557,9 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
                 if (p.thr_g) thr_pending = *(volatile uint32_t*)(p.thr_g + qi);
                 thrp = (__uint_as_float(thr_pending) - qn) * qia;
             }
+            unsigned long long best[W_SMALL_N];   // SMALL: this thread's candidates, ascending keys (approx d2 bits << 32 | row)
+#pragma unroll
+            for (int i = 0; i < W_SMALL_N; ++i) best[i] = KEY_NONE;
             uint32_t hcnt = 0;   // entries in this thread's candidate list (filling, then a max-heap on the approx d2 bits)
             uint32_t pcnt = 0;   // candidates parked since the last fold (heap phase)
             // In the heap phase a candidate costs a chain of dependent shared-memory accesses, and
@@ -613,6 +622,32 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
                             pass |= (v[j] < thrp) ? (1u << j) : 0u;
                         }
                         Q1_LAP(3);
+                        if (SMALL) {
+                            // lane-divergent: every lane walks its own passing rows (rare after the first tiles)
+                            while (pass) {
+                                const uint32_t b = (uint32_t)__ffs((int)pass) - 1u;
+                                pass &= pass - 1u;
+                                float vb = v[0];
+#pragma unroll
+                                for (int j = 1; j < 16; ++j) vb = (b == (uint32_t)j) ? v[j] : vb;
+                                if (vb < thrp) {
+                                    ++st_app;
+                                    unsigned long long k64 = ((unsigned long long)__float_as_uint(fmaxf(fmaf(vb, qa, qn), 0.0f)) << 32) |
+                                                             (unsigned long long)(pos0 + 16u * (uint32_t)g + b);
+#pragma unroll
+                                    for (int i = 0; i < W_SMALL_N; ++i) {   // sorted insertion: the key sinks to its place
+                                        const unsigned long long lo = best[i] < k64 ? best[i] : k64;
+                                        k64 = best[i] < k64 ? k64 : best[i];
+                                        best[i] = lo;
+                                    }
+                                    const uint32_t wb = (uint32_t)(best[W_SMALL_N - 1] >> 32);
+                                    if (wb < F32_INF_BITS) {
+                                        root = wb;
+                                        thrp = fminf(thrp, (__uint_as_float(wb) - qn) * qia);
+                                    }
+                                }
+                            }
+                        } else
                         if (__any_sync(0xffffffffu, pass != 0)) {
                             ++st_rounds;
                             // filling phase: passing rows go straight into the list, in arrival order
@@ -683,6 +718,15 @@ tc_scan_wide_kernel(const __grid_constant__ CUtensorMap tmap, const TcScanParams
             if (__any_sync(0xffffffffu, pcnt != 0)) fold();
             Q1_LAP(7);
             if (have && p.thr_g && root < root_pub) publish_bound(p, qi, root, peer_sent);
+            if (SMALL) {
+                hcnt = 0;
+#pragma unroll
+                for (int i = 0; i < W_SMALL_N; ++i)
+                    if (best[i] != KEY_NONE) {
+                        sts_v2(hb + 8u * (uint32_t)(i + 1), (uint32_t)best[i], (uint32_t)(best[i] >> 32));
+                        hcnt = (uint32_t)(i + 1);
+                    }
+            }
             __syncwarp();
             unsigned todo = __ballot_sync(0xffffffffu, have && hcnt > 0);
             while (todo) {
