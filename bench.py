@@ -692,12 +692,12 @@ def main():
             eng.search(p_q[w % N_QUERY_SETS].array, K, NPROBE, tiers=L.TIER_HISTORICAL, out=out)
         # stream-ordered: fvdb_search_submit per batch (its upload overlaps the previous batch's scan),
         # one fvdb_search_finish per E2E_PIPE batches; every batch has its own result buffers
-        e2e_pipe = max(1, min(4, int(os.environ.get("FVDB_BENCH_E2E_PIPE", 4))))
+        e2e_pipe = max(1, min(8, int(os.environ.get("FVDB_BENCH_E2E_PIPE", 8))))
         p_more = [(PinnedArray((nq, K), np.uint32), PinnedArray((nq, K), np.float32), PinnedArray((nq,), np.uint32))
                   for _ in range(e2e_pipe - 1)]   # (kept alive: the arrays are views of these buffers)
         outs = [out] + [tuple(x.array for x in t_) for t_ in p_more]
         if e2e_pipe > 1:   # warm-up of the stream-ordered path (its slots allocate on first use)
-            for w in range(8):
+            for w in range(2 * e2e_pipe):
                 eng.search_submit(p_q[w % N_QUERY_SETS].array, K, NPROBE, L.TIER_HISTORICAL, outs[w % e2e_pipe])
                 if (w + 1) % e2e_pipe == 0:
                     eng.search_finish()

@@ -235,7 +235,7 @@ struct fvdb_index {
         cudaEvent_t uploaded = nullptr, done = nullptr;
         bool used = false;
     };
-    static constexpr int HOST_SLOTS = 4;
+    static constexpr int HOST_SLOTS = 8;
     HostSlot host_slots[HOST_SLOTS];
     uint32_t host_slot_next = 0;
     cudaStream_t copy_stream = nullptr;
@@ -1765,7 +1765,7 @@ int fvdb_search_submit(fvdb_index* h, const float* q, uint32_t nq, uint32_t k, u
     if (!is_pinned_host(q) || !is_pinned_host(out_ids) || !is_pinned_host(out_dist) || !is_pinned_host(out_count))
         return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_search_submit needs page-locked buffers (fvdb_host_alloc)");
     if (h->pending.size() >= (size_t)fvdb_index::HOST_SLOTS)
-        return h->fail(FVDB_ERR_INVALID_ARG, "4 host-buffer batches are pending: call fvdb_search_finish");
+        return h->fail(FVDB_ERR_INVALID_ARG, "8 host-buffer batches are pending: call fvdb_search_finish");
     if (nq == 0) return FVDB_OK;
     cudaStream_t st = h->stream;
     if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));

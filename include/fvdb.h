@@ -288,7 +288,7 @@ int fvdb_search_device_finish(fvdb_index *h, void *stream);
 
 /* The same pair for HOST buffers, which must be page-locked (fvdb_host_alloc; else
  * FVDB_ERR_INVALID_ARG): the upload of a batch runs on a second stream while the previous batch is
- * still being scanned, the result copies follow the batch.  At most 4 batches may be pending; query
+ * still being scanned, the result copies follow the batch.  At most 8 batches may be pending; query
  * and result buffers belong to the library until fvdb_search_finish returns.  No filter bitmap. */
 int fvdb_search_submit(fvdb_index *h, const float *q, uint32_t nq, uint32_t k, uint32_t nprobe,
                        uint32_t tiers, uint32_t *out_ids, float *out_dist, uint32_t *out_count);

@@ -796,3 +796,51 @@ def test_near_duplicate_neighbourhood_falls_back_and_still_matches():
     want = O.hybrid_batch_search(ivf, None, None, q, 10, nlist, tiers=2)
     assert np.array_equal(o[0].cpu().numpy().view(np.uint32), want[0])
     assert np.array_equal(o[1].cpu().numpy().view(np.uint32), want[1].view(np.uint32))
+
+
+def test_two_slot_pipeline_many_batches_and_mutation_between_groups():
+    """The stream-ordered entries run consecutive batches in two pipeline slots (own stream, own scratch).  Twelve
+    batches in flight, each against the oracle; rows added and tombstoned BETWEEN groups must be seen by the next
+    group (every other entry point drains the slots first); FVDB_OPT_PIPELINE = 0 gives the same bits."""
+    import torch
+    d, n, nlist, nq, k, nprobe = 384, 30000, 48, 200, 10, 8
+    x = _data(n + 4000, d, 77, n_comp=64, sigma=0.8)
+    cents = x[np.random.default_rng(3).choice(n, nlist, replace=False)].copy()
+    ids = np.arange(n + 4000, dtype=np.uint32)
+    eng = Engine(d, k_max=16)
+    _set_mode(eng, "tc")
+    eng.set_centroids(cents)
+    eng.ivf_add(x[:n], ids[:n])
+    qs = [_queries(nq, d, n, 300 + i, n_comp=64, sigma=0.8) for i in range(12)]
+    dq = [torch.from_numpy(q).cuda() for q in qs]
+    outs = [(torch.empty((nq, k), dtype=torch.int32, device="cuda"), torch.empty((nq, k), dtype=torch.float32, device="cuda"),
+             torch.empty((nq,), dtype=torch.int32, device="cuda")) for _ in qs]
+    s = torch.cuda.current_stream().cuda_stream
+
+    def run_group():
+        for q_, o_ in zip(dq, outs):
+            eng.search_device_submit(q_.data_ptr(), nq, k, nprobe, L.TIER_HISTORICAL, 0, 0,
+                                     o_[0].data_ptr(), o_[1].data_ptr(), o_[2].data_ptr(), s)
+        eng.search_device_finish(s)
+        return [tuple(t.cpu().numpy() for t in o_) for o_ in outs]
+
+    def check(res, ivf, deleted=None):
+        for q_, (i_, d_, c_) in zip(qs, res):
+            want = O.hybrid_batch_search(ivf, None, None, q_, k, nprobe, tiers=2, deleted=deleted)
+            _assert_same(i_.view(np.uint32), d_, c_.view(np.uint32), *want)
+
+    piped = run_group()
+    check(piped, O.IVF(cents, x[:n], ids[:n]))
+    assert eng.stats().last_fallback_queries <= 3
+    # mutate between groups: more rows, some tombstones
+    eng.ivf_add(x[n:], ids[n:])
+    dele = np.arange(3, n + 4000, 53, dtype=np.uint32)
+    eng.set_deleted(dele, True)
+    check(run_group(), O.IVF(cents, x, ids), deleted=O.make_bitmap(n + 4000, dele))
+    # pipeline off: the same bits
+    on = run_group()
+    eng.set_option(6, 0)     # FVDB_OPT_PIPELINE
+    off = run_group()
+    for a, b in zip(on, off):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)) and np.array_equal(a[2], b[2])
+    eng.close()
