@@ -1621,26 +1621,38 @@ __global__ void __launch_bounds__(128) merge_rows32_kernel(const uint64_t* __res
                                                            uint64_t* __restrict__ out,
                                                            const uint32_t* __restrict__ row_stamp, uint32_t stamp) {
     // one block per query: warp w folds rows w, w + 4, ... (a chain of P / 4 dependent merges instead of
-    // P, and four times the warps in flight), warp 0 folds the four results
+    // P, and four times the warps in flight), warp 0 folds the four results.
+    // Only rows this launch wrote count (the others hold whatever an earlier batch left there).  The stamps of
+    // 32 candidate rows are read by the 32 lanes at once and turned into a mask; only live rows are fetched,
+    // four at a time.  On a list-sharded index 1 / world of a query's rows are live: the work follows the live
+    // rows, not the nprobe x ranges slots.
     __shared__ uint64_t part[3][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x;
     const uint64_t* base = in + (size_t)q * P * TC_KP;
+    const uint32_t* st_q = row_stamp + (size_t)q * P;
     uint64_t best = KEY_NONE;
-    for (uint32_t s0 = (uint32_t)w; s0 < P; s0 += 16) {
-        uint64_t row[4];
+    for (uint32_t c0 = 0; c0 * 4 + (uint32_t)w < P; c0 += 32) {
+        const uint32_t r_mine = (c0 + (uint32_t)lane) * 4 + (uint32_t)w;
+        unsigned live = __ballot_sync(0xffffffffu, r_mine < P && __ldg(st_q + r_mine) == stamp);
+        while (live) {
+            uint64_t row[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            // only rows this launch wrote (the others hold whatever an earlier batch left there)
-            const bool live = s0 + 4 * g < P && row_stamp[(size_t)q * P + s0 + 4 * g] == stamp;
-            row[g] = live ? base[(size_t)(s0 + 4 * g) * TC_KP + lane] : KEY_NONE;
-        }
+            for (int g = 0; g < 4; ++g) {
+                row[g] = KEY_NONE;
+                if (live) {
+                    const uint32_t r = (c0 + (uint32_t)(__ffs((int)live) - 1)) * 4 + (uint32_t)w;
+                    live &= live - 1;
+                    row[g] = base[(size_t)r * TC_KP + lane];
+                }
+            }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            if (__ballot_sync(0xffffffffu, row[g] != KEY_NONE) == 0) continue;
-            const uint64_t up = shfl_up64(row[g], 1);
-            if (__ballot_sync(0xffffffffu, lane > 0 && up > row[g])) row[g] = warp_sort32(row[g], lane);
-            best = warp_merge32(best, row[g], lane);
+            for (int g = 0; g < 4; ++g) {
+                if (__ballot_sync(0xffffffffu, row[g] != KEY_NONE) == 0) continue;
+                const uint64_t up = shfl_up64(row[g], 1);
+                if (__ballot_sync(0xffffffffu, lane > 0 && up > row[g])) row[g] = warp_sort32(row[g], lane);
+                best = warp_merge32(best, row[g], lane);
+            }
         }
     }
     if (w) part[w - 1][lane] = best;

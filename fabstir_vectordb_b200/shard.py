@@ -104,7 +104,9 @@ class ShardedIndex:
         self._group = []           # ... and every batch submitted since the last finish()
         self._nlist = None
         self._deferred_error = None
-        self.coarse_async = os.environ.get("FVDB_SHARD_COARSE_ASYNC", "0") == "1"
+        # the coarse step of a pipelined batch: stream-ordered until a proof failure shows up there (dense
+        # centroid tables, e.g. nlist 16384), then the synchronous, self-repairing entry (see submit / finish)
+        self.coarse_async = os.environ.get("FVDB_SHARD_COARSE_ASYNC", "1") == "1"
 
     def _setup_bound_sharing(self, nq: int, device):
         """Exchange the inter-process handles of the per-query bound arrays (once per capacity)."""
@@ -252,11 +254,10 @@ class ShardedIndex:
         if n_mine < per:
             mine.fill_(-1)
         if n_mine:
-            # The coarse step of the slice.  Default: the synchronous entry — it repairs on the spot the few
-            # queries whose tensor-core proof fails (dense centroid tables: nlist 16384), and its host
-            # synchronisation only waits for THIS stream, while the previous batch keeps scanning in its slot.
-            # FVDB_SHARD_COARSE_ASYNC=1: the stream-ordered entry (a proof failure then makes finish() re-run
-            # the whole group).
+            # The coarse step of the slice: the stream-ordered entry (no host round trip; a proof failure makes
+            # finish() re-run the group) until such a failure has been seen once — dense centroid tables (nlist
+            # 16384) produce a few per batch — then the synchronous entry, which repairs them on the spot and
+            # whose host synchronisation only waits for THIS stream while the previous batch keeps scanning.
             try:
                 if self.coarse_async:
                     self.eng.coarse_device_submit(q[lo:lo + n_mine].data_ptr(), n_mine, np_, mine.data_ptr(), stream)
@@ -308,12 +309,25 @@ class ShardedIndex:
                               device=torch.device("cuda", torch.cuda.current_device()))
             dist.all_reduce(fb, op=dist.ReduceOp.MAX, group=self.group)
             if int(fb.item()) > 0:
-                for q, k, nprobe, tiers, slot in group:
-                    self.search(q, k, nprobe, tiers=tiers, slot=slot)
-                torch.cuda.synchronize()
+                self.coarse_async = False     # (every rank sees the same all-reduced count)
+                self._redo_exact(group)
+
+    def _redo_exact(self, group):
+        """A tensor-core proof failed for some query on SOME rank.  Rows of that query may have been dropped on
+        OTHER ranks by a bound the failing rank published — their exclusion rested on the proof that failed — so
+        no rank's tensor-core result can be kept: every rank answers the batches on the exact path."""
+        import torch
+        mode = L.SCAN_TC
+        self.eng.set_option(L.OPT_SCAN_MODE, L.SCAN_EXACT)
+        try:
+            for q, k, nprobe, tiers, slot in group:
+                self.search(q, k, nprobe, tiers=tiers, slot=slot, _check=False)
+            torch.cuda.synchronize()
+        finally:
+            self.eng.set_option(L.OPT_SCAN_MODE, mode)
 
     def search(self, q, k: int, nprobe: int, tiers: int = L.TIER_HISTORICAL, filter_bits=None,
-               filter_nbits: int = 0, slot: int = 0):
+               filter_nbits: int = 0, slot: int = 0, _check: bool = True):
         """q: [nq x dim] CUDA tensor, identical on every rank.  Returns (ids, dist, cnt) CUDA
         tensors holding the GLOBAL top-k on every rank."""
         import torch
@@ -357,4 +371,13 @@ class ShardedIndex:
         dist.all_gather_into_tensor(b["g_pack"].view(-1), b["pack"], group=self.group)
         self.eng.merge_topk_packed_device(b["g_pack"].data_ptr(), self.world, nq, k, b["o_ids"].data_ptr(),
                                           b["o_dist"].data_ptr(), b["o_cnt"].data_ptr(), stream)
+        if _check and filter_bits is None and self._tc_mode():
+            # one more small collective on this (synchronous) path: did the proof fail anywhere?  (see _redo_exact)
+            fb = torch.tensor([self.eng.stats().last_fallback_queries], dtype=torch.int32, device=q.device)
+            dist.all_reduce(fb, op=dist.ReduceOp.MAX, group=self.group)
+            if int(fb.item()) > 0:
+                self._redo_exact([(q, k, nprobe, tiers, slot)])
         return b["o_ids"], b["o_dist"], b["o_cnt"]
+
+    def _tc_mode(self) -> bool:
+        return os.environ.get("FVDB_SHARD_CHECK", "1") != "0" and self.share_bounds
