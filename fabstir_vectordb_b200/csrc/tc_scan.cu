@@ -1721,6 +1721,19 @@ static cudaError_t dump_prof(const unsigned long long* d_prof, uint32_t grid, cu
             dur_avg += d / grid; dur_max = std::max(dur_max, d); cyc_avg += (double)r[6] / grid;
             start_max = std::max(start_max, (double)(r[4] - t0));
         }
+        {
+            std::vector<double> ends;
+            for (uint32_t b = 0; b < grid; ++b) {
+                const unsigned long long* r = &hp[((size_t)b * 6 + 3) * 8];
+                if (r[4]) ends.push_back((double)(r[5] - t0) * 1e-3);
+            }
+            std::sort(ends.begin(), ends.end());
+            if (!ends.empty()) {
+                fprintf(stderr, "[tc prof] CTA end times (us), deciles:");
+                for (int d = 0; d <= 10; ++d) fprintf(stderr, " %.0f", ends[std::min(ends.size() - 1, ends.size() * d / 10)]);
+                fprintf(stderr, "\n");
+            }
+        }
         if (t1) fprintf(stderr, "[tc prof] wall: first start -> last end %.1f us; CTA duration avg %.1f max %.1f us; "
                         "latest start +%.1f us; avg cycles %.0f => %.3f GHz\n", (t1 - t0) * 1e-3, dur_avg * 1e-3,
                         dur_max * 1e-3, start_max * 1e-3, cyc_avg, cyc_avg / dur_avg);
