@@ -1886,7 +1886,7 @@ static int finish_pending(fvdb_index* h, cudaStream_t st) {
 
 int fvdb_coarse_device(fvdb_index* h, const float* d_q, uint32_t nq, uint32_t nprobe, uint64_t* d_out_keys,
                        void* stream) {
-    ENTER(h);
+    ENTER_PIPE(h);   // touches nothing a batch in a pipeline slot reads: no drain
     if (!h->trained) return h->fail(FVDB_ERR_NOT_TRAINED, "Index not trained. Call train() before inserting or searching.");
     if (nprobe == 0 || nprobe > h->nlist || nprobe > 512)
         return h->fail(FVDB_ERR_INVALID_ARG, "fvdb_coarse_device needs 1 <= nprobe <= min(nlist, 512)");
@@ -2238,7 +2238,7 @@ int fvdb_bounds_import(fvdb_index* h, const void* handles, uint32_t n_ranks, uin
 }
 
 int fvdb_bounds_begin_batch(fvdb_index* h, uint32_t nq, void* stream) {
-    ENTER(h);
+    ENTER_PIPE(h);   // touches nothing a batch in a pipeline slot reads: no drain
     if (!h->bounds || nq > h->bounds_cap) { h->bounds_armed_nq = 0; return FVDB_OK; }   // not shared: the scan uses its own array
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->bounds_parity ^= 1u;
@@ -2250,7 +2250,7 @@ int fvdb_bounds_begin_batch(fvdb_index* h, uint32_t nq, void* stream) {
 
 int fvdb_merge_topk_packed_device(fvdb_index* h, const uint32_t* d_pack, uint32_t parts, uint32_t nq, uint32_t k,
                                   uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count, void* stream) {
-    ENTER(h);
+    ENTER_PIPE(h);   // touches nothing a batch in a pipeline slot reads: no drain
     if (parts == 0 || parts > 64) return h->fail(FVDB_ERR_INVALID_ARG, "parts must be in 1..64");
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     const size_t nk = (size_t)nq * k, chunk = 2 * nk + nq;
@@ -2262,7 +2262,7 @@ int fvdb_merge_topk_packed_device(fvdb_index* h, const uint32_t* d_pack, uint32_
 int fvdb_merge_topk_device(fvdb_index* h, const uint32_t* d_ids, const float* d_dist, const uint32_t* d_count,
                            uint32_t parts, uint32_t nq, uint32_t k, uint32_t* d_out_ids, float* d_out_dist,
                            uint32_t* d_out_count, void* stream) {
-    ENTER(h);
+    ENTER_PIPE(h);   // touches nothing a batch in a pipeline slot reads: no drain
     if (parts == 0 || parts > 64) return h->fail(FVDB_ERR_INVALID_ARG, "parts must be in 1..64");
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     CK(launch_merge_parts(d_ids, d_dist, d_count, parts, nq, k, d_out_ids, d_out_dist, d_out_count, st));
