@@ -1807,7 +1807,14 @@ static int finish_pending(fvdb_index* h, cudaStream_t st) {
     bool bad = false;
     for (auto& sl : h->slots)
         if (sl.busy && sl.stream) { bad |= cudaStreamSynchronize(sl.stream) != cudaSuccess; sl.busy = false; }
-    if (bad || cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); h->pending.clear(); return h->fail(FVDB_ERR_CUDA, "stream synchronisation failed"); }
+    if (bad || cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaGetLastError();
+        for (const fvdb_index::Pending& pb : h->pending) h->pending_pool.push_back({pb.host, pb.host_words});
+        for (auto& rec : h->pending_coarse) h->pending_pool.push_back(rec);
+        h->pending.clear();
+        h->pending_coarse.clear();
+        return h->fail(FVDB_ERR_CUDA, "stream synchronisation failed");
+    }
     int rc = FVDB_OK;
     std::vector<fvdb_index::Pending> todo;
     todo.swap(h->pending);
