@@ -51,7 +51,9 @@ TRAIN_ITERS = int(os.environ.get("FVDB_BENCH_TRAIN_ITERS", 20))   # SURVEY §8d:
 TRAIN_ROWS_PER_LIST = 64
 N_QUERY_SETS = 4
 RECALL_QUERIES = 256
-CPU_SAMPLE_QUERIES = int(os.environ.get("FVDB_BENCH_CPU_QUERIES", 128))
+# CPU legs: the reference arm times this many queries of every step's batch (30 steps x 256 = ~10 s of work on 16
+# threads); the cpu_baseline / parity leg of the product arm takes 4x as many (a whole 1024-query batch).
+CPU_SAMPLE_QUERIES = int(os.environ.get("FVDB_BENCH_CPU_QUERIES", 256))
 
 
 def n_comp_for(nlist):  # 4 mixture components per list
@@ -816,7 +818,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         import oracle as O
         ivf, _ = host_index_from_device(torch, lib, eng, n_total, n_comp)
-        sample = CPU_SAMPLE_QUERIES
+        sample = min(nq, 4 * CPU_SAMPLE_QUERIES)
         cq = h_q[0][:sample]
         cpu_qps, cpu_dt, cres = cpu_search_qps(ivf, cq, K, NPROBE)
         f1 = 16
