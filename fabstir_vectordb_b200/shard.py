@@ -86,6 +86,15 @@ def merge_parts_reference(ids: np.ndarray, dist: np.ndarray, cnt: np.ndarray, k:
     return out_ids, out_dist, out_cnt
 
 
+def _cur_stream(t=None) -> int:
+    """The caller's CUDA stream (0 when the tensors live on the host: the gloo tests drive this class with a
+    stand-in engine over CPU tensors)."""
+    import torch
+    if t is not None and not t.is_cuda:
+        return 0
+    return torch.cuda.current_stream().cuda_stream
+
+
 class ShardedIndex:
     """One rank's shard + the exchange step.  All tensors are torch CUDA tensors."""
 
@@ -230,7 +239,7 @@ class ShardedIndex:
         import torch.distributed as dist
         nq = q.shape[0]
         b = self._buffers(nq, k, q.device, slot)
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _cur_stream(q)
         if self.world == 1:
             self.eng.search_device_submit(q.data_ptr(), nq, k, nprobe, tiers, 0, 0, b["ids"].data_ptr(),
                                           b["dist"].data_ptr(), b["cnt"].data_ptr(), stream)
@@ -239,7 +248,7 @@ class ShardedIndex:
         np_ = min(nprobe, self.eng.stats().nlist) if self._nlist is None else min(nprobe, self._nlist)
         if self._nlist is None:
             self._nlist = self.eng.stats().nlist
-        if self.share_bounds and self.world <= 8:
+        if self.share_bounds and q.is_cuda and self.world <= 8:
             if nq > self._bounds_cap:
                 self._setup_bound_sharing(nq, q.device)
             self.eng.bounds_begin_batch(nq, stream)
@@ -280,7 +289,7 @@ class ShardedIndex:
         import torch
         import torch.distributed as dist
         b, nq, k = rec
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _cur_stream(b["pack"])
         self.eng.search_device_wait(age, stream)
         dist.all_gather_into_tensor(b["g_pack"].view(-1), b["pack"], group=self.group)
         self.eng.merge_topk_packed_device(b["g_pack"].data_ptr(), self.world, nq, k, b["o_ids"].data_ptr(),
@@ -292,7 +301,8 @@ class ShardedIndex:
         synchronous path, which repairs such queries before results are exchanged."""
         import torch
         import torch.distributed as dist
-        stream = torch.cuda.current_stream().cuda_stream
+        on_host = self._inflight is not None and not self._inflight[0]["pack"].is_cuda
+        stream = 0 if on_host else _cur_stream()
         if self.world > 1 and self._inflight is not None:
             self._exchange(self._inflight, age=0)
             self._inflight = None
@@ -306,7 +316,7 @@ class ShardedIndex:
         if self.world > 1:
             group, self._group = self._group, []
             fb = torch.tensor([self.eng.stats().last_fallback_queries], dtype=torch.int32,
-                              device=torch.device("cuda", torch.cuda.current_device()))
+                              device=torch.device("cpu") if on_host else torch.device("cuda", torch.cuda.current_device()))
             dist.all_reduce(fb, op=dist.ReduceOp.MAX, group=self.group)
             if int(fb.item()) > 0:
                 self.coarse_async = False     # (every rank sees the same all-reduced count)
@@ -322,7 +332,8 @@ class ShardedIndex:
         try:
             for q, k, nprobe, tiers, slot in group:
                 self.search(q, k, nprobe, tiers=tiers, slot=slot, _check=False)
-            torch.cuda.synchronize()
+            if group and group[0][0].is_cuda:
+                torch.cuda.synchronize()
         finally:
             self.eng.set_option(L.OPT_SCAN_MODE, mode)
 
@@ -334,7 +345,7 @@ class ShardedIndex:
         import torch.distributed as dist
         nq = q.shape[0]
         b = self._buffers(nq, k, q.device, slot)
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _cur_stream(q)
         f_ptr = filter_bits.data_ptr() if filter_bits is not None else 0
         if self.world == 1:
             self.eng.search_device(q.data_ptr(), nq, k, nprobe, tiers, f_ptr, filter_nbits,
